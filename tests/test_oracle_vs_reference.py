@@ -1,0 +1,81 @@
+"""CPU, build container only: pin the oracle against the reference's own code on fresh inputs."""
+import contextlib
+import io
+
+import numpy as np
+import pytest
+
+from oracle import lopq_oracle as orc
+from oracle import ref_loader
+from columbiaimagesearch_b200 import synth
+
+pytestmark = pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not present (GPU box)")
+
+
+@pytest.fixture(scope="module")
+def setup():
+    ref = ref_loader.load()
+    train = synth.lattice_gmm(4000, 32, 101, dtype=np.float32)
+    model = ref.LOPQModel(V=4, M=4, subquantizer_clusters=64)
+    model.fit(train, n_init=1, random_state=1)
+    om = orc.OracleModel(model.Cs, model.Rs, model.mus, model.subquantizers)
+    db = synth.lattice_gmm(3000, 32, 102, dup_frac=0.05)
+    Q, _ = synth.lattice_queries(db, 20, 103)
+    return ref, model, om, db, Q
+
+
+def test_codes_luts_cells_bit_identical(setup):
+    ref, model, om, db, Q = setup
+    rc = ref.utils.compute_codes_notparallel(db[:800], model)
+    oc = orc.compute_codes(om, db[:800])
+    assert [tuple(map(int, c.coarse)) + tuple(map(int, c.fine)) for c in rc] == \
+           [tuple(map(int, c.coarse)) + tuple(map(int, c.fine)) for c in oc]
+    for q in Q[:6]:
+        rs = list(ref.multisequence(q, model.Cs))
+        os_ = list(orc.multisequence(q, om.Cs))
+        assert [(float(d), tuple(map(int, c))) for d, c in rs] == [(float(d), tuple(map(int, c))) for d, c in os_]
+        assert type(rs[0][0]) is type(os_[0][0])  # float32 cell distances under float32 centroids
+        c = model.predict_coarse(q)
+        for split in (None, 0, 1):
+            a = np.stack(model.get_subquantizer_distances(q, c, coarse_split=split))
+            b = np.stack(orc.subquantizer_distances(om, q, c, coarse_split=split))
+            assert np.array_equal(a, b)  # same ufunc order => same float64 bits
+        assert np.array_equal(model.reconstruct(rc[0]), orc.reconstruct(om, oc[0]))
+
+
+def test_search_identical(setup):
+    ref, model, om, db, Q = setup
+    ids = np.arange(db.shape[0]) % 2800
+    rcodes = ref.utils.compute_codes_notparallel(db, model)
+    rs = ref.LOPQSearcher(model)
+    rs.add_codes(rcodes, ids)
+    os_ = orc.OracleSearcher(om)
+    os_.add_codes(orc.compute_codes(om, db), ids)
+    assert rs.get_nb_indexed() == os_.nb_indexed
+    coarse = np.array([c.coarse for c in rcodes], np.int32)
+    fine = np.array([c.fine for c in rcodes], np.uint8)
+    index = orc.ArrayIndex(om.V, coarse, fine, ids)
+    for quota, limit in [(1, None), (50, 7), (700, None), (10 ** 6, 40)]:
+        for q in Q:
+            with contextlib.redirect_stdout(io.StringIO()):
+                a, va = rs.search(q, quota, limit, with_dists=True)
+            b, vb = os_.search(q, quota, limit, with_dists=True)
+            assert va == vb and len(a) == len(b)
+            assert [(x.id, float(x.dist)) for x in a] == [(x.id, float(x.dist)) for x in b]
+            r = orc.search_arrays(om, index, q, quota, limit)
+            assert vb == r[4] and [x.id for x in b] == r[0].tolist()
+            assert np.array_equal(np.array([x.dist for x in b]), r[1])
+
+
+def test_pca_model_identical(setup):
+    ref = setup[0]
+    train = synth.lattice_gmm(3000, 24, 111, dtype=np.float32)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = ref.LOPQModelPCA(V=2, M=2, subquantizer_clusters=32, renorm=True)
+        m.fit(train, pca_dims=16, n_init=1, random_state=2)
+    om = orc.OracleModel(m.Cs, m.Rs, m.mus, m.subquantizers, m.pca_P, m.pca_mu, m.renorm)
+    x = train[:50]
+    assert np.array_equal(m.apply_PCA(x), orc.apply_pca(om, x))
+    for row in x[:20]:
+        a, b = m.predict(row), orc.predict(om, row)
+        assert tuple(map(int, a.coarse + a.fine)) == tuple(map(int, b.coarse + b.fine))
