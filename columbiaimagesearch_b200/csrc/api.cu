@@ -1,0 +1,930 @@
+// libb200lopq: C-ABI implementation (host orchestration of the kernels in *.cuh).
+// See include/b200lopq.h for the contract and the reference functions each entry point replaces.
+#include <cub/cub.cuh>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/b200lopq.h"
+#include "common.cuh"
+#include "encode.cuh"
+#include "exact.cuh"
+#include "index.cuh"
+#include "plan.cuh"
+#include "scan.cuh"
+#include "select.cuh"
+
+#define B2L_ABI_VERSION 1
+
+namespace {
+
+std::string g_create_error;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes, bool keep = false, cudaStream_t st = 0) {
+        if (bytes <= cap) return cudaSuccess;
+        size_t ncap = std::max(bytes, cap + cap / 2);
+        ncap = (ncap + 255) & ~(size_t)255;
+        void* np = nullptr;
+        cudaError_t e = cudaMalloc(&np, ncap);
+        if (e != cudaSuccess) return e;
+        if (keep && p && cap) {
+            e = cudaMemcpyAsync(np, p, cap, cudaMemcpyDeviceToDevice, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) { cudaFree(np); return e; }
+        }
+        if (p) cudaFree(p);
+        p = np; cap = ncap;
+        return cudaSuccess;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T* as() const { return (T*)p; }
+};
+
+}  // namespace
+
+struct b2l_ctx {
+    int device = 0, num_sms = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[6] = {};
+    std::string err;
+    std::mutex mu;
+    // model
+    bool has_model = false, has_pca = false;
+    ModelView mv = {};
+    DevBuf dCs, dmus, dRt, dsubs, dP, dpmu;
+    // index: master copy in insertion order
+    int64_t n_items = 0;
+    DevBuf m_coarse, m_fine, m_rowid;
+    // index: cell-major layout
+    bool dirty = true, global_set = false;
+    int64_t rows_padded = 0;
+    DevBuf codes, rowids, cell_start, lsize, gsize, sorted_first;
+    std::vector<int64_t> h_lsize, h_gsize, h_cell_start;
+    // workspaces
+    DevBuf w_q, w_xq, w_px, w_coarse, w_fine, w_lut32, w_lut64, w_p64, w_cellq, w_partial, w_plan, w_sort_a, w_sort_b,
+        w_sort_tmp, w_rec, w_rec2, w_out, w_out2, w_misc;
+    PlanView pv = {};
+    b2l_stats stats = {};
+    int64_t launches = 0;
+};
+
+namespace {
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            char b__[512];                                                                         \
+            snprintf(b__, sizeof b__, "%s:%d: %s failed: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            h->err = b__;                                                                          \
+            return B2L_ERR_CUDA;                                                                   \
+        }                                                                                          \
+    } while (0)
+#define FAIL(code, ...)                                      \
+    do {                                                     \
+        char b__[512];                                       \
+        snprintf(b__, sizeof b__, __VA_ARGS__);              \
+        h->err = b__;                                        \
+        return code;                                         \
+    } while (0)
+#define LAUNCHED() do { ++h->launches; CU(cudaGetLastError()); } while (0)
+
+inline int next_pow2(int x) { int p = 1; while (p < x) p <<= 1; return p; }
+inline int grid_for(int64_t n, int threads, int maxblocks = 148 * 16) {
+    int64_t b = (n + threads - 1) / threads;
+    return (int)std::max<int64_t>(1, std::min<int64_t>(b, maxblocks));
+}
+
+int scan_tile(int MP) { return MP == 4 ? 512 : 1024; }
+
+template <int MP> int launch_scan(b2l_handle h, const ScanArgs& a, int cap) {
+    const size_t smem = scan_smem_bytes<MP>(cap);
+    if (smem > 227 * 1024) FAIL(B2L_ERR_UNSUPPORTED, "scan shared memory %zu too large", smem);
+    CU(cudaFuncSetAttribute(k_scan<MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 1;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_scan<MP>, SCAN_THREADS, smem));
+    if (occ < 1) occ = 1;
+    const unsigned grid = (unsigned)std::min<int64_t>((int64_t)a.n_items, (int64_t)h->num_sms * occ);
+    k_scan<MP><<<grid, SCAN_THREADS, smem, h->stream>>>(a);
+    LAUNCHED();
+    return B2L_OK;
+}
+
+// copy helper honouring on_device
+int copy_in(b2l_handle h, void* dst, const void* src, size_t bytes, int on_device) {
+    CU(cudaMemcpyAsync(dst, src, bytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+    return B2L_OK;
+}
+int copy_out(b2l_handle h, void* dst, const void* src, size_t bytes, int on_device) {
+    if (!dst) return B2L_OK;
+    CU(cudaMemcpyAsync(dst, src, bytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
+    return B2L_OK;
+}
+
+// ---- encode pipeline on device-resident input ----------------------------------------------------
+// X device [n][D0|D]; outputs device.  want_px: also keep the projection in w_px (n rows).
+int encode_device(b2l_handle h, const void* dX, int x_is_f64, int64_t n, const int32_t* d_coarse_in,
+                  int32_t* d_coarse, uint8_t* d_fine) {
+    const ModelView& mv = h->mv;
+    const void* x = dX;
+    int xf64 = x_is_f64;
+    if (h->has_pca) {
+        CU(h->w_xq.reserve((size_t)n * mv.D * 4));
+        const size_t smem = (size_t)(mv.D0 + mv.D) * 8;
+        if (x_is_f64) { CU(cudaFuncSetAttribute(k_pca<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_pca<double><<<(unsigned)n, 128, smem, h->stream>>>(mv, (const double*)dX, n, h->w_xq.as<float>()); }
+        else { CU(cudaFuncSetAttribute(k_pca<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_pca<float><<<(unsigned)n, 128, smem, h->stream>>>(mv, (const float*)dX, n, h->w_xq.as<float>()); }
+        LAUNCHED();
+        x = h->w_xq.p; xf64 = 0;
+    }
+    CU(h->w_px.reserve((size_t)n * mv.D * 8));
+    const unsigned blocks = (unsigned)((n + ENC_WARPS - 1) / ENC_WARPS);
+    const size_t smem = (size_t)ENC_WARPS * mv.h * 8;
+    if (xf64) { CU(cudaFuncSetAttribute(k_coarse_project<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_coarse_project<double><<<blocks, ENC_WARPS * 32, smem, h->stream>>>(mv, (const double*)x, n, d_coarse_in, d_coarse, h->w_px.as<double>()); }
+    else { CU(cudaFuncSetAttribute(k_coarse_project<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_coarse_project<float><<<blocks, ENC_WARPS * 32, smem, h->stream>>>(mv, (const float*)x, n, d_coarse_in, d_coarse, h->w_px.as<double>()); }
+    LAUNCHED();
+    if (d_fine) {
+        int kchunk = mv.K;
+        while ((size_t)kchunk * mv.ds * 8 > 96 * 1024 && kchunk > 1) kchunk = (kchunk + 1) / 2;
+        const size_t sm2 = (size_t)kchunk * mv.ds * 8;
+        const unsigned b2 = (unsigned)((n + FINE_THREADS - 1) / FINE_THREADS);
+#define FINE(DSV)                                                                                               \
+    do {                                                                                                        \
+        CU(cudaFuncSetAttribute(k_fine_argmin<DSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));     \
+        k_fine_argmin<DSV><<<b2, FINE_THREADS, sm2, h->stream>>>(mv, h->w_px.as<double>(), n, d_fine, kchunk);   \
+    } while (0)
+        switch (mv.ds) {
+            case 2: FINE(2); break;
+            case 4: FINE(4); break;
+            case 8: FINE(8); break;
+            case 16: FINE(16); break;
+            default:
+                if (mv.ds > 128) FAIL(B2L_ERR_UNSUPPORTED, "sub-vector length D/M = %d > 128 not supported", mv.ds);
+                FINE(0);
+        }
+#undef FINE
+        LAUNCHED();
+    }
+    return B2L_OK;
+}
+
+// ---- (re)build the cell-major layout ---------------------------------------------------------------
+int ensure_index(b2l_handle h) {
+    if (!h->dirty) return B2L_OK;
+    const ModelView& mv = h->mv;
+    const int ncell = mv.V * mv.V;
+    const int64_t n = h->n_items;
+    h->h_lsize.assign(ncell, 0);
+    h->h_cell_start.assign(ncell, 0);
+    CU(h->lsize.reserve((size_t)ncell * 8));
+    CU(h->gsize.reserve((size_t)ncell * 8));
+    CU(h->cell_start.reserve((size_t)ncell * 8));
+    CU(h->sorted_first.reserve((size_t)ncell * 8));
+    std::vector<int64_t> first(ncell, 0);
+    if (n > 0) {
+        if (n >= (int64_t)1 << 32) FAIL(B2L_ERR_UNSUPPORTED, "more than 2^32 rows per shard");
+        CU(h->w_sort_a.reserve((size_t)n * 8));      // cell[n] | order[n]
+        CU(h->w_sort_b.reserve((size_t)n * 8));      // sorted_cell[n] | sorted_src[n]
+        CU(h->w_misc.reserve((size_t)ncell * 8 + 64));
+        unsigned int* cell = h->w_sort_a.as<unsigned int>();
+        unsigned int* order = cell + n;
+        unsigned int* scell = h->w_sort_b.as<unsigned int>();
+        unsigned int* ssrc = scell + n;
+        unsigned long long* hist = h->w_misc.as<unsigned long long>();
+        int* bad = (int*)(hist + ncell);
+        CU(cudaMemsetAsync(h->w_misc.p, 0, (size_t)ncell * 8 + 64, h->stream));
+        k_cell_ids<<<grid_for(n, 256), 256, 0, h->stream>>>(h->m_coarse.as<int32_t>(), n, mv.V, cell, order, hist, bad);
+        LAUNCHED();
+        int bits = 1;
+        while ((1 << bits) < ncell) ++bits;
+        size_t tmp = 0;
+        CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp, cell, scell, order, ssrc, (int)n, 0, bits, h->stream));
+        CU(h->w_sort_tmp.reserve(tmp));
+        CU(cub::DeviceRadixSort::SortPairs(h->w_sort_tmp.p, tmp, cell, scell, order, ssrc, (int)n, 0, bits, h->stream));
+        ++h->launches;
+        std::vector<unsigned long long> hh(ncell);
+        int hbad = 0;
+        CU(cudaMemcpyAsync(hh.data(), hist, (size_t)ncell * 8, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaMemcpyAsync(&hbad, bad, 4, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        if (hbad) FAIL(B2L_ERR_ARG, "coarse code out of range [0, V) in the index");
+        for (int c = 0; c < ncell; ++c) h->h_lsize[c] = (int64_t)hh[c];
+    }
+    int64_t start = 0, acc = 0;
+    for (int c = 0; c < ncell; ++c) {
+        h->h_cell_start[c] = start;
+        first[c] = acc;
+        acc += h->h_lsize[c];
+        start += (h->h_lsize[c] + 15) & ~(int64_t)15;
+    }
+    h->rows_padded = start + 64;
+    CU(h->codes.reserve((size_t)h->rows_padded * mv.MP));
+    CU(h->rowids.reserve((size_t)h->rows_padded * 8));
+    CU(cudaMemsetAsync(h->codes.p, 0, (size_t)h->rows_padded * mv.MP, h->stream));
+    CU(cudaMemcpyAsync(h->lsize.p, h->h_lsize.data(), (size_t)ncell * 8, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->cell_start.p, h->h_cell_start.data(), (size_t)ncell * 8, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->sorted_first.p, first.data(), (size_t)ncell * 8, cudaMemcpyHostToDevice, h->stream));
+    if (!h->global_set) h->h_gsize = h->h_lsize;
+    if ((int)h->h_gsize.size() != ncell) FAIL(B2L_ERR_STATE, "global cell sizes have the wrong length");
+    CU(cudaMemcpyAsync(h->gsize.p, h->h_gsize.data(), (size_t)ncell * 8, cudaMemcpyHostToDevice, h->stream));
+    if (n > 0) {
+        unsigned int* scell = h->w_sort_b.as<unsigned int>();
+        k_scatter_rows<<<grid_for(n, 256), 256, 0, h->stream>>>(scell, scell + n, n, h->sorted_first.as<int64_t>(),
+                                                                 h->cell_start.as<int64_t>(), h->m_fine.as<uint8_t>(),
+                                                                 h->m_rowid.as<int64_t>(), mv.M, mv.MP, h->codes.as<uint8_t>(),
+                                                                 h->rowids.as<int64_t>());
+        LAUNCHED();
+    }
+    CU(cudaStreamSynchronize(h->stream));   // `first` is a local host buffer
+    h->dirty = false;
+    return B2L_OK;
+}
+
+size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// carve the per-batch plan arrays out of one allocation
+int setup_plan(b2l_handle h, int nq, int segc) {
+    const ModelView& mv = h->mv;
+    const int ncell = mv.V * mv.V, maxvis = ncell;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes); return o; };
+    const size_t o_cnt = take(sizeof(PlanCounters));
+    const size_t o_qc = take((size_t)ncell * 4);            // cell_qcount (zeroed together with the counters)
+    const size_t zero_bytes = off;
+    const size_t o_fill = take((size_t)ncell * 4);
+    const size_t o_coff = take((size_t)(ncell + 1) * 4);
+    const size_t o_ib = take((size_t)(ncell + 1) * 4);
+    const size_t o_nvis = take((size_t)nq * 4);
+    const size_t o_ncand = take((size_t)nq * 8);
+    const size_t o_ncl = take((size_t)nq * 8);
+    const size_t o_npart = take((size_t)nq * 4);
+    const size_t o_pbase = take((size_t)nq * 4);
+    const size_t o_vcell = take((size_t)nq * maxvis * 4);
+    const size_t o_vbase = take((size_t)nq * maxvis * 8);
+    const size_t o_vl0 = take((size_t)nq * maxvis * 4);
+    const size_t o_vl1 = take((size_t)nq * maxvis * 4);
+    const size_t o_vpb = take((size_t)nq * maxvis * 4);
+    const size_t o_desc = take((size_t)nq * 2 * mv.V * 3 * 4);
+    CU(h->w_plan.reserve(off));
+    unsigned char* b = h->w_plan.as<unsigned char>();
+    PlanView& pv = h->pv;
+    pv.nq = nq; pv.maxvis = maxvis; pv.segc = segc;
+    pv.cnt = (PlanCounters*)(b + o_cnt);
+    pv.cell_qcount = (unsigned int*)(b + o_qc);
+    pv.cell_fill = (unsigned int*)(b + o_fill);
+    pv.cellq_off = (unsigned int*)(b + o_coff);
+    pv.item_base = (unsigned int*)(b + o_ib);
+    pv.nvis = (int32_t*)(b + o_nvis);
+    pv.ncand = (int64_t*)(b + o_ncand);
+    pv.ncand_local = (int64_t*)(b + o_ncl);
+    pv.npart = (int32_t*)(b + o_npart);
+    pv.pbase = (int32_t*)(b + o_pbase);
+    pv.vis_cell = (int32_t*)(b + o_vcell);
+    pv.vis_base = (int64_t*)(b + o_vbase);
+    pv.vis_lut0 = (int32_t*)(b + o_vl0);
+    pv.vis_lut1 = (int32_t*)(b + o_vl1);
+    pv.vis_pbase = (int32_t*)(b + o_vpb);
+    pv.lut_desc = (int32_t*)(b + o_desc);
+    pv.cellq = nullptr;
+    pv.vis_dist = nullptr;
+    CU(cudaMemsetAsync(b, 0, zero_bytes, h->stream));
+    return B2L_OK;
+}
+
+int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_device, int64_t quota, int k, int exact,
+                      void* d_records) {
+    if (!h->has_model) FAIL(B2L_ERR_STATE, "no model set");
+    if (nq < 1 || k < 1 || !Q || !d_records) FAIL(B2L_ERR_ARG, "bad search arguments (nq=%d k=%d)", nq, k);
+    if (h->mv.V > B2L_MAX_V) FAIL(B2L_ERR_UNSUPPORTED, "V=%d > %d: large-V multi-index traversal is not implemented", h->mv.V, B2L_MAX_V);
+    int rc = ensure_index(h);
+    if (rc) return rc;
+    const ModelView& mv = h->mv;
+    const int ncell = mv.V * mv.V;
+    int64_t gtotal = 0;
+    for (int c = 0; c < ncell; ++c) gtotal += h->h_gsize[c];
+    if (gtotal >= ((int64_t)1 << 32)) FAIL(B2L_ERR_UNSUPPORTED, "more than 2^32 indexed codes");
+
+    h->launches = 0;
+    memset(&h->stats, 0, sizeof h->stats);
+    CU(cudaEventRecord(h->ev[0], h->stream));
+    // queries -> device, PCA
+    const int Din = h->has_pca ? mv.D0 : mv.D;
+    const size_t esz = q_is_f64 ? 8 : 4;
+    const void* dq = Q;
+    if (!on_device) {
+        CU(h->w_q.reserve((size_t)nq * Din * esz));
+        rc = copy_in(h, h->w_q.p, Q, (size_t)nq * Din * esz, 0);
+        if (rc) return rc;
+        dq = h->w_q.p;
+    }
+    const void* x = dq;
+    int xf64 = q_is_f64;
+    if (h->has_pca) {
+        CU(h->w_xq.reserve((size_t)nq * mv.D * 4));
+        const size_t smem = (size_t)(mv.D0 + mv.D) * 8;
+        if (q_is_f64) { CU(cudaFuncSetAttribute(k_pca<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_pca<double><<<nq, 128, smem, h->stream>>>(mv, (const double*)dq, nq, h->w_xq.as<float>()); }
+        else { CU(cudaFuncSetAttribute(k_pca<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_pca<float><<<nq, 128, smem, h->stream>>>(mv, (const float*)dq, nq, h->w_xq.as<float>()); }
+        LAUNCHED();
+        x = h->w_xq.p; xf64 = 0;
+    }
+    // fast path eligibility
+    const int KP = std::max(16, next_pow2(k + 8));
+    const bool fast = !exact && mv.G > 0 && KP <= 512;
+    const int tile = mv.G > 0 ? scan_tile(mv.MP) : 1024;
+    // segment length: a multiple of the tile, sized so the batch yields enough work items
+    int64_t maxcell = 0;
+    for (int c = 0; c < ncell; ++c) maxcell = std::max(maxcell, h->h_lsize[c]);
+    int segc = 16 * 1024;
+    if (maxcell > 0 && maxcell < segc) segc = (int)(((maxcell + tile - 1) / tile) * tile);
+    rc = setup_plan(h, nq, segc);
+    if (rc) return rc;
+    PlanView& pv = h->pv;
+    {
+        const size_t smem = (size_t)(3 * mv.V + 2) * 8 + (size_t)(7 * mv.V + 4) * 4 + 16;
+        if (xf64) k_coarse_order<double><<<nq, 32, smem, h->stream>>>(mv, (const double*)x, quota, h->gsize.as<int64_t>(), h->lsize.as<int64_t>(), pv);
+        else k_coarse_order<float><<<nq, 32, smem, h->stream>>>(mv, (const float*)x, quota, h->gsize.as<int64_t>(), h->lsize.as<int64_t>(), pv);
+        LAUNCHED();
+    }
+    if (fast) {
+        k_plan<<<1, 1024, 0, h->stream>>>(ncell, mv.G, segc, h->lsize.as<int64_t>(), pv);
+        LAUNCHED();
+    }
+    PlanCounters pc;
+    CU(cudaMemcpyAsync(&pc, pv.cnt, sizeof pc, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->stats.lut_slots = pc.n_lut;
+    h->stats.codes_scanned = (int64_t)pc.cand_local;
+    h->stats.scan_bytes = (int64_t)pc.cand_local * mv.M;
+    h->stats.work_items = fast ? pc.n_items : 0;
+
+    // LUT build
+    CU(h->w_p64.reserve((size_t)std::max(1u, pc.n_lut) * mv.h * 8));
+    float* lut32 = nullptr;
+    double* lut64 = nullptr;
+    if (fast) { CU(h->w_lut32.reserve((size_t)std::max(1u, pc.n_lut) * B2L_LUT_ROWS * mv.m * 4)); lut32 = h->w_lut32.as<float>(); }
+    else { CU(h->w_lut64.reserve((size_t)std::max(1u, pc.n_lut) * mv.m * mv.K * 8)); lut64 = h->w_lut64.as<double>(); }
+    if (pc.n_lut) {
+        const size_t smem = (size_t)2 * mv.h * 8;
+        if (xf64) { CU(cudaFuncSetAttribute(k_lut<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_lut<double><<<pc.n_lut, 256, smem, h->stream>>>(mv, (const double*)x, pv.lut_desc, h->w_p64.as<double>(), lut32, lut64); }
+        else { CU(cudaFuncSetAttribute(k_lut<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_lut<float><<<pc.n_lut, 256, smem, h->stream>>>(mv, (const float*)x, pv.lut_desc, h->w_p64.as<double>(), lut32, lut64); }
+        LAUNCHED();
+    }
+    IndexView ix = {h->codes.as<uint8_t>(), h->rowids.as<int64_t>(), h->cell_start.as<int64_t>(), h->lsize.as<int64_t>()};
+    CU(cudaEventRecord(h->ev[1], h->stream));
+    if (fast) {
+        CU(h->w_cellq.reserve((size_t)std::max(1u, pc.n_pairs) * 8));
+        CU(h->w_partial.reserve((size_t)std::max(1u, pc.n_partial) * KP * 8));
+        pv.cellq = h->w_cellq.as<int2>();
+        k_fill<<<(nq + 255) / 256, 256, 0, h->stream>>>(pv);
+        LAUNCHED();
+        CU(cudaEventRecord(h->ev[2], h->stream));
+        if (pc.n_items) {
+            ScanArgs a;
+            a.codes = ix.codes; a.cell_start = ix.cell_start; a.lsize = ix.lsize; a.lut32 = lut32;
+            a.partial = h->w_partial.as<unsigned long long>();
+            a.pv = pv; a.ncell = ncell; a.KP = KP; a.cap = next_pow2(2 * KP + tile); a.m = mv.m; a.M = mv.M;
+            a.n_items = pc.n_items;
+            switch (mv.MP) {
+                case 4: rc = launch_scan<4>(h, a, a.cap); break;
+                case 8: rc = launch_scan<8>(h, a, a.cap); break;
+                case 16: rc = launch_scan<16>(h, a, a.cap); break;
+                case 32: rc = launch_scan<32>(h, a, a.cap); break;
+                default: FAIL(B2L_ERR_UNSUPPORTED, "no scan instantiation for code stride %d", mv.MP);
+            }
+            if (rc) return rc;
+        }
+        CU(cudaEventRecord(h->ev[3], h->stream));
+        const double eps_rel = (double)(mv.M + 4) * 2.0 * ldexp(1.0, -24);
+        const size_t smem = (size_t)SEL_SB * 8 + (size_t)KP * 28 + 16;
+        CU(cudaFuncSetAttribute(k_merge_rerank, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_merge_rerank<<<nq, SEL_THREADS, smem, h->stream>>>(mv, ix, pv, h->w_partial.as<unsigned long long>(),
+                                                             h->w_p64.as<double>(), KP, k, eps_rel, d_records);
+        LAUNCHED();
+        CU(cudaEventRecord(h->ev[4], h->stream));
+    } else {
+        CU(cudaEventRecord(h->ev[2], h->stream));
+        CU(cudaEventRecord(h->ev[3], h->stream));
+        std::vector<int64_t> ncl(nq);
+        CU(cudaMemcpyAsync(ncl.data(), pv.ncand_local, (size_t)nq * 8, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        int64_t nmax = 1;
+        for (int q = 0; q < nq; ++q) nmax = std::max(nmax, ncl[q]);
+        CU(h->w_sort_a.reserve((size_t)nmax * 12));
+        CU(h->w_sort_b.reserve((size_t)nmax * 12));
+        unsigned long long* ka = h->w_sort_a.as<unsigned long long>();
+        unsigned int* va = (unsigned int*)(ka + nmax);
+        unsigned long long* kb = h->w_sort_b.as<unsigned long long>();
+        unsigned int* vb = (unsigned int*)(kb + nmax);
+        size_t tmp = 0;
+        CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp, ka, kb, va, vb, (int)nmax, 0, 64, h->stream));
+        CU(h->w_sort_tmp.reserve(tmp));
+        for (int q = 0; q < nq; ++q) {
+            const int64_t n = ncl[q];
+            if (n > 0) {
+                const size_t smem = (size_t)(pv.maxvis + 1) * 8;
+                k_exact_dist<<<grid_for(n, 256), 256, smem, h->stream>>>(mv, ix, pv, q, lut64, ka, va, n);
+                LAUNCHED();
+                size_t t2 = tmp;
+                CU(cub::DeviceRadixSort::SortPairs(h->w_sort_tmp.p, t2, ka, kb, va, vb, (int)n, 0, 64, h->stream));
+                ++h->launches;
+            }
+            k_exact_emit<<<1, 256, 0, h->stream>>>(mv, ix, pv, q, q, nq, k, kb, vb, n, d_records);
+            LAUNCHED();
+        }
+        h->stats.exact_queries = nq;
+        CU(cudaEventRecord(h->ev[4], h->stream));
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, h->ev[0], h->ev[2])); h->stats.plan_ms = ms;
+    CU(cudaEventElapsedTime(&ms, h->ev[2], h->ev[3])); h->stats.scan_ms = ms;
+    CU(cudaEventElapsedTime(&ms, h->ev[3], h->ev[4])); h->stats.select_ms = ms;
+    CU(cudaEventElapsedTime(&ms, h->ev[0], h->ev[4])); h->stats.total_ms = ms;
+    h->stats.kernel_launches = h->launches;
+    return B2L_OK;
+}
+
+// single-rank copy-out of records (any k); multi-rank merge through k_final
+int merge_impl(b2l_handle h, const void* d_recs, int nranks, int nq, int k, int on_device, int64_t* rowid, double* dist,
+               int32_t* coarse, uint8_t* fine, int32_t* count, int32_t* visited, uint8_t* certified) {
+    if (!h->has_model) FAIL(B2L_ERR_STATE, "no model set");
+    if (nranks < 1 || nq < 1 || k < 1 || !count) FAIL(B2L_ERR_ARG, "bad merge arguments");
+    const ModelView& mv = h->mv;
+    const int n = next_pow2(nranks * k);
+    const size_t smem = (size_t)n * 16 + 16;
+    if (smem > 200 * 1024) FAIL(B2L_ERR_UNSUPPORTED, "nranks*k = %d too large for the final merge", nranks * k);
+    // device-side outputs
+    int64_t* d_rowid = rowid; double* d_dist = dist; int32_t* d_coarse = coarse; uint8_t* d_fine = fine;
+    int32_t* d_count = count; int32_t* d_visited = visited; uint8_t* d_cert = certified;
+    if (!on_device) {
+        const size_t nk = (size_t)nq * k;
+        size_t off = 0;
+        auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes); return o; };
+        const size_t o1 = take(nk * 8), o2 = take(nk * 8), o3 = take(nk * 8), o4 = take(nk * mv.M), o5 = take((size_t)nq * 4),
+                     o6 = take((size_t)nq * 4), o7 = take((size_t)nq);
+        CU(h->w_out.reserve(off));
+        unsigned char* b = h->w_out.as<unsigned char>();
+        d_rowid = (int64_t*)(b + o1); d_dist = (double*)(b + o2); d_coarse = (int32_t*)(b + o3); d_fine = b + o4;
+        d_count = (int32_t*)(b + o5); d_visited = (int32_t*)(b + o6); d_cert = b + o7;
+        CU(cudaMemsetAsync(b, 0, off, h->stream));
+    }
+    CU(cudaFuncSetAttribute(k_final, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_final<<<nq, 128, smem, h->stream>>>(mv.V, mv.M, d_recs, nranks, nq, k, n, d_rowid, d_dist, d_coarse, d_fine, d_count,
+                                          d_visited, d_cert);
+    LAUNCHED();
+    if (!on_device) {
+        const size_t nk = (size_t)nq * k;
+        int rc;
+        if ((rc = copy_out(h, rowid, d_rowid, nk * 8, 0))) return rc;
+        if ((rc = copy_out(h, dist, d_dist, nk * 8, 0))) return rc;
+        if ((rc = copy_out(h, coarse, d_coarse, nk * 8, 0))) return rc;
+        if ((rc = copy_out(h, fine, d_fine, nk * mv.M, 0))) return rc;
+        if ((rc = copy_out(h, count, d_count, (size_t)nq * 4, 0))) return rc;
+        if ((rc = copy_out(h, visited, d_visited, (size_t)nq * 4, 0))) return rc;
+        if ((rc = copy_out(h, certified, d_cert, (size_t)nq, 0))) return rc;
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    return B2L_OK;
+}
+
+}  // namespace
+
+// ===================================================================================================
+extern "C" {
+
+int b2l_version(void) { return B2L_ABI_VERSION; }
+
+const char* b2l_last_error(b2l_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int b2l_create(int device, b2l_handle* out) {
+    if (!out) { g_create_error = "b2l_create: out is NULL"; return B2L_ERR_ARG; }
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_error = std::string("b2l_create: no CUDA device (") + cudaGetErrorString(e) + "); this library has no CPU fallback";
+        return B2L_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) { g_create_error = "b2l_create: bad device ordinal"; return B2L_ERR_ARG; }
+    b2l_ctx* h = new b2l_ctx();
+    h->device = device;
+    e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreate(&h->ev[i]);
+    cudaDeviceProp prop;
+    if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) {
+        g_create_error = std::string("b2l_create: ") + cudaGetErrorString(e);
+        delete h;
+        return B2L_ERR_CUDA;
+    }
+    h->num_sms = prop.multiProcessorCount;
+    if (prop.major < 10) {
+        g_create_error = "b2l_create: device is not sm_100 class (the library is built for sm_100a only)";
+        delete h;
+        return B2L_ERR_UNSUPPORTED;
+    }
+    *out = h;
+    return B2L_OK;
+}
+
+int b2l_destroy(b2l_handle h) {
+    if (!h) return B2L_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    DevBuf* bufs[] = {&h->dCs, &h->dmus, &h->dRt, &h->dsubs, &h->dP, &h->dpmu, &h->m_coarse, &h->m_fine, &h->m_rowid, &h->codes,
+                      &h->rowids, &h->cell_start, &h->lsize, &h->gsize, &h->sorted_first, &h->w_q, &h->w_xq, &h->w_px,
+                      &h->w_coarse, &h->w_fine, &h->w_lut32, &h->w_lut64, &h->w_p64, &h->w_cellq, &h->w_partial, &h->w_plan,
+                      &h->w_sort_a, &h->w_sort_b, &h->w_sort_tmp, &h->w_rec, &h->w_rec2, &h->w_out, &h->w_out2, &h->w_misc};
+    for (DevBuf* b : bufs) b->release();
+    for (int i = 0; i < 6; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return B2L_OK;
+}
+
+void* b2l_stream(b2l_handle h) { return h ? (void*)h->stream : nullptr; }
+
+int b2l_get_stats(b2l_handle h, b2l_stats* out) {
+    if (!h || !out) return B2L_ERR_ARG;
+    *out = h->stats;
+    return B2L_OK;
+}
+
+int b2l_set_model(b2l_handle h, int D, int V, int M, int K, int coarse_is_f32, const double* Cs, const double* Rs,
+                  const double* mus, const double* subs) {
+    if (!h) return B2L_ERR_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(cudaSetDevice(h->device));
+    if (!Cs || !Rs || !mus || !subs) FAIL(B2L_ERR_ARG, "NULL model parameter");
+    if (D < 2 || (D % 2) || M < 2 || (M % 2) || (D % M) || V < 1 || K < 1)
+        FAIL(B2L_ERR_ARG, "bad model shape D=%d V=%d M=%d K=%d (need D%%2==0, M%%2==0, D%%M==0)", D, V, M, K);
+    if (K > B2L_MAX_K) FAIL(B2L_ERR_UNSUPPORTED, "subquantizer_clusters=%d > 256 (fine codes are bytes)", K);
+    if (V > 65536) FAIL(B2L_ERR_UNSUPPORTED, "V=%d > 65536", V);
+    if (h->n_items) FAIL(B2L_ERR_STATE, "clear the index before changing the model");
+    ModelView& mv = h->mv;
+    mv = ModelView();
+    mv.D = D; mv.V = V; mv.M = M; mv.K = K; mv.h = D / 2; mv.m = M / 2; mv.ds = D / M; mv.coarse_f32 = coarse_is_f32 ? 1 : 0;
+    if (M <= 32) { mv.MP = std::max(4, next_pow2(M)); mv.G = 32 / mv.MP; }
+    else { mv.MP = (M + 15) & ~15; mv.G = 0; }
+    const size_t hh = (size_t)mv.h;
+    const size_t nC = 2 * (size_t)V * hh, nR = nC * hh, nS = (size_t)M * K * mv.ds;
+    CU(h->dCs.reserve(nC * 8)); CU(h->dmus.reserve(nC * 8)); CU(h->dRt.reserve(nR * 8)); CU(h->dsubs.reserve(nS * 8));
+    std::vector<double> rt(nR);
+    for (size_t sc = 0; sc < 2 * (size_t)V; ++sc) {
+        const double* R = Rs + sc * hh * hh;
+        double* T = rt.data() + sc * hh * hh;
+        for (size_t t = 0; t < hh; ++t)
+            for (size_t d = 0; d < hh; ++d) T[d * hh + t] = R[t * hh + d];
+    }
+    CU(cudaMemcpyAsync(h->dCs.p, Cs, nC * 8, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->dmus.p, mus, nC * 8, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->dRt.p, rt.data(), nR * 8, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->dsubs.p, subs, nS * 8, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    mv.Cs = h->dCs.as<double>(); mv.mus = h->dmus.as<double>(); mv.Rt = h->dRt.as<double>(); mv.subs = h->dsubs.as<double>();
+    h->has_model = true; h->has_pca = false; h->dirty = true; h->global_set = false;
+    return B2L_OK;
+}
+
+int b2l_set_pca(b2l_handle h, int D0, const double* P, const double* mu, int renorm) {
+    if (!h) return B2L_ERR_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(cudaSetDevice(h->device));
+    if (!h->has_model) FAIL(B2L_ERR_STATE, "set the model before the PCA");
+    if (D0 < 1 || !P || !mu) FAIL(B2L_ERR_ARG, "bad PCA arguments");
+    if ((size_t)(D0 + h->mv.D) * 8 > 200 * 1024) FAIL(B2L_ERR_UNSUPPORTED, "PCA input dimension %d too large", D0);
+    CU(h->dP.reserve((size_t)D0 * h->mv.D * 8)); CU(h->dpmu.reserve((size_t)D0 * 8));
+    CU(cudaMemcpyAsync(h->dP.p, P, (size_t)D0 * h->mv.D * 8, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->dpmu.p, mu, (size_t)D0 * 8, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->mv.D0 = D0; h->mv.renorm = renorm ? 1 : 0; h->mv.P = h->dP.as<double>(); h->mv.pmu = h->dpmu.as<double>();
+    h->has_pca = true;
+    return B2L_OK;
+}
+
+int b2l_encode(b2l_handle h, const void* X, int x_is_f64, int64_t n, int on_device, int32_t* coarse, uint8_t* fine) {
+    if (!h) return B2L_ERR_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(cudaSetDevice(h->device));
+    if (!h->has_model) FAIL(B2L_ERR_STATE, "no model set");
+    if (n < 0 || (n && (!X || !coarse))) FAIL(B2L_ERR_ARG, "bad encode arguments");
+    const ModelView& mv = h->mv;
+    const int Din = h->has_pca ? mv.D0 : mv.D;
+    const size_t esz = x_is_f64 ? 8 : 4;
+    h->launches = 0;
+    // chunk so that the float64 projection workspace stays <= 1 GiB
+    int64_t chunk = std::max<int64_t>(1024, ((int64_t)1 << 30) / ((int64_t)mv.D * 8));
+    chunk = std::min<int64_t>(chunk, (int64_t)1 << 22);
+    for (int64_t a = 0; a < n; a += chunk) {
+        const int64_t c = std::min(chunk, n - a);
+        const void* dx;
+        int32_t* dco; uint8_t* dfi;
+        if (on_device) {
+            dx = (const char*)X + (size_t)a * Din * esz; dco = coarse + a * 2; dfi = fine ? fine + a * mv.M : nullptr;
+        } else {
+            CU(h->w_q.reserve((size_t)c * Din * esz)); CU(h->w_coarse.reserve((size_t)c * 8)); CU(h->w_fine.reserve((size_t)c * mv.M));
+            CU(cudaMemcpyAsync(h->w_q.p, (const char*)X + (size_t)a * Din * esz, (size_t)c * Din * esz, cudaMemcpyHostToDevice, h->stream));
+            dx = h->w_q.p; dco = h->w_coarse.as<int32_t>(); dfi = fine ? h->w_fine.as<uint8_t>() : nullptr;
+        }
+        int rc = encode_device(h, dx, x_is_f64, c, nullptr, dco, dfi);
+        if (rc) return rc;
+        if (!on_device) {
+            CU(cudaMemcpyAsync(coarse + a * 2, dco, (size_t)c * 8, cudaMemcpyDeviceToHost, h->stream));
+            if (fine) CU(cudaMemcpyAsync(fine + a * mv.M, dfi, (size_t)c * mv.M, cudaMemcpyDeviceToHost, h->stream));
+            CU(cudaStreamSynchronize(h->stream));   // the staging buffers are reused by the next chunk
+        }
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    h->stats.kernel_launches = h->launches;
+    return B2L_OK;
+}
+
+int b2l_apply_pca(b2l_handle h, const void* X, int x_is_f64, int64_t n, int on_device, float* Y) {
+    if (!h) return B2L_ERR_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(cudaSetDevice(h->device));
+    if (!h->has_pca) FAIL(B2L_ERR_STATE, "no PCA set");
+    if (n < 1 || !X || !Y) FAIL(B2L_ERR_ARG, "bad apply_pca arguments");
+    const ModelView& mv = h->mv;
+    const size_t esz = x_is_f64 ? 8 : 4;
+    const void* dx = X;
+    if (!on_device) {
+        CU(h->w_q.reserve((size_t)n * mv.D0 * esz));
+        CU(cudaMemcpyAsync(h->w_q.p, X, (size_t)n * mv.D0 * esz, cudaMemcpyHostToDevice, h->stream));
+        dx = h->w_q.p;
+    }
+    float* dy = Y;
+    if (!on_device) { CU(h->w_xq.reserve((size_t)n * mv.D * 4)); dy = h->w_xq.as<float>(); }
+    const size_t smem = (size_t)(mv.D0 + mv.D) * 8;
+    if (x_is_f64) { CU(cudaFuncSetAttribute(k_pca<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_pca<double><<<(unsigned)n, 128, smem, h->stream>>>(mv, (const double*)dx, n, dy); }
+    else { CU(cudaFuncSetAttribute(k_pca<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_pca<float><<<(unsigned)n, 128, smem, h->stream>>>(mv, (const float*)dx, n, dy); }
+    LAUNCHED();
+    if (!on_device) CU(cudaMemcpyAsync(Y, dy, (size_t)n * mv.D * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return B2L_OK;
+}
+
+int b2l_project_lut(b2l_handle h, const void* X, int x_is_f64, int64_t n, const int32_t* coarse, double* px, double* lut) {
+    if (!h) return B2L_ERR_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(cudaSetDevice(h->device));
+    if (!h->has_model) FAIL(B2L_ERR_STATE, "no model set");
+    if (n < 1 || !X || !coarse) FAIL(B2L_ERR_ARG, "bad project arguments");
+    const ModelView& mv = h->mv;
+    const size_t esz = x_is_f64 ? 8 : 4;
+    CU(h->w_q.reserve((size_t)n * mv.D * esz)); CU(h->w_coarse.reserve((size_t)n * 8));
+    CU(cudaMemcpyAsync(h->w_q.p, X, (size_t)n * mv.D * esz, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->w_coarse.p, coarse, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+    // project only (no PCA here: x is already D-dimensional)
+    const bool pca = h->has_pca;
+    h->has_pca = false;
+    int rc = encode_device(h, h->w_q.p, x_is_f64, n, h->w_coarse.as<int32_t>(), nullptr, nullptr);
+    h->has_pca = pca;
+    if (rc) return rc;
+    if (px) CU(cudaMemcpyAsync(px, h->w_px.p, (size_t)n * mv.D * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (lut) {
+        CU(h->w_lut64.reserve((size_t)n * mv.M * mv.K * 8));
+        k_lut64_probe<<<(unsigned)n, 256, 0, h->stream>>>(mv, h->w_px.as<double>(), n, h->w_lut64.as<double>());
+        LAUNCHED();
+        CU(cudaMemcpyAsync(lut, h->w_lut64.p, (size_t)n * mv.M * mv.K * 8, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    return B2L_OK;
+}
+
+int b2l_index_add(b2l_handle h, const int32_t* coarse, const uint8_t* fine, int64_t n, const int64_t* rowids, int on_device) {
+    if (!h) return B2L_ERR_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(cudaSetDevice(h->device));
+    if (!h->has_model) FAIL(B2L_ERR_STATE, "no model set");
+    if (n < 0 || (n && (!coarse || !fine))) FAIL(B2L_ERR_ARG, "bad index_add arguments");
+    if (n == 0) return B2L_OK;
+    const ModelView& mv = h->mv;
+    const int64_t tot = h->n_items + n;
+    CU(h->m_coarse.reserve((size_t)tot * 8, true, h->stream));
+    CU(h->m_fine.reserve((size_t)tot * mv.M, true, h->stream));
+    CU(h->m_rowid.reserve((size_t)tot * 8, true, h->stream));
+    const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    CU(cudaMemcpyAsync(h->m_coarse.as<int32_t>() + h->n_items * 2, coarse, (size_t)n * 8, kind, h->stream));
+    CU(cudaMemcpyAsync(h->m_fine.as<uint8_t>() + h->n_items * mv.M, fine, (size_t)n * mv.M, kind, h->stream));
+    if (rowids) CU(cudaMemcpyAsync(h->m_rowid.as<int64_t>() + h->n_items, rowids, (size_t)n * 8, kind, h->stream));
+    else { k_iota64<<<grid_for(n, 256), 256, 0, h->stream>>>(h->m_rowid.as<int64_t>() + h->n_items, h->n_items, n); LAUNCHED(); }
+    CU(cudaStreamSynchronize(h->stream));
+    h->n_items = tot;
+    h->dirty = true;
+    return B2L_OK;
+}
+
+int b2l_index_clear(b2l_handle h) {
+    if (!h) return B2L_ERR_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->n_items = 0; h->dirty = true; h->global_set = false;
+    return B2L_OK;
+}
+
+int64_t b2l_index_size(b2l_handle h) { return h ? h->n_items : -1; }
+
+int b2l_index_cell_sizes(b2l_handle h, int64_t* sizes) {
+    if (!h || !sizes) return B2L_ERR_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(cudaSetDevice(h->device));
+    if (!h->has_model) FAIL(B2L_ERR_STATE, "no model set");
+    int rc = ensure_index(h);
+    if (rc) return rc;
+    memcpy(sizes, h->h_lsize.data(), h->h_lsize.size() * 8);
+    return B2L_OK;
+}
+
+int b2l_index_set_global_cell_sizes(b2l_handle h, const int64_t* sizes) {
+    if (!h || !sizes) return B2L_ERR_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(cudaSetDevice(h->device));
+    if (!h->has_model) FAIL(B2L_ERR_STATE, "no model set");
+    const int ncell = h->mv.V * h->mv.V;
+    h->h_gsize.assign(sizes, sizes + ncell);
+    h->global_set = true;
+    if (!h->dirty) {
+        CU(cudaMemcpyAsync(h->gsize.p, h->h_gsize.data(), (size_t)ncell * 8, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+    }
+    return B2L_OK;
+}
+
+int64_t b2l_index_get_cell(b2l_handle h, int c0, int c1, int64_t cap, int64_t* rowids, uint8_t* fine) {
+    if (!h) return B2L_ERR_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(cudaSetDevice(h->device));
+    if (!h->has_model) FAIL(B2L_ERR_STATE, "no model set");
+    const ModelView& mv = h->mv;
+    if (c0 < 0 || c0 >= mv.V || c1 < 0 || c1 >= mv.V) return 0;
+    int rc = ensure_index(h);
+    if (rc) return rc;
+    const int cell = c0 * mv.V + c1;
+    const int64_t n = h->h_lsize[cell], take = std::min(n, cap);
+    if (take > 0) {
+        const int64_t s = h->h_cell_start[cell];
+        if (rowids) CU(cudaMemcpyAsync(rowids, h->rowids.as<int64_t>() + s, (size_t)take * 8, cudaMemcpyDeviceToHost, h->stream));
+        if (fine) CU(cudaMemcpy2DAsync(fine, mv.M, h->codes.as<uint8_t>() + s * mv.MP, mv.MP, mv.M, (size_t)take,
+                                       cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+    }
+    return n;
+}
+
+int b2l_cell_order(b2l_handle h, const void* Q, int q_is_f64, int nq, int64_t quota, int32_t* cells, double* dists, int32_t* nvis) {
+    if (!h) return B2L_ERR_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(cudaSetDevice(h->device));
+    if (!h->has_model) FAIL(B2L_ERR_STATE, "no model set");
+    if (nq < 1 || !Q || !nvis) FAIL(B2L_ERR_ARG, "bad cell_order arguments");
+    if (h->mv.V > B2L_MAX_V) FAIL(B2L_ERR_UNSUPPORTED, "V=%d > %d: large-V multi-index traversal is not implemented", h->mv.V, B2L_MAX_V);
+    int rc = ensure_index(h);
+    if (rc) return rc;
+    const ModelView& mv = h->mv;
+    const int maxvis = mv.V * mv.V;
+    const size_t esz = q_is_f64 ? 8 : 4;
+    CU(h->w_q.reserve((size_t)nq * mv.D * esz));
+    CU(cudaMemcpyAsync(h->w_q.p, Q, (size_t)nq * mv.D * esz, cudaMemcpyHostToDevice, h->stream));
+    rc = setup_plan(h, nq, 1024);
+    if (rc) return rc;
+    PlanView& pv = h->pv;
+    CU(h->w_misc.reserve((size_t)nq * maxvis * 8));
+    pv.vis_dist = h->w_misc.as<double>();
+    const size_t smem = (size_t)(3 * mv.V + 2) * 8 + (size_t)(7 * mv.V + 4) * 4 + 16;
+    if (q_is_f64) k_coarse_order<double><<<nq, 32, smem, h->stream>>>(mv, h->w_q.as<double>(), quota, h->gsize.as<int64_t>(), h->lsize.as<int64_t>(), pv);
+    else k_coarse_order<float><<<nq, 32, smem, h->stream>>>(mv, h->w_q.as<float>(), quota, h->gsize.as<int64_t>(), h->lsize.as<int64_t>(), pv);
+    LAUNCHED();
+    if (cells) CU(cudaMemcpyAsync(cells, pv.vis_cell, (size_t)nq * maxvis * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (dists) CU(cudaMemcpyAsync(dists, pv.vis_dist, (size_t)nq * maxvis * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(nvis, pv.nvis, (size_t)nq * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    pv.vis_dist = nullptr;
+    return B2L_OK;
+}
+
+int64_t b2l_records_bytes(b2l_handle h, int nq, int k) {
+    if (!h || !h->has_model || nq < 1 || k < 1) return -1;
+    return (int64_t)rec_bytes(nq, k, h->mv.M);
+}
+
+int b2l_search_local(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_device, int64_t quota, int k, int exact,
+                     void* d_records) {
+    if (!h) return B2L_ERR_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(cudaSetDevice(h->device));
+    return search_local_impl(h, Q, q_is_f64, nq, on_device, quota, k, exact, d_records);
+}
+
+int b2l_search_merge(b2l_handle h, const void* d_records_all, int nranks, int nq, int k, int on_device, int64_t* rowid,
+                     double* dist, int32_t* coarse, uint8_t* fine, int32_t* count, int32_t* visited, uint8_t* certified) {
+    if (!h) return B2L_ERR_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(cudaSetDevice(h->device));
+    return merge_impl(h, d_records_all, nranks, nq, k, on_device, rowid, dist, coarse, fine, count, visited, certified);
+}
+
+int b2l_search(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_device, int64_t quota, int k, int64_t* rowid,
+               double* dist, int32_t* coarse, uint8_t* fine, int32_t* count, int32_t* visited) {
+    if (!h) return B2L_ERR_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(cudaSetDevice(h->device));
+    if (!h->has_model) FAIL(B2L_ERR_STATE, "no model set");
+    if (nq < 1 || k < 1 || !Q || !count) FAIL(B2L_ERR_ARG, "bad search arguments (nq=%d k=%d)", nq, k);
+    const ModelView& mv = h->mv;
+    CU(h->w_rec.reserve(rec_bytes(nq, k, mv.M)));
+    int rc = search_local_impl(h, Q, q_is_f64, nq, on_device, quota, k, 0, h->w_rec.p);
+    if (rc) return rc;
+    const b2l_stats st = h->stats;
+    // final outputs on the device first (certification flags come back to the host)
+    const size_t nk = (size_t)nq * k;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes); return o; };
+    const size_t o1 = take(nk * 8), o2 = take(nk * 8), o3 = take(nk * 8), o4 = take(nk * mv.M), o5 = take((size_t)nq * 4),
+                 o6 = take((size_t)nq * 4), o7 = take((size_t)nq);
+    CU(h->w_out2.reserve(off));
+    unsigned char* b = h->w_out2.as<unsigned char>();
+    int64_t* d_rowid = (int64_t*)(b + o1); double* d_dist = (double*)(b + o2); int32_t* d_coarse = (int32_t*)(b + o3);
+    uint8_t* d_fine = b + o4; int32_t* d_count = (int32_t*)(b + o5); int32_t* d_visited = (int32_t*)(b + o6); uint8_t* d_cert = b + o7;
+    CU(cudaMemsetAsync(b, 0, off, h->stream));
+    rc = merge_impl(h, h->w_rec.p, 1, nq, k, 1, d_rowid, d_dist, d_coarse, d_fine, d_count, d_visited, d_cert);
+    if (rc) return rc;
+    std::vector<uint8_t> cert(nq);
+    CU(cudaMemcpyAsync(cert.data(), d_cert, nq, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    std::vector<int> redo;
+    for (int q = 0; q < nq; ++q) if (!cert[q]) redo.push_back(q);
+    int64_t exact_q = st.exact_queries;
+    if (!redo.empty()) {
+        // float64 full-sort rerun of the uncertified queries, patched into the outputs row by row
+        const int ns = (int)redo.size();
+        const int Din = h->has_pca ? mv.D0 : mv.D;
+        const size_t qrow = (size_t)Din * (q_is_f64 ? 8 : 4);
+        CU(h->w_misc.reserve((size_t)ns * qrow));
+        const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+        for (int i = 0; i < ns; ++i)
+            CU(cudaMemcpyAsync(h->w_misc.as<char>() + i * qrow, (const char*)Q + redo[i] * qrow, qrow, kind, h->stream));
+        CU(h->w_rec2.reserve(rec_bytes(ns, k, mv.M)));
+        const int64_t launches0 = st.kernel_launches;
+        rc = search_local_impl(h, h->w_misc.p, q_is_f64, ns, 1, quota, k, 1, h->w_rec2.p);
+        if (rc) return rc;
+        RecView rv = rec_view(h->w_rec2.p, ns, k, mv.M);
+        // exact records are already the final order of a single rank: copy rows
+        for (int i = 0; i < ns; ++i) {
+            const int q = redo[i];
+            CU(cudaMemcpyAsync(d_rowid + (size_t)q * k, rv.rowid + (size_t)i * k, (size_t)k * 8, cudaMemcpyDeviceToDevice, h->stream));
+            CU(cudaMemcpyAsync(d_dist + (size_t)q * k, rv.d64 + (size_t)i * k, (size_t)k * 8, cudaMemcpyDeviceToDevice, h->stream));
+            CU(cudaMemcpyAsync(d_fine + (size_t)q * k * mv.M, rv.fine + (size_t)i * k * mv.M, (size_t)k * mv.M, cudaMemcpyDeviceToDevice, h->stream));
+            CU(cudaMemcpyAsync(d_count + q, rv.count + i, 4, cudaMemcpyDeviceToDevice, h->stream));
+        }
+        // coarse pairs of the patched rows: decode cell ids on the host (few rows)
+        std::vector<int32_t> cells((size_t)ns * k), cnt(ns);
+        CU(cudaMemcpyAsync(cells.data(), rv.cell, (size_t)ns * k * 4, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaMemcpyAsync(cnt.data(), rv.count, (size_t)ns * 4, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        std::vector<int32_t> cp((size_t)k * 2);
+        for (int i = 0; i < ns; ++i) {
+            for (int j = 0; j < k; ++j) {
+                const int32_t c = j < cnt[i] ? cells[(size_t)i * k + j] : 0;
+                cp[2 * j] = c / mv.V; cp[2 * j + 1] = c % mv.V;
+            }
+            CU(cudaMemcpyAsync(d_coarse + (size_t)redo[i] * k * 2, cp.data(), (size_t)k * 8, cudaMemcpyHostToDevice, h->stream));
+            CU(cudaStreamSynchronize(h->stream));
+        }
+        exact_q += ns;
+        h->stats = st;
+        h->stats.kernel_launches = launches0 + h->launches;
+    } else {
+        h->stats = st;
+        h->stats.kernel_launches = st.kernel_launches + 1;
+    }
+    h->stats.exact_queries = exact_q;
+    if ((rc = copy_out(h, rowid, d_rowid, nk * 8, on_device))) return rc;
+    if ((rc = copy_out(h, dist, d_dist, nk * 8, on_device))) return rc;
+    if ((rc = copy_out(h, coarse, d_coarse, nk * 8, on_device))) return rc;
+    if ((rc = copy_out(h, fine, d_fine, nk * mv.M, on_device))) return rc;
+    if ((rc = copy_out(h, count, d_count, (size_t)nq * 4, on_device))) return rc;
+    if ((rc = copy_out(h, visited, d_visited, (size_t)nq * 4, on_device))) return rc;
+    CU(cudaStreamSynchronize(h->stream));
+    return B2L_OK;
+}
+
+}  // extern "C"

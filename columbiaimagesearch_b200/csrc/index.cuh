@@ -1,0 +1,37 @@
+// Inverted-index layout kernels (LOPQSearcher.add_codes, search.py:325-369 -- layout only):
+// rows appended in insertion order are regrouped cell-major (stable, so the in-cell order stays the
+// insertion order the reference's per-cell lists have), code rows padded to MP bytes, cell starts
+// aligned to 16 rows so every TMA bulk copy source is 16-byte aligned.
+#pragma once
+#include "common.cuh"
+
+__global__ void k_cell_ids(const int32_t* __restrict__ coarse, int64_t n, int V, unsigned int* __restrict__ cell,
+                           unsigned int* __restrict__ order, unsigned long long* __restrict__ hist, int* __restrict__ bad) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c0 = coarse[2 * i], c1 = coarse[2 * i + 1];
+        unsigned int c = 0;
+        if (c0 < 0 || c0 >= V || c1 < 0 || c1 >= V) atomicExch(bad, 1);
+        else c = (unsigned)(c0 * V + c1);
+        cell[i] = c;
+        order[i] = (unsigned int)i;
+        atomicAdd(&hist[c], 1ull);
+    }
+}
+
+// sorted_cell/sorted_src: stable sort of (cell, insertion index); sorted_first[c] = first sorted slot of cell c
+__global__ void k_scatter_rows(const unsigned int* __restrict__ sorted_cell, const unsigned int* __restrict__ sorted_src, int64_t n,
+                               const int64_t* __restrict__ sorted_first, const int64_t* __restrict__ cell_start,
+                               const uint8_t* __restrict__ fine_in, const int64_t* __restrict__ rowid_in, int M, int MP,
+                               uint8_t* __restrict__ codes, int64_t* __restrict__ rowids) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned int c = sorted_cell[i];
+        const int64_t src = sorted_src[i];
+        const int64_t dst = cell_start[c] + (i - sorted_first[c]);
+        for (int j = 0; j < MP; ++j) codes[dst * MP + j] = (j < M) ? fine_in[src * M + j] : (uint8_t)0;
+        rowids[dst] = rowid_in[src];
+    }
+}
+
+__global__ void k_iota64(int64_t* p, int64_t base, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = base + i;
+}

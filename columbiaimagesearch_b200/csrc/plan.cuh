@@ -1,0 +1,240 @@
+// Query planning kernels: multi-sequence cell order + quota cut (search.py:13-82, 110-135),
+// work-list construction for the scan, and the distance-table (LUT) build (model.py:673-704).
+#pragma once
+#include "common.cuh"
+
+struct PlanCounters {               // zeroed before every batch
+    unsigned int n_lut;             // LUT slots (query, split, coarse code)
+    unsigned int n_partial;         // partial top-k lists (query, visited local cell, segment)
+    unsigned int n_items;           // scan work items (cell, segment, query group)
+    unsigned int n_pairs;           // (query, visited local non-empty cell) pairs
+    unsigned long long cand_local;  // sum over queries of retrieved codes stored on this rank
+    unsigned int next_item;         // dynamic work counter of the persistent scan kernel
+    unsigned int max_parts;         // max partial lists of one query
+};
+
+struct PlanView {                   // per-batch device arrays, maxvis = V*V
+    int nq, maxvis, segc;
+    int32_t* nvis;                  // [nq] cells visited (incl. empty / non-local)
+    int64_t* ncand;                 // [nq] retrieved codes, global
+    int64_t* ncand_local;           // [nq] retrieved codes on this rank
+    int32_t* npart;                 // [nq] partial lists of the query
+    int32_t* pbase;                 // [nq] first partial list
+    int32_t* vis_cell;              // [nq][maxvis] cell id = c0*V + c1
+    int64_t* vis_base;              // [nq][maxvis] retrieval position of the cell's first code
+    int32_t* vis_lut0;              // [nq][maxvis] LUT slot of (split 0, c0), -1 if nothing to scan
+    int32_t* vis_lut1;              // [nq][maxvis]
+    int32_t* vis_pbase;             // [nq][maxvis] partial-list offset inside the query, -1 if none
+    double*  vis_dist;              // [nq][maxvis] cell distance d0+d1 (NULL unless the cell order itself is requested)
+    int32_t* lut_desc;              // [cap][3]  (q, split, c)
+    unsigned int* cell_qcount;      // [V*V] queries visiting the (local, non-empty) cell
+    unsigned int* cell_fill;        // [V*V]
+    unsigned int* cellq_off;        // [V*V+1]
+    unsigned int* item_base;        // [V*V+1]
+    int2* cellq;                    // [n_pairs] (q, visit index), grouped by cell
+    PlanCounters* cnt;
+};
+
+// ---- cell order + quota: one warp per query ---------------------------------------------------
+// shared memory per block: d[2V] double, hd[V+2] double, ord[2V], pc[V], hi0[V+2], hi1[V+2], slotmap[2V] int
+template <typename XT>
+__global__ void __launch_bounds__(32)
+k_coarse_order(ModelView mv, const XT* __restrict__ Xq, int64_t quota,
+               const int64_t* __restrict__ gsize, const int64_t* __restrict__ lsize, PlanView pv) {
+    extern __shared__ double sm_co[];
+    const int V = mv.V, h = mv.h;
+    double* d = sm_co;                       // [2][V]
+    double* hd = d + 2 * V;                  // heap distances [V+2]
+    int* ord = (int*)(hd + V + 2);           // [2][V]
+    int* pc = ord + 2 * V;                   // [V] popped prefix length per row
+    int* hi0 = pc + V;                       // [V+2]
+    int* hi1 = hi0 + V + 2;                  // [V+2]
+    int* slotmap = hi1 + V + 2;              // [2][V]
+    const int q = blockIdx.x, lane = threadIdx.x;
+    const XT* x = Xq + (int64_t)q * mv.D;
+    const bool f32 = (sizeof(XT) == 4) && mv.coarse_f32;
+
+    for (int idx = lane; idx < 2 * V; idx += 32) {
+        const int s = idx / V;
+        const double* C = mv.Cs + (int64_t)idx * h;          // (s*V + v)*h
+        d[idx] = f32 ? (double)sqdist_np<float>(x + s * h, C, h) : sqdist_np<double>(x + s * h, C, h);
+        slotmap[idx] = -1;
+    }
+    for (int v = lane; v < V; v += 32) pc[v] = 0;
+    __syncwarp();
+    for (int idx = lane; idx < 2 * V; idx += 32) {            // stable argsort by rank counting
+        const int s = idx / V, v = idx % V;
+        const double dv = d[idx];
+        int rank = 0;
+        for (int u = 0; u < V; ++u) {
+            const double du = d[s * V + u];
+            rank += (du < dv) || (du == dv && u < v);
+        }
+        ord[s * V + rank] = v;
+    }
+    __syncwarp();
+    if (lane != 0) return;
+
+    int32_t* vcell = pv.vis_cell + (int64_t)q * pv.maxvis;
+    int64_t* vbase = pv.vis_base + (int64_t)q * pv.maxvis;
+    int32_t* vl0 = pv.vis_lut0 + (int64_t)q * pv.maxvis;
+    int32_t* vl1 = pv.vis_lut1 + (int64_t)q * pv.maxvis;
+    int32_t* vpb = pv.vis_pbase + (int64_t)q * pv.maxvis;
+
+    auto celld = [&](int i0, int i1) -> double {             // search.py:52-57: 0 + d0 + d1 in the compute type
+        const double a = d[ord[i0]], b = d[V + ord[V + i1]];
+        return f32 ? (double)__fadd_rn((float)a, (float)b) : __dadd_rn(a, b);
+    };
+    int hn = 0;
+    hd[0] = celld(0, 0); hi0[0] = 0; hi1[0] = 0; hn = 1;
+    int nv = 0, nslots = 0, npart = 0;
+    int64_t got = 0, got_local = 0;
+    while (hn > 0) {
+        int b = 0;                                            // pop the minimum (dist, (i0, i1))
+        for (int e = 1; e < hn; ++e) {
+            if (hd[e] < hd[b] || (hd[e] == hd[b] && (hi0[e] < hi0[b] || (hi0[e] == hi0[b] && hi1[e] < hi1[b])))) b = e;
+        }
+        const int i0 = hi0[b], i1 = hi1[b];
+        const double dpop = hd[b];
+        --hn;
+        hd[b] = hd[hn]; hi0[b] = hi0[hn]; hi1[b] = hi1[hn];
+        pc[i0] = i1 + 1;
+        const int c0 = ord[i0], c1 = ord[V + i1];
+        const int cell = c0 * V + c1;
+        const int64_t gs = gsize[cell], ls = lsize[cell];
+        vcell[nv] = cell;
+        vbase[nv] = got;
+        if (pv.vis_dist) pv.vis_dist[(int64_t)q * pv.maxvis + nv] = dpop;
+        if (ls > 0) {
+            if (slotmap[c0] < 0) slotmap[c0] = nslots++;
+            if (slotmap[V + c1] < 0) slotmap[V + c1] = nslots++;
+            vl0[nv] = slotmap[c0];
+            vl1[nv] = slotmap[V + c1];
+            vpb[nv] = npart;
+            npart += (int)((ls + pv.segc - 1) / pv.segc);
+            got_local += ls;
+        } else {
+            vl0[nv] = -1; vl1[nv] = -1; vpb[nv] = -1;
+        }
+        got += gs;
+        ++nv;
+        if (got >= quota) break;
+        // search.py:70-80 push rules; pc[] encodes the `traversed` set (a staircase)
+        if ((i1 == 0 || pc[i0 + 1 < V ? i0 + 1 : i0] >= i1) && i0 + 1 < V) {
+            hd[hn] = celld(i0 + 1, i1); hi0[hn] = i0 + 1; hi1[hn] = i1; ++hn;
+        }
+        if ((i0 == 0 || pc[i0 - 1] >= i1 + 2) && i1 + 1 < V) {
+            hd[hn] = celld(i0, i1 + 1); hi0[hn] = i0; hi1[hn] = i1 + 1; ++hn;
+        }
+    }
+    pv.nvis[q] = nv;
+    pv.ncand[q] = got;
+    pv.ncand_local[q] = got_local;
+    pv.npart[q] = npart;
+    const unsigned int lbase = nslots ? atomicAdd(&pv.cnt->n_lut, (unsigned)nslots) : 0u;
+    pv.pbase[q] = npart ? (int)atomicAdd(&pv.cnt->n_partial, (unsigned)npart) : 0;
+    atomicMax(&pv.cnt->max_parts, (unsigned)npart);
+    if (got_local) atomicAdd(&pv.cnt->cand_local, (unsigned long long)got_local);
+    for (int idx = 0; idx < 2 * V; ++idx) {
+        if (slotmap[idx] >= 0) {
+            int32_t* de = pv.lut_desc + 3 * (int64_t)(lbase + slotmap[idx]);
+            de[0] = q; de[1] = idx / V; de[2] = idx % V;
+        }
+    }
+    int npairs = 0;
+    for (int v = 0; v < nv; ++v) {
+        if (vpb[v] >= 0) {
+            vl0[v] += (int)lbase; vl1[v] += (int)lbase;
+            atomicAdd(&pv.cell_qcount[vcell[v]], 1u);
+            ++npairs;
+        }
+    }
+    if (npairs) atomicAdd(&pv.cnt->n_pairs, (unsigned)npairs);
+}
+
+// ---- per-cell offsets of the work list: single block -------------------------------------------
+__global__ void __launch_bounds__(1024)
+k_plan(int ncell, int G, int segc, const int64_t* __restrict__ lsize, PlanView pv) {
+    __shared__ unsigned int sq[1024], si[1024];
+    const int per = (ncell + 1023) / 1024;
+    const int c0 = threadIdx.x * per;
+    unsigned int aq = 0, ai = 0;
+    for (int c = c0; c < min(ncell, c0 + per); ++c) {
+        const unsigned int qc = pv.cell_qcount[c];
+        const unsigned int nseg = (unsigned)((lsize[c] + segc - 1) / segc);
+        aq += qc;
+        ai += ((qc + G - 1) / G) * nseg;
+    }
+    sq[threadIdx.x] = aq; si[threadIdx.x] = ai;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {               // Hillis-Steele inclusive scan
+        unsigned int vq = 0, vi = 0;
+        if ((int)threadIdx.x >= o) { vq = sq[threadIdx.x - o]; vi = si[threadIdx.x - o]; }
+        __syncthreads();
+        sq[threadIdx.x] += vq; si[threadIdx.x] += vi;
+        __syncthreads();
+    }
+    unsigned int bq = sq[threadIdx.x] - aq, bi = si[threadIdx.x] - ai;   // exclusive
+    for (int c = c0; c < min(ncell, c0 + per); ++c) {
+        const unsigned int qc = pv.cell_qcount[c];
+        const unsigned int nseg = (unsigned)((lsize[c] + segc - 1) / segc);
+        pv.cellq_off[c] = bq; pv.item_base[c] = bi;
+        pv.cell_fill[c] = 0;
+        bq += qc; bi += ((qc + G - 1) / G) * nseg;
+    }
+    if (threadIdx.x == 1023) {
+        pv.cellq_off[ncell] = sq[1023]; pv.item_base[ncell] = si[1023];
+        pv.cnt->n_items = si[1023];
+    }
+}
+
+// ---- group the (query, visit) pairs by cell -----------------------------------------------------
+__global__ void k_fill(PlanView pv) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= pv.nq) return;
+    const int nv = pv.nvis[q];
+    for (int v = 0; v < nv; ++v) {
+        if (pv.vis_pbase[(int64_t)q * pv.maxvis + v] >= 0) {
+            const int cell = pv.vis_cell[(int64_t)q * pv.maxvis + v];
+            const unsigned int idx = atomicAdd(&pv.cell_fill[cell], 1u);
+            pv.cellq[pv.cellq_off[cell] + idx] = make_int2(q, v);
+        }
+    }
+}
+
+// ---- LUT build: one block per (query, split, coarse code) ---------------------------------------
+// project (model.py:604-641) then ((fx - subC[j])**2).sum(1) for the m sub-vectors of the split
+// (model.py:696-704).  Writes the float64 projection (for the exact re-rank) and the float32 table
+// rounded from float64, k-major: lut32[slot][k][j], j < m  (so one scan-LUT row is contiguous).
+template <typename XT>
+__global__ void __launch_bounds__(256)
+k_lut(ModelView mv, const XT* __restrict__ Xq, const int32_t* __restrict__ lut_desc,
+      double* __restrict__ P64, float* __restrict__ lut32, double* __restrict__ lut64) {
+    extern __shared__ double sm_lut[];      // r[h], p[h]
+    const int h = mv.h, m = mv.m, ds = mv.ds, V = mv.V;
+    double* r = sm_lut;
+    double* p = sm_lut + h;
+    const int slot = blockIdx.x;
+    const int q = lut_desc[3 * slot], s = lut_desc[3 * slot + 1], c = lut_desc[3 * slot + 2];
+    const XT* x = Xq + (int64_t)q * mv.D + s * h;
+    const double* C = mv.Cs + ((int64_t)s * V + c) * h;
+    const double* mu = mv.mus + ((int64_t)s * V + c) * h;
+    for (int d = threadIdx.x; d < h; d += blockDim.x) r[d] = coarse_residual<XT>(x[d], C[d], mu[d], mv.coarse_f32);
+    __syncthreads();
+    const double* Rt = mv.Rt + ((int64_t)s * V + c) * h * (int64_t)h;
+    for (int t = threadIdx.x; t < h; t += blockDim.x) {
+        double acc = 0.0;
+        for (int d = 0; d < h; ++d) acc = fma(Rt[(int64_t)d * h + t], r[d], acc);
+        p[t] = acc;
+        P64[(int64_t)slot * h + t] = acc;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < B2L_LUT_ROWS; k += blockDim.x) {
+        for (int j = 0; j < m; ++j) {
+            double e = 0.0;
+            if (k < mv.K) e = sqdist_np<double>(p + j * ds, mv.subs + (((int64_t)s * m + j) * mv.K + k) * ds, ds);
+            if (lut32) lut32[((int64_t)slot * B2L_LUT_ROWS + k) * m + j] = (float)e;
+            if (lut64 && k < mv.K) lut64[((int64_t)slot * m + j) * mv.K + k] = e;
+        }
+    }
+}

@@ -1,0 +1,270 @@
+// ADC code scan (LOPQSearcherBase.compute_distances, search.py:137-177, + the top-`limit` cut of
+// search.py:210-215) -- the hot kernel.
+//
+// Work item = (cell segment of <= segc codes, group of G = 32/MP queries visiting that cell).
+// Shared-memory "super LUT": 256 rows (code byte) x 32 columns (bank = column):
+//     column g*MP + j  holds  LUT_{query g}[j][row]      (j < M; columns j >= M are zero padding)
+// Lane l of a warp owns query slot g = l / MP and, per pass, code `jl = l % MP` of a block of MP
+// codes; at step s it looks up sub-quantizer j = jl ^ s.  So at every step the 32 lanes of a warp
+// hit 32 distinct columns = 32 distinct banks (conflict free), and the code words they fetch from
+// the TMA-staged tile are conflict free as well (word (jl>>2)^T of code jl; lanes of different
+// query slots read the same word = broadcast).  Each lane accumulates its own (code, query) sum in
+// a register: no shuffles, no reductions.
+// Code tiles are streamed global -> shared with cp.async.bulk (TMA 1-D bulk copy) behind an
+// mbarrier ring.  Survivors (dist <= running k'-th best of the slot) are appended to a per-slot
+// candidate buffer that is compacted by an in-block bitonic sort when it exceeds 2k'.
+// Keys are (float32 dist bits << 32 | retrieval position): order = (dist, retrieval order), the
+// order the reference's stable sort produces (ties keep retrieval order, search.py:210).
+#pragma once
+#include "common.cuh"
+#include "plan.cuh"
+
+#define SCAN_THREADS 256
+#define SCAN_WARPS 8
+#define SCAN_U 4
+
+struct ScanArgs {
+    const uint8_t* codes;           // [rows][MP]
+    const int64_t* cell_start;      // [ncell]
+    const int64_t* lsize;           // [ncell]
+    const float* lut32;             // [slots][256][m]
+    unsigned long long* partial;    // [n_partial][KP]
+    PlanView pv;
+    int ncell, KP, cap, m, M;
+    unsigned int n_items;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    const uint32_t addr = smem_u32(bar);
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <int MP> struct ScanCfg {
+    static constexpr int G = 32 / MP;                       // query slots per group
+    static constexpr int W = MP / 4;                        // 32-bit words per code row
+    static constexpr int TILE = (MP == 4) ? 512 : 1024;     // codes per pipeline stage
+    static constexpr int NSTAGE = (MP == 32) ? 3 : 4;
+    static constexpr int CPW = TILE / SCAN_WARPS;           // codes per warp per tile
+    static constexpr int ITERS = CPW / (SCAN_U * MP);
+    static constexpr int STAGE_BYTES = TILE * MP;
+    static constexpr int LUT_BYTES = B2L_LUT_ROWS * 32 * 4;
+    static_assert(ITERS >= 1 && CPW % (SCAN_U * MP) == 0, "tile shape");
+};
+
+template <int MP>
+size_t scan_smem_bytes(int cap) {
+    typedef ScanCfg<MP> C;
+    return (size_t)C::LUT_BYTES + (size_t)C::NSTAGE * C::STAGE_BYTES + (size_t)C::G * cap * 8 + 256;
+}
+
+template <int MP>
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_scan(ScanArgs a) {
+    typedef ScanCfg<MP> C;
+    constexpr int G = C::G, W = C::W, TILE = C::TILE, NSTAGE = C::NSTAGE;
+    extern __shared__ __align__(128) unsigned char smem[];
+    float* lut = (float*)smem;
+    unsigned char* stages = smem + C::LUT_BYTES;
+    unsigned long long* cand = (unsigned long long*)(stages + NSTAGE * C::STAGE_BYTES);
+    uint64_t* bars = (uint64_t*)(cand + (size_t)G * a.cap);       // [NSTAGE]
+    int* s_cnt = (int*)(bars + NSTAGE);                            // [G]
+    float* s_thr = (float*)(s_cnt + 8);                            // [G]
+    unsigned int* s_posbase = (unsigned int*)(s_thr + 8);          // [G]
+    int* s_pslot = (int*)(s_posbase + 8);                          // [G]  (-1 = empty slot)
+    unsigned int* s_item = (unsigned int*)(s_pslot + 8);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane / MP, jl = lane % MP;
+    const int KP = a.KP, cap = a.cap;
+    const PlanView& pv = a.pv;
+
+    // per-lane constants of the conflict-free mapping
+    uint32_t lut_off[MP];                     // byte offset of column (g*MP + (jl ^ s)) inside a LUT row
+#pragma unroll
+    for (int s = 0; s < MP; ++s) lut_off[s] = 4u * (uint32_t)(g * MP + (jl ^ s));
+    const unsigned char* lutc = (const unsigned char*)lut;
+    uint32_t sel[4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) sel[b] = 0x4440u | (uint32_t)((jl & 3) ^ b);
+
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGE; ++s) mbar_init(&bars[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    uint32_t tiles_done = 0;                  // tiles consumed by this block so far (ring position)
+
+    while (true) {
+        if (tid == 0) *s_item = atomicAdd(&pv.cnt->next_item, 1u);
+        __syncthreads();
+        const unsigned int item = *s_item;
+        if (item >= a.n_items) break;
+
+        // ---- decode the item: cell (binary search over item_base), segment, query group
+        int lo = 0, hi = a.ncell;             // item_base[lo] <= item < item_base[hi]
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (pv.item_base[mid] <= item) lo = mid; else hi = mid;
+        }
+        const int cell = lo;
+        const unsigned int qc = pv.cell_qcount[cell];
+        const unsigned int ng = (qc + G - 1) / G;
+        const unsigned int local = item - pv.item_base[cell];
+        const unsigned int group = local % ng, seg = local / ng;
+        const int64_t first = (int64_t)seg * pv.segc;
+        const int count = (int)min((int64_t)pv.segc, a.lsize[cell] - first);
+        const int ntiles = (count + TILE - 1) / TILE;
+        const unsigned char* src0 = a.codes + (a.cell_start[cell] + first) * MP;
+
+        // ---- producer prologue: fill the ring
+        if (tid == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            for (int t = 0; t < min(ntiles, NSTAGE); ++t) {
+                const uint32_t st = (tiles_done + t) % NSTAGE;
+                const uint32_t bytes = (uint32_t)((min(TILE, count - t * TILE) * MP + 15) & ~15);
+                mbar_expect_tx(&bars[st], bytes);
+                tma_load_1d(stages + st * C::STAGE_BYTES, src0 + (size_t)t * C::STAGE_BYTES, bytes, &bars[st]);
+            }
+        }
+        // ---- slot descriptors
+        int lut0[G], lut1[G];
+#pragma unroll
+        for (int gg = 0; gg < G; ++gg) {
+            const unsigned int pi = group * G + gg;
+            lut0[gg] = -1; lut1[gg] = -1;
+            if (pi < qc) {
+                const int2 qv = pv.cellq[pv.cellq_off[cell] + pi];
+                const int64_t o = (int64_t)qv.x * pv.maxvis + qv.y;
+                lut0[gg] = pv.vis_lut0[o]; lut1[gg] = pv.vis_lut1[o];
+                if (tid == gg) {
+                    s_posbase[gg] = (unsigned int)(pv.vis_base[o] + first);
+                    s_pslot[gg] = pv.pbase[qv.x] + pv.vis_pbase[o] + (int)seg;
+                    s_cnt[gg] = 0;
+                    s_thr[gg] = __int_as_float(0x7f800000);     // +inf
+                }
+            } else if (tid == gg) {
+                s_posbase[gg] = 0; s_pslot[gg] = -1; s_cnt[gg] = 0; s_thr[gg] = -1.0f;
+            }
+        }
+        // ---- super-LUT fill: consecutive threads -> consecutive columns of a row (conflict free)
+        {
+            const int m = a.m, M = a.M;
+            for (int e = tid; e < B2L_LUT_ROWS * 32; e += SCAN_THREADS) {
+                const int row = e >> 5, col = e & 31;
+                const int gg = col / MP, j = col % MP;
+                float v = 0.0f;
+                if (j < M) {
+                    int slot = -1;
+#pragma unroll
+                    for (int t = 0; t < G; ++t) if (t == gg) slot = (j < m) ? lut0[t] : lut1[t];
+                    if (slot >= 0) v = a.lut32[((size_t)slot * B2L_LUT_ROWS + row) * m + (j < m ? j : j - m)];
+                }
+                lut[e] = v;
+            }
+        }
+        __syncthreads();
+        float thr = s_thr[g];
+        const unsigned int posbase = s_posbase[g];
+        int over = 0;                          // this thread pushed a slot's buffer past 2k'
+
+        // ---- main loop over the tiles of the segment
+        for (int t = 0; t < ntiles; ++t) {
+            const uint32_t n = tiles_done + t;
+            const uint32_t st = n % NSTAGE;
+            mbar_wait(&bars[st], (n / NSTAGE) & 1u);
+            const uint32_t* words = (const uint32_t*)(stages + st * C::STAGE_BYTES);
+#pragma unroll 1
+            for (int it = 0; it < C::ITERS; ++it) {
+                const int cbase = warp * C::CPW + it * (SCAN_U * MP) + jl;     // this lane's code of pass 0
+                float acc[SCAN_U];
+#pragma unroll
+                for (int u = 0; u < SCAN_U; ++u) acc[u] = 0.0f;
+#pragma unroll
+                for (int T = 0; T < W; ++T) {
+                    uint32_t wd[SCAN_U];
+#pragma unroll
+                    for (int u = 0; u < SCAN_U; ++u) wd[u] = words[(cbase + u * MP) * W + ((jl >> 2) ^ T)];
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+#pragma unroll
+                        for (int u = 0; u < SCAN_U; ++u) {
+                            const uint32_t c = __byte_perm(wd[u], 0u, sel[b]);
+                            acc[u] += *(const float*)(lutc + (lut_off[T * 4 + b] + (c << 7)));
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < SCAN_U; ++u) {
+                    const int idx = t * TILE + cbase + u * MP;                  // index inside the segment
+                    if (idx < count && acc[u] <= thr) {
+                        const int slot = atomicAdd(&s_cnt[g], 1);
+                        over |= (slot >= 2 * KP);
+                        cand[(size_t)g * cap + slot] =
+                            ((unsigned long long)__float_as_uint(acc[u]) << 32) | (unsigned long long)(posbase + (unsigned)idx);
+                    }
+                }
+            }
+            // every warp is done with stage st; the OR makes the compaction decision uniform (a slot
+            // count read after the barrier could already include appends of warps that ran ahead)
+            const int any = __syncthreads_or(over);
+            if (tid == 0 && t + NSTAGE < ntiles) {
+                const int tn = t + NSTAGE;
+                const uint32_t bytes = (uint32_t)((min(TILE, count - tn * TILE) * MP + 15) & ~15);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(&bars[st], bytes);
+                tma_load_1d(stages + st * C::STAGE_BYTES, src0 + (size_t)tn * C::STAGE_BYTES, bytes, &bars[st]);
+            }
+            // ---- compaction of overfull candidate buffers
+            if (any) {
+                over = 0;
+#pragma unroll 1
+                for (int gg = 0; gg < G; ++gg) {
+                    const int cn = s_cnt[gg];
+                    if (cn > 2 * KP) {
+                        unsigned long long* buf = cand + (size_t)gg * cap;
+                        const int np2 = next_pow2_dev(cn);
+                        for (int i = cn + tid; i < np2; i += SCAN_THREADS) buf[i] = B2L_KEY_EMPTY;
+                        __syncthreads();
+                        bitonic_sort_u64(buf, np2);
+                        if (tid == 0) { s_cnt[gg] = KP; s_thr[gg] = __uint_as_float((unsigned)(buf[KP - 1] >> 32)); }
+                    }
+                }
+                __syncthreads();
+                thr = s_thr[g];
+            }
+        }
+        tiles_done += ntiles;
+
+        // ---- final selection of the segment's k' best per slot -> partial lists
+#pragma unroll 1
+        for (int gg = 0; gg < G; ++gg) {
+            const int ps = s_pslot[gg];
+            if (ps < 0) continue;
+            const int cn = s_cnt[gg];
+            unsigned long long* buf = cand + (size_t)gg * cap;
+            const int np2 = next_pow2_dev(cn < 1 ? 1 : cn);
+            for (int i = cn + tid; i < np2; i += SCAN_THREADS) buf[i] = B2L_KEY_EMPTY;
+            __syncthreads();
+            if (np2 > 1) bitonic_sort_u64(buf, np2);
+            unsigned long long* out = a.partial + (size_t)ps * KP;
+            for (int i = tid; i < KP; i += SCAN_THREADS) out[i] = (i < cn) ? buf[i] : B2L_KEY_EMPTY;
+        }
+        __syncthreads();                                       // s_* and cand are reused by the next item
+    }
+}

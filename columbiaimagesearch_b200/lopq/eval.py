@@ -1,0 +1,64 @@
+"""Mirror of lopq/lopq/eval.py: the recall harness that defines the headline metric."""
+import time
+
+import numpy as np
+
+
+def get_recall(searcher, queries, indices, thresholds=(1, 10, 100, 1000), normalize=True, verbose=False):
+    """eval.py:92-142 -- recall@T: the true nearest neighbour ``indices[i]`` appears among the
+    first T results of ``searcher.search(q, quota=thresholds[-1])``; also the mean query time."""
+    recall = np.zeros(len(thresholds))
+    query_time = 0.0
+    for i, d in enumerate(queries):
+        nn = indices[i]
+        t0 = time.perf_counter()
+        results, _ = searcher.search(d, thresholds[-1])
+        query_time += time.perf_counter() - t0
+        if verbose and i % 50 == 0:
+            print("%d/%d queries" % (i, len(queries)))
+        for j, res in enumerate(results):
+            rid = res[0]
+            if rid == nn:
+                for k, t in enumerate(thresholds):
+                    if j < t:
+                        recall[k] += 1
+    if normalize:
+        N = len(queries)
+        return recall / N, query_time / N
+    return recall, query_time
+
+
+def get_recall_batch(searcher, queries, indices, quota, thresholds=(1, 10, 100), batch=1024):
+    """Batched form of get_recall for large runs: same definition, one ``search_batch`` call per
+    `batch` queries, results cut at thresholds[-1]."""
+    k = int(thresholds[-1])
+    recall = np.zeros(len(thresholds))
+    indices = np.asarray(indices)
+    for a in range(0, len(queries), batch):
+        out = searcher.search_batch(queries[a:a + batch], quota=quota, limit=k)
+        ids = out["ids"]
+        hit = ids == indices[a:a + batch, None]
+        hit &= np.arange(k)[None, :] < out["count"][:, None]
+        rank = np.where(hit.any(axis=1), hit.argmax(axis=1), k)
+        for j, t in enumerate(thresholds):
+            recall[j] += np.count_nonzero(rank < t)
+    return recall / len(queries)
+
+
+def get_cell_histogram(data, model):
+    """eval.py:66-74 -- number of points per multi-index cell."""
+    from .utils import compute_codes_arrays
+    coarse, _ = compute_codes_arrays(data, model)
+    hist = np.zeros(model.V ** 2, dtype=np.int64)
+    np.add.at(hist, coarse[:, 0].astype(np.int64) * model.V + coarse[:, 1], 1)
+    return hist
+
+
+def get_proportion_of_reconstructions_with_same_codes(data, model):
+    """eval.py:77-89 -- encode -> reconstruct -> encode consistency."""
+    from .utils import compute_codes_arrays
+    coarse, fine = compute_codes_arrays(data, model)
+    recon = np.stack([model.reconstruct((tuple(c), tuple(f))) for c, f in zip(coarse, fine)])
+    c2, f2 = compute_codes_arrays(recon, model)
+    same = np.all(coarse == c2, axis=1) & np.all(fine == f2, axis=1)
+    return float(np.count_nonzero(same)) / len(data)

@@ -1,0 +1,238 @@
+"""Mirror of lopq/lopq/model.py (inference half): LOPQModel / LOPQModelPCA with the reference's
+constructor, attributes and method names; every arithmetic step of predict / project /
+get_subquantizer_distances / apply_PCA runs in libb200lopq (CUDA).  Parameter containers stay plain
+NumPy arrays so pickles written by the reference (storer/local.py:58) load into these classes.
+"""
+from collections import namedtuple
+
+import numpy as np
+
+from .. import _native
+from .utils import iterate_splits
+
+LOPQCode = namedtuple("LOPQCode", ["coarse", "fine"])   # model.py:444
+
+_NATIVE_ATTR = "_b2l_handle"
+
+
+def _uint_type(n):
+    return np.uint8 if n <= 256 else (np.uint16 if n <= 65536 else np.uint32)
+
+
+_cluster_cache = {}
+
+
+def _cluster_handle(centroids):
+    """Throw-away model whose first coarse split is `centroids` (for utils.predict_cluster and
+    search.multisequence, which take bare centroid arrays in the reference API)."""
+    key = (id(centroids), centroids.shape, centroids.dtype.str)
+    ent = _cluster_cache.get(key)
+    if ent is not None and ent[0] is centroids:
+        return ent[1]
+    n, d = centroids.shape
+    h = _native.Handle()
+    z = np.zeros((n, d, d))
+    h.set_model((centroids, centroids), (z, z), (np.zeros((n, d)), np.zeros((n, d))),
+                ([np.zeros((1, d))], [np.zeros((1, d))]))
+    if len(_cluster_cache) > 8:
+        _cluster_cache.clear()
+    _cluster_cache[key] = (centroids, h)
+    return h
+
+
+class LOPQModel(object):
+    def __init__(self, V=8, M=4, subquantizer_clusters=256, parameters=None):
+        """model.py:448-493.  parameters = ((C1, C2), (Rs1, Rs2), (mu1, mu2), (subquantizers1, subquantizers2))."""
+        self.Cs, self.Rs, self.mus, self.subquantizers = parameters if parameters is not None else (None, None, None, None)
+        self._init_shape(V, M, subquantizer_clusters)
+
+    def _init_shape(self, V, M, subquantizer_clusters):
+        if self.Cs is not None:
+            self.V = self.Cs[0].shape[0]
+            self.num_coarse_splits = len(self.Cs)
+        else:
+            self.V = V
+            self.num_coarse_splits = 2
+        if self.subquantizers is not None:
+            self.num_fine_splits = len(self.subquantizers[0])
+            self.M = self.num_fine_splits * self.num_coarse_splits
+            self.subquantizer_clusters = self.subquantizers[0][0].shape[0]
+        else:
+            self.num_fine_splits = M // 2
+            self.M = M
+            self.subquantizer_clusters = subquantizer_clusters
+
+    # ---- native handle (never pickled) --------------------------------------------------------
+    def __getstate__(self):
+        d = dict(self.__dict__)
+        d.pop(_NATIVE_ATTR, None)
+        return d
+
+    def _pca_params(self):
+        return None, None, False
+
+    def _native(self):
+        """The model's own library handle (encode / project / LUT probes), created lazily so that a
+        model unpickled before fork() initialises CUDA in the worker that first uses it."""
+        h = self.__dict__.get(_NATIVE_ATTR)
+        if h is None:
+            h = self._new_handle()
+            self.__dict__[_NATIVE_ATTR] = h
+        return h
+
+    def _new_handle(self, device=None):
+        if self.Cs is None or self.Rs is None or self.mus is None or self.subquantizers is None:
+            raise ValueError("model parameters are not set (fit or pass `parameters`)")
+        P, mu, renorm = self._pca_params()
+        h = _native.Handle(device)
+        h.set_model(self.Cs, self.Rs, self.mus, self.subquantizers, P, mu, renorm)
+        return h
+
+    def _invalidate(self):
+        self.__dict__.pop(_NATIVE_ATTR, None)
+
+    # ---- training ("next" row; statistical parity only) -------------------------------------------
+    def fit(self, data, kmeans_coarse_iters=10, kmeans_local_iters=20, n_init=10, subquantizer_sample_ratio=1.0,
+            random_state=None, verbose=False):
+        """model.py:495-519 -> train (model.py:339-437)."""
+        from .train import train
+        self.Cs, self.Rs, self.mus, self.subquantizers = train(
+            data, self.V, self.M, self.subquantizer_clusters, (self.Cs, self.Rs, self.mus, self.subquantizers),
+            kmeans_coarse_iters, kmeans_local_iters, n_init, subquantizer_sample_ratio, random_state, verbose)
+        self._invalidate()
+
+    def get_split_parameters(self, split):
+        """model.py:521-541."""
+        return (self.Cs[split] if self.Cs is not None else None,
+                self.Rs[split] if self.Rs is not None else None,
+                self.mus[split] if self.mus is not None else None,
+                self.subquantizers[split] if self.subquantizers is not None else None)
+
+    # ---- encode --------------------------------------------------------------------------------------
+    def predict(self, x):
+        """model.py:543-561 -- LOPQCode(coarse, fine) of one vector."""
+        coarse, fine = self._native().encode(np.asarray(x)[None, :])
+        ct, ft = _uint_type(self.V), _uint_type(self.subquantizer_clusters)
+        return LOPQCode(tuple(ct(c) for c in coarse[0]), tuple(ft(f) for f in fine[0]))
+
+    def _post_pca(self, x):
+        return np.asarray(x)
+
+    def predict_coarse(self, x):
+        """model.py:563-573 (x is the D-dim, post-PCA vector)."""
+        cells, _, _ = self._native().cell_order(np.asarray(x)[None, :], quota=0)
+        ct = _uint_type(self.V)
+        return (ct(cells[0, 0] // self.V), ct(cells[0, 0] % self.V))
+
+    def predict_fine(self, x, coarse=None):
+        """model.py:575-602 -- fine codes under the given (default: nearest) coarse codes."""
+        if coarse is None:
+            coarse = self.predict_coarse(x)
+        _, lut = self._native().project_lut(np.asarray(x)[None, :], [[int(coarse[0]), int(coarse[1])]], want_px=False)
+        ft = _uint_type(self.subquantizer_clusters)
+        return tuple(ft(k) for k in lut[0].argmin(axis=1))
+
+    def project(self, x, coarse, coarse_split=None):
+        """model.py:604-641 -- R[c] . (x_s - C[c] - mu[c]) per split (float64)."""
+        px, _ = self._native().project_lut(np.asarray(x)[None, :], [[int(coarse[0]), int(coarse[1])]], want_lut=False)
+        if coarse_split is None:
+            return px[0]
+        return np.split(px[0], self.num_coarse_splits)[coarse_split]
+
+    def get_subquantizer_distances(self, x, coarse, coarse_split=None):
+        """model.py:673-704 -- list of M (or M/2) float64 arrays of K squared distances."""
+        _, lut = self._native().project_lut(np.asarray(x)[None, :], [[int(coarse[0]), int(coarse[1])]], want_px=False)
+        m = self.num_fine_splits
+        if coarse_split is None:
+            return [lut[0, j] for j in range(self.M)]
+        return [lut[0, coarse_split * m + j] for j in range(m)]
+
+    def reconstruct(self, codes):
+        """model.py:643-671 -- R[c]^T . concat(sub-centroids) + mu[c] + C[c] per split.  Not on the
+        query path (used by the eval.py invariants); plain NumPy on the host."""
+        coarse, fine = codes
+        out = []
+        for fc, split in iterate_splits(fine, self.num_coarse_splits):
+            C, R, mu, subC = self.get_split_parameters(split)
+            sx = np.concatenate([subC[j][int(f)] for j, f in enumerate(fc)])
+            c = int(coarse[split])
+            out.append(np.dot(R[c].transpose(), sx) + mu[c] + C[c])
+        return np.concatenate(out)
+
+    def get_cell_id_for_coarse_codes(self, coarse_codes):
+        """model.py:706-707 (computed in Python ints: the reference's uint8 arithmetic overflows for V > 16)."""
+        return int(coarse_codes[1]) + int(coarse_codes[0]) * self.V
+
+    def get_coarse_codes_for_cell_id(self, cell_id):
+        """model.py:709-710."""
+        return (int(cell_id // self.V), int(cell_id % self.V))
+
+    # ---- flat persistence (the product pickles models; this is the fixture format) -----------------
+    def to_npz_dict(self):
+        d = {"C0": np.asarray(self.Cs[0]), "C1": np.asarray(self.Cs[1]),
+             "Rs": np.stack([np.asarray(self.Rs[0]), np.asarray(self.Rs[1])]),
+             "mus": np.stack([np.asarray(self.mus[0]), np.asarray(self.mus[1])]),
+             "subs": np.stack([np.asarray(s) for s in list(self.subquantizers[0]) + list(self.subquantizers[1])]),
+             "M": np.int64(self.M)}
+        P, mu, renorm = self._pca_params()
+        if P is not None:
+            d.update(pca_P=np.asarray(P), pca_mu=np.asarray(mu), renorm=np.bool_(renorm))
+        return d
+
+    @staticmethod
+    def from_npz(z, prefix=""):
+        g = lambda k: z[prefix + k]
+        m = int(g("M"))
+        subs = g("subs")
+        params = ((g("C0"), g("C1")), (g("Rs")[0], g("Rs")[1]), (g("mus")[0], g("mus")[1]),
+                  ([subs[j] for j in range(m // 2)], [subs[j] for j in range(m // 2, m)]))
+        if prefix + "pca_P" in z:
+            return LOPQModelPCA(renorm=bool(g("renorm")), parameters=params + (g("pca_P"), g("pca_mu")))
+        return LOPQModel(parameters=params)
+
+
+class LOPQModelPCA(LOPQModel):
+    def __init__(self, V=8, M=4, subquantizer_clusters=256, renorm=False, parameters=None):
+        """model.py:826-875.  parameters = (Cs, Rs, mus, subquantizers, P, mu)."""
+        (self.Cs, self.Rs, self.mus, self.subquantizers, self.pca_P, self.pca_mu) = \
+            parameters if parameters is not None else (None, None, None, None, None, None)
+        self.renorm = renorm
+        self._init_shape(V, M, subquantizer_clusters)
+
+    def _pca_params(self):
+        return self.pca_P, self.pca_mu, self.renorm
+
+    def fit_pca(self, data, pca_dims=256, pca_subsample=None):
+        """model.py:878-886 -> train_pca (model.py:242-287)."""
+        from .train import train_pca
+        if self.pca_P is None or self.pca_mu is None:
+            self.pca_P, self.pca_mu = train_pca(data, pca_dims, pca_subsample)
+            self._invalidate()
+
+    def fit(self, data, pca_dims=None, kmeans_coarse_iters=10, kmeans_local_iters=20, n_init=10,
+            subquantizer_sample_ratio=1.0, random_state=None, verbose=False):
+        """model.py:888-931 -- PCA (if missing) then LOPQ training on the projected data."""
+        if self.pca_P is None:
+            self.fit_pca(data, pca_dims if pca_dims is not None else data.shape[1])
+        proj = self.apply_PCA(np.asarray(data))
+        LOPQModel.fit(self, proj, kmeans_coarse_iters, kmeans_local_iters, n_init, subquantizer_sample_ratio,
+                      random_state, verbose)
+
+    def apply_PCA(self, x, dtype=np.float32):
+        """model.py:961-978 -- (x - mu) . P, optional L2 renorm, cast (float32 on the device)."""
+        x = np.asarray(x)
+        if self.Cs is None:       # model not trained yet: PCA-only handle
+            y = _pca_only_handle(self).apply_pca(x if x.ndim > 1 else x[None, :])
+        else:
+            y = self._native().apply_pca(x if x.ndim > 1 else x[None, :])
+        y = y if x.ndim > 1 else y[0]
+        return y if dtype == np.float32 else y.astype(dtype)
+
+
+def _pca_only_handle(model):
+    D = model.pca_P.shape[1]
+    h = _native.Handle()
+    z = np.zeros((1, D // 2))
+    h.set_model((z, z), (np.zeros((1, D // 2, D // 2)),) * 2, (z, z), ([np.zeros((1, D // 2))], [np.zeros((1, D // 2))]),
+                model.pca_P, model.pca_mu, model.renorm)
+    return h

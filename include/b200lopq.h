@@ -1,0 +1,153 @@
+/*
+ * b200lopq.h -- C-ABI of the B200-native LOPQ hot path (libb200lopq.so).
+ *
+ * The reference (ColumbiaDVMM/ColumbiaImageSearch) has no FFI on this path: everything below
+ * replaces pure-NumPy/Python code in lopq/lopq/{model,search,utils}.py.  Each entry point cites
+ * the reference function whose arithmetic it takes over (paths relative to
+ * /root/reference/lopq/lopq/).  The Python host layer (columbiaimagesearch_b200/lopq/) keeps the
+ * reference class/method names and calls these through ctypes; see INTEGRATION.md.
+ *
+ * Conventions
+ *   - every call returns 0 on success, a negative code on failure; b2l_last_error() gives the text.
+ *   - all buffers are caller-owned, dense, row-major.  Pointers are HOST pointers unless the
+ *     argument is named d_* or the call has an `on_device` flag set to 1 (then they are device
+ *     pointers of the handle's device and the call is asynchronous on the handle's stream up to
+ *     its own final synchronisation).
+ *   - one in-flight call per handle (internal mutex); handles are independent; a handle owns one
+ *     CUDA stream; the CUDA context is created lazily by b2l_create (call it after fork()).
+ *   - no CPU fallback exists: without a CUDA device b2l_create fails.
+ */
+#ifndef B200LOPQ_H
+#define B200LOPQ_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b2l_ctx* b2l_handle;
+
+/* error codes */
+#define B2L_OK            0
+#define B2L_ERR_CUDA     -1
+#define B2L_ERR_ARG      -2
+#define B2L_ERR_STATE    -3
+#define B2L_ERR_UNSUPPORTED -4
+
+/* ---- lifecycle ---------------------------------------------------------------------------- */
+int         b2l_create(int device, b2l_handle* out);
+int         b2l_destroy(b2l_handle h);
+/* h may be NULL: returns the text of the last failure of b2l_create. */
+const char* b2l_last_error(b2l_handle h);
+/* library ABI version (bumped on any signature change) */
+int         b2l_version(void);
+
+/* ---- model parameters ------------------------------------------------------------------------
+ * LOPQModel attributes Cs, Rs, mus, subquantizers (model.py:463-473), all passed as float64
+ * (float32 parameters widen exactly).  `coarse_is_f32` says the coarse centroids were float32 in
+ * the model object: NumPy then evaluates coarse distances, cell ordering and the residual
+ * x - C[c] in float32 for float32 queries, and the device code reproduces that.
+ *   Cs   [2][V][h]        h = D/2
+ *   Rs   [2][V][h][h]     R[s][c] applied as R . v (model.py:635-638, no transpose)
+ *   mus  [2][V][h]
+ *   subs [M][K][ds]       ds = D/M; subquantizers[0] then subquantizers[1]; K <= 256
+ */
+int b2l_set_model(b2l_handle h, int D, int V, int M, int K, int coarse_is_f32,
+                  const double* Cs, const double* Rs, const double* mus, const double* subs);
+/* LOPQModelPCA.apply_PCA (model.py:961-978): y = (x - mu) . P, optional L2 renorm, cast float32.
+ *   P [D0][D], mu [D0].  Call after b2l_set_model (D must match). */
+int b2l_set_pca(b2l_handle h, int D0, const double* P, const double* mu, int renorm);
+
+/* ---- batch encode ----------------------------------------------------------------------------
+ * LOPQModel.predict over rows (model.py:543-602, 980-1003; utils.py:203-218 compute_codes_*).
+ *   X       [n][D0 or D]  float32 (x_is_f64 = 0) or float64 (1)
+ *   coarse  [n][2] int32, fine [n][M] uint8
+ * on_device = 1: X, coarse, fine are device pointers.  fine = NULL: coarse assignment only
+ * (predict_coarse, model.py:563-573; utils.predict_cluster, utils.py:33-53). */
+int b2l_encode(b2l_handle h, const void* X, int x_is_f64, int64_t n, int on_device,
+               int32_t* coarse, uint8_t* fine);
+/* apply_PCA alone (model.py:961-978): Y [n][D] float32. */
+int b2l_apply_pca(b2l_handle h, const void* X, int x_is_f64, int64_t n, int on_device, float* Y);
+/* LOPQModel.project (model.py:604-641) and get_subquantizer_distances (model.py:673-704) for
+ * explicit (vector, coarse pair) inputs; float64 out.  px [n][D], lut [n][M][K] (either may be
+ * NULL).  x is the (post-PCA) D-dim vector. */
+int b2l_project_lut(b2l_handle h, const void* X, int x_is_f64, int64_t n, const int32_t* coarse,
+                    double* px, double* lut);
+
+/* ---- inverted index ---------------------------------------------------------------------------
+ * LOPQSearcher.add_codes (search.py:325-369), layout only: rows are appended in call order and
+ * kept in insertion order inside each cell (ties in search are broken by retrieval order).
+ * Per-cell id de-duplication stays on the host.  rowids may be NULL (then insertion index). */
+int     b2l_index_add(b2l_handle h, const int32_t* coarse, const uint8_t* fine, int64_t n,
+                      const int64_t* rowids, int on_device);
+int     b2l_index_clear(b2l_handle h);
+int64_t b2l_index_size(b2l_handle h);
+/* local per-cell sizes [V*V] (int64) of this handle's shard */
+int     b2l_index_cell_sizes(b2l_handle h, int64_t* sizes);
+/* multi-GPU: the index is sharded by cell; every rank must know the GLOBAL cell sizes because the
+ * quota cut (search.py:128-133) counts all retrieved items.  Default = local sizes. */
+int     b2l_index_set_global_cell_sizes(b2l_handle h, const int64_t* sizes);
+/* read back one cell in insertion order (LOPQSearcher.get_cell, search.py:372-382).
+ * Returns the number of rows in the cell; fills at most `cap` rows. */
+int64_t b2l_index_get_cell(b2l_handle h, int c0, int c1, int64_t cap, int64_t* rowids, uint8_t* fine);
+
+/* ---- cell order -------------------------------------------------------------------------------
+ * search.multisequence (search.py:13-82) cut by the quota rule of get_result_quota (search.py:110-135)
+ * against the handle's global cell sizes; quota = INT64_MAX gives the full V*V order.
+ *   Q [nq][D] (post-PCA vectors), cells [nq][V*V] int32 (c0*V + c1), dists [nq][V*V] float64,
+ *   nvis [nq] cells visited.  Host pointers; cells / dists may be NULL. */
+int b2l_cell_order(b2l_handle h, const void* Q, int q_is_f64, int nq, int64_t quota,
+                   int32_t* cells, double* dists, int32_t* nvis);
+
+/* ---- search ------------------------------------------------------------------------------------
+ * LOPQSearcherBase.search (search.py:179-224) for a batch of queries:
+ *   multisequence cell order (search.py:13-82) -> whole cells until >= quota (110-135) ->
+ *   ADC distances over all retrieved codes (137-177) -> stable ascending order -> first k.
+ * Outputs [nq][k] (rows beyond count[q] are padding):
+ *   rowid int64, dist float64, coarse [nq][k][2] int32, fine [nq][k][M] uint8,
+ *   count [nq] int32 (= min(k, retrieved)), visited [nq] int32 (cells visited, incl. empty).
+ * Any output pointer except count may be NULL.  Queries: [nq][D0 or D] float32/float64, host.
+ * on_device = 1: Q and all outputs are device pointers. */
+int b2l_search(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_device,
+               int64_t quota, int k,
+               int64_t* rowid, double* dist, int32_t* coarse, uint8_t* fine,
+               int32_t* count, int32_t* visited);
+
+/* Two-phase form for an index sharded by cell across ranks (one handle per rank):
+ *   1. every rank: b2l_search_local -> this rank's best k candidates per query (exact float64
+ *      distances, retrieval positions) in a device record buffer of b2l_records_bytes(nq,k) bytes;
+ *   2. the host layer all-gathers the record buffers (NCCL), rank-major;
+ *   3. every rank: b2l_search_merge over the gathered [nranks] buffers -> final outputs and a
+ *      per-query `certified` flag.  certified[q] = 0 means the float32 scan could not prove the
+ *      float64 order of the first k results (ties at the k-th place); rerun those queries with
+ *      exact = 1 (b2l_search does this internally).
+ * exact = 1 ranks every retrieved code in float64 (slow, any k / any M). */
+int64_t b2l_records_bytes(b2l_handle h, int nq, int k);
+int b2l_search_local(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_device,
+                     int64_t quota, int k, int exact, void* d_records);
+int b2l_search_merge(b2l_handle h, const void* d_records_all, int nranks, int nq, int k, int on_device,
+                     int64_t* rowid, double* dist, int32_t* coarse, uint8_t* fine,
+                     int32_t* count, int32_t* visited, uint8_t* certified);
+
+/* ---- introspection (counters of the most recent b2l_search / b2l_search_local) ------------------ */
+typedef struct b2l_stats {
+    double  scan_ms;          /* device time of the ADC scan kernel (CUDA events)            */
+    double  plan_ms;          /* cell order + work list + LUT build                          */
+    double  select_ms;        /* partial top-k merge + float64 re-rank                       */
+    double  total_ms;         /* whole call on the device stream                             */
+    int64_t codes_scanned;    /* sum over queries of retrieved codes ranked on this rank     */
+    int64_t scan_bytes;       /* algorithmic bytes of the scan = M * codes_scanned           */
+    int64_t work_items;       /* (cell segment, query group) items processed                 */
+    int64_t lut_slots;        /* (query, split, coarse code) distance tables built           */
+    int64_t kernel_launches;  /* kernels of this library launched by the call                */
+    int64_t exact_queries;    /* queries that went through the float64 full-sort path        */
+} b2l_stats;
+int b2l_get_stats(b2l_handle h, b2l_stats* out);
+/* the stream the handle launches on (cudaStream_t as void*), for CUDA-event timing by the caller */
+void* b2l_stream(b2l_handle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200LOPQ_H */
