@@ -64,3 +64,52 @@ def near_duplicate_queries(X, nq, rho=0.1, seed=4321):
     idx = rng.randint(0, X.shape[0], size=nq)
     U = _normalise(rng.randn(nq, X.shape[1]))
     return _normalise(X[idx].astype(np.float64) + rho * U).astype(np.float32), idx
+
+
+# ---- device-side (torch) versions of the same recipe, for 1e7-row benchmark databases ---------------
+def dlib_style_torch(n, D=128, seed=1234, device="cuda", centres=4096, sigma=0.35, relu=False, chunk=1 << 20):
+    """Same mixture as dlib_style (identical centres: NumPy RandomState(seed)), points drawn with the
+    torch CUDA generator; returns a float32 [n, D] tensor on `device`."""
+    import torch
+    C = torch.from_numpy(np.random.RandomState(seed).randn(centres, D)).to(device=device, dtype=torch.float32)
+    g = torch.Generator(device=device)
+    g.manual_seed(seed + 1)
+    out = torch.empty((n, D), dtype=torch.float32, device=device)
+    for a in range(0, n, chunk):
+        b = min(n, a + chunk)
+        idx = torch.randint(0, centres, (b - a,), generator=g, device=device)
+        X = C[idx] + sigma * torch.randn((b - a, D), generator=g, device=device, dtype=torch.float32)
+        if relu:
+            X = torch.clamp_min(X, 0.0)
+            X[:, 0] += 1e-3
+        out[a:b] = X / X.norm(dim=1, keepdim=True)
+    return out
+
+
+def near_duplicate_queries_torch(X, nq, rho=0.1, seed=4321):
+    """q = normalise(db[i] + rho * u), u uniform on the sphere; returns (Q float32 [nq, D], i int64 [nq])."""
+    import torch
+    g = torch.Generator(device=X.device)
+    g.manual_seed(seed)
+    idx = torch.randint(0, X.shape[0], (nq,), generator=g, device=X.device)
+    U = torch.randn((nq, X.shape[1]), generator=g, device=X.device, dtype=torch.float32)
+    U = U / U.norm(dim=1, keepdim=True)
+    Q = X[idx] + rho * U
+    return Q / Q.norm(dim=1, keepdim=True), idx
+
+
+def exact_nn_torch(X, Q, chunk=1 << 20):
+    """Exact L2 nearest neighbour of every query by brute force (eval.py:7-38 compute_all_neighbors), on the
+    device: ground truth for recall.  Returns int64 [nq] row indices."""
+    import torch
+    best = torch.full((Q.shape[0],), float("inf"), device=X.device)
+    arg = torch.zeros((Q.shape[0],), dtype=torch.int64, device=X.device)
+    qn = (Q * Q).sum(1)
+    for a in range(0, X.shape[0], chunk):
+        xb = X[a:a + chunk]
+        d = qn[:, None] - 2.0 * (Q @ xb.T) + (xb * xb).sum(1)[None, :]
+        v, i = d.min(dim=1)
+        upd = v < best
+        best = torch.where(upd, v, best)
+        arg = torch.where(upd, i + a, arg)
+    return arg
