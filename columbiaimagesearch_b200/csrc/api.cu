@@ -73,6 +73,7 @@ struct b2l_ctx {
     DevBuf w_q, w_xq, w_px, w_coarse, w_fine, w_lut32, w_lut64, w_p64, w_cellq, w_partial, w_plan, w_sort_a, w_sort_b,
         w_sort_tmp, w_rec, w_rec2, w_out, w_out2, w_misc;
     PlanView pv = {};
+    unsigned int* gthr = nullptr;      // [nq] per-query pruning bound shared by the scan blocks
     b2l_stats stats = {};
     int64_t launches = 0;
 };
@@ -104,7 +105,7 @@ inline int grid_for(int64_t n, int threads, int maxblocks = 148 * 16) {
     return (int)std::max<int64_t>(1, std::min<int64_t>(b, maxblocks));
 }
 
-int scan_tile(int MP) { return MP == 4 ? 512 : 1024; }
+int scan_tile(int) { return 512; }
 
 template <int MP> int launch_scan(b2l_handle h, const ScanArgs& a, int cap) {
     const size_t smem = scan_smem_bytes<MP>(cap);
@@ -277,6 +278,7 @@ int setup_plan(b2l_handle h, int nq, int segc) {
     const size_t o_vl1 = take((size_t)nq * maxvis * 4);
     const size_t o_vpb = take((size_t)nq * maxvis * 4);
     const size_t o_desc = take((size_t)nq * 2 * mv.V * 3 * 4);
+    const size_t o_gthr = take((size_t)nq * 4);
     CU(h->w_plan.reserve(off));
     unsigned char* b = h->w_plan.as<unsigned char>();
     PlanView& pv = h->pv;
@@ -299,7 +301,9 @@ int setup_plan(b2l_handle h, int nq, int segc) {
     pv.lut_desc = (int32_t*)(b + o_desc);
     pv.cellq = nullptr;
     pv.vis_dist = nullptr;
+    h->gthr = (unsigned int*)(b + o_gthr);
     CU(cudaMemsetAsync(b, 0, zero_bytes, h->stream));
+    CU(cudaMemsetAsync(h->gthr, 0x7f, (size_t)nq * 4, h->stream));     // 0x7f7f7f7f = 3.4e38: "no bound yet"
     return B2L_OK;
 }
 
@@ -398,7 +402,8 @@ int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_
             ScanArgs a;
             a.codes = ix.codes; a.cell_start = ix.cell_start; a.lsize = ix.lsize; a.lut32 = lut32;
             a.partial = h->w_partial.as<unsigned long long>();
-            a.pv = pv; a.ncell = ncell; a.KP = KP; a.cap = next_pow2(2 * KP + tile); a.m = mv.m; a.M = mv.M;
+            a.pv = pv; a.ncell = ncell; a.KP = KP; a.cap = next_pow2(tile + std::max(KP, 512)); a.m = mv.m; a.M = mv.M;
+            a.gthr = h->gthr; a.use_tau = (tile / mv.MP >= KP) ? 1 : 0;
             a.n_items = pc.n_items;
             switch (mv.MP) {
                 case 4: rc = launch_scan<4>(h, a, a.cap); break;
