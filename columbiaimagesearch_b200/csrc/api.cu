@@ -256,7 +256,7 @@ int ensure_index(b2l_handle h) {
 size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 // carve the per-batch plan arrays out of one allocation
-int setup_plan(b2l_handle h, int nq, int segc) {
+int setup_plan(b2l_handle h, int nq, int segc, int nsegmax = 1) {
     const ModelView& mv = h->mv;
     const int ncell = mv.V * mv.V, maxvis = ncell;
     size_t off = 0;
@@ -266,7 +266,7 @@ int setup_plan(b2l_handle h, int nq, int segc) {
     const size_t zero_bytes = off;
     const size_t o_fill = take((size_t)ncell * 4);
     const size_t o_coff = take((size_t)(ncell + 1) * 4);
-    const size_t o_ib = take((size_t)(ncell + 1) * 4);
+    const size_t o_ib = take(((size_t)nsegmax * ncell + 1) * 4);
     const size_t o_nvis = take((size_t)nq * 4);
     const size_t o_ncand = take((size_t)nq * 8);
     const size_t o_ncl = take((size_t)nq * 8);
@@ -354,7 +354,8 @@ int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_
     for (int c = 0; c < ncell; ++c) maxcell = std::max(maxcell, h->h_lsize[c]);
     int segc = 16 * 1024;
     if (maxcell > 0 && maxcell < segc) segc = (int)(((maxcell + tile - 1) / tile) * tile);
-    rc = setup_plan(h, nq, segc);
+    const int nsegmax = (int)std::max<int64_t>(1, (maxcell + segc - 1) / segc);
+    rc = setup_plan(h, nq, segc, nsegmax);
     if (rc) return rc;
     PlanView& pv = h->pv;
     {
@@ -364,7 +365,7 @@ int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_
         LAUNCHED();
     }
     if (fast) {
-        k_plan<<<1, 1024, 0, h->stream>>>(ncell, mv.G, segc, h->lsize.as<int64_t>(), pv);
+        k_plan<<<1, 1024, 0, h->stream>>>(ncell, nsegmax, mv.G, segc, h->lsize.as<int64_t>(), pv);
         LAUNCHED();
     }
     PlanCounters pc;
@@ -402,7 +403,7 @@ int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_
             ScanArgs a;
             a.codes = ix.codes; a.cell_start = ix.cell_start; a.lsize = ix.lsize; a.lut32 = lut32;
             a.partial = h->w_partial.as<unsigned long long>();
-            a.pv = pv; a.ncell = ncell; a.KP = KP; a.cap = next_pow2(tile + std::max(KP, 512)); a.m = mv.m; a.M = mv.M;
+            a.pv = pv; a.ncell = ncell; a.nflat = nsegmax * ncell; a.KP = KP; a.cap = next_pow2(tile + std::max(KP, 512)); a.m = mv.m; a.M = mv.M;
             a.gthr = h->gthr; a.use_tau = (tile / mv.MP >= KP) ? 1 : 0;
             a.n_items = pc.n_items;
             switch (mv.MP) {

@@ -30,7 +30,7 @@ struct PlanView {                   // per-batch device arrays, maxvis = V*V
     unsigned int* cell_qcount;      // [V*V] queries visiting the (local, non-empty) cell
     unsigned int* cell_fill;        // [V*V]
     unsigned int* cellq_off;        // [V*V+1]
-    unsigned int* item_base;        // [V*V+1]
+    unsigned int* item_base;        // [nsegmax*V*V+1], f = seg*ncell + cell
     int2* cellq;                    // [n_pairs] (q, visit index), grouped by cell
     PlanCounters* cnt;
 };
@@ -152,40 +152,61 @@ k_coarse_order(ModelView mv, const XT* __restrict__ Xq, int64_t quota,
     if (npairs) atomicAdd(&pv.cnt->n_pairs, (unsigned)npairs);
 }
 
-// ---- per-cell offsets of the work list: single block -------------------------------------------
+// ---- offsets of the work list: single block ------------------------------------------------------
+// Work items are ordered SEGMENT-major: all (cell, query group) items of segment 0, then segment 1, ...
+// so the segments of one query are spread over time and later ones start with the pruning bound the
+// earlier ones published (ScanArgs::gthr); inside a segment level consecutive items share a code segment
+// (L2 reuse).  item_base is indexed by f = seg * ncell + cell.
 __global__ void __launch_bounds__(1024)
-k_plan(int ncell, int G, int segc, const int64_t* __restrict__ lsize, PlanView pv) {
+k_plan(int ncell, int nsegmax, int G, int segc, const int64_t* __restrict__ lsize, PlanView pv) {
     __shared__ unsigned int sq[1024], si[1024];
-    const int per = (ncell + 1023) / 1024;
-    const int c0 = threadIdx.x * per;
-    unsigned int aq = 0, ai = 0;
-    for (int c = c0; c < min(ncell, c0 + per); ++c) {
-        const unsigned int qc = pv.cell_qcount[c];
-        const unsigned int nseg = (unsigned)((lsize[c] + segc - 1) / segc);
-        aq += qc;
-        ai += ((qc + G - 1) / G) * nseg;
+    // pass 1: per-cell query-list offsets
+    {
+        const int per = (ncell + 1023) / 1024;
+        const int c0 = threadIdx.x * per;
+        unsigned int aq = 0;
+        for (int c = c0; c < min(ncell, c0 + per); ++c) aq += pv.cell_qcount[c];
+        sq[threadIdx.x] = aq;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {               // Hillis-Steele inclusive scan
+            unsigned int vq = 0;
+            if ((int)threadIdx.x >= o) vq = sq[threadIdx.x - o];
+            __syncthreads();
+            sq[threadIdx.x] += vq;
+            __syncthreads();
+        }
+        unsigned int bq = sq[threadIdx.x] - aq;            // exclusive
+        for (int c = c0; c < min(ncell, c0 + per); ++c) {
+            pv.cellq_off[c] = bq;
+            pv.cell_fill[c] = 0;
+            bq += pv.cell_qcount[c];
+        }
+        if (threadIdx.x == 1023) pv.cellq_off[ncell] = sq[1023];
+        __syncthreads();
     }
-    sq[threadIdx.x] = aq; si[threadIdx.x] = ai;
+    // pass 2: item offsets over (segment, cell)
+    const int F = nsegmax * ncell;
+    const int per = (F + 1023) / 1024;
+    const int f0 = threadIdx.x * per;
+    auto items_of = [&](int f) -> unsigned int {
+        const int seg = f / ncell, c = f - seg * ncell;
+        const unsigned int nseg = (unsigned)((lsize[c] + segc - 1) / segc);
+        return ((unsigned)seg < nseg) ? (pv.cell_qcount[c] + G - 1) / G : 0u;
+    };
+    unsigned int ai = 0;
+    for (int f = f0; f < min(F, f0 + per); ++f) ai += items_of(f);
+    si[threadIdx.x] = ai;
     __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {               // Hillis-Steele inclusive scan
-        unsigned int vq = 0, vi = 0;
-        if ((int)threadIdx.x >= o) { vq = sq[threadIdx.x - o]; vi = si[threadIdx.x - o]; }
+    for (int o = 1; o < 1024; o <<= 1) {
+        unsigned int vi = 0;
+        if ((int)threadIdx.x >= o) vi = si[threadIdx.x - o];
         __syncthreads();
-        sq[threadIdx.x] += vq; si[threadIdx.x] += vi;
+        si[threadIdx.x] += vi;
         __syncthreads();
     }
-    unsigned int bq = sq[threadIdx.x] - aq, bi = si[threadIdx.x] - ai;   // exclusive
-    for (int c = c0; c < min(ncell, c0 + per); ++c) {
-        const unsigned int qc = pv.cell_qcount[c];
-        const unsigned int nseg = (unsigned)((lsize[c] + segc - 1) / segc);
-        pv.cellq_off[c] = bq; pv.item_base[c] = bi;
-        pv.cell_fill[c] = 0;
-        bq += qc; bi += ((qc + G - 1) / G) * nseg;
-    }
-    if (threadIdx.x == 1023) {
-        pv.cellq_off[ncell] = sq[1023]; pv.item_base[ncell] = si[1023];
-        pv.cnt->n_items = si[1023];
-    }
+    unsigned int bi = si[threadIdx.x] - ai;
+    for (int f = f0; f < min(F, f0 + per); ++f) { pv.item_base[f] = bi; bi += items_of(f); }
+    if (threadIdx.x == 1023) { pv.item_base[F] = si[1023]; pv.cnt->n_items = si[1023]; }
 }
 
 // ---- group the (query, visit) pairs by cell -----------------------------------------------------

@@ -31,7 +31,7 @@ struct ScanArgs {
     unsigned long long* partial;    // [n_partial][KP]
     PlanView pv;
     unsigned int* gthr;             // [nq] float bits: smallest k'-th best distance any finished segment of the query reported
-    int ncell, KP, cap, m, M, use_tau;
+    int ncell, nflat, KP, cap, m, M, use_tau;
     unsigned int n_items;
 };
 
@@ -189,17 +189,16 @@ k_scan(ScanArgs a) {
         const unsigned int item = *s_item;
         if (item >= a.n_items) break;
 
-        // ---- decode the item: cell (binary search over item_base), segment, query group
-        int lo = 0, hi = a.ncell;             // item_base[lo] <= item < item_base[hi]
+        // ---- decode the item: (segment, cell) by binary search over item_base, then the query group
+        int lo = 0, hi = a.nflat;             // item_base[lo] <= item < item_base[hi], f = seg * ncell + cell
         while (hi - lo > 1) {
             const int mid = (lo + hi) >> 1;
             if (pv.item_base[mid] <= item) lo = mid; else hi = mid;
         }
-        const int cell = lo;
+        const unsigned int seg = (unsigned)(lo / a.ncell);
+        const int cell = lo - (int)seg * a.ncell;
         const unsigned int qc = pv.cell_qcount[cell];
-        const unsigned int ng = (qc + G - 1) / G;
-        const unsigned int local = item - pv.item_base[cell];
-        const unsigned int group = local % ng, seg = local / ng;
+        const unsigned int group = item - pv.item_base[lo];
         const int64_t first = (int64_t)seg * pv.segc;
         const int count = (int)min((int64_t)pv.segc, a.lsize[cell] - first);
         const int ntiles = (count + TILE - 1) / TILE;
