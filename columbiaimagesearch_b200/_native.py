@@ -51,6 +51,7 @@ SIGNATURES = {
     "b2l_search_local": (_i, [_h, _vp, _i, _i, _i, _i64, _i, _i, _vp]),
     "b2l_search_merge": (_i, [_h, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b2l_get_stats": (_i, [_h, C.POINTER(Stats)]),
+    "b2l_debug_candidates": (_i, [_h, _i, _vp, _vp]),
     "b2l_stream": (_vp, [_h]),
 }
 
@@ -233,10 +234,15 @@ class Handle(object):
         nq = Q.shape[0]
         assert Q.shape[1] == self.D0, "expected %d-d queries, got %d" % (self.D0, Q.shape[1])
         k = int(k)
-        out = dict(rowid=np.full((nq, k), -1, np.int64), dist=np.full((nq, k), np.nan), coarse=np.zeros((nq, k, 2), np.int32),
-                   fine=np.zeros((nq, k, self.M), np.uint8), count=np.zeros(nq, np.int32), visited=np.zeros(nq, np.int32))
+        # the library writes every element (rows beyond count[q] come back zero-filled)
+        out = dict(rowid=np.empty((nq, k), np.int64), dist=np.empty((nq, k), np.float64), coarse=np.empty((nq, k, 2), np.int32),
+                   fine=np.empty((nq, k, self.M), np.uint8), count=np.empty(nq, np.int32), visited=np.empty(nq, np.int32))
         self._check(self.lib.b2l_search(self.h, _ptr(Q), f64, nq, 0, int(quota), k, _ptr(out["rowid"]), _ptr(out["dist"]),
                                         _ptr(out["coarse"]), _ptr(out["fine"]), _ptr(out["count"]), _ptr(out["visited"])))
+        if nq and int(out["count"].min()) < k:
+            pad = np.arange(k)[None, :] >= out["count"][:, None]
+            out["rowid"][pad] = -1
+            out["dist"][pad] = np.nan
         return out
 
     def search_device(self, q_ptr, nq, quota, k, rowid_ptr, dist_ptr, coarse_ptr, fine_ptr, count_ptr, visited_ptr, f64=False):
@@ -270,6 +276,12 @@ class Handle(object):
         s = Stats()
         self._check(self.lib.b2l_get_stats(self.h, C.byref(s)))
         return s.as_dict()
+
+    def debug_candidates(self, nq):
+        app = np.zeros(nq, np.uint32)
+        bnd = np.zeros(nq, np.uint32)
+        self._check(self.lib.b2l_debug_candidates(self.h, int(nq), _ptr(app), _ptr(bnd)))
+        return app, bnd.view(np.float32)
 
     def stream(self):
         return int(self.lib.b2l_stream(self.h) or 0)

@@ -70,12 +70,15 @@ struct b2l_ctx {
     DevBuf codes, rowids, cell_start, lsize, gsize, sorted_first;
     std::vector<int64_t> h_lsize, h_gsize, h_cell_start;
     // workspaces
-    DevBuf w_q, w_xq, w_px, w_coarse, w_fine, w_lut32, w_lut64, w_p64, w_cellq, w_partial, w_plan, w_sort_a, w_sort_b,
+    DevBuf w_q, w_xq, w_px, w_coarse, w_fine, w_lut32, w_lut64, w_p64, w_cellq, w_cand, w_plan, w_sort_a, w_sort_b,
         w_sort_tmp, w_rec, w_rec2, w_out, w_out2, w_misc;
     PlanView pv = {};
     unsigned int* gthr = nullptr;      // [nq] per-query pruning bound shared by the scan blocks
+    unsigned int* cand_cnt = nullptr;  // [nq] candidates the scan appended
     b2l_stats stats = {};
     int64_t launches = 0;
+    void* h_out = nullptr;             // pinned staging of the search outputs
+    size_t h_out_cap = 0;
 };
 
 namespace {
@@ -105,10 +108,8 @@ inline int grid_for(int64_t n, int threads, int maxblocks = 148 * 16) {
     return (int)std::max<int64_t>(1, std::min<int64_t>(b, maxblocks));
 }
 
-int scan_tile(int) { return 512; }
-
-template <int MP> int launch_scan(b2l_handle h, const ScanArgs& a, int cap) {
-    const size_t smem = scan_smem_bytes<MP>(cap);
+template <int MP> int launch_scan(b2l_handle h, const ScanArgs& a) {
+    const size_t smem = scan_smem_bytes<MP>(a.E);
     if (smem > 227 * 1024) FAIL(B2L_ERR_UNSUPPORTED, "scan shared memory %zu too large", smem);
     CU(cudaFuncSetAttribute(k_scan<MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 1;
@@ -244,7 +245,7 @@ int ensure_index(b2l_handle h) {
         unsigned int* scell = h->w_sort_b.as<unsigned int>();
         k_scatter_rows<<<grid_for(n, 256), 256, 0, h->stream>>>(scell, scell + n, n, h->sorted_first.as<int64_t>(),
                                                                  h->cell_start.as<int64_t>(), h->m_fine.as<uint8_t>(),
-                                                                 h->m_rowid.as<int64_t>(), mv.M, mv.MP, h->codes.as<uint8_t>(),
+                                                                 h->m_rowid.as<int64_t>(), mv.M, mv.MP, mv.SW, h->codes.as<uint8_t>(),
                                                                  h->rowids.as<int64_t>());
         LAUNCHED();
     }
@@ -263,6 +264,7 @@ int setup_plan(b2l_handle h, int nq, int segc, int nsegmax = 1) {
     auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes); return o; };
     const size_t o_cnt = take(sizeof(PlanCounters));
     const size_t o_qc = take((size_t)ncell * 4);            // cell_qcount (zeroed together with the counters)
+    const size_t o_ccnt = take((size_t)nq * 4);             // candidates appended per query
     const size_t zero_bytes = off;
     const size_t o_fill = take((size_t)ncell * 4);
     const size_t o_coff = take((size_t)(ncell + 1) * 4);
@@ -302,13 +304,26 @@ int setup_plan(b2l_handle h, int nq, int segc, int nsegmax = 1) {
     pv.cellq = nullptr;
     pv.vis_dist = nullptr;
     h->gthr = (unsigned int*)(b + o_gthr);
+    h->cand_cnt = (unsigned int*)(b + o_ccnt);
     CU(cudaMemsetAsync(b, 0, zero_bytes, h->stream));
     CU(cudaMemsetAsync(h->gthr, 0x7f, (size_t)nq * 4, h->stream));     // 0x7f7f7f7f = 3.4e38: "no bound yet"
     return B2L_OK;
 }
 
+// stats timing of the most recent search_local_impl (events 0..4 recorded on the stream); call after a stream sync
+int finish_stats(b2l_handle h) {
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, h->ev[0], h->ev[2])); h->stats.plan_ms = ms;
+    CU(cudaEventElapsedTime(&ms, h->ev[2], h->ev[3])); h->stats.scan_ms = ms;
+    CU(cudaEventElapsedTime(&ms, h->ev[3], h->ev[4])); h->stats.select_ms = ms;
+    CU(cudaEventElapsedTime(&ms, h->ev[0], h->ev[4])); h->stats.total_ms = ms;
+    h->stats.kernel_launches = h->launches;
+    return B2L_OK;
+}
+
+// finish = false: return with the work queued on the stream (the caller synchronises and calls finish_stats)
 int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_device, int64_t quota, int k, int exact,
-                      void* d_records) {
+                      void* d_records, bool finish = true) {
     if (!h->has_model) FAIL(B2L_ERR_STATE, "no model set");
     if (nq < 1 || k < 1 || !Q || !d_records) FAIL(B2L_ERR_ARG, "bad search arguments (nq=%d k=%d)", nq, k);
     if (h->mv.V > B2L_MAX_V) FAIL(B2L_ERR_UNSUPPORTED, "V=%d > %d: large-V multi-index traversal is not implemented", h->mv.V, B2L_MAX_V);
@@ -345,15 +360,17 @@ int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_
         LAUNCHED();
         x = h->w_xq.p; xf64 = 0;
     }
-    // fast path eligibility
+    // fast path eligibility: the bound table of the scan needs >= KP entries per slot
     const int KP = std::max(16, next_pow2(k + 8));
+    const int LPS = mv.MP * SCAN_WARPS;
+    const int GEN = std::max(1, KP / std::max(1, LPS));
     const bool fast = !exact && mv.G > 0 && KP <= 512;
-    const int tile = mv.G > 0 ? scan_tile(mv.MP) : 1024;
-    // segment length: a multiple of the tile, sized so the batch yields enough work items
+    const int NS = 2 * mv.G;
+    // segment length: a multiple of 64 codes, sized so the batch yields enough work items
     int64_t maxcell = 0;
     for (int c = 0; c < ncell; ++c) maxcell = std::max(maxcell, h->h_lsize[c]);
     int segc = 16 * 1024;
-    if (maxcell > 0 && maxcell < segc) segc = (int)(((maxcell + tile - 1) / tile) * tile);
+    if (maxcell > 0 && maxcell < segc) segc = (int)(((maxcell + 63) / 64) * 64);
     const int nsegmax = (int)std::max<int64_t>(1, (maxcell + segc - 1) / segc);
     rc = setup_plan(h, nq, segc, nsegmax);
     if (rc) return rc;
@@ -365,7 +382,7 @@ int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_
         LAUNCHED();
     }
     if (fast) {
-        k_plan<<<1, 1024, 0, h->stream>>>(ncell, nsegmax, mv.G, segc, h->lsize.as<int64_t>(), pv);
+        k_plan<<<1, 1024, 0, h->stream>>>(ncell, nsegmax, NS, segc, h->lsize.as<int64_t>(), pv);
         LAUNCHED();
     }
     PlanCounters pc;
@@ -383,18 +400,31 @@ int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_
     if (fast) { CU(h->w_lut32.reserve((size_t)std::max(1u, pc.n_lut) * B2L_LUT_ROWS * mv.m * 4)); lut32 = h->w_lut32.as<float>(); }
     else { CU(h->w_lut64.reserve((size_t)std::max(1u, pc.n_lut) * mv.m * mv.K * 8)); lut64 = h->w_lut64.as<double>(); }
     if (pc.n_lut) {
-        const size_t smem = (size_t)2 * mv.h * 8;
-        if (xf64) { CU(cudaFuncSetAttribute(k_lut<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_lut<double><<<pc.n_lut, 256, smem, h->stream>>>(mv, (const double*)x, pv.lut_desc, h->w_p64.as<double>(), lut32, lut64); }
-        else { CU(cudaFuncSetAttribute(k_lut<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_lut<float><<<pc.n_lut, 256, smem, h->stream>>>(mv, (const float*)x, pv.lut_desc, h->w_p64.as<double>(), lut32, lut64); }
+        const size_t smem = (size_t)(2 * mv.h + LUT_THREADS) * 8;
+#define LUTK(XT, DSV)                                                                                                   \
+    do {                                                                                                                \
+        CU(cudaFuncSetAttribute(k_lut<XT, DSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));               \
+        k_lut<XT, DSV><<<pc.n_lut, LUT_THREADS, smem, h->stream>>>(mv, (const XT*)x, pv.lut_desc, h->w_p64.as<double>(), \
+                                                                   lut32, lut64);                                       \
+    } while (0)
+#define LUTD(XT)                                  \
+    switch (mv.ds) {                              \
+        case 2: LUTK(XT, 2); break;               \
+        case 4: LUTK(XT, 4); break;               \
+        case 8: LUTK(XT, 8); break;               \
+        case 16: LUTK(XT, 16); break;             \
+        default: LUTK(XT, 0);                     \
+    }
+        if (xf64) { LUTD(double); } else { LUTD(float); }
+#undef LUTD
+#undef LUTK
         LAUNCHED();
     }
     IndexView ix = {h->codes.as<uint8_t>(), h->rowids.as<int64_t>(), h->cell_start.as<int64_t>(), h->lsize.as<int64_t>()};
     CU(cudaEventRecord(h->ev[1], h->stream));
     if (fast) {
         CU(h->w_cellq.reserve((size_t)std::max(1u, pc.n_pairs) * 8));
-        CU(h->w_partial.reserve((size_t)std::max(1u, pc.n_partial) * KP * 8));
+        CU(h->w_cand.reserve((size_t)nq * SCAN_CAND_CAP * 8));
         pv.cellq = h->w_cellq.as<int2>();
         k_fill<<<(nq + 255) / 256, 256, 0, h->stream>>>(pv);
         LAUNCHED();
@@ -402,25 +432,26 @@ int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_
         if (pc.n_items) {
             ScanArgs a;
             a.codes = ix.codes; a.cell_start = ix.cell_start; a.lsize = ix.lsize; a.lut32 = lut32;
-            a.partial = h->w_partial.as<unsigned long long>();
-            a.pv = pv; a.ncell = ncell; a.nflat = nsegmax * ncell; a.KP = KP; a.cap = next_pow2(tile + std::max(KP, 512)); a.m = mv.m; a.M = mv.M;
-            a.gthr = h->gthr; a.use_tau = (tile / mv.MP >= KP) ? 1 : 0;
+            a.cand = h->w_cand.as<unsigned long long>(); a.cand_cnt = h->cand_cnt;
+            a.pv = pv; a.ncell = ncell; a.nflat = nsegmax * ncell; a.KP = KP; a.m = mv.m; a.M = mv.M;
+            a.GEN = GEN; a.E = LPS * GEN;
+            a.gthr = h->gthr;
             a.n_items = pc.n_items;
             switch (mv.MP) {
-                case 4: rc = launch_scan<4>(h, a, a.cap); break;
-                case 8: rc = launch_scan<8>(h, a, a.cap); break;
-                case 16: rc = launch_scan<16>(h, a, a.cap); break;
-                case 32: rc = launch_scan<32>(h, a, a.cap); break;
+                case 4: rc = launch_scan<4>(h, a); break;
+                case 8: rc = launch_scan<8>(h, a); break;
+                case 16: rc = launch_scan<16>(h, a); break;
+                case 32: rc = launch_scan<32>(h, a); break;
                 default: FAIL(B2L_ERR_UNSUPPORTED, "no scan instantiation for code stride %d", mv.MP);
             }
             if (rc) return rc;
         }
         CU(cudaEventRecord(h->ev[3], h->stream));
         const double eps_rel = (double)(mv.M + 4) * 2.0 * ldexp(1.0, -24);
-        const size_t smem = (size_t)SEL_SB * 8 + (size_t)KP * 28 + 16;
-        CU(cudaFuncSetAttribute(k_merge_rerank, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_merge_rerank<<<nq, SEL_THREADS, smem, h->stream>>>(mv, ix, pv, h->w_partial.as<unsigned long long>(),
-                                                             h->w_p64.as<double>(), KP, k, eps_rel, d_records);
+        const size_t smem = select_smem_bytes(KP);
+        CU(cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_select<<<nq, SEL_THREADS, smem, h->stream>>>(mv, ix, pv, h->w_cand.as<unsigned long long>(), h->cand_cnt, h->gthr,
+                                                       SCAN_CAND_CAP, h->w_p64.as<double>(), KP, k, eps_rel, d_records);
         LAUNCHED();
         CU(cudaEventRecord(h->ev[4], h->stream));
     } else {
@@ -456,19 +487,14 @@ int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_
         h->stats.exact_queries = nq;
         CU(cudaEventRecord(h->ev[4], h->stream));
     }
+    if (!finish) return B2L_OK;
     CU(cudaStreamSynchronize(h->stream));
-    float ms = 0;
-    CU(cudaEventElapsedTime(&ms, h->ev[0], h->ev[2])); h->stats.plan_ms = ms;
-    CU(cudaEventElapsedTime(&ms, h->ev[2], h->ev[3])); h->stats.scan_ms = ms;
-    CU(cudaEventElapsedTime(&ms, h->ev[3], h->ev[4])); h->stats.select_ms = ms;
-    CU(cudaEventElapsedTime(&ms, h->ev[0], h->ev[4])); h->stats.total_ms = ms;
-    h->stats.kernel_launches = h->launches;
-    return B2L_OK;
+    return finish_stats(h);
 }
 
 // single-rank copy-out of records (any k); multi-rank merge through k_final
 int merge_impl(b2l_handle h, const void* d_recs, int nranks, int nq, int k, int on_device, int64_t* rowid, double* dist,
-               int32_t* coarse, uint8_t* fine, int32_t* count, int32_t* visited, uint8_t* certified) {
+               int32_t* coarse, uint8_t* fine, int32_t* count, int32_t* visited, uint8_t* certified, bool finish = true) {
     if (!h->has_model) FAIL(B2L_ERR_STATE, "no model set");
     if (nranks < 1 || nq < 1 || k < 1 || !count) FAIL(B2L_ERR_ARG, "bad merge arguments");
     const ModelView& mv = h->mv;
@@ -505,7 +531,7 @@ int merge_impl(b2l_handle h, const void* d_recs, int nranks, int nq, int k, int 
         if ((rc = copy_out(h, visited, d_visited, (size_t)nq * 4, 0))) return rc;
         if ((rc = copy_out(h, certified, d_cert, (size_t)nq, 0))) return rc;
     }
-    CU(cudaStreamSynchronize(h->stream));
+    if (finish) CU(cudaStreamSynchronize(h->stream));
     return B2L_OK;
 }
 
@@ -556,9 +582,10 @@ int b2l_destroy(b2l_handle h) {
     cudaStreamSynchronize(h->stream);
     DevBuf* bufs[] = {&h->dCs, &h->dmus, &h->dRt, &h->dsubs, &h->dP, &h->dpmu, &h->m_coarse, &h->m_fine, &h->m_rowid, &h->codes,
                       &h->rowids, &h->cell_start, &h->lsize, &h->gsize, &h->sorted_first, &h->w_q, &h->w_xq, &h->w_px,
-                      &h->w_coarse, &h->w_fine, &h->w_lut32, &h->w_lut64, &h->w_p64, &h->w_cellq, &h->w_partial, &h->w_plan,
+                      &h->w_coarse, &h->w_fine, &h->w_lut32, &h->w_lut64, &h->w_p64, &h->w_cellq, &h->w_cand, &h->w_plan,
                       &h->w_sort_a, &h->w_sort_b, &h->w_sort_tmp, &h->w_rec, &h->w_rec2, &h->w_out, &h->w_out2, &h->w_misc};
     for (DevBuf* b : bufs) b->release();
+    if (h->h_out) cudaFreeHost(h->h_out);
     for (int i = 0; i < 6; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -566,6 +593,17 @@ int b2l_destroy(b2l_handle h) {
 }
 
 void* b2l_stream(b2l_handle h) { return h ? (void*)h->stream : nullptr; }
+
+int b2l_debug_candidates(b2l_handle h, int nq, uint32_t* appended, uint32_t* bound_bits) {
+    if (!h || nq < 1) return B2L_ERR_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(cudaSetDevice(h->device));
+    if (!h->cand_cnt || !h->gthr || nq > h->pv.nq) FAIL(B2L_ERR_STATE, "no fast-path search of >= %d queries has run", nq);
+    if (appended) CU(cudaMemcpyAsync(appended, h->cand_cnt, (size_t)nq * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (bound_bits) CU(cudaMemcpyAsync(bound_bits, h->gthr, (size_t)nq * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return B2L_OK;
+}
 
 int b2l_get_stats(b2l_handle h, b2l_stats* out) {
     if (!h || !out) return B2L_ERR_ARG;
@@ -587,8 +625,8 @@ int b2l_set_model(b2l_handle h, int D, int V, int M, int K, int coarse_is_f32, c
     ModelView& mv = h->mv;
     mv = ModelView();
     mv.D = D; mv.V = V; mv.M = M; mv.K = K; mv.h = D / 2; mv.m = M / 2; mv.ds = D / M; mv.coarse_f32 = coarse_is_f32 ? 1 : 0;
-    if (M <= 32) { mv.MP = std::max(4, next_pow2(M)); mv.G = 32 / mv.MP; }
-    else { mv.MP = (M + 15) & ~15; mv.G = 0; }
+    if (M <= 32) { mv.MP = std::max(4, next_pow2(M)); mv.G = 32 / mv.MP; mv.SW = mv.MP - 1; }
+    else { mv.MP = (M + 15) & ~15; mv.G = 0; mv.SW = 0; }
     const size_t hh = (size_t)mv.h;
     const size_t nC = 2 * (size_t)V * hh, nR = nC * hh, nS = (size_t)M * K * mv.ds;
     CU(h->dCs.reserve(nC * 8)); CU(h->dmus.reserve(nC * 8)); CU(h->dRt.reserve(nR * 8)); CU(h->dsubs.reserve(nS * 8));
@@ -789,8 +827,13 @@ int64_t b2l_index_get_cell(b2l_handle h, int c0, int c1, int64_t cap, int64_t* r
     if (take > 0) {
         const int64_t s = h->h_cell_start[cell];
         if (rowids) CU(cudaMemcpyAsync(rowids, h->rowids.as<int64_t>() + s, (size_t)take * 8, cudaMemcpyDeviceToHost, h->stream));
-        if (fine) CU(cudaMemcpy2DAsync(fine, mv.M, h->codes.as<uint8_t>() + s * mv.MP, mv.MP, mv.M, (size_t)take,
-                                       cudaMemcpyDeviceToHost, h->stream));
+        if (fine) {
+            CU(h->w_fine.reserve((size_t)take * mv.M));
+            k_unswizzle_rows<<<grid_for(take * mv.M, 256), 256, 0, h->stream>>>(h->codes.as<uint8_t>() + s * mv.MP, take, mv.M, mv.MP,
+                                                                                  mv.SW, h->w_fine.as<uint8_t>());
+            LAUNCHED();
+            CU(cudaMemcpyAsync(fine, h->w_fine.p, (size_t)take * mv.M, cudaMemcpyDeviceToHost, h->stream));
+        }
         CU(cudaStreamSynchronize(h->stream));
     }
     return n;
@@ -857,10 +900,10 @@ int b2l_search(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_device,
     if (nq < 1 || k < 1 || !Q || !count) FAIL(B2L_ERR_ARG, "bad search arguments (nq=%d k=%d)", nq, k);
     const ModelView& mv = h->mv;
     CU(h->w_rec.reserve(rec_bytes(nq, k, mv.M)));
-    int rc = search_local_impl(h, Q, q_is_f64, nq, on_device, quota, k, 0, h->w_rec.p);
+    // everything up to the certification flags is queued without a host round trip of its own
+    int rc = search_local_impl(h, Q, q_is_f64, nq, on_device, quota, k, 0, h->w_rec.p, false);
     if (rc) return rc;
-    const b2l_stats st = h->stats;
-    // final outputs on the device first (certification flags come back to the host)
+    // final outputs: one device block [rowid | dist | coarse | fine | count | visited | certified]
     const size_t nk = (size_t)nq * k;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes); return o; };
@@ -871,14 +914,25 @@ int b2l_search(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_device,
     int64_t* d_rowid = (int64_t*)(b + o1); double* d_dist = (double*)(b + o2); int32_t* d_coarse = (int32_t*)(b + o3);
     uint8_t* d_fine = b + o4; int32_t* d_count = (int32_t*)(b + o5); int32_t* d_visited = (int32_t*)(b + o6); uint8_t* d_cert = b + o7;
     CU(cudaMemsetAsync(b, 0, off, h->stream));
-    rc = merge_impl(h, h->w_rec.p, 1, nq, k, 1, d_rowid, d_dist, d_coarse, d_fine, d_count, d_visited, d_cert);
+    rc = merge_impl(h, h->w_rec.p, 1, nq, k, 1, d_rowid, d_dist, d_coarse, d_fine, d_count, d_visited, d_cert, false);
     if (rc) return rc;
-    std::vector<uint8_t> cert(nq);
-    CU(cudaMemcpyAsync(cert.data(), d_cert, nq, cudaMemcpyDeviceToHost, h->stream));
+    // host side: the whole block comes back in one copy into pinned staging (device-resident callers: flags only)
+    if (h->h_out_cap < off) {
+        if (h->h_out) cudaFreeHost(h->h_out);
+        h->h_out = nullptr; h->h_out_cap = 0;
+        CU(cudaHostAlloc(&h->h_out, off + off / 2, cudaHostAllocDefault));
+        h->h_out_cap = off + off / 2;
+    }
+    unsigned char* hb = (unsigned char*)h->h_out;
+    if (on_device) CU(cudaMemcpyAsync(hb + o7, d_cert, nq, cudaMemcpyDeviceToHost, h->stream));
+    else CU(cudaMemcpyAsync(hb, b, off, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
+    if ((rc = finish_stats(h))) return rc;
+    ++h->stats.kernel_launches;                      // k_final
+    const b2l_stats st = h->stats;
+    const uint8_t* cert = hb + o7;
     std::vector<int> redo;
     for (int q = 0; q < nq; ++q) if (!cert[q]) redo.push_back(q);
-    int64_t exact_q = st.exact_queries;
     if (!redo.empty()) {
         // float64 full-sort rerun of the uncertified queries, patched into the outputs row by row
         const int ns = (int)redo.size();
@@ -889,7 +943,6 @@ int b2l_search(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_device,
         for (int i = 0; i < ns; ++i)
             CU(cudaMemcpyAsync(h->w_misc.as<char>() + i * qrow, (const char*)Q + redo[i] * qrow, qrow, kind, h->stream));
         CU(h->w_rec2.reserve(rec_bytes(ns, k, mv.M)));
-        const int64_t launches0 = st.kernel_launches;
         rc = search_local_impl(h, h->w_misc.p, q_is_f64, ns, 1, quota, k, 1, h->w_rec2.p);
         if (rc) return rc;
         RecView rv = rec_view(h->w_rec2.p, ns, k, mv.M);
@@ -906,30 +959,37 @@ int b2l_search(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_device,
         CU(cudaMemcpyAsync(cells.data(), rv.cell, (size_t)ns * k * 4, cudaMemcpyDeviceToHost, h->stream));
         CU(cudaMemcpyAsync(cnt.data(), rv.count, (size_t)ns * 4, cudaMemcpyDeviceToHost, h->stream));
         CU(cudaStreamSynchronize(h->stream));
-        std::vector<int32_t> cp((size_t)k * 2);
-        for (int i = 0; i < ns; ++i) {
+        std::vector<int32_t> cp((size_t)ns * k * 2);
+        for (int i = 0; i < ns; ++i)
             for (int j = 0; j < k; ++j) {
                 const int32_t c = j < cnt[i] ? cells[(size_t)i * k + j] : 0;
-                cp[2 * j] = c / mv.V; cp[2 * j + 1] = c % mv.V;
+                cp[((size_t)i * k + j) * 2] = c / mv.V; cp[((size_t)i * k + j) * 2 + 1] = c % mv.V;
             }
-            CU(cudaMemcpyAsync(d_coarse + (size_t)redo[i] * k * 2, cp.data(), (size_t)k * 8, cudaMemcpyHostToDevice, h->stream));
-            CU(cudaStreamSynchronize(h->stream));
-        }
-        exact_q += ns;
+        for (int i = 0; i < ns; ++i)
+            CU(cudaMemcpyAsync(d_coarse + (size_t)redo[i] * k * 2, cp.data() + (size_t)i * k * 2, (size_t)k * 8, cudaMemcpyHostToDevice, h->stream));
+        if (!on_device) CU(cudaMemcpyAsync(hb, b, off, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        const int64_t l2 = h->launches;
         h->stats = st;
-        h->stats.kernel_launches = launches0 + h->launches;
-    } else {
-        h->stats = st;
-        h->stats.kernel_launches = st.kernel_launches + 1;
+        h->stats.kernel_launches = st.kernel_launches + l2;
+        h->stats.exact_queries = st.exact_queries + ns;
     }
-    h->stats.exact_queries = exact_q;
-    if ((rc = copy_out(h, rowid, d_rowid, nk * 8, on_device))) return rc;
-    if ((rc = copy_out(h, dist, d_dist, nk * 8, on_device))) return rc;
-    if ((rc = copy_out(h, coarse, d_coarse, nk * 8, on_device))) return rc;
-    if ((rc = copy_out(h, fine, d_fine, nk * mv.M, on_device))) return rc;
-    if ((rc = copy_out(h, count, d_count, (size_t)nq * 4, on_device))) return rc;
-    if ((rc = copy_out(h, visited, d_visited, (size_t)nq * 4, on_device))) return rc;
-    CU(cudaStreamSynchronize(h->stream));
+    if (on_device) {
+        if ((rc = copy_out(h, rowid, d_rowid, nk * 8, 1))) return rc;
+        if ((rc = copy_out(h, dist, d_dist, nk * 8, 1))) return rc;
+        if ((rc = copy_out(h, coarse, d_coarse, nk * 8, 1))) return rc;
+        if ((rc = copy_out(h, fine, d_fine, nk * mv.M, 1))) return rc;
+        if ((rc = copy_out(h, count, d_count, (size_t)nq * 4, 1))) return rc;
+        if ((rc = copy_out(h, visited, d_visited, (size_t)nq * 4, 1))) return rc;
+        CU(cudaStreamSynchronize(h->stream));
+    } else {
+        if (rowid) memcpy(rowid, hb + o1, nk * 8);
+        if (dist) memcpy(dist, hb + o2, nk * 8);
+        if (coarse) memcpy(coarse, hb + o3, nk * 8);
+        if (fine) memcpy(fine, hb + o4, nk * mv.M);
+        memcpy(count, hb + o5, (size_t)nq * 4);
+        if (visited) memcpy(visited, hb + o6, (size_t)nq * 4);
+    }
     return B2L_OK;
 }
 

@@ -12,7 +12,9 @@
 struct ModelView {
     int D, V, M, K, h, m, ds;  // h = D/2 (coarse split), m = M/2 (fine splits per coarse split), ds = D/M
     int MP;                    // padded code row stride in bytes on the device (power of two >= 4, or M rounded up)
-    int G;                     // query slots per scan group = 32 / MP (0 when the fast scan is unavailable)
+    int G;                     // lane groups per warp in the scan = 32 / MP (0 when the fast scan is unavailable)
+    int SW;                    // code-row swizzle mask (MP-1 with the fast scan, else 0): stored byte s of in-cell row i
+                               // is code byte (i & SW) ^ s  (see scan.cuh)
     int coarse_f32;            // coarse centroids were float32 in the model object
     const double* Cs;          // [2][V][h]
     const double* mus;         // [2][V][h]
@@ -88,6 +90,11 @@ __device__ __forceinline__ double coarse_residual(XT x, double C, double mu, int
     if (sizeof(XT) == 4 && coarse_f32) r = (double)__fsub_rn((float)x, (float)C);
     else r = __dsub_rn((double)x, C);
     return __dsub_rn(r, mu);
+}
+
+// code byte j of the stored (swizzled) row of in-cell index `incell`
+__device__ __forceinline__ uint8_t code_byte(const uint8_t* row, int64_t incell, int j, int SW) {
+    return row[((int)incell & SW) ^ j];
 }
 
 __device__ __forceinline__ int next_pow2_dev(int x) { int p = 1; while (p < x) p <<= 1; return p; }

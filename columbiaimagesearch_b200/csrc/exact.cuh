@@ -36,7 +36,8 @@ k_exact_dist(ModelView mv, IndexView ix, PlanView pv, int q, const double* __res
         const double* l1 = lut64 + (int64_t)pv.vis_lut1[o + t] * mv.m * mv.K;
         double acc = 0.0;
         for (int j = 0; j < mv.M; ++j) {
-            const double e = (j < mv.m) ? l0[j * mv.K + code[j]] : l1[(j - mv.m) * mv.K + code[j]];
+            const int cb = code_byte(code, idx, j, mv.SW);
+            const double e = (j < mv.m) ? l0[j * mv.K + cb] : l1[(j - mv.m) * mv.K + cb];
             acc = (j == 0) ? e : __dadd_rn(acc, e);
         }
         keys[i] = (unsigned long long)__double_as_longlong(acc);
@@ -61,13 +62,14 @@ k_exact_emit(ModelView mv, IndexView ix, PlanView pv, int q, int qout, int nq_ou
             }
         }
         const int cell = pv.vis_cell[o + v];
-        const int64_t row = ix.cell_start[cell] + ((int64_t)pos - pv.vis_base[o + v]);
+        const int64_t incell = (int64_t)pos - pv.vis_base[o + v];
+        const int64_t row = ix.cell_start[cell] + incell;
         const int64_t e = (int64_t)qout * k + i;
         rv.d64[e] = __longlong_as_double((long long)keys[i]);
         rv.pos[e] = pos;
         rv.rowid[e] = ix.rowids[row];
         rv.cell[e] = cell;
-        for (int j = 0; j < mv.M; ++j) rv.fine[e * mv.M + j] = ix.codes[row * mv.MP + j];
+        for (int j = 0; j < mv.M; ++j) rv.fine[e * mv.M + j] = code_byte(ix.codes + row * mv.MP, incell, j, mv.SW);
     }
     if (threadIdx.x == 0) {
         rv.lb[qout] = __longlong_as_double(0x7FF0000000000000ll);

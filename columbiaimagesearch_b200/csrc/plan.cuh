@@ -227,35 +227,70 @@ __global__ void k_fill(PlanView pv) {
 // project (model.py:604-641) then ((fx - subC[j])**2).sum(1) for the m sub-vectors of the split
 // (model.py:696-704).  Writes the float64 projection (for the exact re-rank) and the float32 table
 // rounded from float64, k-major: lut32[slot][k][j], j < m  (so one scan-LUT row is contiguous).
-template <typename XT>
-__global__ void __launch_bounds__(256)
+// DS > 0: compile-time sub-vector length (unrolled, registers); DS == 0: runtime ds.
+// dynamic smem: r[h] | p[h] | psum[LUT_THREADS] doubles
+#define LUT_THREADS 256
+template <typename XT, int DS>
+__global__ void __launch_bounds__(LUT_THREADS)
 k_lut(ModelView mv, const XT* __restrict__ Xq, const int32_t* __restrict__ lut_desc,
       double* __restrict__ P64, float* __restrict__ lut32, double* __restrict__ lut64) {
-    extern __shared__ double sm_lut[];      // r[h], p[h]
-    const int h = mv.h, m = mv.m, ds = mv.ds, V = mv.V;
+    extern __shared__ double sm_lut[];
+    const int h = mv.h, m = mv.m, V = mv.V;
+    const int ds = DS ? DS : mv.ds;
     double* r = sm_lut;
     double* p = sm_lut + h;
-    const int slot = blockIdx.x;
+    double* psum = p + h;
+    const int slot = blockIdx.x, tid = threadIdx.x;
     const int q = lut_desc[3 * slot], s = lut_desc[3 * slot + 1], c = lut_desc[3 * slot + 2];
     const XT* x = Xq + (int64_t)q * mv.D + s * h;
     const double* C = mv.Cs + ((int64_t)s * V + c) * h;
     const double* mu = mv.mus + ((int64_t)s * V + c) * h;
-    for (int d = threadIdx.x; d < h; d += blockDim.x) r[d] = coarse_residual<XT>(x[d], C[d], mu[d], mv.coarse_f32);
+    for (int d = tid; d < h; d += LUT_THREADS) r[d] = coarse_residual<XT>(x[d], C[d], mu[d], mv.coarse_f32);
     __syncthreads();
+    // rotation p[t] = sum_d Rt[d][t] r[d]: `parts` threads share one output (contiguous d ranges, summed in order)
     const double* Rt = mv.Rt + ((int64_t)s * V + c) * h * (int64_t)h;
-    for (int t = threadIdx.x; t < h; t += blockDim.x) {
+    int parts = 1;
+    while (parts * 2 * h <= LUT_THREADS && parts * 2 <= h) parts *= 2;       // h = 64 -> 4 parts
+    const int tw = LUT_THREADS / parts;                                       // outputs handled per sweep
+    const int part = tid / tw, tl = tid - part * tw;
+    const int dlen = h / parts, d0 = part * dlen;
+    for (int t0 = 0; t0 < h; t0 += tw) {
+        const int t = t0 + tl;
         double acc = 0.0;
-        for (int d = 0; d < h; ++d) acc = fma(Rt[(int64_t)d * h + t], r[d], acc);
-        p[t] = acc;
-        P64[(int64_t)slot * h + t] = acc;
+        if (t < h) {
+#pragma unroll 8
+            for (int d = d0; d < d0 + dlen; ++d) acc = fma(Rt[(int64_t)d * h + t], r[d], acc);
+        }
+        if (parts == 1) { if (t < h) { p[t] = acc; P64[(int64_t)slot * h + t] = acc; } }
+        else {
+            psum[tid] = acc;
+            __syncthreads();
+            if (part == 0 && t < h) {
+                double a = psum[tl];
+                for (int pp = 1; pp < parts; ++pp) a += psum[pp * tw + tl];
+                p[t] = a; P64[(int64_t)slot * h + t] = a;
+            }
+            __syncthreads();
+        }
     }
     __syncthreads();
-    for (int k = threadIdx.x; k < B2L_LUT_ROWS; k += blockDim.x) {
+    for (int k = tid; k < B2L_LUT_ROWS; k += LUT_THREADS) {
+        const bool live = k < mv.K;
+        float* o32 = lut32 ? lut32 + ((int64_t)slot * B2L_LUT_ROWS + k) * m : nullptr;
+#pragma unroll 4
         for (int j = 0; j < m; ++j) {
             double e = 0.0;
-            if (k < mv.K) e = sqdist_np<double>(p + j * ds, mv.subs + (((int64_t)s * m + j) * mv.K + k) * ds, ds);
-            if (lut32) lut32[((int64_t)slot * B2L_LUT_ROWS + k) * m + j] = (float)e;
-            if (lut64 && k < mv.K) lut64[((int64_t)slot * m + j) * mv.K + k] = e;
+            if (live) {
+                const double* cj = mv.subs + (((int64_t)s * m + j) * mv.K + k) * ds;
+                if (DS) {
+                    double cv[DS ? DS : 1];
+#pragma unroll
+                    for (int d = 0; d < DS; ++d) cv[d] = cj[d];
+                    e = sqdist_np<double>(p + j * DS, cv, DS);
+                } else e = sqdist_np<double>(p + j * ds, cj, ds);
+            }
+            if (o32) o32[j] = (float)e;
+            if (lut64 && live) lut64[((int64_t)slot * m + j) * mv.K + k] = e;
         }
     }
 }

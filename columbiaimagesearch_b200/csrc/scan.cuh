@@ -1,79 +1,55 @@
 // ADC code scan (LOPQSearcherBase.compute_distances, search.py:137-177, + the top-`limit` cut of
 // search.py:210-215) -- the hot kernel.
 //
-// Work item = (cell segment of <= segc codes, group of G = 32/MP queries visiting that cell).
-// Shared-memory "super LUT": 256 rows (code byte) x 32 columns (bank = column):
-//     column g*MP + j  holds  LUT_{query g}[j][row]      (j < M; columns j >= M are zero padding)
-// Lane l of a warp owns query slot g = l / MP and, per pass, code `jl = l % MP` of a block of MP
-// codes; at step s it looks up sub-quantizer j = jl ^ s.  So at every step the 32 lanes of a warp
-// hit 32 distinct columns = 32 distinct banks (conflict free), and the code words they fetch from
-// the TMA-staged tile are conflict free as well (word (jl>>2)^T of code jl; lanes of different
-// query slots read the same word = broadcast).  Each lane accumulates its own (code, query) sum in
-// a register: no shuffles, no reductions.
-// Code tiles are streamed global -> shared with cp.async.bulk (TMA 1-D bulk copy) behind an
-// mbarrier ring.  Survivors (dist <= running k'-th best of the slot) are appended to a per-slot
-// candidate buffer that is compacted by an in-block bitonic sort when it exceeds 2k'.
-// Keys are (float32 dist bits << 32 | retrieval position): order = (dist, retrieval order), the
-// order the reference's stable sort produces (ties keep retrieval order, search.py:210).
+// Work item = (cell segment of <= segc codes, group of NS = 2*G queries visiting that cell), G = 32/MP.
+//
+// Shared-memory "super LUT": 256 rows (code byte) x 64 float columns (row = 256 B, bank = column % 32):
+//     column x*32 + g*MP + j  holds  LUT_{slot x*G+g}[j][row]     (j < M; columns j >= M stay zero)
+// Lane l of a warp owns slot pair (g = l / MP; x = 0, 1) and, per pass, code `jl = l % MP` of a block of MP
+// consecutive codes.  At step s it looks up sub-quantizer j = jl ^ s, so the 32 lanes of a warp hit 32 distinct
+// banks at every step (conflict free), and the x = 1 look-up is the same address + 128 B.
+//
+// Code rows are stored pre-swizzled in HBM (index.cuh): stored byte s of in-cell row i = code byte (i % MP) ^ s.
+// A lane therefore loads ITS code row straight from global memory into registers (one coalesced 16-byte load
+// for M = 16), and step s consumes byte s of those registers -- a compile-time position.  One PRMT builds the
+// complete shared-memory offset  (code byte << 8) | column offset  from the code word and a per-lane constant
+// register, so a look-up is PRMT + LDS + FADD for the first slot and LDS + FADD for the second:
+// 2.5 instructions and one conflict-free shared-memory wavefront per 32 look-ups x 2.  Shared memory carries
+// only LUT gathers (the resource that bounds this kernel); codes never pass through it.
+//
+// Top-k' preselection without sorting or block barriers: every lane tracks the minimum distance it has seen per
+// slot; the lanes of a block that serve one slot see disjoint codes, so after grouping the lane minima into
+// KP groups, max(group minima) is an upper bound on the slot's KP-th best distance.  Warps refresh that bound
+// at exponentially spaced checkpoints, share it through shared memory and -- across blocks working on other
+// segments / cells of the same query -- through gthr[q] in global memory (atomicMin).  A (code, query) pair
+// whose float32 distance is <= the current bound is appended to the query's candidate list in global memory
+// (a few hundred per query).  k_select (select.cuh) keeps the KP smallest and re-ranks them in float64.
+// Keys are (float32 dist bits << 32 | retrieval position): order = (dist, retrieval order), the order the
+// reference's stable sort produces (ties keep retrieval order, search.py:210).
 #pragma once
 #include "common.cuh"
 #include "plan.cuh"
 
 #define SCAN_THREADS 256
 #define SCAN_WARPS 8
-#define SCAN_U 4
+#define SCAN_CAND_CAP 4096          // candidate keys per query (overflow => the query is re-ranked by the exact path)
+#define SCAN_NO_BOUND 0x7f7f7f7fu   // "no bound yet" (3.39e38), the memset pattern of gthr
 
 struct ScanArgs {
-    const uint8_t* codes;           // [rows][MP]
+    const uint8_t* codes;           // [rows][MP], swizzled
     const int64_t* cell_start;      // [ncell]
     const int64_t* lsize;           // [ncell]
     const float* lut32;             // [slots][256][m]
-    unsigned long long* partial;    // [n_partial][KP]
+    unsigned long long* cand;       // [nq][SCAN_CAND_CAP]
+    unsigned int* cand_cnt;         // [nq]
     PlanView pv;
-    unsigned int* gthr;             // [nq] float bits: smallest k'-th best distance any finished segment of the query reported
-    int ncell, nflat, KP, cap, m, M, use_tau;
+    unsigned int* gthr;             // [nq] float bits: smallest proven upper bound on the query's KP-th best distance
+    int ncell, nflat, KP, m, M;
+    int E, GEN;                     // bound table: E = MP*SCAN_WARPS*GEN entries per slot (>= KP), GEN generations per lane
     unsigned int n_items;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t done;
-    const uint32_t addr = smem_u32(bar);
-    do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
-template <int MP> struct ScanCfg {
-    static constexpr int G = 32 / MP;                       // query slots per group
-    static constexpr int W = MP / 4;                        // 32-bit words per code row
-    static constexpr int TILE = 512;                        // codes per pipeline stage
-    static constexpr int NSTAGE = 4;
-    static constexpr int CPW = TILE / SCAN_WARPS;           // codes per warp per tile (64)
-    static constexpr int U = (CPW / MP) < SCAN_U ? (CPW / MP) : SCAN_U;   // passes interleaved per iteration
-    static constexpr int ITERS = CPW / (U * MP);
-    static constexpr int STAGE_BYTES = TILE * MP;
-    static constexpr int LUT_BYTES = B2L_LUT_ROWS * 32 * 4;
-    static constexpr int GROUPS = TILE / MP;                // MP-code groups of one slot in a tile (dry-run threshold)
-    static_assert(ITERS >= 1 && CPW % (U * MP) == 0, "tile shape");
-};
-
-template <int MP>
-size_t scan_smem_bytes(int cap) {
-    typedef ScanCfg<MP> C;
-    return (size_t)C::LUT_BYTES + (size_t)C::NSTAGE * C::STAGE_BYTES + (size_t)C::G * cap * 8 + 256;
-}
 
 __device__ __forceinline__ void cp_async(void* dst, const void* src, int bytes) {
     const uint32_t d = smem_u32(dst);
@@ -82,96 +58,139 @@ __device__ __forceinline__ void cp_async(void* dst, const void* src, int bytes) 
     else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src) : "memory");
 }
 
-// One pass of a warp over its share of a staged tile.  DRY: no appends; returns, per lane, the maximum over
-// this lane's MP-code groups of the group minimum (an upper bound on the GROUPS-th best distance of the tile).
-template <int MP, bool DRY>
-__device__ __forceinline__ float scan_tile(const uint32_t* __restrict__ words, const unsigned char* __restrict__ lutc,
-                                           const uint32_t (&lut_off)[MP], const uint32_t (&sel)[4], int warp, int jl, int g,
-                                           int tile_first, int count, float thr, unsigned int posbase, int KP2,
-                                           int* s_cnt, unsigned long long* cand_g, int& over) {
+template <int MP> struct ScanCfg {
+    static constexpr int G = 32 / MP;                       // lane groups per warp
+    static constexpr int NS = 2 * G;                        // query slots per work item
+    static constexpr int W = MP / 4;                        // 32-bit words per code row
+    static constexpr int U = (64 / MP) < 4 ? (64 / MP) : 4; // MP-code blocks interleaved per iteration
+    static constexpr int CHUNK = U * MP;                    // codes per warp per iteration
+    static constexpr int LPS = MP * SCAN_WARPS;             // lanes of a block serving one slot
+    static constexpr int LUT_BYTES = B2L_LUT_ROWS * 256;
+};
+
+template <int MP>
+size_t scan_smem_bytes(int E) {
     typedef ScanCfg<MP> C;
-    constexpr int W = C::W, U = C::U;
-    float gmax = 0.0f;
-#pragma unroll 1
-    for (int it = 0; it < C::ITERS; ++it) {
-        const int cbase = warp * C::CPW + it * (U * MP) + jl;     // this lane's code of pass 0
-        float acc[U];
+    return (size_t)C::LUT_BYTES + (size_t)C::NS * E * 4 + 64 * 4 + 256;
+}
+
+// one code row -> registers
+template <int W> __device__ __forceinline__ void load_row(const uint8_t* p, uint32_t (&w)[W]) {
+    if (W == 1) { w[0] = __ldg((const unsigned int*)p); }
+    else if (W == 2) { const uint2 v = __ldg((const uint2*)p); w[0] = v.x; w[1] = v.y; }
+    else {
 #pragma unroll
-        for (int u = 0; u < U; ++u) acc[u] = 0.0f;
-#pragma unroll
-        for (int T = 0; T < W; ++T) {
-            uint32_t wd[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) wd[u] = words[(cbase + u * MP) * W + ((jl >> 2) ^ T)];
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const uint32_t c = __byte_perm(wd[u], 0u, sel[b]);
-                    acc[u] += *(const float*)(lutc + (lut_off[T * 4 + b] + (c << 7)));
-                }
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int idx = tile_first + cbase + u * MP;                  // index inside the segment
-            if (DRY) {
-                // minimum over the MP lanes of this slot (same code block), then running maximum
-                unsigned int v = (idx < count) ? __float_as_uint(acc[u]) : 0x7f800000u;
-                if (MP == 32) v = __reduce_min_sync(0xffffffffu, v);
-                else {
-#pragma unroll
-                    for (int o = MP / 2; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
-                }
-                gmax = fmaxf(gmax, __uint_as_float(v));
-            } else if (idx < count && acc[u] <= thr) {
-                const int slot = atomicAdd(s_cnt, 1);
-                over |= (slot >= KP2);
-                cand_g[slot] = ((unsigned long long)__float_as_uint(acc[u]) << 32) | (unsigned long long)(posbase + (unsigned)idx);
-            }
+        for (int i = 0; i < W / 4; ++i) {
+            const uint4 v = __ldg((const uint4*)p + i);
+            w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
         }
     }
-    return gmax;
+}
+
+// shared-memory byte offset of a look-up: byte 1 <- code byte b of `word`, byte 0 <- byte b of `cc` (column offset,
+// always < 128, so its replicated sign gives the two zero upper bytes)
+template <int B> __device__ __forceinline__ uint32_t lut_offset(uint32_t word, uint32_t cc) {
+    uint32_t r;
+    constexpr uint32_t sel = (4u + B) | ((uint32_t)B << 4) | ((12u + B) << 8) | ((12u + B) << 12);
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(word), "r"(cc), "n"(sel));
+    return r;
+}
+
+// The super LUT sits at offset 0 of the kernel's dynamic shared memory, which (no static shared memory, no
+// cluster) is shared-window address SCAN_LUT_SADDR: the 1 KB the system reserves per CTA on sm_100.  k_scan checks
+// this at entry and traps otherwise.  Knowing it at compile time lets the base ride in the LDS immediate, so the
+// PRMT result is the complete address register.
+#define SCAN_LUT_SADDR 1024
+template <int OFF> __device__ __forceinline__ float lds_lut(uint32_t o) {
+    float v;
+    asm("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(o), "n"(SCAN_LUT_SADDR + OFF));
+    return v;
+}
+
+template <int MP>
+__device__ __forceinline__ void adc_block(const uint32_t (&w)[MP / 4], const uint32_t (&cc)[MP / 4], float& a0, float& a1) {
+#pragma unroll
+    for (int T = 0; T < MP / 4; ++T) {
+        uint32_t o;
+        o = lut_offset<0>(w[T], cc[T]);
+        if (T == 0) { a0 = lds_lut<0>(o); a1 = lds_lut<128>(o); } else { a0 += lds_lut<0>(o); a1 += lds_lut<128>(o); }
+        o = lut_offset<1>(w[T], cc[T]); a0 += lds_lut<0>(o); a1 += lds_lut<128>(o);
+        o = lut_offset<2>(w[T], cc[T]); a0 += lds_lut<0>(o); a1 += lds_lut<128>(o);
+        o = lut_offset<3>(w[T], cc[T]); a0 += lds_lut<0>(o); a1 += lds_lut<128>(o);
+    }
+}
+
+// Refresh the per-slot bounds from the lane-minimum table (whole warp; result lands in s_thr / gthr).
+// tab[sl][E]: every entry is +inf or the distance of a real candidate of slot sl, distinct entries <-> distinct codes.
+template <int MP>
+__device__ __forceinline__ void refresh_bounds(const ScanArgs& a, const float* tab, unsigned int* s_thr, const int* s_q, int lane) {
+    typedef ScanCfg<MP> C;
+    const int E = a.E, gs = E / a.KP;          // gs entries per group (power of two), KP groups
+    const int epl = E / 32;                    // entries per lane (contiguous)
+#pragma unroll 1
+    for (int sl = 0; sl < C::NS; ++sl) {
+        if (s_q[sl] < 0) continue;             // uniform
+        const float* t = tab + sl * E + lane * epl;
+        float v;
+        if (gs <= epl) {                       // whole groups inside the lane's run: max of group minima
+            v = 0.0f;
+            for (int e0 = 0; e0 < epl; e0 += gs) {
+                float mn = t[e0];
+                for (int e = 1; e < gs; ++e) mn = fminf(mn, t[e0 + e]);
+                v = fmaxf(v, mn);
+            }
+        } else {                               // a group spans gs/epl lanes
+            v = t[0];
+            for (int e = 1; e < epl; ++e) v = fminf(v, t[e]);
+            for (int o = 1; o < gs / epl; o <<= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+        if (lane == 0 && v < 3.0e38f) {
+            const unsigned int bits = __float_as_uint(v);
+            const unsigned int old = atomicMin(&s_thr[sl], bits);
+            if (bits < old) atomicMin(&a.gthr[s_q[sl]], bits);     // every bound a lane may filter with is published
+        }
+    }
+    // pull in what other blocks proved for the same queries
+    if (lane < C::NS && s_q[lane] >= 0) {
+        const unsigned int gb = *(volatile unsigned int*)&a.gthr[s_q[lane]];
+        atomicMin(&s_thr[lane], gb);
+    }
+    __syncwarp();
 }
 
 template <int MP>
 __global__ void __launch_bounds__(SCAN_THREADS, 2)
 k_scan(ScanArgs a) {
     typedef ScanCfg<MP> C;
-    constexpr int G = C::G, TILE = C::TILE, NSTAGE = C::NSTAGE;
-    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int G = C::G, NS = C::NS, W = C::W, U = C::U, CHUNK = C::CHUNK;
+    extern __shared__ __align__(256) unsigned char smem[];
     float* lut = (float*)smem;
-    unsigned char* stages = smem + C::LUT_BYTES;
-    unsigned long long* cand = (unsigned long long*)(stages + NSTAGE * C::STAGE_BYTES);
-    uint64_t* bars = (uint64_t*)(cand + (size_t)G * a.cap);       // [NSTAGE]
-    int* s_cnt = (int*)(bars + NSTAGE);                            // [G]
-    float* s_thr = (float*)(s_cnt + 8);                            // [G]
-    unsigned int* s_posbase = (unsigned int*)(s_thr + 8);          // [G]
-    int* s_pslot = (int*)(s_posbase + 8);                          // [G]  (-1 = empty slot)
-    int* s_q = s_pslot + 8;                                        // [G]  query of the slot
-    unsigned int* s_tau = (unsigned int*)(s_q + 8);                // [G]  dry-run threshold (float bits)
-    unsigned int* s_item = s_tau + 8;
+    float* tab = (float*)(smem + C::LUT_BYTES);                    // [NS][E]
+    unsigned int* s_thr = (unsigned int*)(tab + NS * a.E);         // [NS] float bits (16 slots max)
+    int* s_q = (int*)(s_thr + 16);                                 // [NS] query of the slot, -1 = empty
+    unsigned int* s_posbase = (unsigned int*)(s_q + 16);           // [NS]
+    unsigned int* s_item = s_posbase + 16;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane / MP, jl = lane % MP;
-    const int KP = a.KP, cap = a.cap;
-    const int trigger = cap - TILE;           // compaction when a slot's buffer could overflow in the next tile
     const PlanView& pv = a.pv;
+    if (smem_u32(smem) != SCAN_LUT_SADDR) __trap();
+    const float INF = __int_as_float(0x7f800000);
 
-    // per-lane constants of the conflict-free mapping
-    uint32_t lut_off[MP];                     // byte offset of column (g*MP + (jl ^ s)) inside a LUT row
+    // per-lane column offsets: byte b of cc[T] = 4 * (g*MP + (jl ^ (4T+b)))
+    uint32_t cc[W];
 #pragma unroll
-    for (int s = 0; s < MP; ++s) lut_off[s] = 4u * (uint32_t)(g * MP + (jl ^ s));
-    const unsigned char* lutc = (const unsigned char*)lut;
-    uint32_t sel[4];
+    for (int T = 0; T < W; ++T) {
+        uint32_t v = 0;
 #pragma unroll
-    for (int b = 0; b < 4; ++b) sel[b] = 0x4440u | (uint32_t)((jl & 3) ^ b);
-
-    if (tid == 0) {
-        for (int s = 0; s < NSTAGE; ++s) mbar_init(&bars[s], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int b = 0; b < 4; ++b) v |= (uint32_t)(4 * (g * MP + (jl ^ (4 * T + b)))) << (8 * b);
+        cc[T] = v;
     }
-    for (int e = tid; e < B2L_LUT_ROWS * 32; e += SCAN_THREADS) lut[e] = 0.0f;   // padding columns stay zero
+    const int ent = warp * MP + jl;           // this lane's entry in a slot's bound table (generation 0)
+
+    for (int e = tid; e < B2L_LUT_ROWS * 64; e += SCAN_THREADS) lut[e] = 0.0f;   // padding columns stay zero
     __syncthreads();
 
     // LUT staging geometry: a half row (m floats of one (query, split) table) is copied in CB-byte chunks
@@ -179,11 +198,10 @@ k_scan(ScanArgs a) {
     const int hb = m * 4;
     const int CB = (hb % 16 == 0) ? 16 : ((hb % 8 == 0) ? 8 : 4);
     const int cph = hb / CB;                  // chunks per half row
-    const int cpr = G * 2 * cph;              // chunks per LUT row
-
-    uint32_t tiles_done = 0;                  // tiles consumed by this block so far (ring position)
+    const int cpr = NS * 2 * cph;             // chunks per LUT row
 
     while (true) {
+        __syncthreads();                       // previous item fully consumed (LUT, tables, slot descriptors)
         if (tid == 0) *s_item = atomicAdd(&pv.cnt->next_item, 1u);
         __syncthreads();
         const unsigned int item = *s_item;
@@ -201,125 +219,135 @@ k_scan(ScanArgs a) {
         const unsigned int group = item - pv.item_base[lo];
         const int64_t first = (int64_t)seg * pv.segc;
         const int count = (int)min((int64_t)pv.segc, a.lsize[cell] - first);
-        const int ntiles = (count + TILE - 1) / TILE;
         const unsigned char* src0 = a.codes + (a.cell_start[cell] + first) * MP;
 
-        // ---- producer prologue: fill the ring
-        if (tid == 0) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            for (int t = 0; t < min(ntiles, NSTAGE); ++t) {
-                const uint32_t st = (tiles_done + t) % NSTAGE;
-                const uint32_t bytes = (uint32_t)((min(TILE, count - t * TILE) * MP + 15) & ~15);
-                mbar_expect_tx(&bars[st], bytes);
-                tma_load_1d(stages + st * C::STAGE_BYTES, src0 + (size_t)t * C::STAGE_BYTES, bytes, &bars[st]);
-            }
-        }
-        // ---- slot descriptors
-        int lut0[G], lut1[G];
+        // ---- slot descriptors + super-LUT fill with cp.async: chunk e -> (row, slot, split half, part)
+        int lut0[NS], lut1[NS];
 #pragma unroll
-        for (int gg = 0; gg < G; ++gg) {
-            const unsigned int pi = group * G + gg;
-            lut0[gg] = -1; lut1[gg] = -1;
+        for (int sl = 0; sl < NS; ++sl) {
+            const unsigned int pi = group * NS + sl;
+            lut0[sl] = -1; lut1[sl] = -1;
             if (pi < qc) {
                 const int2 qv = pv.cellq[pv.cellq_off[cell] + pi];
                 const int64_t o = (int64_t)qv.x * pv.maxvis + qv.y;
-                lut0[gg] = pv.vis_lut0[o]; lut1[gg] = pv.vis_lut1[o];
-                if (tid == gg) {
-                    s_posbase[gg] = (unsigned int)(pv.vis_base[o] + first);
-                    s_pslot[gg] = pv.pbase[qv.x] + pv.vis_pbase[o] + (int)seg;
-                    s_cnt[gg] = 0;
-                    s_q[gg] = qv.x;
-                    s_thr[gg] = __uint_as_float(min(a.gthr[qv.x], 0x7f800000u));     // best k'-th distance seen so far for the query
-                    s_tau[gg] = 0u;
+                lut0[sl] = pv.vis_lut0[o]; lut1[sl] = pv.vis_lut1[o];
+                if (tid == sl) {
+                    s_posbase[sl] = (unsigned int)(pv.vis_base[o] + first);
+                    s_q[sl] = qv.x;
+                    s_thr[sl] = *(volatile unsigned int*)&a.gthr[qv.x];
                 }
-            } else if (tid == gg) {
-                s_posbase[gg] = 0; s_pslot[gg] = -1; s_cnt[gg] = 0; s_q[gg] = -1; s_thr[gg] = -1.0f; s_tau[gg] = 0u;
+            } else if (tid == sl) {
+                s_posbase[sl] = 0; s_q[sl] = -1; s_thr[sl] = 0xBF800000u;   // -1.0f: nothing passes
             }
         }
-        // ---- super-LUT fill with cp.async: chunk e -> (row, slot g, split half, part)
         for (int e = tid; e < B2L_LUT_ROWS * cpr; e += SCAN_THREADS) {
             const int row = e / cpr, r = e - row * cpr;
-            const int gg = r / (2 * cph), r2 = r - gg * 2 * cph;
+            const int sl = r / (2 * cph), r2 = r - sl * 2 * cph;
             const int half = r2 / cph, part = r2 - half * cph;
             int slot = -1;
 #pragma unroll
-            for (int t = 0; t < G; ++t) if (t == gg) slot = half ? lut1[t] : lut0[t];
+            for (int t = 0; t < NS; ++t) if (t == sl) slot = half ? lut1[t] : lut0[t];
             if (slot >= 0)
-                cp_async((unsigned char*)lut + row * 128 + (gg * MP + half * m) * 4 + part * CB,
+                cp_async((unsigned char*)lut + row * 256 + ((sl / G) * 32 + (sl % G) * MP + half * m) * 4 + part * CB,
                          (const unsigned char*)(a.lut32 + ((size_t)slot * B2L_LUT_ROWS + row) * m) + part * CB, CB);
         }
+        for (int e = tid; e < NS * a.E; e += SCAN_THREADS) tab[e] = INF;
         asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
         __syncthreads();
-        const unsigned int posbase = s_posbase[g];
-        unsigned long long* cand_g = cand + (size_t)g * cap;
-        int over = 0;                          // this thread pushed a slot's buffer past the trigger
 
-        // ---- dry run of tile 0: threshold = max over MP-code groups of the group minimum (>= k' groups)
-        if (a.use_tau) {
-            mbar_wait(&bars[tiles_done % NSTAGE], (tiles_done / NSTAGE) & 1u);
-            const float gm = scan_tile<MP, true>((const uint32_t*)(stages + (tiles_done % NSTAGE) * C::STAGE_BYTES), lutc, lut_off, sel,
-                                                 warp, jl, g, 0, count, 0.0f, posbase, 0, nullptr, nullptr, over);
-            if (jl == 0 && s_pslot[g] >= 0) atomicMax(&s_tau[g], __float_as_uint(gm));
-            __syncthreads();
-            if (tid < G && s_pslot[tid] >= 0) s_thr[tid] = fminf(s_thr[tid], __uint_as_float(s_tau[tid]));
-            __syncthreads();
-        }
-        float thr = s_thr[g];
+        const int nchunk = (count + CHUNK - 1) / CHUNK;           // chunk c is scanned by warp c % SCAN_WARPS
+        float mn0 = INF, mn1 = INF;                               // lane minima of slots g and G+g
+        float* tab0 = tab + g * a.E;
+        float* tab1 = tab + (G + g) * a.E;
 
-        // ---- main loop over the tiles of the segment
-        for (int t = 0; t < ntiles; ++t) {
-            const uint32_t n = tiles_done + t;
-            const uint32_t st = n % NSTAGE;
-            mbar_wait(&bars[st], (n / NSTAGE) & 1u);
-            scan_tile<MP, false>((const uint32_t*)(stages + st * C::STAGE_BYTES), lutc, lut_off, sel, warp, jl, g, t * TILE, count,
-                                 thr, posbase, trigger, &s_cnt[g], cand_g, over);
-            // every warp is done with stage st; the OR makes the compaction decision uniform (a slot
-            // count read after the barrier could already include appends of warps that ran ahead)
-            const int any = __syncthreads_or(over);
-            if (tid == 0 && t + NSTAGE < ntiles) {
-                const int tn = t + NSTAGE;
-                const uint32_t bytes = (uint32_t)((min(TILE, count - tn * TILE) * MP + 15) & ~15);
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                mbar_expect_tx(&bars[st], bytes);
-                tma_load_1d(stages + st * C::STAGE_BYTES, src0 + (size_t)tn * C::STAGE_BYTES, bytes, &bars[st]);
+        // ---- dry run of the first chunk of every warp when some slot has no bound yet: lane minima only
+        const bool nobound = (tid < NS) && s_q[tid] >= 0 && s_thr[tid] >= SCAN_NO_BOUND;
+        if (__syncthreads_or(nobound)) {
+            if (warp < nchunk) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    uint32_t w[W];
+                    const int idx = warp * CHUNK + u * MP + jl;
+                    load_row<W>(src0 + (size_t)idx * MP, w);
+                    float a0, a1;
+                    adc_block<MP>(w, cc, a0, a1);
+                    if (idx < count) { mn0 = fminf(mn0, a0); mn1 = fminf(mn1, a1); }
+                }
+                tab0[ent] = mn0; tab1[ent] = mn1;
             }
-            // ---- compaction of candidate buffers that could overflow during the next tile
-            if (any) {
-                over = 0;
-#pragma unroll 1
-                for (int gg = 0; gg < G; ++gg) {
-                    const int cn = s_cnt[gg];
-                    if (cn > trigger) {
-                        unsigned long long* buf = cand + (size_t)gg * cap;
-                        const int np2 = next_pow2_dev(cn);
-                        for (int i = cn + tid; i < np2; i += SCAN_THREADS) buf[i] = B2L_KEY_EMPTY;
-                        __syncthreads();
-                        bitonic_sort_u64(buf, np2);
-                        if (tid == 0) { s_cnt[gg] = KP; s_thr[gg] = fminf(s_thr[gg], __uint_as_float((unsigned)(buf[KP - 1] >> 32))); }
+            __syncthreads();
+            refresh_bounds<MP>(a, tab, s_thr, s_q, lane);
+            mn0 = INF; mn1 = INF;
+        }
+
+        // ---- main loop: this warp's chunks; the code rows of the next chunk are in flight (register ping-pong)
+        // while the current one is evaluated.  Common case per chunk: no lane passes -> one vote, no append code.
+        int it = 0, gen = 0;
+        auto eval_chunk = [&](const uint32_t (&w)[U][W], int c) {
+            const float thr0 = __uint_as_float(s_thr[g]), thr1 = __uint_as_float(s_thr[G + g]);
+            float a0[U], a1[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) adc_block<MP>(w[u], cc, a0[u], a1[u]);
+            const int base = c * CHUNK + jl;
+            if (base - jl + CHUNK > count) {                      // last, partial chunk of the segment (warp-uniform)
+#pragma unroll
+                for (int u = 0; u < U; ++u) if (base + u * MP >= count) { a0[u] = INF; a1[u] = INF; }
+            }
+            float c0 = a0[0], c1 = a1[0];
+#pragma unroll
+            for (int u = 1; u < U; ++u) { c0 = fminf(c0, a0[u]); c1 = fminf(c1, a1[u]); }
+            mn0 = fminf(mn0, c0); mn1 = fminf(mn1, c1);
+            if (__any_sync(0xffffffffu, (c0 <= thr0) | (c1 <= thr1))) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (a0[u] <= thr0) {
+                        const int q = s_q[g];
+                        const unsigned int n = atomicAdd(&a.cand_cnt[q], 1u);
+                        if (n < SCAN_CAND_CAP)
+                            a.cand[(size_t)q * SCAN_CAND_CAP + n] = ((unsigned long long)__float_as_uint(a0[u]) << 32) |
+                                                                    (unsigned long long)(s_posbase[g] + (unsigned)(base + u * MP));
+                    }
+                    if (a1[u] <= thr1) {
+                        const int q = s_q[G + g];
+                        const unsigned int n = atomicAdd(&a.cand_cnt[q], 1u);
+                        if (n < SCAN_CAND_CAP)
+                            a.cand[(size_t)q * SCAN_CAND_CAP + n] = ((unsigned long long)__float_as_uint(a1[u]) << 32) |
+                                                                    (unsigned long long)(s_posbase[G + g] + (unsigned)(base + u * MP));
                     }
                 }
-                __syncthreads();
-                thr = s_thr[g];
+            }
+            // checkpoints after iterations 0, 1, 3, 7, 15, ... : flush the lane minima (generation slot), refresh bounds
+            if (((it + 1) & it) == 0) {
+                const int e = ent + C::LPS * (gen & (a.GEN - 1));
+                tab0[e] = fminf(tab0[e], mn0); tab1[e] = fminf(tab1[e], mn1);
+                if (a.GEN > 1) { mn0 = INF; mn1 = INF; ++gen; }
+                __syncwarp();
+                refresh_bounds<MP>(a, tab, s_thr, s_q, lane);
+            }
+            ++it;
+        };
+        const uint8_t* lane_src = src0 + (size_t)jl * MP;
+        auto load_chunk = [&](uint32_t (&w)[U][W], int c) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) load_row<W>(lane_src + ((size_t)c * CHUNK + u * MP) * MP, w[u]);
+        };
+        uint32_t wa[U][W], wb[U][W];
+        if (warp < nchunk) load_chunk(wa, warp);
+        for (int c = warp; c < nchunk; c += 2 * SCAN_WARPS) {
+            const bool more = c + SCAN_WARPS < nchunk;
+            if (more) load_chunk(wb, c + SCAN_WARPS);
+            eval_chunk(wa, c);
+            if (more) {
+                if (c + 2 * SCAN_WARPS < nchunk) load_chunk(wa, c + 2 * SCAN_WARPS);
+                eval_chunk(wb, c + SCAN_WARPS);
             }
         }
-        tiles_done += ntiles;
-
-        // ---- final selection of the segment's k' best per slot -> partial lists
-#pragma unroll 1
-        for (int gg = 0; gg < G; ++gg) {
-            const int ps = s_pslot[gg];
-            if (ps < 0) continue;
-            const int cn = s_cnt[gg];
-            unsigned long long* buf = cand + (size_t)gg * cap;
-            const int np2 = next_pow2_dev(cn < 1 ? 1 : cn);
-            for (int i = cn + tid; i < np2; i += SCAN_THREADS) buf[i] = B2L_KEY_EMPTY;
-            __syncthreads();
-            if (np2 > 1) bitonic_sort_u64(buf, np2);
-            unsigned long long* out = a.partial + (size_t)ps * KP;
-            for (int i = tid; i < KP; i += SCAN_THREADS) out[i] = (i < cn) ? buf[i] : B2L_KEY_EMPTY;
-            // publish the k'-th best distance of this segment: a valid pruning bound for every other segment of the query
-            if (tid == 0 && cn >= KP) atomicMin(&a.gthr[s_q[gg]], (unsigned int)(buf[KP - 1] >> 32));
+        // final flush: what this warp learned helps the other segments of the queries
+        if (warp < nchunk) {
+            const int e = ent + C::LPS * (gen & (a.GEN - 1));
+            tab0[e] = fminf(tab0[e], mn0); tab1[e] = fminf(tab1[e], mn1);
+            __syncwarp();
+            refresh_bounds<MP>(a, tab, s_thr, s_q, lane);
         }
-        __syncthreads();                                       // s_* and cand are reused by the next item
     }
 }

@@ -1,4 +1,4 @@
-// Selection kernels: merge of the per-segment partial lists, float64 re-rank of the survivors in the
+// Selection kernels: selection among the scan's candidates, float64 re-rank of the survivors in the
 // reference's summation order (search.py:173: left-to-right python sum over the M LUT entries, each
 // entry ((fx - subC[j][k])**2).sum() in NumPy order, model.py:702), certification, and the final
 // merge over ranks (consumes the all-gathered record buffers directly).
@@ -44,13 +44,13 @@ struct IndexView {
     const int64_t* lsize;        // [ncell]
 };
 
-// exact ADC distance of one code: float64, reference summation order
-__device__ inline double exact_adc(const ModelView& mv, const uint8_t* code, const double* p0, const double* p1) {
+// exact ADC distance of one code (stored row `code`, in-cell index `incell`): float64, reference summation order
+__device__ inline double exact_adc(const ModelView& mv, const uint8_t* code, int64_t incell, const double* p0, const double* p1) {
     double acc = 0.0;
     for (int j = 0; j < mv.M; ++j) {
         const int s = j / mv.m;
         const double* p = (s ? p1 : p0) + (j - s * mv.m) * mv.ds;
-        const double* c = mv.subs + ((int64_t)j * mv.K + code[j]) * mv.ds;
+        const double* c = mv.subs + ((int64_t)j * mv.K + code_byte(code, incell, j, mv.SW)) * mv.ds;
         const double e = sqdist_np<double>(p, c, mv.ds);
         acc = (j == 0) ? e : __dadd_rn(acc, e);
     }
@@ -79,37 +79,117 @@ __device__ inline void bitonic_sort_dp(unsigned long long* dk, unsigned int* pk,
     }
 }
 
-#define SEL_SB 2048     // merge buffer entries
+#define SEL_HB 1024       // histogram buckets of the selection
+#define SEL_LIST 1024     // capacity of the boundary list that is actually sorted (>= KP)
+#define SEL_PART 2048     // float64 partial sums staged per chunk of candidates
 #define SEL_THREADS 256
-// one block per query.  dynamic smem: keys[SEL_SB] u64 | dk[KP] u64 | pk[KP] u32 | idx[KP] int | rows[KP] i64 | vis[KP] int
+__host__ __device__ inline size_t select_smem_bytes(int KP) {
+    return (size_t)SEL_LIST * 8 + (size_t)KP * 28 + (size_t)SEL_PART * 8 + (size_t)SEL_HB * 4 + 64;
+}
+
+__device__ __forceinline__ int sel_bucket(unsigned int dbits, float lo, float scale) {
+    return min(SEL_HB - 1, (int)((__uint_as_float(dbits) - lo) * scale));      // monotone non-decreasing in the distance
+}
+
+// one block per query.  The scan appended every candidate whose float32 distance is <= the query's final bound
+// gthr[q] (and at least KP of them are).  Select the KP smallest without sorting them all: a 1024-bucket histogram
+// over [min, max] of the passing distances locates the bucket holding the KP-th smallest; only candidates up to that
+// bucket are sorted (bitonic, by (dist32, retrieval position)).  The KP best are re-evaluated in float64 in the
+// reference's summation order, ordered by (dist64, retrieval position), and the first k emitted with the
+// certification bound.
+// dynamic smem: list[SEL_LIST] u64 | dk[KP] u64 | rows[KP] i64 | part[SEL_PART] f64 | pk[KP] u32 | idx[KP] int | vis[KP] int | hist[SEL_HB] u32
 __global__ void __launch_bounds__(SEL_THREADS)
-k_merge_rerank(ModelView mv, IndexView ix, PlanView pv, const unsigned long long* __restrict__ partial,
-               const double* __restrict__ P64, int KP, int k, double eps_rel, void* recbuf) {
+k_select(ModelView mv, IndexView ix, PlanView pv, const unsigned long long* __restrict__ cand,
+         const unsigned int* __restrict__ cand_cnt, const unsigned int* __restrict__ gthr, int cand_cap,
+         const double* __restrict__ P64, int KP, int k, double eps_rel, void* recbuf) {
     extern __shared__ __align__(16) unsigned char sm_sel[];
     unsigned long long* keys = (unsigned long long*)sm_sel;
-    unsigned long long* dk = keys + SEL_SB;
+    unsigned long long* dk = keys + SEL_LIST;
     int64_t* rows = (int64_t*)(dk + KP);
-    unsigned int* pk = (unsigned int*)(rows + KP);
+    double* part = (double*)(rows + KP);
+    unsigned int* pk = (unsigned int*)(part + SEL_PART);
     int* idx = (int*)(pk + KP);
     int* visv = idx + KP;
-    const int q = blockIdx.x, tid = threadIdx.x;
-    const int npart = pv.npart[q];
-    const unsigned long long* src = partial + (size_t)pv.pbase[q] * KP;
-    const int64_t total = (int64_t)npart * KP;
+    unsigned int* hist = (unsigned int*)(visv + KP);
+    __shared__ unsigned int s_red[3][SEL_THREADS / 32];
+    __shared__ unsigned int s_scan[SEL_THREADS / 32];
+    __shared__ int s_n, s_bstar;
+    const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     RecView rv = rec_view(recbuf, pv.nq, k, mv.M);
+    const unsigned int appended = cand_cnt[q];
+    const int n = (int)min(appended, (unsigned int)cand_cap);
+    const unsigned int bound = gthr[q];
+    const unsigned long long* src = cand + (size_t)q * cand_cap;
 
-    for (int i = tid; i < KP; i += SEL_THREADS) keys[i] = B2L_KEY_EMPTY;
-    const int chunk = SEL_SB - KP;
-    for (int64_t off = 0; off < total; off += chunk) {
-        for (int i = tid; i < chunk; i += SEL_THREADS) {
-            const int64_t e = off + i;
-            keys[KP + i] = (e < total) ? src[e] : B2L_KEY_EMPTY;
-        }
-        __syncthreads();
-        bitonic_sort_u64(keys, SEL_SB);
+    // ---- pass 1: range and count of the passing candidates
+    unsigned int lo = 0xFFFFFFFFu, hi = 0u, cnt = 0u;
+    for (int i = tid; i < n; i += SEL_THREADS) {
+        const unsigned int d = (unsigned int)(src[i] >> 32);
+        if (d <= bound) { lo = min(lo, d); hi = max(hi, d); ++cnt; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    if (lane == 0) { s_red[0][wid] = lo; s_red[1][wid] = hi; s_red[2][wid] = cnt; }
+    for (int i = tid; i < SEL_HB; i += SEL_THREADS) hist[i] = 0u;
+    if (tid == 0) s_n = 0;
+    __syncthreads();
+    lo = 0xFFFFFFFFu; hi = 0u; cnt = 0u;
+    for (int w = 0; w < SEL_THREADS / 32; ++w) { lo = min(lo, s_red[0][w]); hi = max(hi, s_red[1][w]); cnt += s_red[2][w]; }
+    const int npass = (int)cnt;
+    const float flo = __uint_as_float(lo), fhi = __uint_as_float(hi);
+    const float scale = (npass > 0 && fhi > flo) ? (float)(SEL_HB - 1) / (fhi - flo) : 0.0f;
+    const int want = min(KP, npass);
+
+    // ---- pass 2: histogram, then the bucket b* where the running count reaches `want`
+    for (int i = tid; i < n; i += SEL_THREADS) {
+        const unsigned int d = (unsigned int)(src[i] >> 32);
+        if (d <= bound) atomicAdd(&hist[sel_bucket(d, flo, scale)], 1u);
     }
     __syncthreads();
-    // exact float64 distances of the k' survivors
+    {
+        constexpr int PER = SEL_HB / SEL_THREADS;
+        unsigned int loc[PER], sum = 0;
+#pragma unroll
+        for (int e = 0; e < PER; ++e) { loc[e] = hist[tid * PER + e]; sum += loc[e]; }
+        unsigned int inc = sum;
+        for (int o = 1; o < 32; o <<= 1) { const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) s_scan[wid] = inc;
+        __syncthreads();
+        unsigned int base = 0;
+        for (int w = 0; w < wid; ++w) base += s_scan[w];
+        unsigned int run = base + inc - sum;                       // exclusive prefix of this thread's first bucket
+#pragma unroll
+        for (int e = 0; e < PER; ++e) {
+            if (run < (unsigned)want && run + loc[e] >= (unsigned)want) s_bstar = tid * PER + e;
+            run += loc[e];
+        }
+        if (want == 0 && tid == 0) s_bstar = -1;
+    }
+    __syncthreads();
+    const int bstar = s_bstar;
+
+    // ---- pass 3: gather the candidates up to bucket b*, sort them
+    for (int i = tid; i < n; i += SEL_THREADS) {
+        const unsigned long long key = src[i];
+        const unsigned int d = (unsigned int)(key >> 32);
+        if (d <= bound && sel_bucket(d, flo, scale) <= bstar) {
+            const int j = atomicAdd(&s_n, 1);
+            if (j < SEL_LIST) keys[j] = key;
+        }
+    }
+    __syncthreads();
+    const int nl = s_n;
+    const bool lost = appended > (unsigned int)cand_cap || nl > SEL_LIST;      // some candidate could not be kept
+    const int nk = min(nl, SEL_LIST);
+    const int np2 = max(KP, next_pow2_dev(nk));
+    for (int i = nk + tid; i < np2; i += SEL_THREADS) keys[i] = B2L_KEY_EMPTY;
+    __syncthreads();
+    bitonic_sort_u64(keys, np2);
+
+    // ---- exact float64 distances of the KP best: locate the rows, then one (candidate, sub-quantizer) term per thread
     const int nv = pv.nvis[q];
     const int64_t o = (int64_t)q * pv.maxvis;
     for (int i = tid; i < KP; i += SEL_THREADS) {
@@ -129,38 +209,56 @@ k_merge_rerank(ModelView mv, IndexView ix, PlanView pv, const unsigned long long
                 }
             }
             if (v < 0) continue;                           // cannot happen: positions come from scanned cells
-            const int cell = pv.vis_cell[o + v];
-            const int64_t row = ix.cell_start[cell] + ((int64_t)pos - pv.vis_base[o + v]);
-            const double d = exact_adc(mv, ix.codes + row * mv.MP, P64 + (int64_t)pv.vis_lut0[o + v] * mv.h,
-                                       P64 + (int64_t)pv.vis_lut1[o + v] * mv.h);
-            dk[i] = (unsigned long long)__double_as_longlong(d);
             pk[i] = pos;
-            rows[i] = row;
+            rows[i] = ix.cell_start[pv.vis_cell[o + v]] + ((int64_t)pos - pv.vis_base[o + v]);
             visv[i] = v;
         }
     }
     __syncthreads();
-    int ncoll = 0;                                           // keys are sorted: EMPTY entries are last
-    {
-        int lo = 0, hi = KP;
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (keys[mid] != B2L_KEY_EMPTY) lo = mid + 1; else hi = mid; }
-        ncoll = lo;
+    const int M = mv.M, CH = SEL_PART / M;
+    for (int i0 = 0; i0 < KP; i0 += CH) {
+        const int nc = min(CH, KP - i0);
+        for (int t = tid; t < nc * M; t += SEL_THREADS) {
+            const int i = i0 + t / M, j = t % M;
+            if (rows[i] >= 0) {
+                const int v = visv[i];
+                const int64_t incell = (int64_t)pk[i] - pv.vis_base[o + v];
+                const int s = j / mv.m;
+                const double* p = P64 + (int64_t)(s ? pv.vis_lut1[o + v] : pv.vis_lut0[o + v]) * mv.h + (j - s * mv.m) * mv.ds;
+                const double* c = mv.subs + ((int64_t)j * mv.K + code_byte(ix.codes + rows[i] * mv.MP, incell, j, mv.SW)) * mv.ds;
+                part[t] = sqdist_np<double>(p, c, mv.ds);
+            }
+        }
+        __syncthreads();
+        for (int i = i0 + tid; i < i0 + nc; i += SEL_THREADS) {
+            if (rows[i] >= 0) {
+                const double* e = part + (i - i0) * M;
+                double acc = e[0];
+                for (int j = 1; j < M; ++j) acc = __dadd_rn(acc, e[j]);      // left-to-right, search.py:173
+                dk[i] = (unsigned long long)__double_as_longlong(acc);
+            }
+        }
+        __syncthreads();
     }
+    const int ncoll = min(nk, KP);
     bitonic_sort_dp(dk, pk, idx, KP);
     const int nout = min(k, ncoll);
     for (int i = tid; i < nout; i += SEL_THREADS) {
         const int sidx = idx[i];
         const int64_t row = rows[sidx];
+        const int v = visv[sidx];
         const int64_t e = (int64_t)q * k + i;
         rv.d64[e] = __longlong_as_double((long long)dk[i]);
         rv.pos[e] = pk[i];
         rv.rowid[e] = ix.rowids[row];
-        rv.cell[e] = pv.vis_cell[o + visv[sidx]];
-        for (int j = 0; j < mv.M; ++j) rv.fine[e * mv.M + j] = ix.codes[row * mv.MP + j];
+        rv.cell[e] = pv.vis_cell[o + v];
+        const int64_t incell = (int64_t)pk[i] - pv.vis_base[o + v];
+        for (int j = 0; j < mv.M; ++j) rv.fine[e * mv.M + j] = code_byte(ix.codes + row * mv.MP, incell, j, mv.SW);
     }
     if (tid == 0) {
         double lb = __longlong_as_double(0x7FF0000000000000ll);
-        if (pv.ncand_local[q] > (int64_t)ncoll) {            // some local candidates were not collected
+        if (lost) lb = -1.0;                                  // never certified: exact re-rank
+        else if (pv.ncand_local[q] > (int64_t)ncoll) {        // some local candidates are not among the KP collected
             const float amax = __uint_as_float((unsigned int)(keys[KP - 1] >> 32));
             lb = (double)amax * (1.0 - eps_rel) - 1e-300;
         }

@@ -280,8 +280,7 @@ class LOPQSearcher(LOPQSearcherBase):
     def _ids_of_rows(self, rowids):
         if self._row_ids_flat is None:
             self._row_ids_flat = np.concatenate(self._row_ids) if self._row_ids else np.zeros(0, np.int64)
-        nums = self._row_ids_flat[np.clip(rowids, 0, max(0, self._row_ids_flat.shape[0] - 1))] if self._row_ids_flat.size else \
-            np.zeros_like(rowids)
+        nums = np.take(self._row_ids_flat, rowids, mode="clip") if self._row_ids_flat.size else np.zeros_like(rowids)
         if self._numeric:
             return nums
         out = np.empty(nums.shape, dtype=object)
@@ -306,11 +305,12 @@ class LOPQSearcher(LOPQSearcherBase):
         k = int(max(1, min(int(limit), max(1, self.nb_indexed))))
         out = self._handle.search(self._query_vector(X), quota, k)
         ids = self._ids_of_rows(out["rowid"])
-        pad = np.arange(k)[None, :] >= out["count"][:, None]
-        if self._numeric:
-            ids = np.where(pad, -1, ids)
-        else:
-            ids[pad] = None
+        if out["count"].size and int(out["count"].min()) < k:
+            pad = np.arange(k)[None, :] >= out["count"][:, None]
+            if self._numeric:
+                ids = np.where(pad, -1, ids)
+            else:
+                ids[pad] = None
         out["ids"] = ids
         return out
 

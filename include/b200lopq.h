@@ -144,6 +144,9 @@ typedef struct b2l_stats {
     int64_t exact_queries;    /* queries that went through the float64 full-sort path        */
 } b2l_stats;
 int b2l_get_stats(b2l_handle h, b2l_stats* out);
+/* diagnostics of the most recent fast-path search: per query, candidates the scan appended and the final
+ * pruning bound (float32 bits).  Either pointer may be NULL. */
+int b2l_debug_candidates(b2l_handle h, int nq, uint32_t* appended, uint32_t* bound_bits);
 /* the stream the handle launches on (cudaStream_t as void*), for CUDA-event timing by the caller */
 void* b2l_stream(b2l_handle h);
 
