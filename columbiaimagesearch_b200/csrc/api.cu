@@ -70,7 +70,7 @@ struct b2l_ctx {
     DevBuf codes, rowids, cell_start, lsize, gsize, sorted_first;
     std::vector<int64_t> h_lsize, h_gsize, h_cell_start;
     // workspaces
-    DevBuf w_q, w_xq, w_px, w_coarse, w_fine, w_lut32, w_lut64, w_p64, w_cellq, w_cand, w_plan, w_sort_a, w_sort_b,
+    DevBuf w_q, w_xq, w_px, w_coarse, w_fine, w_lut32, w_lut64, w_p64, w_cellq, w_cand, w_gtab, w_plan, w_sort_a, w_sort_b,
         w_sort_tmp, w_rec, w_rec2, w_out, w_out2, w_misc;
     PlanView pv = {};
     unsigned int* gthr = nullptr;      // [nq] per-query pruning bound shared by the scan blocks
@@ -425,6 +425,9 @@ int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_
     if (fast) {
         CU(h->w_cellq.reserve((size_t)std::max(1u, pc.n_pairs) * 8));
         CU(h->w_cand.reserve((size_t)nq * SCAN_CAND_CAP * 8));
+        CU(h->w_gtab.reserve((size_t)nq * LPS * GEN * 4));
+        CU(cudaMemsetAsync(h->w_gtab.p, 0x7f, (size_t)nq * LPS * GEN * 4, h->stream));      // 3.39e38: "nothing seen"
+
         pv.cellq = h->w_cellq.as<int2>();
         k_fill<<<(nq + 255) / 256, 256, 0, h->stream>>>(pv);
         LAUNCHED();
@@ -435,7 +438,7 @@ int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_
             a.cand = h->w_cand.as<unsigned long long>(); a.cand_cnt = h->cand_cnt;
             a.pv = pv; a.ncell = ncell; a.nflat = nsegmax * ncell; a.KP = KP; a.m = mv.m; a.M = mv.M;
             a.GEN = GEN; a.E = LPS * GEN;
-            a.gthr = h->gthr;
+            a.gthr = h->gthr; a.gtab = h->w_gtab.as<float>();
             a.n_items = pc.n_items;
             switch (mv.MP) {
                 case 4: rc = launch_scan<4>(h, a); break;
@@ -582,7 +585,7 @@ int b2l_destroy(b2l_handle h) {
     cudaStreamSynchronize(h->stream);
     DevBuf* bufs[] = {&h->dCs, &h->dmus, &h->dRt, &h->dsubs, &h->dP, &h->dpmu, &h->m_coarse, &h->m_fine, &h->m_rowid, &h->codes,
                       &h->rowids, &h->cell_start, &h->lsize, &h->gsize, &h->sorted_first, &h->w_q, &h->w_xq, &h->w_px,
-                      &h->w_coarse, &h->w_fine, &h->w_lut32, &h->w_lut64, &h->w_p64, &h->w_cellq, &h->w_cand, &h->w_plan,
+                      &h->w_coarse, &h->w_fine, &h->w_lut32, &h->w_lut64, &h->w_p64, &h->w_cellq, &h->w_cand, &h->w_gtab, &h->w_plan,
                       &h->w_sort_a, &h->w_sort_b, &h->w_sort_tmp, &h->w_rec, &h->w_rec2, &h->w_out, &h->w_out2, &h->w_misc};
     for (DevBuf* b : bufs) b->release();
     if (h->h_out) cudaFreeHost(h->h_out);

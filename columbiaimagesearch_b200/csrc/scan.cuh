@@ -33,6 +33,7 @@
 #define SCAN_THREADS 256
 #define SCAN_WARPS 8
 #define SCAN_CAND_CAP 4096          // candidate keys per query (overflow => the query is re-ranked by the exact path)
+#define SCAN_DRY 4                  // chunks per warp evaluated without appending when a query has no bound yet
 #define SCAN_NO_BOUND 0x7f7f7f7fu   // "no bound yet" (3.39e38), the memset pattern of gthr
 
 struct ScanArgs {
@@ -44,6 +45,7 @@ struct ScanArgs {
     unsigned int* cand_cnt;         // [nq]
     PlanView pv;
     unsigned int* gthr;             // [nq] float bits: smallest proven upper bound on the query's KP-th best distance
+    float* gtab;                    // [nq][E] lane-minimum table of the query merged over finished work items
     int ncell, nflat, KP, m, M;
     int E, GEN;                     // bound table: E = MP*SCAN_WARPS*GEN entries per slot (>= KP), GEN generations per lane
     unsigned int n_items;
@@ -123,7 +125,8 @@ __device__ __forceinline__ void adc_block(const uint32_t (&w)[MP / 4], const uin
 // Refresh the per-slot bounds from the lane-minimum table (whole warp; result lands in s_thr / gthr).
 // tab[sl][E]: every entry is +inf or the distance of a real candidate of slot sl, distinct entries <-> distinct codes.
 template <int MP>
-__device__ __forceinline__ void refresh_bounds(const ScanArgs& a, const float* tab, unsigned int* s_thr, const int* s_q, int lane) {
+__device__ __forceinline__ void refresh_bounds(const ScanArgs& a, const float* tab, unsigned int* s_thr, const int* s_q, int lane,
+                                               unsigned int& gpre) {
     typedef ScanCfg<MP> C;
     const int E = a.E, gs = E / a.KP;          // gs entries per group (power of two), KP groups
     const int epl = E / 32;                    // entries per lane (contiguous)
@@ -152,10 +155,11 @@ __device__ __forceinline__ void refresh_bounds(const ScanArgs& a, const float* t
             if (bits < old) atomicMin(&a.gthr[s_q[sl]], bits);     // every bound a lane may filter with is published
         }
     }
-    // pull in what other blocks proved for the same queries
+    // pull in what other blocks proved for the same queries: the value loaded at the previous refresh is merged now,
+    // the next one is requested (its latency hides behind the chunks evaluated until the next refresh)
     if (lane < C::NS && s_q[lane] >= 0) {
-        const unsigned int gb = *(volatile unsigned int*)&a.gthr[s_q[lane]];
-        atomicMin(&s_thr[lane], gb);
+        atomicMin(&s_thr[lane], gpre);
+        gpre = *(volatile unsigned int*)&a.gthr[s_q[lane]];
     }
     __syncwarp();
 }
@@ -199,13 +203,19 @@ k_scan(ScanArgs a) {
     const int CB = (hb % 16 == 0) ? 16 : ((hb % 8 == 0) ? 8 : 4);
     const int cph = hb / CB;                  // chunks per half row
     const int cpr = NS * 2 * cph;             // chunks per LUT row
+    const bool fill_fast = (SCAN_THREADS % cpr) == 0;      // a thread then copies one fixed column chunk of every rstep-th row
+    const int f_r = tid % cpr, f_sl = f_r / (2 * cph), f_r2 = f_r - f_sl * 2 * cph;
+    const int f_half = f_r2 / cph, f_part = f_r2 - f_half * cph;
+    const int f_row0 = tid / cpr, f_rstep = SCAN_THREADS / cpr;
+    const int f_dst = ((f_sl / G) * 32 + (f_sl % G) * MP + f_half * m) * 4 + f_part * CB;
 
+    unsigned int nxt = 0;
+    if (tid == 0) *s_item = atomicAdd(&pv.cnt->next_item, 1u);
     while (true) {
-        __syncthreads();                       // previous item fully consumed (LUT, tables, slot descriptors)
-        if (tid == 0) *s_item = atomicAdd(&pv.cnt->next_item, 1u);
-        __syncthreads();
+        __syncthreads();                       // previous item fully consumed (LUT, tables, slot descriptors); s_item published
         const unsigned int item = *s_item;
         if (item >= a.n_items) break;
+        if (tid == 0) nxt = atomicAdd(&pv.cnt->next_item, 1u);     // next item: the round trip overlaps this item
 
         // ---- decode the item: (segment, cell) by binary search over item_base, then the query group
         int lo = 0, hi = a.nflat;             // item_base[lo] <= item < item_base[hi], f = seg * ncell + cell
@@ -221,16 +231,16 @@ k_scan(ScanArgs a) {
         const int count = (int)min((int64_t)pv.segc, a.lsize[cell] - first);
         const unsigned char* src0 = a.codes + (a.cell_start[cell] + first) * MP;
 
-        // ---- slot descriptors + super-LUT fill with cp.async: chunk e -> (row, slot, split half, part)
-        int lut0[NS], lut1[NS];
+        // ---- slot descriptors + super-LUT fill with cp.async: chunk -> (row, slot, split half, part)
+        int lut0[NS], lut1[NS], sq[NS];
 #pragma unroll
         for (int sl = 0; sl < NS; ++sl) {
             const unsigned int pi = group * NS + sl;
-            lut0[sl] = -1; lut1[sl] = -1;
+            lut0[sl] = -1; lut1[sl] = -1; sq[sl] = -1;
             if (pi < qc) {
                 const int2 qv = pv.cellq[pv.cellq_off[cell] + pi];
                 const int64_t o = (int64_t)qv.x * pv.maxvis + qv.y;
-                lut0[sl] = pv.vis_lut0[o]; lut1[sl] = pv.vis_lut1[o];
+                lut0[sl] = pv.vis_lut0[o]; lut1[sl] = pv.vis_lut1[o]; sq[sl] = qv.x;
                 if (tid == sl) {
                     s_posbase[sl] = (unsigned int)(pv.vis_base[o] + first);
                     s_q[sl] = qv.x;
@@ -240,18 +250,36 @@ k_scan(ScanArgs a) {
                 s_posbase[sl] = 0; s_q[sl] = -1; s_thr[sl] = 0xBF800000u;   // -1.0f: nothing passes
             }
         }
-        for (int e = tid; e < B2L_LUT_ROWS * cpr; e += SCAN_THREADS) {
-            const int row = e / cpr, r = e - row * cpr;
-            const int sl = r / (2 * cph), r2 = r - sl * 2 * cph;
-            const int half = r2 / cph, part = r2 - half * cph;
+        if (fill_fast) {
             int slot = -1;
 #pragma unroll
-            for (int t = 0; t < NS; ++t) if (t == sl) slot = half ? lut1[t] : lut0[t];
-            if (slot >= 0)
-                cp_async((unsigned char*)lut + row * 256 + ((sl / G) * 32 + (sl % G) * MP + half * m) * 4 + part * CB,
-                         (const unsigned char*)(a.lut32 + ((size_t)slot * B2L_LUT_ROWS + row) * m) + part * CB, CB);
+            for (int t = 0; t < NS; ++t) if (t == f_sl) slot = f_half ? lut1[t] : lut0[t];
+            if (slot >= 0) {
+                const unsigned char* srcl = (const unsigned char*)(a.lut32 + (size_t)slot * B2L_LUT_ROWS * m) + f_part * CB;
+                unsigned char* dstl = (unsigned char*)lut + f_dst;
+                for (int row = f_row0; row < B2L_LUT_ROWS; row += f_rstep) cp_async(dstl + row * 256, srcl + (size_t)row * hb, CB);
+            }
+        } else {
+            for (int e = tid; e < B2L_LUT_ROWS * cpr; e += SCAN_THREADS) {
+                const int row = e / cpr, r = e - row * cpr;
+                const int sl = r / (2 * cph), r2 = r - sl * 2 * cph;
+                const int half = r2 / cph, part = r2 - half * cph;
+                int slot = -1;
+#pragma unroll
+                for (int t = 0; t < NS; ++t) if (t == sl) slot = half ? lut1[t] : lut0[t];
+                if (slot >= 0)
+                    cp_async((unsigned char*)lut + row * 256 + ((sl / G) * 32 + (sl % G) * MP + half * m) * 4 + part * CB,
+                             (const unsigned char*)(a.lut32 + ((size_t)slot * B2L_LUT_ROWS + row) * m) + part * CB, CB);
+            }
         }
-        for (int e = tid; e < NS * a.E; e += SCAN_THREADS) tab[e] = INF;
+        // bound tables start from what finished items of the same queries left in gtab (disjoint codes: still valid)
+        for (int e = tid; e < NS * a.E; e += SCAN_THREADS) {
+            const int sl = e / a.E;
+            int q = -1;
+#pragma unroll
+            for (int t = 0; t < NS; ++t) if (t == sl) q = sq[t];
+            tab[e] = (q >= 0) ? a.gtab[(size_t)q * a.E + (e - sl * a.E)] : INF;
+        }
         asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
         __syncthreads();
 
@@ -260,23 +288,26 @@ k_scan(ScanArgs a) {
         float* tab0 = tab + g * a.E;
         float* tab1 = tab + (G + g) * a.E;
 
-        // ---- dry run of the first chunk of every warp when some slot has no bound yet: lane minima only
+        unsigned int gpre = (lane < NS) ? s_thr[lane] : 0u;        // (slots' gthr as just loaded)
+        // ---- dry run of the first SCAN_DRY chunks of every warp when some slot has no bound yet: lane minima only
         const bool nobound = (tid < NS) && s_q[tid] >= 0 && s_thr[tid] >= SCAN_NO_BOUND;
         if (__syncthreads_or(nobound)) {
-            if (warp < nchunk) {
+            // (with several generations per lane only the first chunk: it is the one generation 0 will hold)
+            const int ndry = a.GEN > 1 ? 1 : SCAN_DRY;
+            for (int c = warp, n = 0; c < nchunk && n < ndry; c += SCAN_WARPS, ++n) {
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     uint32_t w[W];
-                    const int idx = warp * CHUNK + u * MP + jl;
+                    const int idx = c * CHUNK + u * MP + jl;
                     load_row<W>(src0 + (size_t)idx * MP, w);
                     float a0, a1;
                     adc_block<MP>(w, cc, a0, a1);
                     if (idx < count) { mn0 = fminf(mn0, a0); mn1 = fminf(mn1, a1); }
                 }
-                tab0[ent] = mn0; tab1[ent] = mn1;
             }
+            tab0[ent] = fminf(tab0[ent], mn0); tab1[ent] = fminf(tab1[ent], mn1);
             __syncthreads();
-            refresh_bounds<MP>(a, tab, s_thr, s_q, lane);
+            refresh_bounds<MP>(a, tab, s_thr, s_q, lane, gpre);
             mn0 = INF; mn1 = INF;
         }
 
@@ -322,7 +353,7 @@ k_scan(ScanArgs a) {
                 tab0[e] = fminf(tab0[e], mn0); tab1[e] = fminf(tab1[e], mn1);
                 if (a.GEN > 1) { mn0 = INF; mn1 = INF; ++gen; }
                 __syncwarp();
-                refresh_bounds<MP>(a, tab, s_thr, s_q, lane);
+                refresh_bounds<MP>(a, tab, s_thr, s_q, lane, gpre);
             }
             ++it;
         };
@@ -347,7 +378,16 @@ k_scan(ScanArgs a) {
             const int e = ent + C::LPS * (gen & (a.GEN - 1));
             tab0[e] = fminf(tab0[e], mn0); tab1[e] = fminf(tab1[e], mn1);
             __syncwarp();
-            refresh_bounds<MP>(a, tab, s_thr, s_q, lane);
+            refresh_bounds<MP>(a, tab, s_thr, s_q, lane, gpre);
         }
+        __syncthreads();
+        // leave the useful part of the table (entries at or below the bound) to later items of the same queries
+        for (int e = tid; e < NS * a.E; e += SCAN_THREADS) {
+            const int sl = e / a.E;
+            const int q = s_q[sl];
+            const float v = tab[e];
+            if (q >= 0 && __float_as_uint(v) <= s_thr[sl]) atomicMin((unsigned int*)&a.gtab[(size_t)q * a.E + (e - sl * a.E)], __float_as_uint(v));
+        }
+        if (tid == 0) *s_item = nxt;
     }
 }
