@@ -11,7 +11,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200lopq.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class NativeError(RuntimeError):
@@ -21,7 +21,10 @@ class NativeError(RuntimeError):
 class Stats(C.Structure):
     _fields_ = [("scan_ms", C.c_double), ("plan_ms", C.c_double), ("select_ms", C.c_double), ("total_ms", C.c_double),
                 ("codes_scanned", C.c_int64), ("scan_bytes", C.c_int64), ("work_items", C.c_int64),
-                ("lut_slots", C.c_int64), ("kernel_launches", C.c_int64), ("exact_queries", C.c_int64)]
+                ("lut_slots", C.c_int64), ("kernel_launches", C.c_int64), ("exact_queries", C.c_int64),
+                ("acc_calls", C.c_int64), ("acc_scan_ms", C.c_double), ("acc_plan_ms", C.c_double), ("acc_select_ms", C.c_double),
+                ("acc_total_ms", C.c_double), ("acc_codes_scanned", C.c_int64), ("acc_scan_bytes", C.c_int64),
+                ("acc_work_items", C.c_int64), ("acc_kernel_launches", C.c_int64), ("acc_exact_queries", C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -51,6 +54,9 @@ SIGNATURES = {
     "b2l_search_local": (_i, [_h, _vp, _i, _i, _i, _i64, _i, _i, _vp]),
     "b2l_search_merge": (_i, [_h, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b2l_get_stats": (_i, [_h, C.POINTER(Stats)]),
+    "b2l_reset_stats": (_i, [_h]),
+    "b2l_set_async": (_i, [_h, _i]),
+    "b2l_sync": (_i, [_h]),
     "b2l_debug_candidates": (_i, [_h, _i, _vp, _vp]),
     "b2l_stream": (_vp, [_h]),
 }
@@ -276,6 +282,22 @@ class Handle(object):
         s = Stats()
         self._check(self.lib.b2l_get_stats(self.h, C.byref(s)))
         return s.as_dict()
+
+    def reset_stats(self):
+        self._check(self.lib.b2l_reset_stats(self.h))
+
+    def set_async(self, enabled):
+        self._check(self.lib.b2l_set_async(self.h, int(bool(enabled))))
+
+    def sync(self):
+        self._check(self.lib.b2l_sync(self.h))
+
+    def search_merge_ptrs(self, records_all_ptr, nranks, nq, k, rowid_ptr, dist_ptr, coarse_ptr, fine_ptr, count_ptr, visited_ptr,
+                          certified_ptr, on_device):
+        """Merge into caller-owned buffers given as raw pointers (device, or pinned host); asynchronous when set_async(True)."""
+        p = lambda v: None if v is None else _ptr(int(v))
+        self._check(self.lib.b2l_search_merge(self.h, _ptr(int(records_all_ptr)), int(nranks), int(nq), int(k), int(on_device), p(rowid_ptr),
+                                              p(dist_ptr), p(coarse_ptr), p(fine_ptr), p(count_ptr), p(visited_ptr), p(certified_ptr)))
 
     def debug_candidates(self, nq):
         app = np.zeros(nq, np.uint32)

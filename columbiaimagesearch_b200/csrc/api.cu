@@ -20,7 +20,7 @@
 #include "scan.cuh"
 #include "select.cuh"
 
-#define B2L_ABI_VERSION 1
+#define B2L_ABI_VERSION 2
 
 namespace {
 
@@ -54,7 +54,19 @@ struct DevBuf {
 struct b2l_ctx {
     int device = 0, num_sms = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[6] = {};
+    // per-call records (CUDA events + pinned plan counters): a ring, so that several asynchronous searches can be in
+    // flight and still be timed individually
+    struct CallRec {
+        cudaEvent_t ev[5] = {};
+        PlanCounters* h_pc = nullptr;      // pinned
+        bool pending = false, has_pc = false;
+        int64_t launch0 = 0;
+        b2l_stats st = {};
+    };
+    static const int NREC = 8;
+    CallRec ring[NREC];
+    CallRec* cr = nullptr;
+    uint64_t seq = 0;
     std::string err;
     std::mutex mu;
     // model
@@ -77,6 +89,7 @@ struct b2l_ctx {
     unsigned int* cand_cnt = nullptr;  // [nq] candidates the scan appended
     b2l_stats stats = {};
     int64_t launches = 0;
+    bool async_mode = false;
     void* h_out = nullptr;             // pinned staging of the search outputs
     size_t h_out_cap = 0;
 };
@@ -115,7 +128,7 @@ template <int MP> int launch_scan(b2l_handle h, const ScanArgs& a) {
     int occ = 1;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_scan<MP>, SCAN_THREADS, smem));
     if (occ < 1) occ = 1;
-    const unsigned grid = (unsigned)std::min<int64_t>((int64_t)a.n_items, (int64_t)h->num_sms * occ);
+    const unsigned grid = (unsigned)(h->num_sms * occ);        // persistent; blocks without work leave at once
     k_scan<MP><<<grid, SCAN_THREADS, smem, h->stream>>>(a);
     LAUNCHED();
     return B2L_OK;
@@ -310,14 +323,42 @@ int setup_plan(b2l_handle h, int nq, int segc, int nsegmax = 1) {
     return B2L_OK;
 }
 
-// stats timing of the most recent search_local_impl (events 0..4 recorded on the stream); call after a stream sync
-int finish_stats(b2l_handle h) {
+// Turn one finished call record into statistics: h->stats = that call, accumulators += that call.
+int collect_call(b2l_handle h, b2l_ctx::CallRec& r) {
+    if (!r.pending) return B2L_OK;
+    r.pending = false;
+    CU(cudaEventSynchronize(r.ev[4]));
+    if (r.has_pc) {
+        const PlanCounters& pc = *r.h_pc;
+        r.st.lut_slots = pc.n_lut;
+        r.st.codes_scanned = (int64_t)pc.cand_local;
+        r.st.scan_bytes = (int64_t)pc.cand_local * h->mv.M;
+        r.st.work_items = pc.n_items;
+    }
     float ms = 0;
-    CU(cudaEventElapsedTime(&ms, h->ev[0], h->ev[2])); h->stats.plan_ms = ms;
-    CU(cudaEventElapsedTime(&ms, h->ev[2], h->ev[3])); h->stats.scan_ms = ms;
-    CU(cudaEventElapsedTime(&ms, h->ev[3], h->ev[4])); h->stats.select_ms = ms;
-    CU(cudaEventElapsedTime(&ms, h->ev[0], h->ev[4])); h->stats.total_ms = ms;
-    h->stats.kernel_launches = h->launches;
+    CU(cudaEventElapsedTime(&ms, r.ev[0], r.ev[2])); r.st.plan_ms = ms;
+    CU(cudaEventElapsedTime(&ms, r.ev[2], r.ev[3])); r.st.scan_ms = ms;
+    CU(cudaEventElapsedTime(&ms, r.ev[3], r.ev[4])); r.st.select_ms = ms;
+    CU(cudaEventElapsedTime(&ms, r.ev[0], r.ev[4])); r.st.total_ms = ms;
+    b2l_stats acc = h->stats;                       // carries the accumulators
+    b2l_stats cur = r.st;
+    cur.acc_calls = acc.acc_calls + 1;
+    cur.acc_scan_ms = acc.acc_scan_ms + cur.scan_ms; cur.acc_plan_ms = acc.acc_plan_ms + cur.plan_ms;
+    cur.acc_select_ms = acc.acc_select_ms + cur.select_ms; cur.acc_total_ms = acc.acc_total_ms + cur.total_ms;
+    cur.acc_codes_scanned = acc.acc_codes_scanned + cur.codes_scanned; cur.acc_scan_bytes = acc.acc_scan_bytes + cur.scan_bytes;
+    cur.acc_work_items = acc.acc_work_items + cur.work_items; cur.acc_kernel_launches = acc.acc_kernel_launches + cur.kernel_launches;
+    cur.acc_exact_queries = acc.acc_exact_queries + cur.exact_queries;
+    h->stats = cur;
+    return B2L_OK;
+}
+
+// collect every call record that is still pending, oldest first (waits for them)
+int finish_stats(b2l_handle h) {
+    for (uint64_t i = 0; i < b2l_ctx::NREC; ++i) {
+        b2l_ctx::CallRec& r = h->ring[(h->seq + i) % b2l_ctx::NREC];      // h->seq % NREC is the oldest slot
+        int rc = collect_call(h, r);
+        if (rc) return rc;
+    }
     return B2L_OK;
 }
 
@@ -335,9 +376,17 @@ int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_
     for (int c = 0; c < ncell; ++c) gtotal += h->h_gsize[c];
     if (gtotal >= ((int64_t)1 << 32)) FAIL(B2L_ERR_UNSUPPORTED, "more than 2^32 indexed codes");
 
-    h->launches = 0;
-    memset(&h->stats, 0, sizeof h->stats);
-    CU(cudaEventRecord(h->ev[0], h->stream));
+    {   // next call record; if the ring wrapped onto a call that was never collected, collect it now
+        b2l_ctx::CallRec& r = h->ring[h->seq % b2l_ctx::NREC];
+        int rc2 = collect_call(h, r);
+        if (rc2) return rc2;
+        ++h->seq;
+        h->cr = &r;
+        memset(&r.st, 0, sizeof r.st);
+        r.has_pc = false;
+        r.launch0 = h->launches;
+    }
+    CU(cudaEventRecord(h->cr->ev[0], h->stream));
     // queries -> device, PCA
     const int Din = h->has_pca ? mv.D0 : mv.D;
     const size_t esz = q_is_f64 ? 8 : 4;
@@ -385,27 +434,35 @@ int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_
         k_plan<<<1, 1024, 0, h->stream>>>(ncell, nsegmax, NS, segc, h->lsize.as<int64_t>(), pv);
         LAUNCHED();
     }
-    PlanCounters pc;
-    CU(cudaMemcpyAsync(&pc, pv.cnt, sizeof pc, cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
-    h->stats.lut_slots = pc.n_lut;
-    h->stats.codes_scanned = (int64_t)pc.cand_local;
-    h->stats.scan_bytes = (int64_t)pc.cand_local * mv.M;
-    h->stats.work_items = fast ? pc.n_items : 0;
+    // Buffer sizes: the fast path sizes everything for the worst case the plan can produce (2V tables and V*V visited
+    // cells per query), so nothing has to come back to the host between the kernels; the counters are fetched
+    // with the results.  The exact path (and worst cases beyond B2L_ASYNC_WS bytes) reads the counters first.
+    const size_t lut_row_bytes = (size_t)B2L_LUT_ROWS * mv.m * 4 + (size_t)mv.h * 8;
+    const size_t worst_lut = (size_t)nq * 2 * mv.V;
+    const bool nosync = fast && worst_lut * lut_row_bytes <= ((size_t)2 << 30);
+    PlanCounters pc = {};
+    size_t cap_lut = worst_lut, cap_pairs = (size_t)nq * ncell;
+    if (!nosync) {
+        CU(cudaMemcpyAsync(&pc, pv.cnt, sizeof pc, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        cap_lut = std::max(1u, pc.n_lut); cap_pairs = std::max(1u, pc.n_pairs);
+    }
+    h->cr->has_pc = nosync;
 
     // LUT build
-    CU(h->w_p64.reserve((size_t)std::max(1u, pc.n_lut) * mv.h * 8));
+    CU(h->w_p64.reserve(cap_lut * mv.h * 8));
     float* lut32 = nullptr;
     double* lut64 = nullptr;
-    if (fast) { CU(h->w_lut32.reserve((size_t)std::max(1u, pc.n_lut) * B2L_LUT_ROWS * mv.m * 4)); lut32 = h->w_lut32.as<float>(); }
-    else { CU(h->w_lut64.reserve((size_t)std::max(1u, pc.n_lut) * mv.m * mv.K * 8)); lut64 = h->w_lut64.as<double>(); }
-    if (pc.n_lut) {
+    if (fast) { CU(h->w_lut32.reserve(cap_lut * B2L_LUT_ROWS * mv.m * 4)); lut32 = h->w_lut32.as<float>(); }
+    else { CU(h->w_lut64.reserve(cap_lut * mv.m * mv.K * 8)); lut64 = h->w_lut64.as<double>(); }
+    if (nosync || pc.n_lut) {
         const size_t smem = (size_t)(2 * mv.h + LUT_THREADS) * 8;
+        const unsigned lgrid = (unsigned)std::min<size_t>(cap_lut, (size_t)h->num_sms * 8);
 #define LUTK(XT, DSV)                                                                                                   \
     do {                                                                                                                \
         CU(cudaFuncSetAttribute(k_lut<XT, DSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));               \
-        k_lut<XT, DSV><<<pc.n_lut, LUT_THREADS, smem, h->stream>>>(mv, (const XT*)x, pv.lut_desc, h->w_p64.as<double>(), \
-                                                                   lut32, lut64);                                       \
+        k_lut<XT, DSV><<<lgrid, LUT_THREADS, smem, h->stream>>>(mv, (const XT*)x, pv.lut_desc, pv.cnt, h->w_p64.as<double>(), \
+                                                                lut32, lut64);                                          \
     } while (0)
 #define LUTD(XT)                                  \
     switch (mv.ds) {                              \
@@ -421,9 +478,9 @@ int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_
         LAUNCHED();
     }
     IndexView ix = {h->codes.as<uint8_t>(), h->rowids.as<int64_t>(), h->cell_start.as<int64_t>(), h->lsize.as<int64_t>()};
-    CU(cudaEventRecord(h->ev[1], h->stream));
+    CU(cudaEventRecord(h->cr->ev[1], h->stream));
     if (fast) {
-        CU(h->w_cellq.reserve((size_t)std::max(1u, pc.n_pairs) * 8));
+        CU(h->w_cellq.reserve(cap_pairs * 8));
         CU(h->w_cand.reserve((size_t)nq * SCAN_CAND_CAP * 8));
         CU(h->w_gtab.reserve((size_t)nq * LPS * GEN * 4));
         CU(cudaMemsetAsync(h->w_gtab.p, 0x7f, (size_t)nq * LPS * GEN * 4, h->stream));      // 3.39e38: "nothing seen"
@@ -431,15 +488,14 @@ int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_
         pv.cellq = h->w_cellq.as<int2>();
         k_fill<<<(nq + 255) / 256, 256, 0, h->stream>>>(pv);
         LAUNCHED();
-        CU(cudaEventRecord(h->ev[2], h->stream));
-        if (pc.n_items) {
+        CU(cudaEventRecord(h->cr->ev[2], h->stream));
+        if (nosync || pc.n_items) {
             ScanArgs a;
             a.codes = ix.codes; a.cell_start = ix.cell_start; a.lsize = ix.lsize; a.lut32 = lut32;
             a.cand = h->w_cand.as<unsigned long long>(); a.cand_cnt = h->cand_cnt;
             a.pv = pv; a.ncell = ncell; a.nflat = nsegmax * ncell; a.KP = KP; a.m = mv.m; a.M = mv.M;
             a.GEN = GEN; a.E = LPS * GEN;
             a.gthr = h->gthr; a.gtab = h->w_gtab.as<float>();
-            a.n_items = pc.n_items;
             switch (mv.MP) {
                 case 4: rc = launch_scan<4>(h, a); break;
                 case 8: rc = launch_scan<8>(h, a); break;
@@ -449,17 +505,17 @@ int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_
             }
             if (rc) return rc;
         }
-        CU(cudaEventRecord(h->ev[3], h->stream));
+        CU(cudaEventRecord(h->cr->ev[3], h->stream));
         const double eps_rel = (double)(mv.M + 4) * 2.0 * ldexp(1.0, -24);
         const size_t smem = select_smem_bytes(KP);
         CU(cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_select<<<nq, SEL_THREADS, smem, h->stream>>>(mv, ix, pv, h->w_cand.as<unsigned long long>(), h->cand_cnt, h->gthr,
                                                        SCAN_CAND_CAP, h->w_p64.as<double>(), KP, k, eps_rel, d_records);
         LAUNCHED();
-        CU(cudaEventRecord(h->ev[4], h->stream));
+        CU(cudaEventRecord(h->cr->ev[4], h->stream));
     } else {
-        CU(cudaEventRecord(h->ev[2], h->stream));
-        CU(cudaEventRecord(h->ev[3], h->stream));
+        CU(cudaEventRecord(h->cr->ev[2], h->stream));
+        CU(cudaEventRecord(h->cr->ev[3], h->stream));
         std::vector<int64_t> ncl(nq);
         CU(cudaMemcpyAsync(ncl.data(), pv.ncand_local, (size_t)nq * 8, cudaMemcpyDeviceToHost, h->stream));
         CU(cudaStreamSynchronize(h->stream));
@@ -487,9 +543,20 @@ int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_
             k_exact_emit<<<1, 256, 0, h->stream>>>(mv, ix, pv, q, q, nq, k, kb, vb, n, d_records);
             LAUNCHED();
         }
-        h->stats.exact_queries = nq;
-        CU(cudaEventRecord(h->ev[4], h->stream));
+        h->cr->st.exact_queries = nq;
+        CU(cudaEventRecord(h->cr->ev[4], h->stream));
     }
+    if (h->cr->has_pc) {
+        CU(cudaMemcpyAsync(h->cr->h_pc, pv.cnt, sizeof(PlanCounters), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaEventRecord(h->cr->ev[4], h->stream));        // (re-recorded after the copy: the record is complete when it fires)
+    } else {
+        h->cr->st.lut_slots = pc.n_lut;
+        h->cr->st.codes_scanned = (int64_t)pc.cand_local;
+        h->cr->st.scan_bytes = (int64_t)pc.cand_local * mv.M;
+        h->cr->st.work_items = fast ? pc.n_items : 0;
+    }
+    h->cr->st.kernel_launches = h->launches - h->cr->launch0;
+    h->cr->pending = true;
     if (!finish) return B2L_OK;
     CU(cudaStreamSynchronize(h->stream));
     return finish_stats(h);
@@ -561,7 +628,11 @@ int b2l_create(int device, b2l_handle* out) {
     h->device = device;
     e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
-    for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreate(&h->ev[i]);
+    for (int r = 0; r < b2l_ctx::NREC && e == cudaSuccess; ++r) {
+        for (int i = 0; i < 5 && e == cudaSuccess; ++i) e = cudaEventCreate(&h->ring[r].ev[i]);
+        if (e == cudaSuccess) e = cudaHostAlloc((void**)&h->ring[r].h_pc, sizeof(PlanCounters), cudaHostAllocDefault);
+    }
+    h->cr = &h->ring[0];
     cudaDeviceProp prop;
     if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device);
     if (e != cudaSuccess) {
@@ -589,7 +660,10 @@ int b2l_destroy(b2l_handle h) {
                       &h->w_sort_a, &h->w_sort_b, &h->w_sort_tmp, &h->w_rec, &h->w_rec2, &h->w_out, &h->w_out2, &h->w_misc};
     for (DevBuf* b : bufs) b->release();
     if (h->h_out) cudaFreeHost(h->h_out);
-    for (int i = 0; i < 6; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    for (int r = 0; r < b2l_ctx::NREC; ++r) {
+        for (int i = 0; i < 5; ++i) if (h->ring[r].ev[i]) cudaEventDestroy(h->ring[r].ev[i]);
+        if (h->ring[r].h_pc) cudaFreeHost(h->ring[r].h_pc);
+    }
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return B2L_OK;
@@ -610,8 +684,37 @@ int b2l_debug_candidates(b2l_handle h, int nq, uint32_t* appended, uint32_t* bou
 
 int b2l_get_stats(b2l_handle h, b2l_stats* out) {
     if (!h || !out) return B2L_ERR_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(cudaSetDevice(h->device));
+    int rc = finish_stats(h);                  // waits for searches still in flight
+    if (rc) return rc;
     *out = h->stats;
     return B2L_OK;
+}
+
+int b2l_reset_stats(b2l_handle h) {
+    if (!h) return B2L_ERR_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(cudaSetDevice(h->device));
+    int rc = finish_stats(h);
+    if (rc) return rc;
+    memset(&h->stats, 0, sizeof h->stats);
+    return B2L_OK;
+}
+
+int b2l_set_async(b2l_handle h, int enabled) {
+    if (!h) return B2L_ERR_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->async_mode = enabled != 0;
+    return B2L_OK;
+}
+
+int b2l_sync(b2l_handle h) {
+    if (!h) return B2L_ERR_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    return finish_stats(h);
 }
 
 int b2l_set_model(b2l_handle h, int D, int V, int M, int K, int coarse_is_f32, const double* Cs, const double* Rs,
@@ -883,7 +986,7 @@ int b2l_search_local(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_d
     if (!h) return B2L_ERR_ARG;
     std::lock_guard<std::mutex> lk(h->mu);
     CU(cudaSetDevice(h->device));
-    return search_local_impl(h, Q, q_is_f64, nq, on_device, quota, k, exact, d_records);
+    return search_local_impl(h, Q, q_is_f64, nq, on_device, quota, k, exact, d_records, !h->async_mode);
 }
 
 int b2l_search_merge(b2l_handle h, const void* d_records_all, int nranks, int nq, int k, int on_device, int64_t* rowid,
@@ -891,7 +994,8 @@ int b2l_search_merge(b2l_handle h, const void* d_records_all, int nranks, int nq
     if (!h) return B2L_ERR_ARG;
     std::lock_guard<std::mutex> lk(h->mu);
     CU(cudaSetDevice(h->device));
-    return merge_impl(h, d_records_all, nranks, nq, k, on_device, rowid, dist, coarse, fine, count, visited, certified);
+    return merge_impl(h, d_records_all, nranks, nq, k, on_device, rowid, dist, coarse, fine, count, visited, certified,
+                      !h->async_mode);
 }
 
 int b2l_search(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_device, int64_t quota, int k, int64_t* rowid,
@@ -931,7 +1035,7 @@ int b2l_search(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_device,
     else CU(cudaMemcpyAsync(hb, b, off, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     if ((rc = finish_stats(h))) return rc;
-    ++h->stats.kernel_launches;                      // k_final
+    ++h->stats.kernel_launches; ++h->stats.acc_kernel_launches;      // k_final
     const b2l_stats st = h->stats;
     const uint8_t* cert = hb + o7;
     std::vector<int> redo;
@@ -972,10 +1076,15 @@ int b2l_search(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_device,
             CU(cudaMemcpyAsync(d_coarse + (size_t)redo[i] * k * 2, cp.data() + (size_t)i * k * 2, (size_t)k * 8, cudaMemcpyHostToDevice, h->stream));
         if (!on_device) CU(cudaMemcpyAsync(hb, b, off, cudaMemcpyDeviceToHost, h->stream));
         CU(cudaStreamSynchronize(h->stream));
-        const int64_t l2 = h->launches;
+        const b2l_stats s2 = h->stats;           // the exact rerun (collected by its own synchronous call)
         h->stats = st;
-        h->stats.kernel_launches = st.kernel_launches + l2;
+        h->stats.kernel_launches = st.kernel_launches + s2.kernel_launches;
         h->stats.exact_queries = st.exact_queries + ns;
+        h->stats.acc_calls = st.acc_calls;
+        h->stats.acc_kernel_launches = s2.acc_kernel_launches; h->stats.acc_exact_queries = s2.acc_exact_queries;
+        h->stats.acc_scan_ms = st.acc_scan_ms; h->stats.acc_plan_ms = st.acc_plan_ms; h->stats.acc_select_ms = st.acc_select_ms;
+        h->stats.acc_total_ms = st.acc_total_ms; h->stats.acc_codes_scanned = st.acc_codes_scanned;
+        h->stats.acc_scan_bytes = st.acc_scan_bytes; h->stats.acc_work_items = st.acc_work_items;
     }
     if (on_device) {
         if ((rc = copy_out(h, rowid, d_rowid, nk * 8, 1))) return rc;

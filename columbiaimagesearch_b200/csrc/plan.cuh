@@ -232,7 +232,7 @@ __global__ void k_fill(PlanView pv) {
 #define LUT_THREADS 256
 template <typename XT, int DS>
 __global__ void __launch_bounds__(LUT_THREADS)
-k_lut(ModelView mv, const XT* __restrict__ Xq, const int32_t* __restrict__ lut_desc,
+k_lut(ModelView mv, const XT* __restrict__ Xq, const int32_t* __restrict__ lut_desc, const PlanCounters* __restrict__ cnt,
       double* __restrict__ P64, float* __restrict__ lut32, double* __restrict__ lut64) {
     extern __shared__ double sm_lut[];
     const int h = mv.h, m = mv.m, V = mv.V;
@@ -240,7 +240,10 @@ k_lut(ModelView mv, const XT* __restrict__ Xq, const int32_t* __restrict__ lut_d
     double* r = sm_lut;
     double* p = sm_lut + h;
     double* psum = p + h;
-    const int slot = blockIdx.x, tid = threadIdx.x;
+    const int tid = threadIdx.x;
+    const int nslot = (int)cnt->n_lut;             // grid-stride over the slots the plan produced (no host round trip)
+  for (int slot = blockIdx.x; slot < nslot; slot += gridDim.x) {
+    __syncthreads();
     const int q = lut_desc[3 * slot], s = lut_desc[3 * slot + 1], c = lut_desc[3 * slot + 2];
     const XT* x = Xq + (int64_t)q * mv.D + s * h;
     const double* C = mv.Cs + ((int64_t)s * V + c) * h;
@@ -293,4 +296,5 @@ k_lut(ModelView mv, const XT* __restrict__ Xq, const int32_t* __restrict__ lut_d
             if (lut64 && live) lut64[((int64_t)slot * m + j) * mv.K + k] = e;
         }
     }
+  }
 }

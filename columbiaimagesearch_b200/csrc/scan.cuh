@@ -48,7 +48,6 @@ struct ScanArgs {
     float* gtab;                    // [nq][E] lane-minimum table of the query merged over finished work items
     int ncell, nflat, KP, m, M;
     int E, GEN;                     // bound table: E = MP*SCAN_WARPS*GEN entries per slot (>= KP), GEN generations per lane
-    unsigned int n_items;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -135,7 +134,15 @@ __device__ __forceinline__ void refresh_bounds(const ScanArgs& a, const float* t
         if (s_q[sl] < 0) continue;             // uniform
         const float* t = tab + sl * E + lane * epl;
         float v;
-        if (gs <= epl) {                       // whole groups inside the lane's run: max of group minima
+        if (epl == 4) {                        // common shapes: one 16-byte load per lane
+            const float4 f = *(const float4*)t;
+            if (gs == 1) v = fmaxf(fmaxf(f.x, f.y), fmaxf(f.z, f.w));
+            else if (gs == 2) v = fmaxf(fminf(f.x, f.y), fminf(f.z, f.w));
+            else {
+                v = fminf(fminf(f.x, f.y), fminf(f.z, f.w));
+                for (int o = 1; o < gs / 4; o <<= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+            }
+        } else if (gs <= epl) {                // whole groups inside the lane's run: max of group minima
             v = 0.0f;
             for (int e0 = 0; e0 < epl; e0 += gs) {
                 float mn = t[e0];
@@ -209,12 +216,13 @@ k_scan(ScanArgs a) {
     const int f_row0 = tid / cpr, f_rstep = SCAN_THREADS / cpr;
     const int f_dst = ((f_sl / G) * 32 + (f_sl % G) * MP + f_half * m) * 4 + f_part * CB;
 
+    const unsigned int n_items = pv.cnt->n_items;      // written by k_plan (no host round trip)
     unsigned int nxt = 0;
     if (tid == 0) *s_item = atomicAdd(&pv.cnt->next_item, 1u);
     while (true) {
         __syncthreads();                       // previous item fully consumed (LUT, tables, slot descriptors); s_item published
         const unsigned int item = *s_item;
-        if (item >= a.n_items) break;
+        if (item >= n_items) break;
         if (tid == 0) nxt = atomicAdd(&pv.cnt->next_item, 1u);     // next item: the round trip overlaps this item
 
         // ---- decode the item: (segment, cell) by binary search over item_base, then the query group

@@ -116,6 +116,13 @@ k_select(ModelView mv, IndexView ix, PlanView pv, const unsigned long long* __re
     __shared__ int s_n, s_bstar;
     const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     RecView rv = rec_view(recbuf, pv.nq, k, mv.M);
+    if (pv.ncand_local[q] == 0) {                     // nothing of this query is stored on this rank (uniform exit)
+        if (tid == 0) {
+            rv.lb[q] = __longlong_as_double(0x7FF0000000000000ll);
+            rv.count[q] = 0; rv.visited[q] = pv.nvis[q]; rv.ncand[q] = pv.ncand[q];
+        }
+        return;
+    }
     const unsigned int appended = cand_cnt[q];
     const int n = (int)min(appended, (unsigned int)cand_cap);
     const unsigned int bound = gthr[q];

@@ -30,6 +30,11 @@ class ShardedLOPQSearcher(object):
         self.nb_local = 0
         self._tdev = backend_device if backend_device is not None else "cuda:%d" % self._handle.device
         self._dirty = False
+        # the CUDA library handle gets the stream-ordered pipeline; an injected stand-in (CPU tests) the plain one
+        self._pipelined = handle is None
+        self._stream = None
+        self._pool = {}
+        self._pool_next = 0
 
     # ---- index ------------------------------------------------------------------------------------
     def add_codes_arrays(self, coarse, fine, row_base=None):
@@ -94,14 +99,103 @@ class ShardedLOPQSearcher(object):
             allrec = rec
         return h.search_merge(allrec.data_ptr(), self.world, nq, k)
 
-    def search_batch(self, X, quota=10, limit=None):
-        """X: ndarray (host) or torch CUDA tensor [nq, D0] float32.  Returns dict(ids = global insertion indices
-        [nq,k], dist, coarse, fine, count, visited); identical on every rank."""
+    # ---- stream-ordered pipeline (CUDA handle) ---------------------------------------------------------
+    def _buffers(self, nq, k, D):
+        """One of three rotating buffer sets for (nq, k): records, gathered records, one packed output block on the
+        device and its pinned host mirror.  Three sets let two batches be in flight while a third is being read."""
+        import torch
+        key = (nq, k, D)
+        sets = self._pool.get(key)
+        if sets is None:
+            M = self.model.M
+            nk = nq * k
+            a256 = lambda n: (n + 255) & ~255
+            offs, off = {}, 0
+            for name, nbytes in (("rowid", nk * 8), ("dist", nk * 8), ("coarse", nk * 8), ("fine", nk * M), ("count", nq * 4),
+                                 ("visited", nq * 4), ("certified", nq)):
+                offs[name] = off
+                off += a256(nbytes)
+            nbytes = self._handle.records_bytes(nq, k)
+            sets = []
+            for _ in range(3):
+                sets.append(dict(rec=torch.empty(nbytes, dtype=torch.uint8, device=self._tdev),
+                                 allrec=torch.empty(nbytes * self.world, dtype=torch.uint8, device=self._tdev) if self.world > 1 else None,
+                                 out_h=torch.zeros(off, dtype=torch.uint8).pin_memory(),
+                                 q_h=torch.empty((nq, D), dtype=torch.float32).pin_memory(),
+                                 event=torch.cuda.Event(), offs=offs))
+            self._pool[key] = sets
+        self._pool_next = (self._pool_next + 1) % 3
+        return sets[self._pool_next]
+
+    def search_batch_async(self, X, quota=10, limit=None):
+        """Enqueue one batch on the handle's stream (local search -> all-gather -> merge -> one device-to-host copy)
+        and return a pending object; ``.result()`` waits for it.  Up to two batches may be pending at a time, so the
+        host-side launch work of batch i+1 overlaps the device work of batch i.  Every rank must call this (and
+        ``result``) in the same order."""
+        import torch
         if self._dirty:
             self.finalize()
         if limit is None:
             limit = quota
         k = int(max(1, min(int(limit), max(1, self.nb_indexed))))
+        h = self._handle
+        if self._stream is None:
+            self._stream = torch.cuda.ExternalStream(h.stream(), device=self._tdev)
+            h.set_async(True)
+        on_dev = hasattr(X, "data_ptr")
+        nq, D = int(X.shape[0]), int(X.shape[1])
+        b = self._buffers(nq, k, D)
+        o = b["offs"]
+        base = b["out_h"].data_ptr()
+        # All copies from / to the pinned host buffers are enqueued by the library on its own stream (raw pointers):
+        # torch only sees that stream for the all-gather and the completion event.
+        if on_dev:
+            assert X.is_contiguous() and X.dtype == torch.float32
+            self._stream.wait_stream(torch.cuda.current_stream(X.device))
+            h.search_local(X.data_ptr(), quota, k, b["rec"].data_ptr(), exact=False, on_device=True, nq=nq)
+        else:
+            qh = b["q_h"].numpy()
+            np.copyto(qh, X, casting="same_kind")
+            h.search_local(qh, quota, k, b["rec"].data_ptr(), exact=False)
+        if self.world > 1:
+            with torch.cuda.stream(self._stream):
+                self.dist.all_gather_into_tensor(b["allrec"], b["rec"], group=self.group)
+            allrec = b["allrec"]
+        else:
+            allrec = b["rec"]
+        h.search_merge_ptrs(allrec.data_ptr(), self.world, nq, k, base + o["rowid"], base + o["dist"], base + o["coarse"],
+                            base + o["fine"], base + o["count"], base + o["visited"], base + o["certified"], on_device=False)
+        b["event"].record(self._stream)
+        return _PendingSearch(self, b, X, nq, k, quota)
+
+    def search_batch(self, X, quota=10, limit=None):
+        """X: ndarray (host) or torch CUDA tensor [nq, D0] float32.  Returns dict(ids = global insertion indices
+        [nq,k], dist, coarse, fine, count, visited); identical on every rank."""
+        if self._pipelined:
+            if not hasattr(X, "data_ptr"):
+                X = np.asarray(X)
+                X = X[None, :] if X.ndim == 1 else X
+                if X.dtype != np.float32:            # float64 queries: the synchronous path keeps their precision
+                    return self._search_batch_sync(X, quota, limit)
+            return self.search_batch_async(X, quota, limit).result()
+        return self._search_batch_sync(X, quota, limit)
+
+    def _search_batch_sync(self, X, quota=10, limit=None):
+        if self._dirty:
+            self.finalize()
+        if limit is None:
+            limit = quota
+        k = int(max(1, min(int(limit), max(1, self.nb_indexed))))
+        if self._stream is not None:
+            self._handle.sync()
+            self._handle.set_async(False)
+        try:
+            return self._search_batch_sync_impl(X, quota, k)
+        finally:
+            if self._stream is not None:
+                self._handle.set_async(True)
+
+    def _search_batch_sync_impl(self, X, quota, k):
         on_dev = hasattr(X, "data_ptr")
         if on_dev:
             assert X.is_contiguous() and X.dim() == 2
@@ -126,3 +220,64 @@ class ShardedLOPQSearcher(object):
 
     def stats(self):
         return self._handle.stats()
+
+    def close(self):
+        """Wait for work in flight, then release the buffer pool before the library handle (and its stream) goes away."""
+        h = getattr(self, "_handle", None)
+        if h is not None and self._stream is not None:
+            try:
+                h.sync()
+            except Exception:
+                pass
+        self._pool = {}
+        self._stream = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class _PendingSearch(object):
+    """A batch enqueued by ShardedLOPQSearcher.search_batch_async."""
+
+    def __init__(self, searcher, bufs, X, nq, k, quota):
+        self.s, self.b, self.X, self.nq, self.k, self.quota = searcher, bufs, X, nq, k, quota
+        self._out = None
+
+    def result(self):
+        if self._out is not None:
+            return self._out
+        s, b, nq, k = self.s, self.b, self.nq, self.k
+        M = s.model.M
+        b["event"].synchronize()
+        raw = b["out_h"].numpy()
+        o = b["offs"]
+        view = lambda name, dt, shape: raw[o[name]:o[name] + int(np.prod(shape)) * np.dtype(dt).itemsize].view(dt).reshape(shape).copy()
+        out = dict(rowid=view("rowid", np.int64, (nq, k)), dist=view("dist", np.float64, (nq, k)),
+                   coarse=view("coarse", np.int32, (nq, k, 2)), fine=view("fine", np.uint8, (nq, k, M)),
+                   count=view("count", np.int32, (nq,)), visited=view("visited", np.int32, (nq,)),
+                   certified=view("certified", np.uint8, (nq,)))
+        redo = np.nonzero(out["certified"] == 0)[0]
+        if redo.size:           # same set on every rank (the flags are computed from the gathered buffers)
+            X = self.X
+            Xr = X[redo].cpu().numpy() if hasattr(X, "data_ptr") else np.asarray(X)[redo]
+            s._handle.sync()
+            s._handle.set_async(False)
+            try:
+                sub = s._gather_merge(np.ascontiguousarray(Xr), self.quota, k, True, int(redo.size))
+            finally:
+                s._handle.set_async(True)
+            for key in ("rowid", "dist", "coarse", "fine", "count"):
+                out[key][redo] = sub[key]
+        out["exact_queries"] = int(redo.size)
+        ids = out["rowid"]
+        if nq and int(out["count"].min()) < k:
+            pad = np.arange(k)[None, :] >= out["count"][:, None]
+            ids = ids.copy()
+            ids[pad] = -1
+            out["dist"][pad] = np.nan
+        out["ids"] = ids
+        self._out = out
+        return out

@@ -142,8 +142,21 @@ typedef struct b2l_stats {
     int64_t lut_slots;        /* (query, split, coarse code) distance tables built           */
     int64_t kernel_launches;  /* kernels of this library launched by the call                */
     int64_t exact_queries;    /* queries that went through the float64 full-sort path        */
+    /* sums of the fields above over every search collected since b2l_reset_stats (asynchronous searches are timed
+     * individually, each with its own CUDA events) */
+    int64_t acc_calls;
+    double  acc_scan_ms, acc_plan_ms, acc_select_ms, acc_total_ms;
+    int64_t acc_codes_scanned, acc_scan_bytes, acc_work_items, acc_kernel_launches, acc_exact_queries;
 } b2l_stats;
+/* waits for searches still in flight on the handle, then returns the statistics */
 int b2l_get_stats(b2l_handle h, b2l_stats* out);
+int b2l_reset_stats(b2l_handle h);
+/* Asynchronous mode (pipelined / multi-GPU searches).  While enabled, b2l_search_local and b2l_search_merge only
+ * enqueue their work (including the copies from / to host buffers, which must then be PINNED and stay alive) on the
+ * handle's stream and return; the caller orders other work against that stream (b2l_stream) and waits for it
+ * (an event recorded on the stream, or b2l_sync) before reading results.  Default: disabled. */
+int b2l_set_async(b2l_handle h, int enabled);
+int b2l_sync(b2l_handle h);
 /* diagnostics of the most recent fast-path search: per query, candidates the scan appended and the final
  * pruning bound (float32 bits).  Either pointer may be NULL. */
 int b2l_debug_candidates(b2l_handle h, int nq, uint32_t* appended, uint32_t* bound_bits);
