@@ -472,7 +472,15 @@ int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_
         case 16: LUTK(XT, 16); break;             \
         default: LUTK(XT, 0);                     \
     }
-        if (xf64) { LUTD(double); } else { LUTD(float); }
+        if (fast && mv.ds == 8 && mv.m == 8 && mv.K <= 256) {
+            // headline shape: sub-quantizer codebook register-resident, one block per SM bound to one coarse split
+            const size_t smr = (size_t)(2 * mv.h + LUTR_THREADS) * 8;
+            const unsigned rgrid = (unsigned)(2 * std::max(1, h->num_sms / 2));
+            if (xf64) k_lut_reg<double, 8, 4><<<rgrid, LUTR_THREADS, smr, h->stream>>>(mv, (const double*)x, pv.lut_desc, pv.cnt,
+                                                                                     h->w_p64.as<double>(), lut32);
+            else k_lut_reg<float, 8, 4><<<rgrid, LUTR_THREADS, smr, h->stream>>>(mv, (const float*)x, pv.lut_desc, pv.cnt,
+                                                                                 h->w_p64.as<double>(), lut32);
+        } else if (xf64) { LUTD(double); } else { LUTD(float); }
 #undef LUTD
 #undef LUTK
         LAUNCHED();

@@ -298,3 +298,80 @@ k_lut(ModelView mv, const XT* __restrict__ Xq, const int32_t* __restrict__ lut_d
     }
   }
 }
+
+// ---- LUT build, register-resident sub-centroids ----------------------------------------------------
+// Same arithmetic as k_lut for the shapes where a thread can keep its share of the sub-quantizer codebook in
+// registers: block = 512 threads bound to ONE coarse split (blockIdx.x & 1); thread (k = tid % 256, jh = tid / 256)
+// holds centroid k of sub-quantizers jh*MH .. jh*MH+MH-1 of that split (MH*DS doubles) for the whole kernel and walks
+// over the slots of its split, so the codebook is read once per block instead of once per slot.
+// Needs m == 2*MH, ds == DS, K <= 256.  dynamic smem: r[h] | p[h] | psum[512] doubles
+#define LUTR_THREADS 512
+template <typename XT, int DS, int MH>
+__global__ void __launch_bounds__(LUTR_THREADS)
+k_lut_reg(ModelView mv, const XT* __restrict__ Xq, const int32_t* __restrict__ lut_desc, const PlanCounters* __restrict__ cnt,
+          double* __restrict__ P64, float* __restrict__ lut32) {
+    extern __shared__ double sm_lutr[];
+    const int h = mv.h, m = mv.m, V = mv.V;
+    double* r = sm_lutr;
+    double* p = sm_lutr + h;
+    double* psum = p + h;
+    const int tid = threadIdx.x, k = tid & 255, jh = tid >> 8;
+    const int s = blockIdx.x & 1, nb = gridDim.x >> 1, b = blockIdx.x >> 1;
+    const int nslot = (int)cnt->n_lut;
+    const bool live = k < mv.K;
+    double cv[MH][DS];
+#pragma unroll
+    for (int jj = 0; jj < MH; ++jj) {
+        const double* cj = mv.subs + (((int64_t)s * m + jh * MH + jj) * mv.K + (live ? k : 0)) * DS;
+#pragma unroll
+        for (int d = 0; d < DS; ++d) cv[jj][d] = cj[d];
+    }
+    int parts = 1;
+    while (parts * 2 * h <= LUTR_THREADS && parts * 2 <= h) parts *= 2;      // h = 64 -> 8 parts
+    const int tw = LUTR_THREADS / parts;
+    const int part = tid / tw, tl = tid - part * tw;
+    const int dlen = h / parts, d0 = part * dlen;
+    for (int slot = b; slot < nslot; slot += nb) {
+        if (lut_desc[3 * slot + 1] != s) continue;                            // block-uniform
+        __syncthreads();
+        const int q = lut_desc[3 * slot], c = lut_desc[3 * slot + 2];
+        const XT* x = Xq + (int64_t)q * mv.D + s * h;
+        const double* C = mv.Cs + ((int64_t)s * V + c) * h;
+        const double* mu = mv.mus + ((int64_t)s * V + c) * h;
+        for (int d = tid; d < h; d += LUTR_THREADS) r[d] = coarse_residual<XT>(x[d], C[d], mu[d], mv.coarse_f32);
+        __syncthreads();
+        const double* Rt = mv.Rt + ((int64_t)s * V + c) * h * (int64_t)h;
+        for (int t0 = 0; t0 < h; t0 += tw) {
+            const int t = t0 + tl;
+            double acc = 0.0;
+            if (t < h) {
+#pragma unroll 8
+                for (int d = d0; d < d0 + dlen; ++d) acc = fma(Rt[(int64_t)d * h + t], r[d], acc);
+            }
+            if (parts == 1) { if (t < h) { p[t] = acc; P64[(int64_t)slot * h + t] = acc; } }
+            else {
+                psum[tid] = acc;
+                __syncthreads();
+                if (part == 0 && t < h) {
+                    double a = psum[tl];
+                    for (int pp = 1; pp < parts; ++pp) a += psum[pp * tw + tl];
+                    p[t] = a; P64[(int64_t)slot * h + t] = a;
+                }
+                __syncthreads();
+            }
+        }
+        __syncthreads();
+        float e32[MH];
+#pragma unroll
+        for (int jj = 0; jj < MH; ++jj) {
+            const double e = live ? sqdist_np<double>(p + (jh * MH + jj) * DS, cv[jj], DS) : 0.0;
+            e32[jj] = (float)e;
+        }
+        float* o32 = lut32 + ((int64_t)slot * B2L_LUT_ROWS + k) * m + jh * MH;
+        if (MH == 4) *(float4*)o32 = make_float4(e32[0], e32[1], e32[2], e32[3]);
+        else {
+#pragma unroll
+            for (int jj = 0; jj < MH; ++jj) o32[jj] = e32[jj];
+        }
+    }
+}

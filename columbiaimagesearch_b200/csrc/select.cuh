@@ -98,7 +98,7 @@ __device__ __forceinline__ int sel_bucket(unsigned int dbits, float lo, float sc
 // reference's summation order, ordered by (dist64, retrieval position), and the first k emitted with the
 // certification bound.
 // dynamic smem: list[SEL_LIST] u64 | dk[KP] u64 | rows[KP] i64 | part[SEL_PART] f64 | pk[KP] u32 | idx[KP] int | vis[KP] int | hist[SEL_HB] u32
-__global__ void __launch_bounds__(SEL_THREADS)
+__global__ void __launch_bounds__(SEL_THREADS, 4)
 k_select(ModelView mv, IndexView ix, PlanView pv, const unsigned long long* __restrict__ cand,
          const unsigned int* __restrict__ cand_cnt, const unsigned int* __restrict__ gthr, int cand_cap,
          const double* __restrict__ P64, int KP, int k, double eps_rel, void* recbuf) {
