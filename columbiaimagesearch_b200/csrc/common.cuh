@@ -43,33 +43,56 @@ template <> struct Ex<double> {
 // term(i), i in [lo, lo+n): the order `ndarray.sum(axis=-1)` uses on a contiguous axis, which is what
 // utils.py:47 / search.py:39 / model.py:702 evaluate.  Verified against NumPy 2.3 for n = 1..4096.
 template <typename T, typename F>
-__device__ T pairwise_sum(const F& term, int lo, int n) {
+__device__ __forceinline__ T pairwise_leaf(const F& term, int lo, int n) {      // n <= 128
     if (n < 8) {
         T r = (T)0;
         for (int i = 0; i < n; ++i) r = Ex<T>::add(r, term(lo + i));
         return r;
-    } else if (n <= 128) {
-        T r0 = term(lo + 0), r1 = term(lo + 1), r2 = term(lo + 2), r3 = term(lo + 3);
-        T r4 = term(lo + 4), r5 = term(lo + 5), r6 = term(lo + 6), r7 = term(lo + 7);
-        int i = 8;
-        const int n8 = n - (n % 8);
-        for (; i < n8; i += 8) {
-            r0 = Ex<T>::add(r0, term(lo + i + 0)); r1 = Ex<T>::add(r1, term(lo + i + 1));
-            r2 = Ex<T>::add(r2, term(lo + i + 2)); r3 = Ex<T>::add(r3, term(lo + i + 3));
-            r4 = Ex<T>::add(r4, term(lo + i + 4)); r5 = Ex<T>::add(r5, term(lo + i + 5));
-            r6 = Ex<T>::add(r6, term(lo + i + 6)); r7 = Ex<T>::add(r7, term(lo + i + 7));
-        }
-        T res = Ex<T>::add(Ex<T>::add(Ex<T>::add(r0, r1), Ex<T>::add(r2, r3)),
-                           Ex<T>::add(Ex<T>::add(r4, r5), Ex<T>::add(r6, r7)));
-        for (; i < n; ++i) res = Ex<T>::add(res, term(lo + i));
-        return res;
-    } else {
-        int n2 = n / 2;
-        n2 -= n2 % 8;
-        T a = pairwise_sum<T>(term, lo, n2);
-        T b = pairwise_sum<T>(term, lo + n2, n - n2);
-        return Ex<T>::add(a, b);
     }
+    T r0 = term(lo + 0), r1 = term(lo + 1), r2 = term(lo + 2), r3 = term(lo + 3);
+    T r4 = term(lo + 4), r5 = term(lo + 5), r6 = term(lo + 6), r7 = term(lo + 7);
+    int i = 8;
+    const int n8 = n - (n % 8);
+    for (; i < n8; i += 8) {
+        r0 = Ex<T>::add(r0, term(lo + i + 0)); r1 = Ex<T>::add(r1, term(lo + i + 1));
+        r2 = Ex<T>::add(r2, term(lo + i + 2)); r3 = Ex<T>::add(r3, term(lo + i + 3));
+        r4 = Ex<T>::add(r4, term(lo + i + 4)); r5 = Ex<T>::add(r5, term(lo + i + 5));
+        r6 = Ex<T>::add(r6, term(lo + i + 6)); r7 = Ex<T>::add(r7, term(lo + i + 7));
+    }
+    T res = Ex<T>::add(Ex<T>::add(Ex<T>::add(r0, r1), Ex<T>::add(r2, r3)),
+                       Ex<T>::add(Ex<T>::add(r4, r5), Ex<T>::add(r6, r7)));
+    for (; i < n; ++i) res = Ex<T>::add(res, term(lo + i));
+    return res;
+}
+
+// n > 128: NumPy halves the range (first half rounded down to a multiple of 8) and adds the two partial sums.
+// Evaluated with an explicit frame stack (no device recursion: its stack need cannot be sized statically).
+template <typename T, typename F>
+__device__ T pairwise_sum(const F& term, int lo, int n) {
+    if (n <= 128) return pairwise_leaf<T>(term, lo, n);
+    int f_lo[24], f_n[24], f_state[24];
+    T f_left[24];
+    int sp = 0;
+    f_lo[0] = lo; f_n[0] = n; f_state[0] = 0; f_left[0] = (T)0;
+    T ret = (T)0;
+    while (sp >= 0) {
+        if (f_n[sp] <= 128) { ret = pairwise_leaf<T>(term, f_lo[sp], f_n[sp]); --sp; continue; }
+        int n2 = f_n[sp] / 2;
+        n2 -= n2 % 8;
+        if (f_state[sp] == 0) {
+            f_state[sp] = 1;
+            f_lo[sp + 1] = f_lo[sp]; f_n[sp + 1] = n2; f_state[sp + 1] = 0;
+            ++sp;
+        } else if (f_state[sp] == 1) {
+            f_left[sp] = ret; f_state[sp] = 2;
+            f_lo[sp + 1] = f_lo[sp] + n2; f_n[sp + 1] = f_n[sp] - n2; f_state[sp + 1] = 0;
+            ++sp;
+        } else {
+            ret = Ex<T>::add(f_left[sp], ret);
+            --sp;
+        }
+    }
+    return ret;
 }
 
 // squared L2 distance ((x - c)**2).sum() in NumPy order, x and c already in the compute type T

@@ -326,8 +326,8 @@ k_lut_reg(ModelView mv, const XT* __restrict__ Xq, const int32_t* __restrict__ l
 #pragma unroll
         for (int d = 0; d < DS; ++d) cv[jj][d] = cj[d];
     }
-    int parts = 1;
-    while (parts * 2 * h <= LUTR_THREADS && parts * 2 <= h) parts *= 2;      // h = 64 -> 8 parts
+    int parts = 1;                            // same split of the d range as k_lut (same float64 summation order)
+    while (parts * 2 * h <= LUT_THREADS && parts * 2 <= h) parts *= 2;        // h = 64 -> 4 parts
     const int tw = LUTR_THREADS / parts;
     const int part = tid / tw, tl = tid - part * tw;
     const int dlen = h / parts, d0 = part * dlen;
