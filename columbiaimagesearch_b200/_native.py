@@ -24,7 +24,8 @@ class Stats(C.Structure):
                 ("lut_slots", C.c_int64), ("kernel_launches", C.c_int64), ("exact_queries", C.c_int64),
                 ("acc_calls", C.c_int64), ("acc_scan_ms", C.c_double), ("acc_plan_ms", C.c_double), ("acc_select_ms", C.c_double),
                 ("acc_total_ms", C.c_double), ("acc_codes_scanned", C.c_int64), ("acc_scan_bytes", C.c_int64),
-                ("acc_work_items", C.c_int64), ("acc_kernel_launches", C.c_int64), ("acc_exact_queries", C.c_int64)]
+                ("acc_work_items", C.c_int64), ("acc_kernel_launches", C.c_int64), ("acc_exact_queries", C.c_int64),
+                ("packed", C.c_int64), ("rescan_queries", C.c_int64), ("acc_rescan_queries", C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -55,6 +56,7 @@ SIGNATURES = {
     "b2l_search_merge": (_i, [_h, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b2l_get_stats": (_i, [_h, C.POINTER(Stats)]),
     "b2l_reset_stats": (_i, [_h]),
+    "b2l_set_scan_mode": (_i, [_h, _i]),
     "b2l_set_async": (_i, [_h, _i]),
     "b2l_sync": (_i, [_h]),
     "b2l_debug_candidates": (_i, [_h, _i, _vp, _vp]),
@@ -285,6 +287,10 @@ class Handle(object):
 
     def reset_stats(self):
         self._check(self.lib.b2l_reset_stats(self.h))
+
+    def set_scan_mode(self, mode):
+        """0: 16-bit packed tables first (default); 1: float32 tables only."""
+        self._check(self.lib.b2l_set_scan_mode(self.h, int(mode)))
 
     def set_async(self, enabled):
         self._check(self.lib.b2l_set_async(self.h, int(bool(enabled))))

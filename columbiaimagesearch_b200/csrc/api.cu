@@ -18,6 +18,7 @@
 #include "index.cuh"
 #include "plan.cuh"
 #include "scan.cuh"
+#include "scan_pk.cuh"
 #include "select.cuh"
 
 #define B2L_ABI_VERSION 2
@@ -82,7 +83,7 @@ struct b2l_ctx {
     DevBuf codes, rowids, cell_start, lsize, gsize, sorted_first;
     std::vector<int64_t> h_lsize, h_gsize, h_cell_start;
     // workspaces
-    DevBuf w_q, w_xq, w_px, w_coarse, w_fine, w_lut32, w_lut64, w_p64, w_cellq, w_cand, w_gtab, w_plan, w_sort_a, w_sort_b,
+    DevBuf w_q, w_xq, w_px, w_coarse, w_fine, w_lut32, w_lut64, w_p64, w_cellq, w_cand, w_gtab, w_lut16, w_quant, w_plan, w_sort_a, w_sort_b,
         w_sort_tmp, w_rec, w_rec2, w_out, w_out2, w_misc;
     PlanView pv = {};
     unsigned int* gthr = nullptr;      // [nq] per-query pruning bound shared by the scan blocks
@@ -90,6 +91,7 @@ struct b2l_ctx {
     b2l_stats stats = {};
     int64_t launches = 0;
     bool async_mode = false;
+    int scan_mode = 0;                 // 0: packed 16-bit tables first (default), 1: float32 tables only
     void* h_out = nullptr;             // pinned staging of the search outputs
     size_t h_out_cap = 0;
 };
@@ -130,6 +132,19 @@ template <int MP> int launch_scan(b2l_handle h, const ScanArgs& a) {
     if (occ < 1) occ = 1;
     const unsigned grid = (unsigned)(h->num_sms * occ);        // persistent; blocks without work leave at once
     k_scan<MP><<<grid, SCAN_THREADS, smem, h->stream>>>(a);
+    LAUNCHED();
+    return B2L_OK;
+}
+
+template <int MP> int launch_scan_pk(b2l_handle h, const ScanArgs& a) {
+    const size_t smem = scan_pk_smem_bytes<MP>(a.E);
+    if (smem > 227 * 1024) FAIL(B2L_ERR_UNSUPPORTED, "scan shared memory %zu too large", smem);
+    CU(cudaFuncSetAttribute(k_scan_pk<MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 1;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_scan_pk<MP>, SCAN_THREADS, smem));
+    if (occ < 1) occ = 1;
+    const unsigned grid = (unsigned)(h->num_sms * occ);
+    k_scan_pk<MP><<<grid, SCAN_THREADS, smem, h->stream>>>(a);
     LAUNCHED();
     return B2L_OK;
 }
@@ -348,6 +363,7 @@ int collect_call(b2l_handle h, b2l_ctx::CallRec& r) {
     cur.acc_codes_scanned = acc.acc_codes_scanned + cur.codes_scanned; cur.acc_scan_bytes = acc.acc_scan_bytes + cur.scan_bytes;
     cur.acc_work_items = acc.acc_work_items + cur.work_items; cur.acc_kernel_launches = acc.acc_kernel_launches + cur.kernel_launches;
     cur.acc_exact_queries = acc.acc_exact_queries + cur.exact_queries;
+    cur.acc_rescan_queries = acc.acc_rescan_queries + cur.rescan_queries;
     h->stats = cur;
     return B2L_OK;
 }
@@ -413,8 +429,11 @@ int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_
     const int KP = std::max(16, next_pow2(k + 8));
     const int LPS = mv.MP * SCAN_WARPS;
     const int GEN = std::max(1, KP / std::max(1, LPS));
-    const bool fast = !exact && mv.G > 0 && KP <= 512;
-    const int NS = 2 * mv.G;
+    // exact: 0 = default fast scan (16-bit packed tables unless the handle is set to float32), 1 = float64 full sort,
+    // 2 = fast scan with float32 tables
+    const bool fast = exact != 1 && mv.G > 0 && KP <= 512;
+    const bool packed = fast && exact == 0 && h->scan_mode == 0 && 65535 / mv.M >= 255;
+    const int NS = (packed ? 4 : 2) * mv.G;
     // segment length: a multiple of 64 codes, sized so the batch yields enough work items
     int64_t maxcell = 0;
     for (int c = 0; c < ncell; ++c) maxcell = std::max(maxcell, h->h_lsize[c]);
@@ -485,6 +504,26 @@ int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_
 #undef LUTK
         LAUNCHED();
     }
+    QuantView qv = {};
+    if (packed) {
+        // 16-bit tables: per-query bias / step from the ranges of the float32 tables, then the codes
+        const size_t o_qmin = 0, o_qmax = align256((size_t)nq * mv.M * 4), o_inv = o_qmax + align256((size_t)nq * 4),
+                     o_B = o_inv + align256((size_t)nq * 4), o_dl = o_B + align256((size_t)nq * 8), qbytes = o_dl + align256((size_t)nq * 8);
+        CU(h->w_quant.reserve(qbytes));
+        CU(h->w_lut16.reserve(cap_lut * B2L_LUT_ROWS * mv.m * 2));
+        unsigned char* qb = h->w_quant.as<unsigned char>();
+        qv.qmin = (unsigned int*)(qb + o_qmin); qv.qmax = (unsigned int*)(qb + o_qmax); qv.inv = (float*)(qb + o_inv);
+        qv.B = (double*)(qb + o_B); qv.delta = (double*)(qb + o_dl); qv.qmax_code = 65535 / mv.M;
+        CU(cudaMemsetAsync(qv.qmin, 0xFF, (size_t)nq * mv.M * 4, h->stream));
+        CU(cudaMemsetAsync(qv.qmax, 0, (size_t)nq * 4, h->stream));
+        const unsigned qgrid = (unsigned)std::min<size_t>(cap_lut, (size_t)h->num_sms * 8);
+        k_lut_range<<<qgrid, 256, 0, h->stream>>>(mv.m, pv.lut_desc, pv.cnt, lut32, mv.K, qv, mv.M);
+        LAUNCHED();
+        k_lut_scale<<<(nq + 127) / 128, 128, 0, h->stream>>>(nq, mv.M, qv);
+        LAUNCHED();
+        k_lut_quant<<<qgrid, 256, 0, h->stream>>>(mv.m, pv.lut_desc, pv.cnt, lut32, qv, mv.M, h->w_lut16.as<unsigned short>());
+        LAUNCHED();
+    }
     IndexView ix = {h->codes.as<uint8_t>(), h->rowids.as<int64_t>(), h->cell_start.as<int64_t>(), h->lsize.as<int64_t>()};
     CU(cudaEventRecord(h->cr->ev[1], h->stream));
     if (fast) {
@@ -504,11 +543,12 @@ int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_
             a.pv = pv; a.ncell = ncell; a.nflat = nsegmax * ncell; a.KP = KP; a.m = mv.m; a.M = mv.M;
             a.GEN = GEN; a.E = LPS * GEN;
             a.gthr = h->gthr; a.gtab = h->w_gtab.as<float>();
+            a.lut16 = packed ? h->w_lut16.as<unsigned short>() : nullptr; a.qfill = (unsigned)qv.qmax_code;
             switch (mv.MP) {
-                case 4: rc = launch_scan<4>(h, a); break;
-                case 8: rc = launch_scan<8>(h, a); break;
-                case 16: rc = launch_scan<16>(h, a); break;
-                case 32: rc = launch_scan<32>(h, a); break;
+                case 4: rc = packed ? launch_scan_pk<4>(h, a) : launch_scan<4>(h, a); break;
+                case 8: rc = packed ? launch_scan_pk<8>(h, a) : launch_scan<8>(h, a); break;
+                case 16: rc = packed ? launch_scan_pk<16>(h, a) : launch_scan<16>(h, a); break;
+                case 32: rc = packed ? launch_scan_pk<32>(h, a) : launch_scan<32>(h, a); break;
                 default: FAIL(B2L_ERR_UNSUPPORTED, "no scan instantiation for code stride %d", mv.MP);
             }
             if (rc) return rc;
@@ -518,8 +558,10 @@ int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_
         const size_t smem = select_smem_bytes(KP);
         CU(cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_select<<<nq, SEL_THREADS, smem, h->stream>>>(mv, ix, pv, h->w_cand.as<unsigned long long>(), h->cand_cnt, h->gthr,
-                                                       SCAN_CAND_CAP, h->w_p64.as<double>(), KP, k, eps_rel, d_records);
+                                                       SCAN_CAND_CAP, h->w_p64.as<double>(), KP, k, eps_rel, d_records,
+                                                       packed ? 1 : 0, qv.B, qv.delta);
         LAUNCHED();
+        h->cr->st.packed = packed ? 1 : 0;
         CU(cudaEventRecord(h->cr->ev[4], h->stream));
     } else {
         CU(cudaEventRecord(h->cr->ev[2], h->stream));
@@ -664,7 +706,7 @@ int b2l_destroy(b2l_handle h) {
     cudaStreamSynchronize(h->stream);
     DevBuf* bufs[] = {&h->dCs, &h->dmus, &h->dRt, &h->dsubs, &h->dP, &h->dpmu, &h->m_coarse, &h->m_fine, &h->m_rowid, &h->codes,
                       &h->rowids, &h->cell_start, &h->lsize, &h->gsize, &h->sorted_first, &h->w_q, &h->w_xq, &h->w_px,
-                      &h->w_coarse, &h->w_fine, &h->w_lut32, &h->w_lut64, &h->w_p64, &h->w_cellq, &h->w_cand, &h->w_gtab, &h->w_plan,
+                      &h->w_coarse, &h->w_fine, &h->w_lut32, &h->w_lut64, &h->w_p64, &h->w_cellq, &h->w_cand, &h->w_gtab, &h->w_lut16, &h->w_quant, &h->w_plan,
                       &h->w_sort_a, &h->w_sort_b, &h->w_sort_tmp, &h->w_rec, &h->w_rec2, &h->w_out, &h->w_out2, &h->w_misc};
     for (DevBuf* b : bufs) b->release();
     if (h->h_out) cudaFreeHost(h->h_out);
@@ -707,6 +749,13 @@ int b2l_reset_stats(b2l_handle h) {
     int rc = finish_stats(h);
     if (rc) return rc;
     memset(&h->stats, 0, sizeof h->stats);
+    return B2L_OK;
+}
+
+int b2l_set_scan_mode(b2l_handle h, int mode) {
+    if (!h || mode < 0 || mode > 1) return B2L_ERR_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->scan_mode = mode;
     return B2L_OK;
 }
 
@@ -1048,8 +1097,10 @@ int b2l_search(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_device,
     const uint8_t* cert = hb + o7;
     std::vector<int> redo;
     for (int q = 0; q < nq; ++q) if (!cert[q]) redo.push_back(q);
-    if (!redo.empty()) {
-        // float64 full-sort rerun of the uncertified queries, patched into the outputs row by row
+    // Uncertified queries go down the chain: float32 tables (if the first pass used the 16-bit ones), then the float64
+    // full sort.  Each stage re-runs the subset, merges it into a scratch block and patches the output rows.
+    int64_t n_rescan = 0, n_exact = 0, extra_launches = 0;
+    for (int stage = (st.packed ? 2 : 1); !redo.empty(); stage = 1) {
         const int ns = (int)redo.size();
         const int Din = h->has_pca ? mv.D0 : mv.D;
         const size_t qrow = (size_t)Din * (q_is_f64 ? 8 : 4);
@@ -1058,41 +1109,47 @@ int b2l_search(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_device,
         for (int i = 0; i < ns; ++i)
             CU(cudaMemcpyAsync(h->w_misc.as<char>() + i * qrow, (const char*)Q + redo[i] * qrow, qrow, kind, h->stream));
         CU(h->w_rec2.reserve(rec_bytes(ns, k, mv.M)));
-        rc = search_local_impl(h, h->w_misc.p, q_is_f64, ns, 1, quota, k, 1, h->w_rec2.p);
+        rc = search_local_impl(h, h->w_misc.p, q_is_f64, ns, 1, quota, k, stage, h->w_rec2.p, false);
         if (rc) return rc;
-        RecView rv = rec_view(h->w_rec2.p, ns, k, mv.M);
-        // exact records are already the final order of a single rank: copy rows
+        const size_t sk = (size_t)ns * k;
+        size_t so = 0;
+        auto stake = [&](size_t bytes) { size_t o = so; so += align256(bytes); return o; };
+        const size_t s1 = stake(sk * 8), s2 = stake(sk * 8), s3 = stake(sk * 8), s4 = stake(sk * mv.M), s5 = stake((size_t)ns * 4),
+                     s6 = stake((size_t)ns * 4), s7 = stake((size_t)ns);
+        CU(h->w_out.reserve(so));
+        unsigned char* sb = h->w_out.as<unsigned char>();
+        CU(cudaMemsetAsync(sb, 0, so, h->stream));
+        rc = merge_impl(h, h->w_rec2.p, 1, ns, k, 1, (int64_t*)(sb + s1), (double*)(sb + s2), (int32_t*)(sb + s3), sb + s4,
+                        (int32_t*)(sb + s5), (int32_t*)(sb + s6), sb + s7, false);
+        if (rc) return rc;
+        std::vector<uint8_t> c2(ns);
+        CU(cudaMemcpyAsync(c2.data(), sb + s7, ns, cudaMemcpyDeviceToHost, h->stream));
         for (int i = 0; i < ns; ++i) {
-            const int q = redo[i];
-            CU(cudaMemcpyAsync(d_rowid + (size_t)q * k, rv.rowid + (size_t)i * k, (size_t)k * 8, cudaMemcpyDeviceToDevice, h->stream));
-            CU(cudaMemcpyAsync(d_dist + (size_t)q * k, rv.d64 + (size_t)i * k, (size_t)k * 8, cudaMemcpyDeviceToDevice, h->stream));
-            CU(cudaMemcpyAsync(d_fine + (size_t)q * k * mv.M, rv.fine + (size_t)i * k * mv.M, (size_t)k * mv.M, cudaMemcpyDeviceToDevice, h->stream));
-            CU(cudaMemcpyAsync(d_count + q, rv.count + i, 4, cudaMemcpyDeviceToDevice, h->stream));
+            const size_t q = (size_t)redo[i];
+            CU(cudaMemcpyAsync(d_rowid + q * k, (int64_t*)(sb + s1) + (size_t)i * k, (size_t)k * 8, cudaMemcpyDeviceToDevice, h->stream));
+            CU(cudaMemcpyAsync(d_dist + q * k, (double*)(sb + s2) + (size_t)i * k, (size_t)k * 8, cudaMemcpyDeviceToDevice, h->stream));
+            CU(cudaMemcpyAsync(d_coarse + q * k * 2, (int32_t*)(sb + s3) + (size_t)i * k * 2, (size_t)k * 8, cudaMemcpyDeviceToDevice, h->stream));
+            CU(cudaMemcpyAsync(d_fine + q * k * mv.M, sb + s4 + (size_t)i * k * mv.M, (size_t)k * mv.M, cudaMemcpyDeviceToDevice, h->stream));
+            CU(cudaMemcpyAsync(d_count + q, (int32_t*)(sb + s5) + i, 4, cudaMemcpyDeviceToDevice, h->stream));
         }
-        // coarse pairs of the patched rows: decode cell ids on the host (few rows)
-        std::vector<int32_t> cells((size_t)ns * k), cnt(ns);
-        CU(cudaMemcpyAsync(cells.data(), rv.cell, (size_t)ns * k * 4, cudaMemcpyDeviceToHost, h->stream));
-        CU(cudaMemcpyAsync(cnt.data(), rv.count, (size_t)ns * 4, cudaMemcpyDeviceToHost, h->stream));
         CU(cudaStreamSynchronize(h->stream));
-        std::vector<int32_t> cp((size_t)ns * k * 2);
-        for (int i = 0; i < ns; ++i)
-            for (int j = 0; j < k; ++j) {
-                const int32_t c = j < cnt[i] ? cells[(size_t)i * k + j] : 0;
-                cp[((size_t)i * k + j) * 2] = c / mv.V; cp[((size_t)i * k + j) * 2 + 1] = c % mv.V;
-            }
-        for (int i = 0; i < ns; ++i)
-            CU(cudaMemcpyAsync(d_coarse + (size_t)redo[i] * k * 2, cp.data() + (size_t)i * k * 2, (size_t)k * 8, cudaMemcpyHostToDevice, h->stream));
+        if ((rc = finish_stats(h))) return rc;
+        extra_launches += h->stats.kernel_launches + 1;
+        if (stage == 2) n_rescan += ns; else n_exact += ns;
+        std::vector<int> next;
+        if (stage == 2) for (int i = 0; i < ns; ++i) if (!c2[i]) next.push_back(redo[i]);
+        redo.swap(next);
+    }
+    if (n_rescan || n_exact) {
+        const b2l_stats s2 = h->stats;           // carries the accumulators of the reruns
+        h->stats = st;
+        h->stats.kernel_launches = st.kernel_launches + extra_launches;
+        h->stats.exact_queries = n_exact; h->stats.rescan_queries = n_rescan;
+        h->stats.acc_kernel_launches = s2.acc_kernel_launches + (n_rescan ? 1 : 0) + (n_exact ? 1 : 0);
+        h->stats.acc_exact_queries = st.acc_exact_queries + n_exact;
+        h->stats.acc_rescan_queries = st.acc_rescan_queries + n_rescan;
         if (!on_device) CU(cudaMemcpyAsync(hb, b, off, cudaMemcpyDeviceToHost, h->stream));
         CU(cudaStreamSynchronize(h->stream));
-        const b2l_stats s2 = h->stats;           // the exact rerun (collected by its own synchronous call)
-        h->stats = st;
-        h->stats.kernel_launches = st.kernel_launches + s2.kernel_launches;
-        h->stats.exact_queries = st.exact_queries + ns;
-        h->stats.acc_calls = st.acc_calls;
-        h->stats.acc_kernel_launches = s2.acc_kernel_launches; h->stats.acc_exact_queries = s2.acc_exact_queries;
-        h->stats.acc_scan_ms = st.acc_scan_ms; h->stats.acc_plan_ms = st.acc_plan_ms; h->stats.acc_select_ms = st.acc_select_ms;
-        h->stats.acc_total_ms = st.acc_total_ms; h->stats.acc_codes_scanned = st.acc_codes_scanned;
-        h->stats.acc_scan_bytes = st.acc_scan_bytes; h->stats.acc_work_items = st.acc_work_items;
     }
     if (on_device) {
         if ((rc = copy_out(h, rowid, d_rowid, nk * 8, 1))) return rc;

@@ -375,3 +375,82 @@ k_lut_reg(ModelView mv, const XT* __restrict__ Xq, const int32_t* __restrict__ l
         }
     }
 }
+
+// ---- 16-bit quantised tables for the packed scan ---------------------------------------------------
+// Per query q: bias b[q][j] = min over the query's tables of sub-quantizer j (both splits: j < M) and over the 256
+// centroids; step Delta[q] = (max entry - min bias) / QMAX * (1 + 2^-20); code = floor((e - b[q][j]) / Delta[q]),
+// clamped to [0, QMAX], QMAX = 65535 / M so that a sum of M codes fits 16 bits.  Then for every candidate
+//     float32 ADC sum  >=  B[q] + Delta[q] * (S - 0.1),   S = sum of its M codes, B[q] = sum_j b[q][j]
+// (floor never rounds up by more than the float32 error of the scaled value, < 0.002 per term).
+struct QuantView {
+    unsigned int* qmin;     // [nq][M] float bits (entries are >= 0, so unsigned order == float order)
+    unsigned int* qmax;     // [nq]    float bits
+    float* inv;             // [nq]    1 / Delta
+    double* B;              // [nq]
+    double* delta;          // [nq]
+    int qmax_code;          // QMAX
+};
+
+// one block per LUT slot: ranges of its m columns -> per-query minima / maximum
+__global__ void __launch_bounds__(256)
+k_lut_range(int m, const int32_t* __restrict__ lut_desc, const PlanCounters* __restrict__ cnt, const float* __restrict__ lut32,
+            int K, QuantView qv, int M) {
+    __shared__ unsigned int s_min[32], s_max;
+    const int nslot = (int)cnt->n_lut;
+    for (int slot = blockIdx.x; slot < nslot; slot += gridDim.x) {
+        __syncthreads();
+        if (threadIdx.x < 32) s_min[threadIdx.x] = 0x7f800000u;
+        if (threadIdx.x == 0) s_max = 0u;
+        __syncthreads();
+        const int q = lut_desc[3 * slot], s = lut_desc[3 * slot + 1];
+        const float* t = lut32 + (size_t)slot * B2L_LUT_ROWS * m;
+        unsigned int mx = 0u;
+        for (int e = threadIdx.x; e < K * m; e += blockDim.x) {
+            const unsigned int v = __float_as_uint(t[e]);
+            atomicMin(&s_min[e % m], v);
+            mx = max(mx, v);
+        }
+        for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if ((threadIdx.x & 31) == 0) atomicMax(&s_max, mx);
+        __syncthreads();
+        if (threadIdx.x < m) atomicMin(&qv.qmin[(size_t)q * M + s * m + threadIdx.x], s_min[threadIdx.x]);
+        if (threadIdx.x == 0) atomicMax(&qv.qmax[q], s_max);
+    }
+}
+
+// one thread per query: scale and bias sum
+__global__ void k_lut_scale(int nq, int M, QuantView qv) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    float bmin = __int_as_float(0x7f800000);
+    double B = 0.0;
+    bool any = false;
+    for (int j = 0; j < M; ++j) {
+        const unsigned int b = qv.qmin[(size_t)q * M + j];
+        if (b < 0x7f800000u) { const float f = __uint_as_float(b); bmin = fminf(bmin, f); B += (double)f; any = true; }
+        else qv.qmin[(size_t)q * M + j] = 0u;                      // sub-quantizer without a table on this rank: bias 0
+    }
+    const float range = any ? fmaxf(__uint_as_float(qv.qmax[q]) - bmin, 1e-30f) : 1.0f;
+    const double delta = (double)range / (double)qv.qmax_code * (1.0 + 9.5367431640625e-07);
+    qv.delta[q] = delta;
+    qv.inv[q] = (float)(1.0 / delta);
+    qv.B[q] = B;
+}
+
+// one block per LUT slot: lut16[slot][k][j] = clamp(floor((e - b) * inv), 0, QMAX)
+__global__ void __launch_bounds__(256)
+k_lut_quant(int m, const int32_t* __restrict__ lut_desc, const PlanCounters* __restrict__ cnt, const float* __restrict__ lut32,
+            QuantView qv, int M, unsigned short* __restrict__ lut16) {
+    const int nslot = (int)cnt->n_lut;
+    for (int slot = blockIdx.x; slot < nslot; slot += gridDim.x) {
+        const int q = lut_desc[3 * slot], s = lut_desc[3 * slot + 1];
+        const float inv = qv.inv[q];
+        const float* t = lut32 + (size_t)slot * B2L_LUT_ROWS * m;
+        unsigned short* o = lut16 + (size_t)slot * B2L_LUT_ROWS * m;
+        for (int e = threadIdx.x; e < B2L_LUT_ROWS * m; e += blockDim.x) {
+            const float b = __uint_as_float(qv.qmin[(size_t)q * M + s * m + (e % m)]);
+            const float x = __fmul_rn(__fsub_rn(t[e], b), inv);
+            o[e] = (unsigned short)min(qv.qmax_code, max(0, (int)floorf(x)));
+        }
+    }
+}

@@ -41,6 +41,8 @@ struct ScanArgs {
     const int64_t* cell_start;      // [ncell]
     const int64_t* lsize;           // [ncell]
     const float* lut32;             // [slots][256][m]
+    const unsigned short* lut16;    // [slots][256][m] quantised tables (packed scan, scan_pk.cuh)
+    unsigned int qfill;             // code an empty slot is filled with (QMAX)
     unsigned long long* cand;       // [nq][SCAN_CAND_CAP]
     unsigned int* cand_cnt;         // [nq]
     PlanView pv;

@@ -87,8 +87,11 @@ __host__ __device__ inline size_t select_smem_bytes(int KP) {
     return (size_t)SEL_LIST * 8 + (size_t)KP * 28 + (size_t)SEL_PART * 8 + (size_t)SEL_HB * 4 + 64;
 }
 
-__device__ __forceinline__ int sel_bucket(unsigned int dbits, float lo, float scale) {
-    return min(SEL_HB - 1, (int)((__uint_as_float(dbits) - lo) * scale));      // monotone non-decreasing in the distance
+// histogram bucket of a key (monotone non-decreasing in the key).  Float32 scan: keys are float bits; packed scan:
+// keys are integer code sums, `lo_bits` / `scale` then hold the integer minimum and SEL_HB / (range + 1).
+__device__ __forceinline__ int sel_bucket(unsigned int dbits, unsigned int lo_bits, float scale, int packed) {
+    const float x = packed ? (float)(dbits - lo_bits) : (__uint_as_float(dbits) - __uint_as_float(lo_bits));
+    return min(SEL_HB - 1, (int)(x * scale));
 }
 
 // one block per query.  The scan appended every candidate whose float32 distance is <= the query's final bound
@@ -101,7 +104,8 @@ __device__ __forceinline__ int sel_bucket(unsigned int dbits, float lo, float sc
 __global__ void __launch_bounds__(SEL_THREADS, 4)
 k_select(ModelView mv, IndexView ix, PlanView pv, const unsigned long long* __restrict__ cand,
          const unsigned int* __restrict__ cand_cnt, const unsigned int* __restrict__ gthr, int cand_cap,
-         const double* __restrict__ P64, int KP, int k, double eps_rel, void* recbuf) {
+         const double* __restrict__ P64, int KP, int k, double eps_rel, void* recbuf,
+         int packed, const double* __restrict__ qB, const double* __restrict__ qDelta) {
     extern __shared__ __align__(16) unsigned char sm_sel[];
     unsigned long long* keys = (unsigned long long*)sm_sel;
     unsigned long long* dk = keys + SEL_LIST;
@@ -147,13 +151,14 @@ k_select(ModelView mv, IndexView ix, PlanView pv, const unsigned long long* __re
     for (int w = 0; w < SEL_THREADS / 32; ++w) { lo = min(lo, s_red[0][w]); hi = max(hi, s_red[1][w]); cnt += s_red[2][w]; }
     const int npass = (int)cnt;
     const float flo = __uint_as_float(lo), fhi = __uint_as_float(hi);
-    const float scale = (npass > 0 && fhi > flo) ? (float)(SEL_HB - 1) / (fhi - flo) : 0.0f;
+    float scale = 0.0f;
+    if (npass > 0 && hi > lo) scale = packed ? (float)(SEL_HB - 1) / (float)(hi - lo) : (float)(SEL_HB - 1) / (fhi - flo);
     const int want = min(KP, npass);
 
     // ---- pass 2: histogram, then the bucket b* where the running count reaches `want`
     for (int i = tid; i < n; i += SEL_THREADS) {
         const unsigned int d = (unsigned int)(src[i] >> 32);
-        if (d <= bound) atomicAdd(&hist[sel_bucket(d, flo, scale)], 1u);
+        if (d <= bound) atomicAdd(&hist[sel_bucket(d, lo, scale, packed)], 1u);
     }
     __syncthreads();
     {
@@ -182,7 +187,7 @@ k_select(ModelView mv, IndexView ix, PlanView pv, const unsigned long long* __re
     for (int i = tid; i < n; i += SEL_THREADS) {
         const unsigned long long key = src[i];
         const unsigned int d = (unsigned int)(key >> 32);
-        if (d <= bound && sel_bucket(d, flo, scale) <= bstar) {
+        if (d <= bound && sel_bucket(d, lo, scale, packed) <= bstar) {
             const int j = atomicAdd(&s_n, 1);
             if (j < SEL_LIST) keys[j] = key;
         }
@@ -266,8 +271,9 @@ k_select(ModelView mv, IndexView ix, PlanView pv, const unsigned long long* __re
         double lb = __longlong_as_double(0x7FF0000000000000ll);
         if (lost) lb = -1.0;                                  // never certified: exact re-rank
         else if (pv.ncand_local[q] > (int64_t)ncoll) {        // some local candidates are not among the KP collected
-            const float amax = __uint_as_float((unsigned int)(keys[KP - 1] >> 32));
-            lb = (double)amax * (1.0 - eps_rel) - 1e-300;
+            const unsigned int kb = (unsigned int)(keys[KP - 1] >> 32);
+            if (packed) lb = (qB[q] + qDelta[q] * ((double)kb - 1.0)) * (1.0 - 1e-6) - 1e-300;      // see plan.cuh (k_lut_quant)
+            else lb = (double)__uint_as_float(kb) * (1.0 - eps_rel) - 1e-300;
         }
         rv.lb[q] = lb;
         rv.count[q] = nout;

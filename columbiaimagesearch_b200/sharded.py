@@ -207,12 +207,8 @@ class ShardedLOPQSearcher(object):
             nq = X.shape[0]
             out = self._gather_merge(X, quota, k, False, nq)
         redo = np.nonzero(out["certified"] == 0)[0]
-        if redo.size:           # same set on every rank (the flags are computed from the gathered buffers)
-            Xr = X[redo].cpu().numpy() if on_dev else X[redo]
-            sub = self._gather_merge(np.ascontiguousarray(Xr), quota, k, True, int(redo.size))
-            for key in ("rowid", "dist", "coarse", "fine", "count"):
-                out[key][redo] = sub[key]
-        out["exact_queries"] = int(redo.size)
+        n32, nex = self._redo_chain(out, (lambda idx: X[idx].cpu().numpy()) if on_dev else (lambda idx: X[idx]), redo, quota, k)
+        out["exact_queries"], out["rescan_queries"] = nex, n32
         ids = out["rowid"].copy()
         ids[np.arange(k)[None, :] >= out["count"][:, None]] = -1
         out["ids"] = ids
@@ -220,6 +216,25 @@ class ShardedLOPQSearcher(object):
 
     def stats(self):
         return self._handle.stats()
+
+    def _redo_chain(self, out, Xsel, redo, quota, k):
+        """Uncertified queries (the same set on every rank: the flags come from the gathered buffers) are re-run with
+        float32 tables, and what is still uncertified with the float64 full sort; rows of `out` are patched.  `Xsel(idx)`
+        returns the host rows of the given query indices.  Returns (#float32 re-runs, #exact re-runs)."""
+        n32 = nex = 0
+        for mode in (2, 1):
+            if not redo.size:
+                break
+            sub = self._gather_merge(np.ascontiguousarray(Xsel(redo)), quota, k, mode, int(redo.size))
+            for key in ("rowid", "dist", "coarse", "fine", "count"):
+                out[key][redo] = sub[key]
+            if mode == 2:
+                n32 += int(redo.size)
+                redo = redo[sub["certified"] == 0]
+            else:
+                nex += int(redo.size)
+                redo = redo[:0]
+        return n32, nex
 
     def close(self):
         """Wait for work in flight, then release the buffer pool before the library handle (and its stream) goes away."""
@@ -260,18 +275,17 @@ class _PendingSearch(object):
                    count=view("count", np.int32, (nq,)), visited=view("visited", np.int32, (nq,)),
                    certified=view("certified", np.uint8, (nq,)))
         redo = np.nonzero(out["certified"] == 0)[0]
-        if redo.size:           # same set on every rank (the flags are computed from the gathered buffers)
+        n32 = nex = 0
+        if redo.size:
             X = self.X
-            Xr = X[redo].cpu().numpy() if hasattr(X, "data_ptr") else np.asarray(X)[redo]
+            sel = (lambda idx: X[idx].cpu().numpy()) if hasattr(X, "data_ptr") else (lambda idx: np.asarray(X)[idx])
             s._handle.sync()
             s._handle.set_async(False)
             try:
-                sub = s._gather_merge(np.ascontiguousarray(Xr), self.quota, k, True, int(redo.size))
+                n32, nex = s._redo_chain(out, sel, redo, self.quota, k)
             finally:
                 s._handle.set_async(True)
-            for key in ("rowid", "dist", "coarse", "fine", "count"):
-                out[key][redo] = sub[key]
-        out["exact_queries"] = int(redo.size)
+        out["exact_queries"], out["rescan_queries"] = nex, n32
         ids = out["rowid"]
         if nq and int(out["count"].min()) < k:
             pad = np.arange(k)[None, :] >= out["count"][:, None]

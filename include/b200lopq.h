@@ -122,7 +122,8 @@ int b2l_search(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_device,
  *      per-query `certified` flag.  certified[q] = 0 means the float32 scan could not prove the
  *      float64 order of the first k results (ties at the k-th place); rerun those queries with
  *      exact = 1 (b2l_search does this internally).
- * exact = 1 ranks every retrieved code in float64 (slow, any k / any M). */
+ * exact = 1 ranks every retrieved code in float64 (slow, any k / any M); exact = 2 forces the float32-table
+ * fast scan (the middle stage of the chain  16-bit tables -> float32 tables -> float64 full sort). */
 int64_t b2l_records_bytes(b2l_handle h, int nq, int k);
 int b2l_search_local(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_device,
                      int64_t quota, int k, int exact, void* d_records);
@@ -147,10 +148,16 @@ typedef struct b2l_stats {
     int64_t acc_calls;
     double  acc_scan_ms, acc_plan_ms, acc_select_ms, acc_total_ms;
     int64_t acc_codes_scanned, acc_scan_bytes, acc_work_items, acc_kernel_launches, acc_exact_queries;
+    int64_t packed;           /* 1: the scan used the 16-bit packed tables                  */
+    int64_t rescan_queries;   /* queries re-run with float32 tables (not certifiable from the 16-bit ones) */
+    int64_t acc_rescan_queries;
 } b2l_stats;
 /* waits for searches still in flight on the handle, then returns the statistics */
 int b2l_get_stats(b2l_handle h, b2l_stats* out);
 int b2l_reset_stats(b2l_handle h);
+/* Table precision of the fast scan.  0 (default): 16-bit quantised tables, two queries per shared-memory word; queries
+ * whose float64 order cannot be proven from them are re-run with float32 tables, then exactly.  1: float32 tables only. */
+int b2l_set_scan_mode(b2l_handle h, int mode);
 /* Asynchronous mode (pipelined / multi-GPU searches).  While enabled, b2l_search_local and b2l_search_merge only
  * enqueue their work (including the copies from / to host buffers, which must then be PINNED and stay alive) on the
  * handle's stream and return; the caller orders other work against that stream (b2l_stream) and waits for it
