@@ -405,7 +405,7 @@ def run_b200(a):
     run_pipelined(host_batch, 0, a.warmup)                   # warm-up of the host-buffer path
     barrier()
     t0 = time.perf_counter()
-    run_pipelined(host_batch, 0, a.steps)
+    redo_e2e, _ = run_pipelined(host_batch, 0, a.steps)
     barrier()
     t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
@@ -473,7 +473,8 @@ def run_b200(a):
                 "wall_s_timed_region": wall_s,
                 "e2e": {"value": a.steps * nq / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "api": "search_batch_async, 2 batches in flight, pinned host queries in / host results out every step",
-                        "sync_api_value": a.steps * nq / e2e_sync_s},
+                        "sync_api_value": a.steps * nq / e2e_sync_s,
+                        "exact_fallback_queries": int(redo_e2e[0]), "float32_rescan_queries": int(redo_e2e[1])},
                 "gpu_launches": int(launches), "exact_fallback_queries": int(exact_q), "float32_rescan_queries": int(rescan_q),
                 "time_split_ms_per_step": {"plan+lut": plan_ms / max(1, timed_calls), "scan": scan_ms / max(1, timed_calls),
                                            "select": sel_ms / max(1, timed_calls)},

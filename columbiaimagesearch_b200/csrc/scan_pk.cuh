@@ -13,10 +13,11 @@
 #pragma once
 #include "scan.cuh"
 
+#define SCAN_STAGE 256     // candidate keys staged in shared memory per slot and work item (overflow: direct global append)
 template <int MP>
 size_t scan_pk_smem_bytes(int E) {
     typedef ScanCfg<MP> C;
-    return (size_t)C::LUT_BYTES + (size_t)4 * C::G * E * 4 + 5 * 32 * 4 + 256;
+    return (size_t)C::LUT_BYTES + (size_t)4 * C::G * SCAN_STAGE * 8 + (size_t)4 * C::G * E * 4 + 6 * 32 * 4 + 256;
 }
 
 template <int OFF> __device__ __forceinline__ uint32_t lds_lut_u(uint32_t o) {
@@ -90,13 +91,15 @@ k_scan_pk(ScanArgs a) {
     constexpr int NS = 4 * G, PR = 2 * G;                          // query slots / slot pairs per work item
     extern __shared__ __align__(256) unsigned char smem[];
     uint32_t* lut = (uint32_t*)smem;
-    unsigned int* tab = (unsigned int*)(smem + C::LUT_BYTES);      // [NS][E]
+    unsigned long long* stage = (unsigned long long*)(smem + C::LUT_BYTES);   // [NS][SCAN_STAGE] candidate keys of this item
+    unsigned int* tab = (unsigned int*)(stage + NS * SCAN_STAGE);  // [NS][E]
     unsigned int* s_thr = tab + NS * a.E;                          // [32]
     int* s_q = (int*)(s_thr + 32);                                 // [32] query of the slot, -1 = empty
     unsigned int* s_posbase = (unsigned int*)(s_q + 32);           // [32]
     int* s_lut0 = (int*)(s_posbase + 32);                          // [32] table of split 0 (-1 = empty)
     int* s_lut1 = s_lut0 + 32;                                     // [32]
-    unsigned int* s_item = (unsigned int*)(s_lut1 + 32);
+    unsigned int* s_nst = (unsigned int*)(s_lut1 + 32);            // [32] keys staged per slot
+    unsigned int* s_item = s_nst + 32;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane / MP, jl = lane % MP;
@@ -162,7 +165,9 @@ k_scan_pk(ScanArgs a) {
                 s_posbase[tid] = (unsigned int)(pv.vis_base[o] + first);
                 s_q[tid] = qv.x;
                 s_thr[tid] = *(volatile unsigned int*)&a.gthr[qv.x];
+                s_nst[tid] = 0u;
             } else {
+                s_nst[tid] = 0u;
                 s_lut0[tid] = -1; s_lut1[tid] = -1; s_posbase[tid] = 0; s_q[tid] = -1;
                 s_thr[tid] = 0u;                                   // an empty slot sums to M * QMAX > 0: nothing passes
             }
@@ -175,7 +180,7 @@ k_scan_pk(ScanArgs a) {
             const unsigned short* pa = a.lut16 + (size_t)(sa < 0 ? 0 : sa) * B2L_LUT_ROWS * m + f_ch * 8;
             const unsigned short* pb = a.lut16 + (size_t)(sb < 0 ? 0 : sb) * B2L_LUT_ROWS * m + f_ch * 8;
             unsigned char* dstl = (unsigned char*)lut + f_dst;
-#pragma unroll 4
+#pragma unroll 8
             for (int row = f_row0; row < B2L_LUT_ROWS; row += f_rstep) {
                 uint4 A = make_uint4(fillw, fillw, fillw, fillw), Bv = A;
                 if (sa >= 0) A = __ldg((const uint4*)(pa + (size_t)row * m));
@@ -241,11 +246,17 @@ k_scan_pk(ScanArgs a) {
         }
 
         int it = 0, gen = 0;
+        // candidates are staged per slot in shared memory (one shared-memory atomic each) and moved to the query's
+        // global list once per work item; only a full staging buffer falls back to the direct global append
         auto append = [&](unsigned int v, int sl, int idx) {
-            const int q = s_q[sl];
-            const unsigned int n = atomicAdd(&a.cand_cnt[q], 1u);
-            if (n < SCAN_CAND_CAP)
-                a.cand[(size_t)q * SCAN_CAND_CAP + n] = ((unsigned long long)v << 32) | (unsigned long long)(s_posbase[sl] + (unsigned)idx);
+            const unsigned long long key = ((unsigned long long)v << 32) | (unsigned long long)(s_posbase[sl] + (unsigned)idx);
+            const unsigned int n = atomicAdd(&s_nst[sl], 1u);
+            if (n < SCAN_STAGE) stage[sl * SCAN_STAGE + n] = key;
+            else {
+                const int q = s_q[sl];
+                const unsigned int gn = atomicAdd(&a.cand_cnt[q], 1u);
+                if (gn < SCAN_CAND_CAP) a.cand[(size_t)q * SCAN_CAND_CAP + gn] = key;
+            }
         };
         auto eval_chunk = [&](const uint32_t (&w)[U][W], int c) {
             const unsigned int t0 = s_thr[sl0], t1 = s_thr[sl1], t2 = s_thr[sl2], t3 = s_thr[sl3];
@@ -273,12 +284,16 @@ k_scan_pk(ScanArgs a) {
                     if (v3[u] <= t3) append(v3[u], sl3, base + u * MP);
                 }
             }
-            if (((it + 1) & it) == 0) {
+            const int cx = it + 1, cy = cx & (cx - 1);              // checkpoints after 1, 2, 3, 4, 6, 8, 12, 16, 24, ... chunks
+            if (cy == 0 || ((cy & (cy - 1)) == 0 && (cx - cy) * 2 == cy)) {
+                // checkpoint: every warp flushes its lane minima, one warp
+                // (rotating with the checkpoint number) recomputes the bounds; the others pick them up from s_thr
                 const int e = ent + C::LPS * (gen & (a.GEN - 1));
                 tab0[e] = min(tab0[e], mn0); tab1[e] = min(tab1[e], mn1); tab2[e] = min(tab2[e], mn2); tab3[e] = min(tab3[e], mn3);
-                if (a.GEN > 1) { mn0 = INFU; mn1 = INFU; mn2 = INFU; mn3 = INFU; ++gen; }
+                if (a.GEN > 1) { mn0 = INFU; mn1 = INFU; mn2 = INFU; mn3 = INFU; }
+                ++gen;
                 __syncwarp();
-                refresh_bounds_u<NS>(a, tab, s_thr, s_q, lane, gpre);
+                if (((gen + 7) & (SCAN_WARPS - 1)) == warp || nchunk <= SCAN_WARPS) refresh_bounds_u<NS>(a, tab, s_thr, s_q, lane, gpre);
             }
             ++it;
         };
@@ -301,8 +316,19 @@ k_scan_pk(ScanArgs a) {
         if (warp < nchunk) {
             const int e = ent + C::LPS * (gen & (a.GEN - 1));
             tab0[e] = min(tab0[e], mn0); tab1[e] = min(tab1[e], mn1); tab2[e] = min(tab2[e], mn2); tab3[e] = min(tab3[e], mn3);
-            __syncwarp();
-            refresh_bounds_u<NS>(a, tab, s_thr, s_q, lane, gpre);
+        }
+        __syncthreads();
+        if (warp == 0) refresh_bounds_u<NS>(a, tab, s_thr, s_q, lane, gpre);       // what this item proved, for the other items
+        // staged candidates -> the queries' global lists (one global atomic per slot)
+        for (int sl = warp; sl < NS; sl += SCAN_WARPS) {
+            const int q = s_q[sl];
+            const unsigned int n = min(s_nst[sl], (unsigned int)SCAN_STAGE);
+            if (q < 0 || n == 0) continue;
+            unsigned int gbase = 0;
+            if (lane == 0) gbase = atomicAdd(&a.cand_cnt[q], n);
+            gbase = __shfl_sync(0xffffffffu, gbase, 0);
+            for (unsigned int i = lane; i < n; i += 32)
+                if (gbase + i < SCAN_CAND_CAP) a.cand[(size_t)q * SCAN_CAND_CAP + gbase + i] = stage[sl * SCAN_STAGE + i];
         }
         __syncthreads();
         for (int e = tid; e < NS * a.E; e += SCAN_THREADS) {
