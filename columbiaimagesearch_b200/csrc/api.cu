@@ -474,9 +474,23 @@ int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_
     double* lut64 = nullptr;
     if (fast) { CU(h->w_lut32.reserve(cap_lut * B2L_LUT_ROWS * mv.m * 4)); lut32 = h->w_lut32.as<float>(); }
     else { CU(h->w_lut64.reserve(cap_lut * mv.m * mv.K * 8)); lut64 = h->w_lut64.as<double>(); }
+    QuantView qv = {};
+    if (packed) {
+        // 16-bit tables: per-query bias / step from the ranges of the float32 tables, then the codes
+        const size_t o_qmin = 0, o_qmax = align256((size_t)nq * mv.M * 4), o_B = o_qmax + align256((size_t)nq * 4),
+                     o_dl = o_B + align256((size_t)nq * 8), qbytes = o_dl + align256((size_t)nq * 8);
+        CU(h->w_quant.reserve(qbytes));
+        CU(h->w_lut16.reserve(cap_lut * B2L_LUT_ROWS * mv.m * 2));
+        unsigned char* qb = h->w_quant.as<unsigned char>();
+        qv.qmin = (unsigned int*)(qb + o_qmin); qv.qmax = (unsigned int*)(qb + o_qmax);
+        qv.B = (double*)(qb + o_B); qv.delta = (double*)(qb + o_dl); qv.qmax_code = 65535 / mv.M;
+        CU(cudaMemsetAsync(qv.qmin, 0xFF, (size_t)nq * mv.M * 4, h->stream));
+        CU(cudaMemsetAsync(qv.qmax, 0, (size_t)nq * 4, h->stream));
+    }
     if (nosync || pc.n_lut) {
         const size_t smem = (size_t)(2 * mv.h + LUT_THREADS) * 8;
         const unsigned lgrid = (unsigned)std::min<size_t>(cap_lut, (size_t)h->num_sms * 8);
+        bool ranged = false;
 #define LUTK(XT, DSV)                                                                                                   \
     do {                                                                                                                \
         CU(cudaFuncSetAttribute(k_lut<XT, DSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));               \
@@ -492,37 +506,28 @@ int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_
         default: LUTK(XT, 0);                     \
     }
         if (fast && mv.ds == 8 && mv.m == 8 && mv.K <= 256) {
-            // headline shape: sub-quantizer codebook register-resident, one block per SM bound to one coarse split
+            // headline shape: sub-quantizer codebook register-resident, one block per SM bound to one coarse split;
+            // the column ranges the 16-bit tables need are reduced on the way
             const size_t smr = (size_t)(2 * mv.h + LUTR_THREADS) * 8;
             const unsigned rgrid = (unsigned)(2 * std::max(1, h->num_sms / 2));
             if (xf64) k_lut_reg<double, 8, 4><<<rgrid, LUTR_THREADS, smr, h->stream>>>(mv, (const double*)x, pv.lut_desc, pv.cnt,
-                                                                                     h->w_p64.as<double>(), lut32);
+                                                                                     h->w_p64.as<double>(), lut32, qv.qmin, qv.qmax);
             else k_lut_reg<float, 8, 4><<<rgrid, LUTR_THREADS, smr, h->stream>>>(mv, (const float*)x, pv.lut_desc, pv.cnt,
-                                                                                 h->w_p64.as<double>(), lut32);
+                                                                                 h->w_p64.as<double>(), lut32, qv.qmin, qv.qmax);
+            ranged = true;
         } else if (xf64) { LUTD(double); } else { LUTD(float); }
 #undef LUTD
 #undef LUTK
         LAUNCHED();
-    }
-    QuantView qv = {};
-    if (packed) {
-        // 16-bit tables: per-query bias / step from the ranges of the float32 tables, then the codes
-        const size_t o_qmin = 0, o_qmax = align256((size_t)nq * mv.M * 4), o_inv = o_qmax + align256((size_t)nq * 4),
-                     o_B = o_inv + align256((size_t)nq * 4), o_dl = o_B + align256((size_t)nq * 8), qbytes = o_dl + align256((size_t)nq * 8);
-        CU(h->w_quant.reserve(qbytes));
-        CU(h->w_lut16.reserve(cap_lut * B2L_LUT_ROWS * mv.m * 2));
-        unsigned char* qb = h->w_quant.as<unsigned char>();
-        qv.qmin = (unsigned int*)(qb + o_qmin); qv.qmax = (unsigned int*)(qb + o_qmax); qv.inv = (float*)(qb + o_inv);
-        qv.B = (double*)(qb + o_B); qv.delta = (double*)(qb + o_dl); qv.qmax_code = 65535 / mv.M;
-        CU(cudaMemsetAsync(qv.qmin, 0xFF, (size_t)nq * mv.M * 4, h->stream));
-        CU(cudaMemsetAsync(qv.qmax, 0, (size_t)nq * 4, h->stream));
-        const unsigned qgrid = (unsigned)std::min<size_t>(cap_lut, (size_t)h->num_sms * 8);
-        k_lut_range<<<qgrid, 256, 0, h->stream>>>(mv.m, pv.lut_desc, pv.cnt, lut32, mv.K, qv, mv.M);
-        LAUNCHED();
-        k_lut_scale<<<(nq + 127) / 128, 128, 0, h->stream>>>(nq, mv.M, qv);
-        LAUNCHED();
-        k_lut_quant<<<qgrid, 256, 0, h->stream>>>(mv.m, pv.lut_desc, pv.cnt, lut32, qv, mv.M, h->w_lut16.as<unsigned short>());
-        LAUNCHED();
+        if (packed) {
+            const unsigned qgrid = (unsigned)std::min<size_t>(cap_lut, (size_t)h->num_sms * 8);
+            if (!ranged) {
+                k_lut_range<<<qgrid, 256, 0, h->stream>>>(mv.m, pv.lut_desc, pv.cnt, lut32, mv.K, qv, mv.M);
+                LAUNCHED();
+            }
+            k_lut_quant<<<qgrid, 256, 0, h->stream>>>(mv.m, pv.lut_desc, pv.cnt, lut32, qv, mv.M, h->w_lut16.as<unsigned short>());
+            LAUNCHED();
+        }
     }
     IndexView ix = {h->codes.as<uint8_t>(), h->rowids.as<int64_t>(), h->cell_start.as<int64_t>(), h->lsize.as<int64_t>()};
     CU(cudaEventRecord(h->cr->ev[1], h->stream));

@@ -304,18 +304,20 @@ k_lut(ModelView mv, const XT* __restrict__ Xq, const int32_t* __restrict__ lut_d
 // registers: block = 512 threads bound to ONE coarse split (blockIdx.x & 1); thread (k = tid % 256, jh = tid / 256)
 // holds centroid k of sub-quantizers jh*MH .. jh*MH+MH-1 of that split (MH*DS doubles) for the whole kernel and walks
 // over the slots of its split, so the codebook is read once per block instead of once per slot.
-// Needs m == 2*MH, ds == DS, K <= 256.  dynamic smem: r[h] | p[h] | psum[512] doubles
+// Also reduces, per query, the minimum of every table column and the overall maximum (qmin / qmax, for the 16-bit
+// tables of the packed scan; NULL: skipped).  Needs m == 2*MH, ds == DS, K <= 256.  dynamic smem: r[h] | p[h] | psum[512] doubles
 #define LUTR_THREADS 512
 template <typename XT, int DS, int MH>
 __global__ void __launch_bounds__(LUTR_THREADS)
 k_lut_reg(ModelView mv, const XT* __restrict__ Xq, const int32_t* __restrict__ lut_desc, const PlanCounters* __restrict__ cnt,
-          double* __restrict__ P64, float* __restrict__ lut32) {
+          double* __restrict__ P64, float* __restrict__ lut32, unsigned int* __restrict__ qmin, unsigned int* __restrict__ qmax) {
     extern __shared__ double sm_lutr[];
+    __shared__ unsigned int s_cmin[2 * MH], s_cmax;
     const int h = mv.h, m = mv.m, V = mv.V;
     double* r = sm_lutr;
     double* p = sm_lutr + h;
     double* psum = p + h;
-    const int tid = threadIdx.x, k = tid & 255, jh = tid >> 8;
+    const int tid = threadIdx.x, k = tid & 255, jh = tid >> 8, lane = tid & 31;
     const int s = blockIdx.x & 1, nb = gridDim.x >> 1, b = blockIdx.x >> 1;
     const int nslot = (int)cnt->n_lut;
     const bool live = k < mv.K;
@@ -339,6 +341,8 @@ k_lut_reg(ModelView mv, const XT* __restrict__ Xq, const int32_t* __restrict__ l
         const double* C = mv.Cs + ((int64_t)s * V + c) * h;
         const double* mu = mv.mus + ((int64_t)s * V + c) * h;
         for (int d = tid; d < h; d += LUTR_THREADS) r[d] = coarse_residual<XT>(x[d], C[d], mu[d], mv.coarse_f32);
+        if (tid < 2 * MH) s_cmin[tid] = 0xFFFFFFFFu;
+        if (tid == 0) s_cmax = 0u;
         __syncthreads();
         const double* Rt = mv.Rt + ((int64_t)s * V + c) * h * (int64_t)h;
         for (int t0 = 0; t0 < h; t0 += tw) {
@@ -373,6 +377,21 @@ k_lut_reg(ModelView mv, const XT* __restrict__ Xq, const int32_t* __restrict__ l
 #pragma unroll
             for (int jj = 0; jj < MH; ++jj) o32[jj] = e32[jj];
         }
+        if (qmin) {              // per query: minimum of every table column and the overall maximum (QuantView, 16-bit tables)
+            unsigned int mx = 0u;
+#pragma unroll
+            for (int jj = 0; jj < MH; ++jj) {
+                const unsigned int v = live ? __float_as_uint(e32[jj]) : 0xFFFFFFFFu;
+                const unsigned int wm = __reduce_min_sync(0xffffffffu, v);
+                if (lane == 0) atomicMin(&s_cmin[jh * MH + jj], wm);
+                mx = max(mx, live ? v : 0u);
+            }
+            mx = __reduce_max_sync(0xffffffffu, mx);
+            if (lane == 0) atomicMax(&s_cmax, mx);
+            __syncthreads();
+            if (tid < 2 * MH) atomicMin(&qmin[(size_t)q * mv.M + s * m + tid], s_cmin[tid]);
+            if (tid == 0) atomicMax(&qmax[q], s_cmax);
+        }
     }
 }
 
@@ -385,7 +404,6 @@ k_lut_reg(ModelView mv, const XT* __restrict__ Xq, const int32_t* __restrict__ l
 struct QuantView {
     unsigned int* qmin;     // [nq][M] float bits (entries are >= 0, so unsigned order == float order)
     unsigned int* qmax;     // [nq]    float bits
-    float* inv;             // [nq]    1 / Delta
     double* B;              // [nq]
     double* delta;          // [nq]
     int qmax_code;          // QMAX
@@ -418,38 +436,40 @@ k_lut_range(int m, const int32_t* __restrict__ lut_desc, const PlanCounters* __r
     }
 }
 
-// one thread per query: scale and bias sum
-__global__ void k_lut_scale(int nq, int M, QuantView qv) {
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= nq) return;
-    float bmin = __int_as_float(0x7f800000);
-    double B = 0.0;
-    bool any = false;
-    for (int j = 0; j < M; ++j) {
-        const unsigned int b = qv.qmin[(size_t)q * M + j];
-        if (b < 0x7f800000u) { const float f = __uint_as_float(b); bmin = fminf(bmin, f); B += (double)f; any = true; }
-        else qv.qmin[(size_t)q * M + j] = 0u;                      // sub-quantizer without a table on this rank: bias 0
-    }
-    const float range = any ? fmaxf(__uint_as_float(qv.qmax[q]) - bmin, 1e-30f) : 1.0f;
-    const double delta = (double)range / (double)qv.qmax_code * (1.0 + 9.5367431640625e-07);
-    qv.delta[q] = delta;
-    qv.inv[q] = (float)(1.0 / delta);
-    qv.B[q] = B;
-}
-
-// one block per LUT slot: lut16[slot][k][j] = clamp(floor((e - b) * inv), 0, QMAX)
+// one block per LUT slot: scale and bias of the slot's query (recomputed by every block of the query, identical values),
+// then lut16[slot][k][j] = clamp(floor((e - b) * inv), 0, QMAX)
 __global__ void __launch_bounds__(256)
 k_lut_quant(int m, const int32_t* __restrict__ lut_desc, const PlanCounters* __restrict__ cnt, const float* __restrict__ lut32,
             QuantView qv, int M, unsigned short* __restrict__ lut16) {
+    __shared__ float s_b[64], s_inv;
     const int nslot = (int)cnt->n_lut;
     for (int slot = blockIdx.x; slot < nslot; slot += gridDim.x) {
         const int q = lut_desc[3 * slot], s = lut_desc[3 * slot + 1];
-        const float inv = qv.inv[q];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float bmin = __int_as_float(0x7f800000);
+            double B = 0.0;
+            bool any = false;
+            for (int j = 0; j < M; ++j) {
+                const unsigned int b = qv.qmin[(size_t)q * M + j];
+                if (b < 0x7f800000u) { const float f = __uint_as_float(b); bmin = fminf(bmin, f); B += (double)f; any = true; }
+            }                                                           // (a sub-quantizer without a table on this rank: bias 0)
+            const float range = any ? fmaxf(__uint_as_float(qv.qmax[q]) - bmin, 1e-30f) : 1.0f;
+            const double delta = (double)range / (double)qv.qmax_code * (1.0 + 9.5367431640625e-07);
+            qv.delta[q] = delta;
+            qv.B[q] = B;
+            s_inv = (float)(1.0 / delta);
+        }
+        if (threadIdx.x < m) {
+            const unsigned int b = qv.qmin[(size_t)q * M + s * m + threadIdx.x];
+            s_b[threadIdx.x] = b < 0x7f800000u ? __uint_as_float(b) : 0.0f;
+        }
+        __syncthreads();
+        const float inv = s_inv;
         const float* t = lut32 + (size_t)slot * B2L_LUT_ROWS * m;
         unsigned short* o = lut16 + (size_t)slot * B2L_LUT_ROWS * m;
         for (int e = threadIdx.x; e < B2L_LUT_ROWS * m; e += blockDim.x) {
-            const float b = __uint_as_float(qv.qmin[(size_t)q * M + s * m + (e % m)]);
-            const float x = __fmul_rn(__fsub_rn(t[e], b), inv);
+            const float x = __fmul_rn(__fsub_rn(t[e], s_b[e % m]), inv);
             o[e] = (unsigned short)min(qv.qmax_code, max(0, (int)floorf(x)));
         }
     }
