@@ -436,7 +436,19 @@ def run_b200(a):
                 "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": scan_bytes / max(1, timed_calls), "scan_ms_per_launch": scan_ms / max(1, timed_calls),
                 "launches_timed": timed_calls,
-                "note": "algorithmic bytes = M x codes ranked, summed over the batch's queries, on this rank (no credit for cross-query reuse)"}
+                "note": "algorithmic bytes = M x codes ranked, summed over the batch's queries, on this rank (no credit for cross-query "
+                        "reuse: a code tile read once from HBM/L2 serves every query of the batch that visits the cell, which is why "
+                        "`traffic` is far below it and frac can exceed 1); the resource that actually bounds the kernel is the "
+                        "shared-memory gather pipe, see `gather`"}
+    # secondary roofline: shared-memory LUT gathers.  One conflict-free LDS wavefront serves 32 lanes x 2 packed queries.
+    nsm = torch.cuda.get_device_properties(local).multi_processor_count
+    sm_hz = 1e6 * float(clocks["sm_mhz"] or clocks["sm_max_mhz"] or 1965)
+    lookups = scan_bytes                                   # one table look-up per code byte ranked
+    wf_min = lookups / 64.0
+    roofline["gather"] = {"bound": "shared-memory wavefronts (1 per clock per SM)", "lookups_per_launch": lookups / max(1, timed_calls),
+                          "min_wavefronts_per_launch": wf_min / max(1, timed_calls),
+                          "achieved": wf_min / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0, "peak": nsm * sm_hz / 1e9,
+                          "unit": "Gwavefront/s", "frac": (wf_min / (scan_ms * 1e-3)) / (nsm * sm_hz) if scan_ms > 0 else 0.0}
 
     # ---- CPU baseline (rank 0, N = 1): the reference's per-item Python loop on a bounded sample ---------
     cpu = None
