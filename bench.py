@@ -40,6 +40,7 @@ def parse():
     p.add_argument("--seed", type=int, default=1234)
     p.add_argument("--cpu-queries", type=int, default=6, help="queries of the bounded CPU-baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--emulate-shard", type=int, default=0, help="profiling aid (1 process): act as rank 0 of an N-way cell-sharded index")
     p.add_argument("--sweep", default="", help="comma-separated quotas: print recall/QPS per quota and exit")
     return p.parse_args()
 
@@ -305,9 +306,15 @@ def run_b200(a):
     enc_s = time.perf_counter() - t0
 
     # one searcher class for every N: the inverted lists are sharded by coarse cell over the ranks (N = 1: one shard)
-    searcher = ShardedLOPQSearcher(model, device=local)
-    searcher.add_codes_device(coarse_t, fine_t)
-    searcher.finalize()
+    if a.emulate_shard > 1 and world == 1:
+        searcher = ShardedLOPQSearcher(model, device=local, emulate=(a.emulate_shard, 0))
+        searcher.add_codes_device(coarse_t, fine_t)
+        cell_all = coarse_t[:, 0].long() * model.V + coarse_t[:, 1].long()
+        searcher.finalize(global_sizes=torch.bincount(cell_all, minlength=model.V ** 2).cpu().numpy())
+    else:
+        searcher = ShardedLOPQSearcher(model, device=local)
+        searcher.add_codes_device(coarse_t, fine_t)
+        searcher.finalize()
     handle = searcher._handle
 
     # ---- queries: (warmup + steps) distinct batches of near-duplicates, exact ground truth for recall ----

@@ -62,6 +62,7 @@ struct b2l_ctx {
         PlanCounters* h_pc = nullptr;      // pinned
         bool pending = false, has_pc = false;
         int64_t launch0 = 0;
+        int nq = 0, segc = 0;              // shape of the call (segment-length feedback)
         b2l_stats st = {};
     };
     static const int NREC = 8;
@@ -91,6 +92,8 @@ struct b2l_ctx {
     b2l_stats stats = {};
     int64_t launches = 0;
     bool async_mode = false;
+    int fb_nq = 0, fb_segc = 0;        // last collected fast search: batch size, segment length, work items it produced
+    int64_t fb_items = 0;
     int scan_mode = 0;                 // 0: packed 16-bit tables first (default), 1: float32 tables only
     void* h_out = nullptr;             // pinned staging of the search outputs
     size_t h_out_cap = 0;
@@ -285,7 +288,7 @@ int ensure_index(b2l_handle h) {
 size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 // carve the per-batch plan arrays out of one allocation
-int setup_plan(b2l_handle h, int nq, int segc, int nsegmax = 1) {
+int setup_plan(b2l_handle h, int nq, int segc, int nsegmax = 1, int nseg_cap = 1) {
     const ModelView& mv = h->mv;
     const int ncell = mv.V * mv.V, maxvis = ncell;
     size_t off = 0;
@@ -296,7 +299,10 @@ int setup_plan(b2l_handle h, int nq, int segc, int nsegmax = 1) {
     const size_t zero_bytes = off;
     const size_t o_fill = take((size_t)ncell * 4);
     const size_t o_coff = take((size_t)(ncell + 1) * 4);
-    const size_t o_ib = take(((size_t)nsegmax * ncell + 1) * 4);
+    const size_t o_ib = take(((size_t)std::max(nsegmax, nseg_cap) * ncell + 1) * 4);    // (sized for the shortest segments)
+    const size_t item_cap = std::min<size_t>((size_t)1 << 20,
+                                             (size_t)std::max(nsegmax, nseg_cap) * ((size_t)nq * ncell / 2 + ncell) + 1);
+    const size_t o_if = take(item_cap * 4);
     const size_t o_nvis = take((size_t)nq * 4);
     const size_t o_ncand = take((size_t)nq * 8);
     const size_t o_ncl = take((size_t)nq * 8);
@@ -318,6 +324,7 @@ int setup_plan(b2l_handle h, int nq, int segc, int nsegmax = 1) {
     pv.cell_fill = (unsigned int*)(b + o_fill);
     pv.cellq_off = (unsigned int*)(b + o_coff);
     pv.item_base = (unsigned int*)(b + o_ib);
+    pv.item_f = (unsigned int*)(b + o_if); pv.item_cap = (unsigned int)item_cap;
     pv.nvis = (int32_t*)(b + o_nvis);
     pv.ncand = (int64_t*)(b + o_ncand);
     pv.ncand_local = (int64_t*)(b + o_ncl);
@@ -355,6 +362,7 @@ int collect_call(b2l_handle h, b2l_ctx::CallRec& r) {
     CU(cudaEventElapsedTime(&ms, r.ev[2], r.ev[3])); r.st.scan_ms = ms;
     CU(cudaEventElapsedTime(&ms, r.ev[3], r.ev[4])); r.st.select_ms = ms;
     CU(cudaEventElapsedTime(&ms, r.ev[0], r.ev[4])); r.st.total_ms = ms;
+    if (r.segc > 0 && r.st.work_items > 0) { h->fb_nq = r.nq; h->fb_segc = r.segc; h->fb_items = r.st.work_items; }
     b2l_stats acc = h->stats;                       // carries the accumulators
     b2l_stats cur = r.st;
     cur.acc_calls = acc.acc_calls + 1;
@@ -401,6 +409,7 @@ int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_
         memset(&r.st, 0, sizeof r.st);
         r.has_pc = false;
         r.launch0 = h->launches;
+        r.nq = nq; r.segc = 0;
     }
     CU(cudaEventRecord(h->cr->ev[0], h->stream));
     // queries -> device, PCA
@@ -437,11 +446,24 @@ int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_
     // segment length: a multiple of 64 codes, sized so the batch yields enough work items
     int64_t maxcell = 0;
     for (int c = 0; c < ncell; ++c) maxcell = std::max(maxcell, h->h_lsize[c]);
+    // Start from 16K codes; the last finished search of the same batch size tells whether that gave the persistent grid
+    // enough items (few queries, or a small shard of a multi-GPU index: shorter segments) -- results do not depend on it.
     int segc = 16 * 1024;
+    if (fast && h->fb_nq == nq && h->fb_segc > 0) {
+        const int64_t grid = (int64_t)h->num_sms * 2;
+        segc = h->fb_segc;
+        if (h->fb_items < 3 * grid || h->fb_items > 24 * grid) {           // aim at ~6 items per block, in one jump
+            const double want = (double)segc * (double)h->fb_items / (6.0 * (double)grid);
+            int s2 = 2048;
+            while (s2 * 2 <= want * 1.42 && s2 < 16 * 1024) s2 *= 2;        // nearest power of two
+            segc = s2;
+        }
+    }
     if (maxcell > 0 && maxcell < segc) segc = (int)(((maxcell + 63) / 64) * 64);
     const int nsegmax = (int)std::max<int64_t>(1, (maxcell + segc - 1) / segc);
-    rc = setup_plan(h, nq, segc, nsegmax);
+    rc = setup_plan(h, nq, segc, nsegmax, (int)((maxcell + 2047) / 2048) + 1);
     if (rc) return rc;
+    if (fast) h->cr->segc = segc;
     PlanView& pv = h->pv;
     {
         const size_t smem = (size_t)(3 * mv.V + 2) * 8 + (size_t)(7 * mv.V + 4) * 4 + 16;
@@ -451,6 +473,8 @@ int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_
     }
     if (fast) {
         k_plan<<<1, 1024, 0, h->stream>>>(ncell, nsegmax, NS, segc, h->lsize.as<int64_t>(), pv);
+        LAUNCHED();
+        k_item_table<<<(nsegmax * ncell + 255) / 256, 256, 0, h->stream>>>(nsegmax * ncell, pv);
         LAUNCHED();
     }
     // Buffer sizes: the fast path sizes everything for the worst case the plan can produce (2V tables and V*V visited

@@ -31,6 +31,8 @@ struct PlanView {                   // per-batch device arrays, maxvis = V*V
     unsigned int* cell_fill;        // [V*V]
     unsigned int* cellq_off;        // [V*V+1]
     unsigned int* item_base;        // [nsegmax*V*V+1], f = seg*ncell + cell
+    unsigned int* item_f;           // [item_cap] f of every work item (items beyond the capacity are located by search)
+    unsigned int item_cap;
     int2* cellq;                    // [n_pairs] (q, visit index), grouped by cell
     PlanCounters* cnt;
 };
@@ -207,6 +209,14 @@ k_plan(int ncell, int nsegmax, int G, int segc, const int64_t* __restrict__ lsiz
     unsigned int bi = si[threadIdx.x] - ai;
     for (int f = f0; f < min(F, f0 + per); ++f) { pv.item_base[f] = bi; bi += items_of(f); }
     if (threadIdx.x == 1023) { pv.item_base[F] = si[1023]; pv.cnt->n_items = si[1023]; }
+}
+
+// ---- item -> (segment, cell) table, so a scan block finds its item with one load instead of a binary search ----
+__global__ void k_item_table(int F, PlanView pv) {
+    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < F; f += gridDim.x * blockDim.x) {
+        const unsigned int a = pv.item_base[f], b = min(pv.item_base[f + 1], pv.item_cap);
+        for (unsigned int i = a; i < b; ++i) pv.item_f[i] = (unsigned int)f;
+    }
 }
 
 // ---- group the (query, visit) pairs by cell -----------------------------------------------------

@@ -229,9 +229,12 @@ k_scan(ScanArgs a) {
 
         // ---- decode the item: (segment, cell) by binary search over item_base, then the query group
         int lo = 0, hi = a.nflat;             // item_base[lo] <= item < item_base[hi], f = seg * ncell + cell
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (pv.item_base[mid] <= item) lo = mid; else hi = mid;
+        if (item < pv.item_cap) lo = (int)pv.item_f[item];
+        else {
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (pv.item_base[mid] <= item) lo = mid; else hi = mid;
+            }
         }
         const unsigned int seg = (unsigned)(lo / a.ncell);
         const int cell = lo - (int)seg * a.ncell;

@@ -142,10 +142,13 @@ k_scan_pk(ScanArgs a) {
         if (item >= n_items) break;
         if (tid == 0) nxt = atomicAdd(&pv.cnt->next_item, 1u);
 
-        int lo = 0, hi = a.nflat;
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (pv.item_base[mid] <= item) lo = mid; else hi = mid;
+        int lo = 0, hi = a.nflat;             // item_base[lo] <= item < item_base[hi], f = seg * ncell + cell
+        if (item < pv.item_cap) lo = (int)pv.item_f[item];
+        else {
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (pv.item_base[mid] <= item) lo = mid; else hi = mid;
+            }
         }
         const unsigned int seg = (unsigned)(lo / a.ncell);
         const int cell = lo - (int)seg * a.ncell;

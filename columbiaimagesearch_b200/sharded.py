@@ -17,7 +17,9 @@ def cell_owner(V, world):
 
 
 class ShardedLOPQSearcher(object):
-    def __init__(self, model, group=None, device=None, handle=None, backend_device=None):
+    def __init__(self, model, group=None, device=None, handle=None, backend_device=None, emulate=None):
+        """emulate = (world, rank): profiling aid -- behave as that rank of a `world`-way sharded index inside a single
+        process (no collective; the caller supplies the global cell sizes through finalize(global_sizes=...))."""
         import torch.distributed as dist
         self.dist = dist
         self.group = group
@@ -26,6 +28,9 @@ class ShardedLOPQSearcher(object):
         self.model = model
         self._handle = handle if handle is not None else model._new_handle(device)
         self.owner = cell_owner(model.V, self.world)
+        if emulate is not None:
+            self.owner = cell_owner(model.V, int(emulate[0]))
+            self.rank = int(emulate[1])
         self.nb_indexed = 0             # global
         self.nb_local = 0
         self._tdev = backend_device if backend_device is not None else "cuda:%d" % self._handle.device
@@ -70,9 +75,13 @@ class ShardedLOPQSearcher(object):
         self.nb_indexed = base + n
         self._dirty = True
 
-    def finalize(self):
+    def finalize(self, global_sizes=None):
         """Exchange cell sizes: the quota cut needs the GLOBAL size of every cell on every rank."""
         import torch
+        if global_sizes is not None:
+            self._handle.set_global_cell_sizes(np.asarray(global_sizes, dtype=np.int64))
+            self._dirty = False
+            return
         local = self._handle.cell_sizes()
         t = torch.from_numpy(local.copy()).to(self._tdev)
         if self.world > 1:
