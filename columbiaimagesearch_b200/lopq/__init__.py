@@ -10,9 +10,9 @@ import sys
 
 from . import model, search, utils, eval  # noqa: F401
 from .model import LOPQModel, LOPQModelPCA, LOPQCode
-from .search import LOPQSearcher, LOPQSearcherGPU, multisequence
+from .search import LOPQSearcher, LOPQSearcherGPU, LOPQSearcherLMDB, multisequence
 
-__all__ = ["LOPQModel", "LOPQModelPCA", "LOPQCode", "LOPQSearcher", "LOPQSearcherGPU", "multisequence",
+__all__ = ["LOPQModel", "LOPQModelPCA", "LOPQCode", "LOPQSearcher", "LOPQSearcherGPU", "LOPQSearcherLMDB", "multisequence",
            "model", "search", "utils", "eval", "install_as_lopq"]
 
 

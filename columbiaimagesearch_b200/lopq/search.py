@@ -317,6 +317,130 @@ class LOPQSearcher(LOPQSearcherBase):
     def stats(self):
         return self._handle.stats()
 
+    # ---- flat persistence of the index (restart without re-encoding) -------------------
+    def export_arrays(self):
+        """(coarse [n,2] int32, fine [n,M] uint8, ids) of everything indexed, cell by cell in in-cell order: adding them
+        back in this order to an empty searcher rebuilds the same index (same retrieval order, same results)."""
+        V = self.model.V
+        sizes = self._handle.cell_sizes()
+        co, fi, rows = [], [], []
+        for c in np.nonzero(sizes)[0]:
+            r, f = self._handle.get_cell(int(c) // V, int(c) % V)
+            co.append(np.tile(np.array([int(c) // V, int(c) % V], np.int32), (r.shape[0], 1)))
+            fi.append(f)
+            rows.append(r)
+        if not rows:
+            return np.zeros((0, 2), np.int32), np.zeros((0, self.model.M), np.uint8), np.zeros(0, np.int64)
+        return np.concatenate(co), np.concatenate(fi), self._ids_of_rows(np.concatenate(rows))
+
+    def save_index(self, path):
+        coarse, fine, ids = self.export_arrays()
+        np.savez(path, coarse=coarse, fine=fine, ids=ids, allow_pickle=True)
+
+    def load_index(self, path):
+        z = np.load(path, allow_pickle=True)
+        self.add_codes((z["coarse"], z["fine"]), z["ids"])
+
+
+class LOPQSearcherLMDB(LOPQSearcher):
+    """search.py:385-499 -- the product's default searcher (searcher_lopqhbase.py:198-206): the index is persisted in an
+    LMDB database (key = cell as 2 x native uint16 + str(id) bytes, value = M fine-code bytes, search.py:425-470) and a
+    cell is returned in KEY order (search.py:486-496), so ties in distance are ordered by the bytes of str(id) -- not by
+    insertion as in LOPQSearcher -- and re-adding an id in a cell overwrites it (txn.put).
+
+    Here LMDB stays the persistent store (when the `lmdb` module is present and a path is given; it is opened exactly as
+    the reference does) and the search index is the GPU-resident one, rebuilt in key order after every change.
+    `lmdb_path=None` keeps the same semantics in memory only.  A path without the `lmdb` module is an ImportError."""
+
+    def __init__(self, model, lmdb_path=None, id_lambda=int, device=None):
+        super(LOPQSearcherLMDB, self).__init__(model, device)
+        self.lmdb_path, self.id_lambda = lmdb_path, id_lambda
+        self.env = self.index_db = None
+        self._items = {}                  # key bytes -> fine codes (uint8 array)
+        self._stale = False
+        if lmdb_path is not None:
+            import lmdb                   # fails loudly when the module is missing
+            self.env = lmdb.open(self.lmdb_path, map_size=1024 * 1000000 * 32, max_dbs=1)
+            self.index_db = self.env.open_db(b"index")
+            with self.env.begin(db=self.index_db) as txn:
+                for key, value in txn.cursor():
+                    self._items[bytes(key)] = np.frombuffer(bytes(value), np.uint8)
+            self._stale = bool(self._items)
+        self.nb_indexed = len(self._items)
+
+    # wire format of search.py:425-443
+    @staticmethod
+    def encode_cell(cell):
+        return np.asarray(cell, dtype=np.uint16).tobytes()
+
+    @staticmethod
+    def decode_cell(cell_bytes):
+        return tuple(int(v) for v in np.frombuffer(cell_bytes, np.uint16))
+
+    @staticmethod
+    def encode_fine_codes(fine):
+        return np.asarray(fine, dtype=np.uint8).tobytes()
+
+    @staticmethod
+    def decode_fine_codes(fine_bytes):
+        return tuple(int(v) for v in np.frombuffer(fine_bytes, np.uint8))
+
+    def get_nb_indexed(self):
+        self.nb_indexed = len(self._items)
+        return self.nb_indexed
+
+    def add_codes(self, codes, ids=None):
+        """search.py:445-470."""
+        coarse, fine = codes_to_arrays(codes, self.model.M)
+        n = coarse.shape[0]
+        if ids is None:
+            ids = count()
+        txn = self.env.begin(db=self.index_db, write=True) if self.env is not None else None
+        try:
+            for i, item_id in zip(range(n), ids):
+                item_id = item_id.item() if isinstance(item_id, np.generic) else item_id
+                key = self.encode_cell(coarse[i]) + str(item_id).encode()
+                self._items[key] = fine[i].copy()
+                if txn is not None:
+                    txn.put(key, self.encode_fine_codes(fine[i]))
+        finally:
+            if txn is not None:
+                txn.commit()
+                self.env.sync()
+        self.nb_indexed = len(self._items)
+        self._stale = True
+
+    def _rebuild(self):
+        """Device index in key order: rows sorted by the full LMDB key (cell bytes, then str(id) bytes)."""
+        self._handle.index_clear()
+        keys = sorted(self._items)
+        n = len(keys)
+        self._row_ids, self._row_cells, self._row_ids_flat = [], [], None
+        self._numeric, self._id2num, self._num2id = False, {}, []
+        if n:
+            coarse = np.frombuffer(b"".join(k[:4] for k in keys), np.uint16).reshape(n, 2).astype(np.int32)
+            fine = np.stack([self._items[k] for k in keys])
+            self._num2id = [self.id_lambda(k[4:]) for k in keys]
+            self._handle.index_add(coarse, fine, np.arange(n, dtype=np.int64))
+            self._row_ids = [np.arange(n, dtype=np.int64)]
+            self._row_cells = [coarse[:, 0].astype(np.int64) * self.model.V + coarse[:, 1]]
+        self._stale = False
+
+    def get_cell(self, cell):
+        if self._stale:
+            self._rebuild()
+        return super(LOPQSearcherLMDB, self).get_cell(cell)
+
+    def search_batch(self, X, quota=10, limit=None):
+        if self._stale:
+            self._rebuild()
+        return super(LOPQSearcherLMDB, self).search_batch(X, quota, limit)
+
+    def get_result_quota(self, x, quota=10):
+        if self._stale:
+            self._rebuild()
+        return super(LOPQSearcherLMDB, self).get_result_quota(x, quota)
+
 
 # name the plugin accepts in conf key `lopq_searcher` (searcher_lopqhbase.py:198-222, see INTEGRATION.md)
 LOPQSearcherGPU = LOPQSearcher
