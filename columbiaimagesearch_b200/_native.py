@@ -41,6 +41,8 @@ SIGNATURES = {
     "b2l_set_model": (_i, [_h, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "b2l_set_pca": (_i, [_h, _i, _vp, _vp, _i]),
     "b2l_encode": (_i, [_h, _vp, _i, _i64, _i, _vp, _vp]),
+    "b2l_set_fine_mode": (_i, [_h, _i]),
+    "b2l_encode_guard_count": (_i64, [_h, _i]),
     "b2l_apply_pca": (_i, [_h, _vp, _i, _i64, _i, _vp]),
     "b2l_project_lut": (_i, [_h, _vp, _i, _i64, _vp, _vp, _vp]),
     "b2l_index_add": (_i, [_h, _vp, _vp, _i64, _vp, _i]),
@@ -171,6 +173,12 @@ class Handle(object):
     def encode_device(self, x_ptr, n, coarse_ptr, fine_ptr, f64=False):
         """Device-resident encode: raw device pointers (e.g. torch tensor .data_ptr())."""
         self._check(self.lib.b2l_encode(self.h, _ptr(int(x_ptr)), int(f64), int(n), 1, _ptr(int(coarse_ptr)), _ptr(int(fine_ptr))))
+
+    def set_fine_mode(self, mode):
+        self._check(self.lib.b2l_set_fine_mode(self.h, int(mode)))
+
+    def encode_guard_count(self, reset=False):
+        return int(self._check(self.lib.b2l_encode_guard_count(self.h, int(bool(reset)))))
 
     def apply_pca(self, X):
         X, f64 = _as_queries(X)

@@ -74,7 +74,7 @@ struct b2l_ctx {
     // model
     bool has_model = false, has_pca = false;
     ModelView mv = {};
-    DevBuf dCs, dmus, dRt, dsubs, dP, dpmu;
+    DevBuf dCs, dmus, dRt, dsubs, dsubs32, dc2max, dP, dpmu;
     // index: master copy in insertion order
     int64_t n_items = 0;
     DevBuf m_coarse, m_fine, m_rowid;
@@ -94,6 +94,8 @@ struct b2l_ctx {
     bool async_mode = false;
     int fb_nq = 0, fb_segc = 0;        // last collected fast search: batch size, segment length, work items it produced
     int64_t fb_items = 0;
+    int fine_mode = 0;                 // 0: float32 first stage + float64 guard in the fine argmin, 1: float64 only
+    unsigned long long* d_nguard = nullptr;   // sub-vectors the guard re-evaluated in float64 (device counter)
     int scan_mode = 0;                 // 0: packed 16-bit tables first (default), 1: float32 tables only
     void* h_out = nullptr;             // pinned staging of the search outputs
     size_t h_out_cap = 0;
@@ -183,11 +185,39 @@ int encode_device(b2l_handle h, const void* dX, int x_is_f64, int64_t n, const i
     CU(h->w_px.reserve((size_t)n * mv.D * 8));
     const unsigned blocks = (unsigned)((n + ENC_WARPS - 1) / ENC_WARPS);
     const size_t smem = (size_t)ENC_WARPS * mv.h * 8;
-    if (xf64) { CU(cudaFuncSetAttribute(k_coarse_project<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_coarse_project<double><<<blocks, ENC_WARPS * 32, smem, h->stream>>>(mv, (const double*)x, n, d_coarse_in, d_coarse, h->w_px.as<double>()); }
+    // batch encode of the common shape: coarse assignment, then the rotation as a grouped float64 tensor-core GEMM
+    const bool gemm = d_fine && !d_coarse_in && d_coarse && mv.h == ROT_H && n >= 2048 && n < ((int64_t)1 << 31);
+    double* px_out = gemm ? nullptr : h->w_px.as<double>();
+    if (gemm && mv.h % 8 == 0 && mv.h <= 128) {
+        if (xf64) k_coarse_assign<double><<<blocks, ENC_WARPS * 32, 0, h->stream>>>(mv, (const double*)x, n, d_coarse);
+        else k_coarse_assign<float><<<blocks, ENC_WARPS * 32, 0, h->stream>>>(mv, (const float*)x, n, d_coarse);
+    } else if (xf64) { CU(cudaFuncSetAttribute(k_coarse_project<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_coarse_project<double><<<blocks, ENC_WARPS * 32, smem, h->stream>>>(mv, (const double*)x, n, d_coarse_in, d_coarse, px_out); }
     else { CU(cudaFuncSetAttribute(k_coarse_project<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_coarse_project<float><<<blocks, ENC_WARPS * 32, smem, h->stream>>>(mv, (const float*)x, n, d_coarse_in, d_coarse, h->w_px.as<double>()); }
+        k_coarse_project<float><<<blocks, ENC_WARPS * 32, smem, h->stream>>>(mv, (const float*)x, n, d_coarse_in, d_coarse, px_out); }
     LAUNCHED();
+    if (gemm) {
+        const int nb = 2 * mv.V;
+        CU(h->w_sort_a.reserve((size_t)2 * n * 4));                       // perm[2][n]
+        CU(h->w_misc.reserve((size_t)(4 * nb + 4) * 4));                   // cnt | base | cursor | tile_base
+        unsigned int* cnt = h->w_misc.as<unsigned int>();
+        unsigned int* base = cnt + nb; unsigned int* cursor = base + nb; unsigned int* tile_base = cursor + nb;
+        unsigned int* perm = h->w_sort_a.as<unsigned int>();
+        CU(cudaMemsetAsync(cnt, 0, (size_t)nb * 4, h->stream));
+        k_enc_hist<<<grid_for(n, 256), 256, 0, h->stream>>>(d_coarse, n, mv.V, cnt);
+        LAUNCHED();
+        k_enc_offsets<<<1, 32, 0, h->stream>>>(mv.V, cnt, base, cursor, tile_base);
+        LAUNCHED();
+        k_enc_scatter<<<grid_for(n, 256), 256, 0, h->stream>>>(d_coarse, n, mv.V, base, cursor, perm);
+        LAUNCHED();
+        const unsigned tiles = (unsigned)(2 * ((n + 63) / 64) + nb);       // upper bound; surplus blocks leave at once
+        const size_t smr = (size_t)2 * ROT_H * ROT_LD * 8 + 64 * 4;
+        if (xf64) { CU(cudaFuncSetAttribute(k_rotate_dmma<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr));
+            k_rotate_dmma<double><<<tiles, 128, smr, h->stream>>>(mv, (const double*)x, n, cnt, base, tile_base, perm, h->w_px.as<double>()); }
+        else { CU(cudaFuncSetAttribute(k_rotate_dmma<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr));
+            k_rotate_dmma<float><<<tiles, 128, smr, h->stream>>>(mv, (const float*)x, n, cnt, base, tile_base, perm, h->w_px.as<double>()); }
+        LAUNCHED();
+    }
     if (d_fine) {
         int kchunk = mv.K;
         while ((size_t)kchunk * mv.ds * 8 > 96 * 1024 && kchunk > 1) kchunk = (kchunk + 1) / 2;
@@ -198,15 +228,22 @@ int encode_device(b2l_handle h, const void* dX, int x_is_f64, int64_t n, const i
         CU(cudaFuncSetAttribute(k_fine_argmin<DSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));     \
         k_fine_argmin<DSV><<<b2, FINE_THREADS, sm2, h->stream>>>(mv, h->w_px.as<double>(), n, d_fine, kchunk);   \
     } while (0)
+#define FINE32(DSV)                                                                                             \
+    do {                                                                                                        \
+        const size_t sm3 = (size_t)mv.K * DSV * 4;                                                              \
+        k_fine_argmin32<DSV><<<b2, FINE_THREADS, sm3, h->stream>>>(mv, h->w_px.as<double>(), n, d_fine, h->d_nguard); \
+    } while (0)
+        const bool f32stage = h->fine_mode == 0 && n >= 2048;    // float32 first stage + float64 guard (same codes)
         switch (mv.ds) {
-            case 2: FINE(2); break;
-            case 4: FINE(4); break;
-            case 8: FINE(8); break;
-            case 16: FINE(16); break;
+            case 2: if (f32stage) FINE32(2); else FINE(2); break;
+            case 4: if (f32stage) FINE32(4); else FINE(4); break;
+            case 8: if (f32stage) FINE32(8); else FINE(8); break;
+            case 16: if (f32stage) FINE32(16); else FINE(16); break;
             default:
                 if (mv.ds > 128) FAIL(B2L_ERR_UNSUPPORTED, "sub-vector length D/M = %d > 128 not supported", mv.ds);
                 FINE(0);
         }
+#undef FINE32
 #undef FINE
         LAUNCHED();
     }
@@ -400,6 +437,7 @@ int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_
     for (int c = 0; c < ncell; ++c) gtotal += h->h_gsize[c];
     if (gtotal >= ((int64_t)1 << 32)) FAIL(B2L_ERR_UNSUPPORTED, "more than 2^32 indexed codes");
 
+    { cudaError_t pre = cudaGetLastError(); if (pre != cudaSuccess) FAIL(B2L_ERR_CUDA, "stale CUDA error at search entry: %s", cudaGetErrorString(pre)); }
     {   // next call record; if the ring wrapped onto a call that was never collected, collect it now
         b2l_ctx::CallRec& r = h->ring[h->seq % b2l_ctx::NREC];
         int rc2 = collect_call(h, r);
@@ -720,6 +758,7 @@ int b2l_create(int device, b2l_handle* out) {
         return B2L_ERR_CUDA;
     }
     h->num_sms = prop.multiProcessorCount;
+    if (cudaMalloc((void**)&h->d_nguard, 8) == cudaSuccess) cudaMemset(h->d_nguard, 0, 8);
     if (prop.major < 10) {
         g_create_error = "b2l_create: device is not sm_100 class (the library is built for sm_100a only)";
         delete h;
@@ -733,12 +772,13 @@ int b2l_destroy(b2l_handle h) {
     if (!h) return B2L_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    DevBuf* bufs[] = {&h->dCs, &h->dmus, &h->dRt, &h->dsubs, &h->dP, &h->dpmu, &h->m_coarse, &h->m_fine, &h->m_rowid, &h->codes,
+    DevBuf* bufs[] = {&h->dCs, &h->dmus, &h->dRt, &h->dsubs, &h->dsubs32, &h->dc2max, &h->dP, &h->dpmu, &h->m_coarse, &h->m_fine, &h->m_rowid, &h->codes,
                       &h->rowids, &h->cell_start, &h->lsize, &h->gsize, &h->sorted_first, &h->w_q, &h->w_xq, &h->w_px,
                       &h->w_coarse, &h->w_fine, &h->w_lut32, &h->w_lut64, &h->w_p64, &h->w_cellq, &h->w_cand, &h->w_gtab, &h->w_lut16, &h->w_quant, &h->w_plan,
                       &h->w_sort_a, &h->w_sort_b, &h->w_sort_tmp, &h->w_rec, &h->w_rec2, &h->w_out, &h->w_out2, &h->w_misc};
     for (DevBuf* b : bufs) b->release();
     if (h->h_out) cudaFreeHost(h->h_out);
+    if (h->d_nguard) cudaFree(h->d_nguard);
     for (int r = 0; r < b2l_ctx::NREC; ++r) {
         for (int i = 0; i < 5; ++i) if (h->ring[r].ev[i]) cudaEventDestroy(h->ring[r].ev[i]);
         if (h->ring[r].h_pc) cudaFreeHost(h->ring[r].h_pc);
@@ -779,6 +819,26 @@ int b2l_reset_stats(b2l_handle h) {
     if (rc) return rc;
     memset(&h->stats, 0, sizeof h->stats);
     return B2L_OK;
+}
+
+int b2l_set_fine_mode(b2l_handle h, int mode) {
+    if (!h || mode < 0 || mode > 1) return B2L_ERR_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->fine_mode = mode;
+    return B2L_OK;
+}
+
+int64_t b2l_encode_guard_count(b2l_handle h, int reset) {
+    if (!h) return B2L_ERR_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(cudaSetDevice(h->device));
+    unsigned long long v = 0;
+    if (h->d_nguard) {
+        CU(cudaMemcpyAsync(&v, h->d_nguard, 8, cudaMemcpyDeviceToHost, h->stream));
+        if (reset) CU(cudaMemsetAsync(h->d_nguard, 0, 8, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+    }
+    return (int64_t)v;
 }
 
 int b2l_set_scan_mode(b2l_handle h, int mode) {
@@ -833,7 +893,21 @@ int b2l_set_model(b2l_handle h, int D, int V, int M, int K, int coarse_is_f32, c
     CU(cudaMemcpyAsync(h->dmus.p, mus, nC * 8, cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(h->dRt.p, rt.data(), nR * 8, cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(h->dsubs.p, subs, nS * 8, cudaMemcpyHostToDevice, h->stream));
+    std::vector<float> s32(nS), c2(M);
+    for (int j = 0; j < M; ++j) {
+        double mx = 0.0;
+        for (int k = 0; k < K; ++k) {
+            double n2 = 0.0;
+            for (int d = 0; d < mv.ds; ++d) { const double v = subs[((size_t)j * K + k) * mv.ds + d]; n2 += v * v; s32[((size_t)j * K + k) * mv.ds + d] = (float)v; }
+            mx = std::max(mx, n2);
+        }
+        c2[j] = (float)(mx * 1.001 + 1e-30);
+    }
+    CU(h->dsubs32.reserve(nS * 4)); CU(h->dc2max.reserve((size_t)M * 4));
+    CU(cudaMemcpyAsync(h->dsubs32.p, s32.data(), nS * 4, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->dc2max.p, c2.data(), (size_t)M * 4, cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
+    mv.subs32 = h->dsubs32.as<float>(); mv.c2max = h->dc2max.as<float>();
     mv.Cs = h->dCs.as<double>(); mv.mus = h->dmus.as<double>(); mv.Rt = h->dRt.as<double>(); mv.subs = h->dsubs.as<double>();
     h->has_model = true; h->has_pca = false; h->dirty = true; h->global_set = false;
     return B2L_OK;

@@ -126,6 +126,112 @@ k_fine_argmin(ModelView mv, const double* __restrict__ PX, int64_t n, uint8_t* _
     }
 }
 
+// ---- coarse assignment alone, 8 lanes per centroid ------------------------------------------------
+// predict_coarse (model.py:563-573 -> utils.py:33-53) for h % 8 == 0, h <= 128: NumPy's pairwise sum of such a row is
+// eight strided accumulators r_j = sum_i term(j + 8 i) combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)).  Lane (v, j)
+// builds r_j of centroid v and an xor-butterfly over the 8 lanes performs exactly those additions (IEEE addition is
+// commutative), so the distance bits equal sqdist_np's -- with 8x the lanes busy of the one-lane-per-centroid form.
+template <typename XT, typename T>
+__device__ __forceinline__ void coarse_argmin_split(const ModelView& mv, const XT* x, int s, int lane, int& bestv_out) {
+    const int h = mv.h, V = mv.V;
+    T best = (T)3.0e38;
+    int bestv = 0x7fffffff;
+    for (int t0 = 0; t0 < V * 8; t0 += 32) {
+        const int task = t0 + lane, v = task >> 3, j = task & 7;
+        T r = (T)0;
+        if (v < V) {
+            const double* C = mv.Cs + ((int64_t)s * V + v) * h;
+            for (int i = j; i < h; i += 8) {
+                const T t = Ex<T>::sub((T)x[s * h + i], (T)C[i]);
+                const T sq = Ex<T>::mul(t, t);
+                r = (i == j) ? sq : Ex<T>::add(r, sq);
+            }
+        }
+        r = Ex<T>::add(r, __shfl_xor_sync(0xffffffffu, r, 1));
+        r = Ex<T>::add(r, __shfl_xor_sync(0xffffffffu, r, 2));
+        r = Ex<T>::add(r, __shfl_xor_sync(0xffffffffu, r, 4));
+        if (v < V && (r < best || (r == best && v < bestv))) { best = r; bestv = v; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const T ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int ov = __shfl_xor_sync(0xffffffffu, bestv, o);
+        if (ob < best || (ob == best && ov < bestv)) { best = ob; bestv = ov; }
+    }
+    bestv_out = bestv;
+}
+
+template <typename XT>
+__global__ void __launch_bounds__(ENC_WARPS * 32)
+k_coarse_assign(ModelView mv, const XT* __restrict__ X, int64_t n, int32_t* __restrict__ coarse_out) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t i = (int64_t)blockIdx.x * ENC_WARPS + warp;
+    if (i >= n) return;
+    const XT* x = X + i * (int64_t)mv.D;
+    const bool f32 = (sizeof(XT) == 4) && mv.coarse_f32;
+    for (int s = 0; s < 2; ++s) {
+        int c;
+        if (f32) coarse_argmin_split<XT, float>(mv, x, s, lane, c);
+        else coarse_argmin_split<XT, double>(mv, x, s, lane, c);
+        if (lane == 0) coarse_out[i * 2 + s] = c;
+    }
+}
+
+// ---- fine argmin, float32 first stage with a float64 guard ------------------------------------------
+// Same result as k_fine_argmin (bit-exact with the reference), 3x less work on the float64 pipe: every distance is first
+// evaluated in float32 (FSUB + FFMA); the float32 winner is accepted only if the runner-up is farther than a rigorous
+// bound on the float32 evaluation error of both,
+//     |d32 - d| <= E(d) = 8 * 2^-24 * ( sqrt(d * (|p|^2 + max_k |c_k|^2)) + ds * d )
+// (input rounding of p and c, the subtraction, the products and the FMA chain; Cauchy-Schwarz on the cross terms).
+// Otherwise -- a near tie or an exact tie, a few rows per 100 000 -- that sub-vector is redone in float64 in NumPy's
+// order with the first-minimum rule (utils.py:33-53).
+template <int DS>
+__global__ void __launch_bounds__(FINE_THREADS)
+k_fine_argmin32(ModelView mv, const double* __restrict__ PX, int64_t n, uint8_t* __restrict__ fine, unsigned long long* __restrict__ nguard) {
+    extern __shared__ float sm_sub32[];   // [K][DS]
+    const int64_t i = (int64_t)blockIdx.x * FINE_THREADS + threadIdx.x;
+    const bool live = i < n;
+    const float U8 = 8.0f * 5.9604645e-08f;
+    unsigned int guards = 0;
+    for (int j = 0; j < mv.M; ++j) {
+        __syncthreads();
+        const float* src = mv.subs32 + (int64_t)j * mv.K * DS;
+        for (int e = threadIdx.x; e < mv.K * DS; e += FINE_THREADS) sm_sub32[e] = src[e];
+        __syncthreads();
+        if (!live) continue;
+        const double* p64 = PX + i * (int64_t)mv.D + (int64_t)j * DS;
+        float p[DS];
+        float p2 = 0.0f;
+#pragma unroll
+        for (int d = 0; d < DS; ++d) { p[d] = (float)p64[d]; p2 = fmaf(p[d], p[d], p2); }
+        float best = 3.0e38f, second = 3.0e38f;
+        int bestk = 0;
+#pragma unroll 4
+        for (int k = 0; k < mv.K; ++k) {
+            const float* c = sm_sub32 + k * DS;
+            float d = 0.0f;
+#pragma unroll
+            for (int t = 0; t < DS; ++t) { const float df = p[t] - c[t]; d = fmaf(df, df, d); }
+            if (d < best) { second = best; best = d; bestk = k; }
+            else second = fminf(second, d);
+        }
+        const float s2 = (p2 + mv.c2max[j]) * 1.0001f + 1e-30f;
+        const float err = U8 * (sqrtf(second * s2) + (float)DS * second) + 1e-13f * s2;
+        if (!(second - best > 2.0f * err)) {           // cannot be proven in float32: exact evaluation of this sub-vector
+            double pj[DS];
+#pragma unroll
+            for (int d = 0; d < DS; ++d) pj[d] = p64[d];
+            double b64 = 1e300;
+            for (int k = 0; k < mv.K; ++k) {
+                const double d64 = sqdist_np<double>(pj, mv.subs + ((int64_t)j * mv.K + k) * DS, DS);
+                if (d64 < b64) { b64 = d64; bestk = k; }
+            }
+            ++guards;
+        }
+        fine[i * (int64_t)mv.M + j] = (uint8_t)bestk;
+    }
+    if (guards && nguard) atomicAdd(nguard, (unsigned long long)guards);
+}
+
 // ---- float64 LUT rows for explicit probes (get_subquantizer_distances, model.py:673-704) ------
 // one block per vector, thread per sub-centroid; lut [n][M][K] float64
 __global__ void __launch_bounds__(256)
@@ -138,4 +244,122 @@ k_lut64_probe(ModelView mv, const double* __restrict__ PX, int64_t n, double* __
             const double* c = mv.subs + ((int64_t)j * mv.K + k) * mv.ds;
             lut[(i * mv.M + j) * (int64_t)mv.K + k] = sqdist_np<double>(p, c, mv.ds);
         }
+}
+
+// ---- batch rotation as a grouped float64 tensor-core GEMM ------------------------------------------
+// project (model.py:604-641) for a whole batch: rows are bucketed by (split, coarse code); every bucket is the dense
+// contraction  P[rows, h] = Resid[rows, h] . R[c]^T  and runs on the float64 tensor cores (mma.sync m8n8k4 f64,
+// DMMA in SASS) with R[c] and a 64-row residual tile staged in shared memory -- instead of one mat-vec per row
+// re-reading R[c] from L2 (k_coarse_project).  float64 throughout, so codes stay bit-comparable with the reference
+// up to the summation order of the rotation (the reference's own order is BLAS-defined).
+// Buckets: cnt / base / tile_base are indexed by b = s*V + c;  perm[s][.] lists the rows of split s bucket by bucket.
+
+__global__ void k_enc_hist(const int32_t* __restrict__ coarse, int64_t n, int V, unsigned int* __restrict__ cnt) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ((n + 31) / 32) * 32; i += (int64_t)gridDim.x * blockDim.x) {
+        const bool live = i < n;
+        for (int s = 0; s < 2; ++s) {
+            const int c = live ? coarse[2 * i + s] : -1;
+            const unsigned int peers = __match_any_sync(0xffffffffu, c);
+            if (live && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&cnt[s * V + c], (unsigned)__popc(peers));
+        }
+    }
+}
+
+// single block: per split, exclusive prefix of the bucket sizes (row offsets) and of their 64-row tile counts
+__global__ void k_enc_offsets(int V, const unsigned int* __restrict__ cnt, unsigned int* __restrict__ base,
+                              unsigned int* __restrict__ cursor, unsigned int* __restrict__ tile_base) {
+    if (threadIdx.x != 0) return;
+    unsigned int tiles = 0;
+    for (int s = 0; s < 2; ++s) {
+        unsigned int rows = 0;
+        for (int c = 0; c < V; ++c) {
+            const int b = s * V + c;
+            base[b] = rows; cursor[b] = 0u; tile_base[b] = tiles;
+            rows += cnt[b];
+            tiles += (cnt[b] + 63u) / 64u;
+        }
+    }
+    tile_base[2 * V] = tiles;
+}
+
+__global__ void k_enc_scatter(const int32_t* __restrict__ coarse, int64_t n, int V, const unsigned int* __restrict__ base,
+                              unsigned int* __restrict__ cursor, unsigned int* __restrict__ perm) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ((n + 31) / 32) * 32; i += (int64_t)gridDim.x * blockDim.x) {
+        const bool live = i < n;
+        const int lane = threadIdx.x & 31;
+        for (int s = 0; s < 2; ++s) {
+            const int c = live ? coarse[2 * i + s] : -1;
+            const unsigned int peers = __match_any_sync(0xffffffffu, c);
+            const int leader = __ffs(peers) - 1;
+            unsigned int start = 0;
+            if (live && lane == leader) start = atomicAdd(&cursor[s * V + c], (unsigned)__popc(peers));
+            start = __shfl_sync(0xffffffffu, start, leader);
+            if (live) perm[(size_t)s * n + base[s * V + c] + start + __popc(peers & ((1u << lane) - 1u))] = (unsigned int)i;
+        }
+    }
+}
+
+__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// one block (4 warps) per 64-row tile of one bucket; h == 64.  dynamic smem: Rt[64][68] | resid[64][68] doubles | rows[64] int
+#define ROT_H 64
+#define ROT_LD 68
+template <typename XT>
+__global__ void __launch_bounds__(128)
+k_rotate_dmma(ModelView mv, const XT* __restrict__ X, int64_t n, const unsigned int* __restrict__ cnt,
+              const unsigned int* __restrict__ base, const unsigned int* __restrict__ tile_base, const unsigned int* __restrict__ perm,
+              double* __restrict__ PX) {
+    extern __shared__ double sm_rot[];
+    double* Rs = sm_rot;                       // Rs[d][t] = Rt[d][t]
+    double* Es = sm_rot + ROT_H * ROT_LD;      // Es[row][d]
+    int* rows = (int*)(Es + ROT_H * ROT_LD);
+    const int V = mv.V, nb = 2 * V;
+    const unsigned int tile = blockIdx.x;
+    if (tile >= tile_base[nb]) return;
+    int lo = 0, hi = nb;                       // tile_base[lo] <= tile < tile_base[hi]
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (tile_base[mid] <= tile) lo = mid; else hi = mid; }
+    const int b = lo, s = b / V;
+    const unsigned int row0 = (tile - tile_base[b]) * 64u;
+    const int nrow = (int)min(64u, cnt[b] - row0);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const double* Rt = mv.Rt + (int64_t)b * ROT_H * ROT_H;
+    const double* C = mv.Cs + (int64_t)b * ROT_H;
+    const double* mu = mv.mus + (int64_t)b * ROT_H;
+    if (tid < 64) rows[tid] = tid < nrow ? (int)perm[(size_t)s * n + base[b] + row0 + tid] : -1;
+    for (int e = tid; e < ROT_H * ROT_H; e += 128) Rs[(e >> 6) * ROT_LD + (e & 63)] = Rt[e];
+    __syncthreads();
+    for (int e = tid; e < ROT_H * ROT_H; e += 128) {
+        const int r = e >> 6, d = e & 63;
+        const int i = rows[r];
+        Es[r * ROT_LD + d] = i >= 0 ? coarse_residual<XT>(X[(int64_t)i * mv.D + s * ROT_H + d], C[d], mu[d], mv.coarse_f32) : 0.0;
+    }
+    __syncthreads();
+    double acc[2][8][2];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) { acc[mt][nt][0] = 0.0; acc[mt][nt][1] = 0.0; }
+    const int ar = lane >> 2, ak = lane & 3;
+#pragma unroll 4
+    for (int k0 = 0; k0 < ROT_H; k0 += 4) {
+        double a[2], bb[8];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) a[mt] = Es[(16 * warp + 8 * mt + ar) * ROT_LD + k0 + ak];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) bb[nt] = Rs[(k0 + ak) * ROT_LD + 8 * nt + ar];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], a[mt], bb[nt]);
+    }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+        const int i = rows[16 * warp + 8 * mt + ar];
+        if (i < 0) continue;
+        double* o = PX + (int64_t)i * mv.D + s * ROT_H + 2 * ak;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) *(double2*)(o + 8 * nt) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+    }
 }

@@ -67,6 +67,11 @@ int b2l_set_pca(b2l_handle h, int D0, const double* P, const double* mu, int ren
  * (predict_coarse, model.py:563-573; utils.predict_cluster, utils.py:33-53). */
 int b2l_encode(b2l_handle h, const void* X, int x_is_f64, int64_t n, int on_device,
                int32_t* coarse, uint8_t* fine);
+/* Fine-argmin arithmetic of b2l_encode.  0 (default): every distance first in float32, the winner accepted only when a
+ * rigorous bound on the float32 error separates it from the runner-up, otherwise that sub-vector is redone in float64
+ * (same codes, ~3x less float64 work).  1: float64 only.  b2l_encode_guard_count: sub-vectors redone in float64 so far. */
+int     b2l_set_fine_mode(b2l_handle h, int mode);
+int64_t b2l_encode_guard_count(b2l_handle h, int reset);
 /* apply_PCA alone (model.py:961-978): Y [n][D] float32. */
 int b2l_apply_pca(b2l_handle h, const void* X, int x_is_f64, int64_t n, int on_device, float* Y);
 /* LOPQModel.project (model.py:604-641) and get_subquantizer_distances (model.py:673-704) for
