@@ -57,7 +57,7 @@ class OracleShardHandle(object):
         assert not on_device
         Q = np.asarray(Q)
         nq = Q.shape[0]
-        self.calls.append(("local", nq, bool(exact)))
+        self.calls.append(("local", nq, int(exact)))
         buf = (ctypes.c_uint8 * self.records_bytes(nq, k)).from_address(records_ptr)
         raw = np.frombuffer(buf, dtype=np.uint8)
         raw[:] = 0
@@ -84,7 +84,10 @@ class OracleShardHandle(object):
             ents.sort(key=lambda e: (e[0], e[1]))
             ents = ents[:k]
             o = qi * (REC_Q + k * REC_E)
-            hdr = np.array([len(ents), visited, int((not exact) and qi in self.force_uncertified), 0], np.int32)
+            # stage 0 (default scan): the forced queries come back uncertified; stage 2 (float32-table re-run): the second
+            # query of the re-run still does; stage 1 (exact) certifies everything
+            unc = (int(exact) == 0 and qi in self.force_uncertified) or (int(exact) == 2 and qi == 1)
+            hdr = np.array([len(ents), visited, int(unc), 0], np.int32)
             raw[o:o + REC_Q] = hdr.view(np.uint8)
             if ents:
                 e = np.zeros(len(ents), dtype=[("d", "<f8"), ("p", "<i8"), ("r", "<i8")])
@@ -149,7 +152,7 @@ def _rank_main(rank, world, port, retq):
         out = s.search_batch(Q[:nq], quota=700, limit=10)
         gs = np.bincount(cell, minlength=omodel.V ** 2)
         assert np.array_equal(h.gsize, gs), "global cell sizes after the all-reduce"
-        retq.put((rank, out["ids"], out["dist"], out["visited"], out["count"], out["exact_queries"], h.calls))
+        retq.put((rank, out["ids"], out["dist"], out["visited"], out["count"], (out["exact_queries"], out["rescan_queries"]), h.calls))
     finally:
         dist.destroy_process_group()
 
@@ -184,8 +187,8 @@ def test_sharded_search_world2_gloo():
             assert np.array_equal(ids[i][:len(e_ids)], e_ids), "rank %d query %d ids" % (rank, i)
             assert np.array_equal(dist_[i][:len(e_ids)], e_d), "rank %d query %d dists" % (rank, i)
             assert visited[i] == e_vis
-        # the two queries flagged uncertified were re-run exactly, once, as one extra local+merge round
-        assert exact_q == 2
-        assert calls == [("local", nq, False), ("merge", world, nq), ("local", 2, True), ("merge", world, 2)]
+        # the two queries flagged uncertified were re-run with float32 tables, the one still uncertified exactly
+        assert exact_q == (1, 2)
+        assert calls == [("local", nq, 0), ("merge", world, nq), ("local", 2, 2), ("merge", world, 2), ("local", 1, 1), ("merge", world, 1)]
     # identical on every rank
     assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
