@@ -56,6 +56,8 @@ SIGNATURES = {
     "b2l_records_bytes": (_i64, [_h, _i, _i]),
     "b2l_search_local": (_i, [_h, _vp, _i, _i, _i, _i64, _i, _i, _vp]),
     "b2l_search_merge": (_i, [_h, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b2l_merge_block_bytes": (_i64, [_h, _i, _i]),
+    "b2l_search_merge_block": (_i, [_h, _vp, _i, _i, _i, _vp, _i]),
     "b2l_get_stats": (_i, [_h, C.POINTER(Stats)]),
     "b2l_reset_stats": (_i, [_h]),
     "b2l_set_scan_mode": (_i, [_h, _i]),
@@ -287,6 +289,14 @@ class Handle(object):
                                               _ptr(out["dist"]), _ptr(out["coarse"]), _ptr(out["fine"]), _ptr(out["count"]),
                                               _ptr(out["visited"]), _ptr(out["certified"])))
         return out
+
+    def merge_block_bytes(self, nq, k):
+        return int(self._check(self.lib.b2l_merge_block_bytes(self.h, int(nq), int(k))))
+
+    def search_merge_block(self, records_all_ptr, nranks, nq, k, block_ptr, on_device=False):
+        """Merge into one packed block (layout: include/b200lopq.h); asynchronous when set_async(True)."""
+        self._check(self.lib.b2l_search_merge_block(self.h, _ptr(int(records_all_ptr)), int(nranks), int(nq), int(k),
+                                                    _ptr(int(block_ptr)), int(on_device)))
 
     def stats(self):
         s = Stats()

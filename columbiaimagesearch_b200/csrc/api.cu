@@ -378,7 +378,6 @@ int setup_plan(b2l_handle h, int nq, int segc, int nsegmax = 1, int nseg_cap = 1
     h->gthr = (unsigned int*)(b + o_gthr);
     h->cand_cnt = (unsigned int*)(b + o_ccnt);
     CU(cudaMemsetAsync(b, 0, zero_bytes, h->stream));
-    CU(cudaMemsetAsync(h->gthr, 0x7f, (size_t)nq * 4, h->stream));     // 0x7f7f7f7f = 3.4e38: "no bound yet"
     return B2L_OK;
 }
 
@@ -503,10 +502,27 @@ int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_
     if (rc) return rc;
     if (fast) h->cr->segc = segc;
     PlanView& pv = h->pv;
+    // per-query scratch of the fast path (bounds, bound tables, quantiser ranges): initialised by k_coarse_order
+    QuantView qv = {};
+    InitView iv = {};
+    iv.gthr = h->gthr;
+    if (fast) {
+        CU(h->w_gtab.reserve((size_t)nq * LPS * GEN * 4));
+        iv.gtab = h->w_gtab.as<unsigned int>(); iv.E = LPS * GEN;
+    }
+    if (packed) {
+        const size_t o_qmin = 0, o_qmax = align256((size_t)nq * mv.M * 4), o_B = o_qmax + align256((size_t)nq * 4),
+                     o_dl = o_B + align256((size_t)nq * 8), qbytes = o_dl + align256((size_t)nq * 8);
+        CU(h->w_quant.reserve(qbytes));
+        unsigned char* qb = h->w_quant.as<unsigned char>();
+        qv.qmin = (unsigned int*)(qb + o_qmin); qv.qmax = (unsigned int*)(qb + o_qmax);
+        qv.B = (double*)(qb + o_B); qv.delta = (double*)(qb + o_dl); qv.qmax_code = 65535 / mv.M;
+        iv.qmin = qv.qmin; iv.qmax = qv.qmax; iv.M = mv.M;
+    }
     {
         const size_t smem = (size_t)(3 * mv.V + 2) * 8 + (size_t)(7 * mv.V + 4) * 4 + 16;
-        if (xf64) k_coarse_order<double><<<nq, 32, smem, h->stream>>>(mv, (const double*)x, quota, h->gsize.as<int64_t>(), h->lsize.as<int64_t>(), pv);
-        else k_coarse_order<float><<<nq, 32, smem, h->stream>>>(mv, (const float*)x, quota, h->gsize.as<int64_t>(), h->lsize.as<int64_t>(), pv);
+        if (xf64) k_coarse_order<double><<<nq, 32, smem, h->stream>>>(mv, (const double*)x, quota, h->gsize.as<int64_t>(), h->lsize.as<int64_t>(), pv, iv);
+        else k_coarse_order<float><<<nq, 32, smem, h->stream>>>(mv, (const float*)x, quota, h->gsize.as<int64_t>(), h->lsize.as<int64_t>(), pv, iv);
         LAUNCHED();
     }
     if (fast) {
@@ -536,19 +552,7 @@ int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_
     double* lut64 = nullptr;
     if (fast) { CU(h->w_lut32.reserve(cap_lut * B2L_LUT_ROWS * mv.m * 4)); lut32 = h->w_lut32.as<float>(); }
     else { CU(h->w_lut64.reserve(cap_lut * mv.m * mv.K * 8)); lut64 = h->w_lut64.as<double>(); }
-    QuantView qv = {};
-    if (packed) {
-        // 16-bit tables: per-query bias / step from the ranges of the float32 tables, then the codes
-        const size_t o_qmin = 0, o_qmax = align256((size_t)nq * mv.M * 4), o_B = o_qmax + align256((size_t)nq * 4),
-                     o_dl = o_B + align256((size_t)nq * 8), qbytes = o_dl + align256((size_t)nq * 8);
-        CU(h->w_quant.reserve(qbytes));
-        CU(h->w_lut16.reserve(cap_lut * B2L_LUT_ROWS * mv.m * 2));
-        unsigned char* qb = h->w_quant.as<unsigned char>();
-        qv.qmin = (unsigned int*)(qb + o_qmin); qv.qmax = (unsigned int*)(qb + o_qmax);
-        qv.B = (double*)(qb + o_B); qv.delta = (double*)(qb + o_dl); qv.qmax_code = 65535 / mv.M;
-        CU(cudaMemsetAsync(qv.qmin, 0xFF, (size_t)nq * mv.M * 4, h->stream));
-        CU(cudaMemsetAsync(qv.qmax, 0, (size_t)nq * 4, h->stream));
-    }
+    if (packed) CU(h->w_lut16.reserve(cap_lut * B2L_LUT_ROWS * mv.m * 2));
     if (nosync || pc.n_lut) {
         const size_t smem = (size_t)(2 * mv.h + LUT_THREADS) * 8;
         const unsigned lgrid = (unsigned)std::min<size_t>(cap_lut, (size_t)h->num_sms * 8);
@@ -596,8 +600,6 @@ int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_
     if (fast) {
         CU(h->w_cellq.reserve(cap_pairs * 8));
         CU(h->w_cand.reserve((size_t)nq * SCAN_CAND_CAP * 8));
-        CU(h->w_gtab.reserve((size_t)nq * LPS * GEN * 4));
-        CU(cudaMemsetAsync(h->w_gtab.p, 0x7f, (size_t)nq * LPS * GEN * 4, h->stream));      // 3.39e38: "nothing seen"
 
         pv.cellq = h->w_cellq.as<int2>();
         k_fill<<<(nq + 255) / 256, 256, 0, h->stream>>>(pv);
@@ -701,7 +703,6 @@ int merge_impl(b2l_handle h, const void* d_recs, int nranks, int nq, int k, int 
         unsigned char* b = h->w_out.as<unsigned char>();
         d_rowid = (int64_t*)(b + o1); d_dist = (double*)(b + o2); d_coarse = (int32_t*)(b + o3); d_fine = b + o4;
         d_count = (int32_t*)(b + o5); d_visited = (int32_t*)(b + o6); d_cert = b + o7;
-        CU(cudaMemsetAsync(b, 0, off, h->stream));
     }
     CU(cudaFuncSetAttribute(k_final, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_final<<<nq, 128, smem, h->stream>>>(mv.V, mv.M, d_recs, nranks, nq, k, n, d_rowid, d_dist, d_coarse, d_fine, d_count,
@@ -1125,8 +1126,8 @@ int b2l_cell_order(b2l_handle h, const void* Q, int q_is_f64, int nq, int64_t qu
     CU(h->w_misc.reserve((size_t)nq * maxvis * 8));
     pv.vis_dist = h->w_misc.as<double>();
     const size_t smem = (size_t)(3 * mv.V + 2) * 8 + (size_t)(7 * mv.V + 4) * 4 + 16;
-    if (q_is_f64) k_coarse_order<double><<<nq, 32, smem, h->stream>>>(mv, h->w_q.as<double>(), quota, h->gsize.as<int64_t>(), h->lsize.as<int64_t>(), pv);
-    else k_coarse_order<float><<<nq, 32, smem, h->stream>>>(mv, h->w_q.as<float>(), quota, h->gsize.as<int64_t>(), h->lsize.as<int64_t>(), pv);
+    if (q_is_f64) k_coarse_order<double><<<nq, 32, smem, h->stream>>>(mv, h->w_q.as<double>(), quota, h->gsize.as<int64_t>(), h->lsize.as<int64_t>(), pv, InitView());
+    else k_coarse_order<float><<<nq, 32, smem, h->stream>>>(mv, h->w_q.as<float>(), quota, h->gsize.as<int64_t>(), h->lsize.as<int64_t>(), pv, InitView());
     LAUNCHED();
     if (cells) CU(cudaMemcpyAsync(cells, pv.vis_cell, (size_t)nq * maxvis * 4, cudaMemcpyDeviceToHost, h->stream));
     if (dists) CU(cudaMemcpyAsync(dists, pv.vis_dist, (size_t)nq * maxvis * 8, cudaMemcpyDeviceToHost, h->stream));
@@ -1158,6 +1159,33 @@ int b2l_search_merge(b2l_handle h, const void* d_records_all, int nranks, int nq
                       !h->async_mode);
 }
 
+int64_t b2l_merge_block_bytes(b2l_handle h, int nq, int k) {
+    if (!h || !h->has_model || nq < 1 || k < 1) return -1;
+    const size_t nk = (size_t)nq * k;
+    return (int64_t)(3 * align256(nk * 8) + align256(nk * h->mv.M) + 2 * align256((size_t)nq * 4) + align256((size_t)nq));
+}
+
+int b2l_search_merge_block(b2l_handle h, const void* d_records_all, int nranks, int nq, int k, void* block, int on_device) {
+    if (!h || !block) return B2L_ERR_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(cudaSetDevice(h->device));
+    if (!h->has_model) FAIL(B2L_ERR_STATE, "no model set");
+    const ModelView& mv = h->mv;
+    const size_t nk = (size_t)nq * k;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes); return o; };
+    const size_t o1 = take(nk * 8), o2 = take(nk * 8), o3 = take(nk * 8), o4 = take(nk * mv.M), o5 = take((size_t)nq * 4),
+                 o6 = take((size_t)nq * 4), o7 = take((size_t)nq);
+    unsigned char* b = (unsigned char*)block;
+    if (!on_device) { CU(h->w_out.reserve(off)); b = h->w_out.as<unsigned char>(); }
+    int rc = merge_impl(h, d_records_all, nranks, nq, k, 1, (int64_t*)(b + o1), (double*)(b + o2), (int32_t*)(b + o3), b + o4,
+                        (int32_t*)(b + o5), (int32_t*)(b + o6), b + o7, false);
+    if (rc) return rc;
+    if (!on_device) CU(cudaMemcpyAsync(block, b, off, cudaMemcpyDeviceToHost, h->stream));
+    if (!h->async_mode) CU(cudaStreamSynchronize(h->stream));
+    return B2L_OK;
+}
+
 int b2l_search(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_device, int64_t quota, int k, int64_t* rowid,
                double* dist, int32_t* coarse, uint8_t* fine, int32_t* count, int32_t* visited) {
     if (!h) return B2L_ERR_ARG;
@@ -1180,7 +1208,6 @@ int b2l_search(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_device,
     unsigned char* b = h->w_out2.as<unsigned char>();
     int64_t* d_rowid = (int64_t*)(b + o1); double* d_dist = (double*)(b + o2); int32_t* d_coarse = (int32_t*)(b + o3);
     uint8_t* d_fine = b + o4; int32_t* d_count = (int32_t*)(b + o5); int32_t* d_visited = (int32_t*)(b + o6); uint8_t* d_cert = b + o7;
-    CU(cudaMemsetAsync(b, 0, off, h->stream));
     rc = merge_impl(h, h->w_rec.p, 1, nq, k, 1, d_rowid, d_dist, d_coarse, d_fine, d_count, d_visited, d_cert, false);
     if (rc) return rc;
     // host side: the whole block comes back in one copy into pinned staging (device-resident callers: flags only)
@@ -1221,7 +1248,6 @@ int b2l_search(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_device,
                      s6 = stake((size_t)ns * 4), s7 = stake((size_t)ns);
         CU(h->w_out.reserve(so));
         unsigned char* sb = h->w_out.as<unsigned char>();
-        CU(cudaMemsetAsync(sb, 0, so, h->stream));
         rc = merge_impl(h, h->w_rec2.p, 1, ns, k, 1, (int64_t*)(sb + s1), (double*)(sb + s2), (int32_t*)(sb + s3), sb + s4,
                         (int32_t*)(sb + s5), (int32_t*)(sb + s6), sb + s7, false);
         if (rc) return rc;

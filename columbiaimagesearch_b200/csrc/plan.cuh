@@ -37,12 +37,22 @@ struct PlanView {                   // per-batch device arrays, maxvis = V*V
     PlanCounters* cnt;
 };
 
+// per-query scratch the later kernels expect initialised; done by the query's own block of k_coarse_order instead of
+// one memset per array (all pointers may be NULL)
+struct InitView {
+    unsigned int* gthr;     // [nq]      <- "no bound yet"
+    unsigned int* gtab;     // [nq][E]   <- "nothing seen"
+    unsigned int* qmin;     // [nq][M]   <- +inf pattern
+    unsigned int* qmax;     // [nq]      <- 0
+    int E, M;
+};
+
 // ---- cell order + quota: one warp per query ---------------------------------------------------
 // shared memory per block: d[2V] double, hd[V+2] double, ord[2V], pc[V], hi0[V+2], hi1[V+2], slotmap[2V] int
 template <typename XT>
 __global__ void __launch_bounds__(32)
 k_coarse_order(ModelView mv, const XT* __restrict__ Xq, int64_t quota,
-               const int64_t* __restrict__ gsize, const int64_t* __restrict__ lsize, PlanView pv) {
+               const int64_t* __restrict__ gsize, const int64_t* __restrict__ lsize, PlanView pv, InitView iv) {
     extern __shared__ double sm_co[];
     const int V = mv.V, h = mv.h;
     double* d = sm_co;                       // [2][V]
@@ -55,6 +65,10 @@ k_coarse_order(ModelView mv, const XT* __restrict__ Xq, int64_t quota,
     const int q = blockIdx.x, lane = threadIdx.x;
     const XT* x = Xq + (int64_t)q * mv.D;
     const bool f32 = (sizeof(XT) == 4) && mv.coarse_f32;
+    if (iv.gthr && lane == 0) iv.gthr[q] = 0x7f7f7f7fu;
+    if (iv.qmax && lane == 0) iv.qmax[q] = 0u;
+    if (iv.gtab) for (int e = lane; e < iv.E; e += 32) iv.gtab[(size_t)q * iv.E + e] = 0x7f7f7f7fu;
+    if (iv.qmin) for (int e = lane; e < iv.M; e += 32) iv.qmin[(size_t)q * iv.M + e] = 0xFFFFFFFFu;
 
     for (int idx = lane; idx < 2 * V; idx += 32) {
         const int s = idx / V;

@@ -323,6 +323,13 @@ k_final(int V, int M, const void* __restrict__ recs_all, int nranks, int nq, int
         if (coarse) { coarse[d * 2] = rv.cell[s] / V; coarse[d * 2 + 1] = rv.cell[s] % V; }
         if (fine) for (int t = 0; t < M; ++t) fine[d * M + t] = rv.fine[s * M + t];
     }
+    for (int i = nout + tid; i < k; i += blockDim.x) {           // rows beyond the count come back zero-filled
+        const int64_t d = (int64_t)q * k + i;
+        if (rowid) rowid[d] = 0;
+        if (dist) dist[d] = 0.0;
+        if (coarse) { coarse[d * 2] = 0; coarse[d * 2 + 1] = 0; }
+        if (fine) for (int t = 0; t < M; ++t) fine[d * M + t] = 0;
+    }
     if (tid == 0) {
         RecView r0 = rec_view((unsigned char*)recs_all, nq, k, M);
         count[q] = nout;

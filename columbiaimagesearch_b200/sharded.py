@@ -124,6 +124,7 @@ class ShardedLOPQSearcher(object):
                                  ("visited", nq * 4), ("certified", nq)):
                 offs[name] = off
                 off += a256(nbytes)
+            assert off == self._handle.merge_block_bytes(nq, k)
             nbytes = self._handle.records_bytes(nq, k)
             sets = []
             for _ in range(3):
@@ -172,8 +173,7 @@ class ShardedLOPQSearcher(object):
             allrec = b["allrec"]
         else:
             allrec = b["rec"]
-        h.search_merge_ptrs(allrec.data_ptr(), self.world, nq, k, base + o["rowid"], base + o["dist"], base + o["coarse"],
-                            base + o["fine"], base + o["count"], base + o["visited"], base + o["certified"], on_device=False)
+        h.search_merge_block(allrec.data_ptr(), self.world, nq, k, base, on_device=False)      # one copy, same layout as `offs`
         b["event"].record(self._stream)
         return _PendingSearch(self, b, X, nq, k, quota)
 

@@ -136,6 +136,13 @@ int b2l_search_merge(b2l_handle h, const void* d_records_all, int nranks, int nq
                      int64_t* rowid, double* dist, int32_t* coarse, uint8_t* fine,
                      int32_t* count, int32_t* visited, uint8_t* certified);
 
+/* b2l_search_merge with all outputs in ONE block (one device-to-host copy instead of seven): fields in the order
+ * rowid [nq][k] i64 | dist [nq][k] f64 | coarse [nq][k][2] i32 | fine [nq][k][M] u8 | count [nq] i32 | visited [nq] i32 |
+ * certified [nq] u8, each starting on a 256-byte boundary; b2l_merge_block_bytes gives the total.  `block` is a host
+ * (pinned, in asynchronous mode) or device buffer. */
+int64_t b2l_merge_block_bytes(b2l_handle h, int nq, int k);
+int b2l_search_merge_block(b2l_handle h, const void* d_records_all, int nranks, int nq, int k, void* block, int on_device);
+
 /* ---- introspection (counters of the most recent b2l_search / b2l_search_local) ------------------ */
 typedef struct b2l_stats {
     double  scan_ms;          /* device time of the ADC scan kernel (CUDA events)            */
