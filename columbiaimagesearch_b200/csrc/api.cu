@@ -94,6 +94,7 @@ struct b2l_ctx {
     bool async_mode = false;
     int fb_nq = 0, fb_segc = 0;        // last collected fast search: batch size, segment length, work items it produced
     int64_t fb_items = 0;
+    float c2m = 0.0f;                  // max_j max_k |subs[j][k]|^2 (upper bound), for the float32 table error model
     int fine_mode = 0;                 // 0: float32 first stage + float64 guard in the fine argmin, 1: float64 only
     unsigned long long* d_nguard = nullptr;   // sub-vectors the guard re-evaluated in float64 (device counter)
     int scan_mode = 0;                 // 0: packed 16-bit tables first (default), 1: float32 tables only
@@ -512,11 +513,12 @@ int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_
     }
     if (packed) {
         const size_t o_qmin = 0, o_qmax = align256((size_t)nq * mv.M * 4), o_B = o_qmax + align256((size_t)nq * 4),
-                     o_dl = o_B + align256((size_t)nq * 8), qbytes = o_dl + align256((size_t)nq * 8);
+                     o_dl = o_B + align256((size_t)nq * 8), o_sl = o_dl + align256((size_t)nq * 8), qbytes = o_sl + align256((size_t)nq * 8);
         CU(h->w_quant.reserve(qbytes));
         unsigned char* qb = h->w_quant.as<unsigned char>();
         qv.qmin = (unsigned int*)(qb + o_qmin); qv.qmax = (unsigned int*)(qb + o_qmax);
-        qv.B = (double*)(qb + o_B); qv.delta = (double*)(qb + o_dl); qv.qmax_code = 65535 / mv.M;
+        qv.B = (double*)(qb + o_B); qv.delta = (double*)(qb + o_dl); qv.slack = (double*)(qb + o_sl); qv.qmax_code = 65535 / mv.M;
+        qv.ds = mv.ds; qv.c2m = h->c2m; qv.f32_entries = (mv.ds == 8 && mv.m == 8 && mv.K <= 256) ? 1 : 0;
         iv.qmin = qv.qmin; iv.qmax = qv.qmax; iv.M = mv.M;
     }
     {
@@ -571,7 +573,17 @@ int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_
         case 16: LUTK(XT, 16); break;             \
         default: LUTK(XT, 0);                     \
     }
-        if (fast && mv.ds == 8 && mv.m == 8 && mv.K <= 256) {
+        if (packed && qv.f32_entries) {
+            // headline shape, packed scan: float64 projection, table entries in float32 from the register-resident float32
+            // codebook (their evaluation error is part of the certification bound), column ranges reduced on the way
+            const size_t sm32 = (size_t)(2 * mv.h + 256) * 8 + (size_t)mv.h * 4;
+            const unsigned rgrid = (unsigned)(2 * h->num_sms);
+            if (xf64) k_lut_f32<double, 8, 8><<<rgrid, 256, sm32, h->stream>>>(mv, (const double*)x, pv.lut_desc, pv.cnt,
+                                                                              h->w_p64.as<double>(), lut32, qv.qmin, qv.qmax);
+            else k_lut_f32<float, 8, 8><<<rgrid, 256, sm32, h->stream>>>(mv, (const float*)x, pv.lut_desc, pv.cnt,
+                                                                          h->w_p64.as<double>(), lut32, qv.qmin, qv.qmax);
+            ranged = true;
+        } else if (fast && mv.ds == 8 && mv.m == 8 && mv.K <= 256) {
             // headline shape: sub-quantizer codebook register-resident, one block per SM bound to one coarse split;
             // the column ranges the 16-bit tables need are reduced on the way
             const size_t smr = (size_t)(2 * mv.h + LUTR_THREADS) * 8;
@@ -628,7 +640,7 @@ int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_
         CU(cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_select<<<nq, SEL_THREADS, smem, h->stream>>>(mv, ix, pv, h->w_cand.as<unsigned long long>(), h->cand_cnt, h->gthr,
                                                        SCAN_CAND_CAP, h->w_p64.as<double>(), KP, k, eps_rel, d_records,
-                                                       packed ? 1 : 0, qv.B, qv.delta);
+                                                       packed ? 1 : 0, qv.B, qv.delta, qv.slack);
         LAUNCHED();
         h->cr->st.packed = packed ? 1 : 0;
         CU(cudaEventRecord(h->cr->ev[4], h->stream));
@@ -903,6 +915,7 @@ int b2l_set_model(b2l_handle h, int D, int V, int M, int K, int coarse_is_f32, c
             mx = std::max(mx, n2);
         }
         c2[j] = (float)(mx * 1.001 + 1e-30);
+        h->c2m = std::max(j ? h->c2m : 0.0f, c2[j]);
     }
     CU(h->dsubs32.reserve(nS * 4)); CU(h->dc2max.reserve((size_t)M * 4));
     CU(cudaMemcpyAsync(h->dsubs32.p, s32.data(), nS * 4, cudaMemcpyHostToDevice, h->stream));

@@ -419,6 +419,101 @@ k_lut_reg(ModelView mv, const XT* __restrict__ Xq, const int32_t* __restrict__ l
     }
 }
 
+// ---- LUT entries in float32 (packed scan only) --------------------------------------------------------
+// The packed scan only needs table entries to within a stated error: its candidates are re-evaluated in float64 from
+// the float64 projection P64 and the exact sub-quantizer codebook (k_select).  So the 2048 entries of a table are
+// evaluated in float32 (FSUB + FFMA on the float32 codebook, register-resident: 8 sub-quantizers x 8 floats per
+// thread); the projection itself stays float64.  The evaluation error of an entry,
+//     |e32 - e| <= Emax = 8 * 2^-24 * (sqrt(emax * S2) + ds * emax) + 1e-13 * S2,   S2 >= |p|^2 + |c|^2,
+// is folded into the certification bound by k_lut_quant (QuantView::slack = M * Emax).
+// Block = 256 threads bound to one coarse split; needs m == MJ, ds == DS, K <= 256.
+// dynamic smem: r[h] | p[h] | psum[256] doubles | p32[h] floats
+template <typename XT, int DS, int MJ>
+__global__ void __launch_bounds__(256, 2)
+k_lut_f32(ModelView mv, const XT* __restrict__ Xq, const int32_t* __restrict__ lut_desc, const PlanCounters* __restrict__ cnt,
+          double* __restrict__ P64, float* __restrict__ lut32, unsigned int* __restrict__ qmin, unsigned int* __restrict__ qmax) {
+    extern __shared__ double sm_l32[];
+    __shared__ unsigned int s_cmin[MJ], s_cmax;
+    const int h = mv.h, V = mv.V;
+    double* r = sm_l32;
+    double* p = sm_l32 + h;
+    double* psum = p + h;
+    float* p32 = (float*)(psum + 256);
+    const int tid = threadIdx.x, k = tid, lane = tid & 31;
+    const int s = blockIdx.x & 1, nb = gridDim.x >> 1, b = blockIdx.x >> 1;
+    const int nslot = (int)cnt->n_lut;
+    const bool live = k < mv.K;
+    float cv[MJ][DS];
+#pragma unroll
+    for (int jj = 0; jj < MJ; ++jj) {
+        const float* cj = mv.subs32 + (((int64_t)s * MJ + jj) * mv.K + (live ? k : 0)) * DS;
+#pragma unroll
+        for (int d = 0; d < DS; ++d) cv[jj][d] = cj[d];
+    }
+    int parts = 1;                            // same split of the d range as k_lut (same float64 projection bits)
+    while (parts * 2 * h <= LUT_THREADS && parts * 2 <= h) parts *= 2;
+    const int tw = 256 / parts;
+    const int part = tid / tw, tl = tid - part * tw;
+    const int dlen = h / parts, d0 = part * dlen;
+    for (int slot = b; slot < nslot; slot += nb) {
+        if (lut_desc[3 * slot + 1] != s) continue;                            // block-uniform
+        __syncthreads();
+        const int q = lut_desc[3 * slot], c = lut_desc[3 * slot + 2];
+        const XT* x = Xq + (int64_t)q * mv.D + s * h;
+        const double* C = mv.Cs + ((int64_t)s * V + c) * h;
+        const double* mu = mv.mus + ((int64_t)s * V + c) * h;
+        for (int d = tid; d < h; d += 256) r[d] = coarse_residual<XT>(x[d], C[d], mu[d], mv.coarse_f32);
+        if (tid < MJ) s_cmin[tid] = 0xFFFFFFFFu;
+        if (tid == 0) s_cmax = 0u;
+        __syncthreads();
+        const double* Rt = mv.Rt + ((int64_t)s * V + c) * h * (int64_t)h;
+        for (int t0 = 0; t0 < h; t0 += tw) {
+            const int t = t0 + tl;
+            double acc = 0.0;
+            if (t < h) {
+#pragma unroll 8
+                for (int d = d0; d < d0 + dlen; ++d) acc = fma(Rt[(int64_t)d * h + t], r[d], acc);
+            }
+            if (parts == 1) { if (t < h) { p[t] = acc; p32[t] = (float)acc; P64[(int64_t)slot * h + t] = acc; } }
+            else {
+                psum[tid] = acc;
+                __syncthreads();
+                if (part == 0 && t < h) {
+                    double a = psum[tl];
+                    for (int pp = 1; pp < parts; ++pp) a += psum[pp * tw + tl];
+                    p[t] = a; p32[t] = (float)a; P64[(int64_t)slot * h + t] = a;
+                }
+                __syncthreads();
+            }
+        }
+        __syncthreads();
+        float e32[MJ];
+#pragma unroll
+        for (int jj = 0; jj < MJ; ++jj) {
+            float d = 0.0f;
+#pragma unroll
+            for (int t = 0; t < DS; ++t) { const float df = p32[jj * DS + t] - cv[jj][t]; d = fmaf(df, df, d); }
+            e32[jj] = live ? d : 0.0f;
+        }
+        float* o32 = lut32 + ((int64_t)slot * B2L_LUT_ROWS + k) * MJ;
+#pragma unroll
+        for (int jj = 0; jj < MJ; jj += 4) *(float4*)(o32 + jj) = make_float4(e32[jj], e32[jj + 1], e32[jj + 2], e32[jj + 3]);
+        unsigned int mx = 0u;
+#pragma unroll
+        for (int jj = 0; jj < MJ; ++jj) {
+            const unsigned int v = live ? __float_as_uint(e32[jj]) : 0xFFFFFFFFu;
+            const unsigned int wm = __reduce_min_sync(0xffffffffu, v);
+            if (lane == 0) atomicMin(&s_cmin[jj], wm);
+            mx = max(mx, live ? v : 0u);
+        }
+        mx = __reduce_max_sync(0xffffffffu, mx);
+        if (lane == 0) atomicMax(&s_cmax, mx);
+        __syncthreads();
+        if (tid < MJ) atomicMin(&qmin[(size_t)q * mv.M + s * MJ + tid], s_cmin[tid]);
+        if (tid == 0) atomicMax(&qmax[q], s_cmax);
+    }
+}
+
 // ---- 16-bit quantised tables for the packed scan ---------------------------------------------------
 // Per query q: bias b[q][j] = min over the query's tables of sub-quantizer j (both splits: j < M) and over the 256
 // centroids; step Delta[q] = (max entry - min bias) / QMAX * (1 + 2^-20); code = floor((e - b[q][j]) / Delta[q]),
@@ -430,7 +525,11 @@ struct QuantView {
     unsigned int* qmax;     // [nq]    float bits
     double* B;              // [nq]
     double* delta;          // [nq]
+    double* slack;          // [nq] M * (bound on the evaluation error of a table entry); 0 for the float64-built tables
     int qmax_code;          // QMAX
+    int f32_entries;        // the tables were evaluated in float32 (k_lut_f32)
+    int ds;                 // sub-vector length
+    float c2m;              // max_j max_k |subs[j][k]|^2 (upper bound)
 };
 
 // one block per LUT slot: ranges of its m columns -> per-query minima / maximum
@@ -482,6 +581,14 @@ k_lut_quant(int m, const int32_t* __restrict__ lut_desc, const PlanCounters* __r
             const double delta = (double)range / (double)qv.qmax_code * (1.0 + 9.5367431640625e-07);
             qv.delta[q] = delta;
             qv.B[q] = B;
+            double slack = 0.0;
+            if (qv.f32_entries) {                // evaluation error of the float32 entries (see k_lut_f32)
+                const float emax = __uint_as_float(qv.qmax[q]);
+                const float sp = sqrtf(emax) + sqrtf(qv.c2m);
+                const float S2 = (sp * sp + qv.c2m) * 1.001f;
+                slack = (double)M * ((double)(8.0f * 5.9604645e-08f) * ((double)sqrtf(emax * S2) + (double)qv.ds * (double)emax) * 1.01 + 1e-13 * (double)S2);
+            }
+            qv.slack[q] = slack;
             s_inv = (float)(1.0 / delta);
         }
         if (threadIdx.x < m) {

@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(SEL_THREADS, 4)
 k_select(ModelView mv, IndexView ix, PlanView pv, const unsigned long long* __restrict__ cand,
          const unsigned int* __restrict__ cand_cnt, const unsigned int* __restrict__ gthr, int cand_cap,
          const double* __restrict__ P64, int KP, int k, double eps_rel, void* recbuf,
-         int packed, const double* __restrict__ qB, const double* __restrict__ qDelta) {
+         int packed, const double* __restrict__ qB, const double* __restrict__ qDelta, const double* __restrict__ qSlack) {
     extern __shared__ __align__(16) unsigned char sm_sel[];
     unsigned long long* keys = (unsigned long long*)sm_sel;
     unsigned long long* dk = keys + SEL_LIST;
@@ -272,7 +272,7 @@ k_select(ModelView mv, IndexView ix, PlanView pv, const unsigned long long* __re
         if (lost) lb = -1.0;                                  // never certified: exact re-rank
         else if (pv.ncand_local[q] > (int64_t)ncoll) {        // some local candidates are not among the KP collected
             const unsigned int kb = (unsigned int)(keys[KP - 1] >> 32);
-            if (packed) lb = (qB[q] + qDelta[q] * ((double)kb - 1.0)) * (1.0 - 1e-6) - 1e-300;      // see plan.cuh (k_lut_quant)
+            if (packed) lb = (qB[q] + qDelta[q] * ((double)kb - 1.0) - qSlack[q]) * (1.0 - 1e-6) - 1e-300;      // see plan.cuh (k_lut_quant)
             else lb = (double)__uint_as_float(kb) * (1.0 - eps_rel) - 1e-300;
         }
         rv.lb[q] = lb;
