@@ -82,7 +82,7 @@ __device__ inline void bitonic_sort_dp(unsigned long long* dk, unsigned int* pk,
 #define SEL_HB 1024       // histogram buckets of the selection
 #define SEL_LIST 1024     // capacity of the boundary list that is actually sorted (>= KP)
 #define SEL_PART 2048     // float64 partial sums staged per chunk of candidates
-#define SEL_THREADS 256
+#define SEL_THREADS 128
 __host__ __device__ inline size_t select_smem_bytes(int KP) {
     return (size_t)SEL_LIST * 8 + (size_t)KP * 28 + (size_t)SEL_PART * 8 + (size_t)SEL_HB * 4 + 64;
 }
@@ -101,7 +101,7 @@ __device__ __forceinline__ int sel_bucket(unsigned int dbits, unsigned int lo_bi
 // reference's summation order, ordered by (dist64, retrieval position), and the first k emitted with the
 // certification bound.
 // dynamic smem: list[SEL_LIST] u64 | dk[KP] u64 | rows[KP] i64 | part[SEL_PART] f64 | pk[KP] u32 | idx[KP] int | vis[KP] int | hist[SEL_HB] u32
-__global__ void __launch_bounds__(SEL_THREADS, 4)
+__global__ void __launch_bounds__(SEL_THREADS, 8)
 k_select(ModelView mv, IndexView ix, PlanView pv, const unsigned long long* __restrict__ cand,
          const unsigned int* __restrict__ cand_cnt, const unsigned int* __restrict__ gthr, int cand_cap,
          const double* __restrict__ P64, int KP, int k, double eps_rel, void* recbuf,
