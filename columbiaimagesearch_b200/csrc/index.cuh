@@ -8,14 +8,20 @@
 
 __global__ void k_cell_ids(const int32_t* __restrict__ coarse, int64_t n, int V, unsigned int* __restrict__ cell,
                            unsigned int* __restrict__ order, unsigned long long* __restrict__ hist, int* __restrict__ bad) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const int c0 = coarse[2 * i], c1 = coarse[2 * i + 1];
-        unsigned int c = 0;
-        if (c0 < 0 || c0 >= V || c1 < 0 || c1 >= V) atomicExch(bad, 1);
-        else c = (unsigned)(c0 * V + c1);
-        cell[i] = c;
-        order[i] = (unsigned int)i;
-        atomicAdd(&hist[c], 1ull);
+    // (warp-aggregated histogram: the lanes of a warp that fall into the same cell issue one atomic)
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ((n + 31) / 32) * 32; i += (int64_t)gridDim.x * blockDim.x) {
+        const bool live = i < n;
+        unsigned int c = 0xFFFFFFFFu;
+        if (live) {
+            const int c0 = coarse[2 * i], c1 = coarse[2 * i + 1];
+            c = 0;
+            if (c0 < 0 || c0 >= V || c1 < 0 || c1 >= V) atomicExch(bad, 1);
+            else c = (unsigned)(c0 * V + c1);
+            cell[i] = c;
+            order[i] = (unsigned int)i;
+        }
+        const unsigned int peers = __match_any_sync(0xffffffffu, c);
+        if (live && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[c], (unsigned long long)__popc(peers));
     }
 }
 
