@@ -63,6 +63,7 @@ SIGNATURES = {
     "b2l_set_scan_mode": (_i, [_h, _i]),
     "b2l_set_async": (_i, [_h, _i]),
     "b2l_sync": (_i, [_h]),
+    "b2l_debug_force_redo": (_i, [_h, _i]),
     "b2l_debug_candidates": (_i, [_h, _i, _vp, _vp]),
     "b2l_stream": (_vp, [_h]),
 }
@@ -322,6 +323,9 @@ class Handle(object):
         p = lambda v: None if v is None else _ptr(int(v))
         self._check(self.lib.b2l_search_merge(self.h, _ptr(int(records_all_ptr)), int(nranks), int(nq), int(k), int(on_device), p(rowid_ptr),
                                               p(dist_ptr), p(coarse_ptr), p(fine_ptr), p(count_ptr), p(visited_ptr), p(certified_ptr)))
+
+    def debug_force_redo(self, mask):
+        self._check(self.lib.b2l_debug_force_redo(self.h, int(mask)))
 
     def debug_candidates(self, nq):
         app = np.zeros(nq, np.uint32)

@@ -95,6 +95,7 @@ struct b2l_ctx {
     int fb_nq = 0, fb_segc = 0;        // last collected fast search: batch size, segment length, work items it produced
     int64_t fb_items = 0;
     float c2m = 0.0f;                  // max_j max_k |subs[j][k]|^2 (upper bound), for the float32 table error model
+    int force_redo = 0;                // test knob: bit 0 / 1 = treat every query as uncertified after the first / second stage
     int fine_mode = 0;                 // 0: float32 first stage + float64 guard in the fine argmin, 1: float64 only
     unsigned long long* d_nguard = nullptr;   // sub-vectors the guard re-evaluated in float64 (device counter)
     int scan_mode = 0;                 // 0: packed 16-bit tables first (default), 1: float32 tables only
@@ -834,6 +835,13 @@ int b2l_reset_stats(b2l_handle h) {
     return B2L_OK;
 }
 
+int b2l_debug_force_redo(b2l_handle h, int mask) {
+    if (!h) return B2L_ERR_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->force_redo = mask & 3;
+    return B2L_OK;
+}
+
 int b2l_set_fine_mode(b2l_handle h, int mode) {
     if (!h || mode < 0 || mode > 1) return B2L_ERR_ARG;
     std::lock_guard<std::mutex> lk(h->mu);
@@ -1239,7 +1247,7 @@ int b2l_search(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_device,
     const b2l_stats st = h->stats;
     const uint8_t* cert = hb + o7;
     std::vector<int> redo;
-    for (int q = 0; q < nq; ++q) if (!cert[q]) redo.push_back(q);
+    for (int q = 0; q < nq; ++q) if (!cert[q] || (h->force_redo & 1)) redo.push_back(q);
     // Uncertified queries go down the chain: float32 tables (if the first pass used the 16-bit ones), then the float64
     // full sort.  Each stage re-runs the subset, merges it into a scratch block and patches the output rows.
     int64_t n_rescan = 0, n_exact = 0, extra_launches = 0;
@@ -1279,7 +1287,7 @@ int b2l_search(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_device,
         extra_launches += h->stats.kernel_launches + 1;
         if (stage == 2) n_rescan += ns; else n_exact += ns;
         std::vector<int> next;
-        if (stage == 2) for (int i = 0; i < ns; ++i) if (!c2[i]) next.push_back(redo[i]);
+        if (stage == 2) for (int i = 0; i < ns; ++i) if (!c2[i] || (h->force_redo & 2)) next.push_back(redo[i]);
         redo.swap(next);
     }
     if (n_rescan || n_exact) {

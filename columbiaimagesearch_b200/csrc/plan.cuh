@@ -599,9 +599,21 @@ k_lut_quant(int m, const int32_t* __restrict__ lut_desc, const PlanCounters* __r
         const float inv = s_inv;
         const float* t = lut32 + (size_t)slot * B2L_LUT_ROWS * m;
         unsigned short* o = lut16 + (size_t)slot * B2L_LUT_ROWS * m;
-        for (int e = threadIdx.x; e < B2L_LUT_ROWS * m; e += blockDim.x) {
-            const float x = __fmul_rn(__fsub_rn(t[e], s_b[e % m]), inv);
-            o[e] = (unsigned short)min(qv.qmax_code, max(0, (int)floorf(x)));
+        if ((m & 3) == 0) {                         // four entries per step: one 16-byte load, one 8-byte store
+            for (int e4 = threadIdx.x; e4 < B2L_LUT_ROWS * m / 4; e4 += blockDim.x) {
+                const float4 v = *(const float4*)(t + 4 * e4);
+                const int j = (4 * e4) % m;
+                const int q0 = min(qv.qmax_code, max(0, (int)floorf(__fmul_rn(__fsub_rn(v.x, s_b[j]), inv))));
+                const int q1 = min(qv.qmax_code, max(0, (int)floorf(__fmul_rn(__fsub_rn(v.y, s_b[j + 1]), inv))));
+                const int q2 = min(qv.qmax_code, max(0, (int)floorf(__fmul_rn(__fsub_rn(v.z, s_b[j + 2]), inv))));
+                const int q3 = min(qv.qmax_code, max(0, (int)floorf(__fmul_rn(__fsub_rn(v.w, s_b[j + 3]), inv))));
+                *(uint2*)(o + 4 * e4) = make_uint2((unsigned)q0 | ((unsigned)q1 << 16), (unsigned)q2 | ((unsigned)q3 << 16));
+            }
+        } else {
+            for (int e = threadIdx.x; e < B2L_LUT_ROWS * m; e += blockDim.x) {
+                const float x = __fmul_rn(__fsub_rn(t[e], s_b[e % m]), inv);
+                o[e] = (unsigned short)min(qv.qmax_code, max(0, (int)floorf(x)));
+            }
         }
     }
 }

@@ -176,6 +176,9 @@ int b2l_set_scan_mode(b2l_handle h, int mode);
  * (an event recorded on the stream, or b2l_sync) before reading results.  Default: disabled. */
 int b2l_set_async(b2l_handle h, int enabled);
 int b2l_sync(b2l_handle h);
+/* test knob for b2l_search: bit 0 sends every query of a batch to the second stage of the certification chain
+ * (float32 tables) even if the first certified it, bit 1 sends every query of that stage on to the float64 full sort. */
+int b2l_debug_force_redo(b2l_handle h, int mask);
 /* diagnostics of the most recent fast-path search: per query, candidates the scan appended and the final
  * pruning bound (float32 bits).  Either pointer may be NULL. */
 int b2l_debug_candidates(b2l_handle h, int nq, uint32_t* appended, uint32_t* bound_bits);
