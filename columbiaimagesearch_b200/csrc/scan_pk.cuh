@@ -13,11 +13,11 @@
 #pragma once
 #include "scan.cuh"
 
-#define SCAN_STAGE 256     // candidate keys staged in shared memory per slot and work item (overflow: direct global append)
+#define SCAN_STAGE 176    // candidates staged in shared memory per slot and work item, 4 bytes each (overflow: direct global append)
 template <int MP>
 size_t scan_pk_smem_bytes(int E) {
     typedef ScanCfg<MP> C;
-    return (size_t)C::LUT_BYTES + (size_t)4 * C::G * SCAN_STAGE * 8 + (size_t)4 * C::G * E * 4 + 6 * 32 * 4 + 256;
+    return (size_t)C::LUT_BYTES + (size_t)4 * C::G * SCAN_STAGE * 4 + (size_t)4 * C::G * E * 4 + 6 * 32 * 4 + 256;
 }
 
 template <int OFF> __device__ __forceinline__ uint32_t lds_lut_u(uint32_t o) {
@@ -84,15 +84,15 @@ __device__ __forceinline__ void refresh_bounds_u(const ScanArgs& a, const unsign
 }
 
 template <int MP>
-__global__ void __launch_bounds__(SCAN_THREADS, 2)
+__global__ void __launch_bounds__(SCAN_THREADS, 3)
 k_scan_pk(ScanArgs a) {
     typedef ScanCfg<MP> C;
     constexpr int G = C::G, W = C::W, U = C::U, CHUNK = C::CHUNK;
     constexpr int NS = 4 * G, PR = 2 * G;                          // query slots / slot pairs per work item
     extern __shared__ __align__(256) unsigned char smem[];
     uint32_t* lut = (uint32_t*)smem;
-    unsigned long long* stage = (unsigned long long*)(smem + C::LUT_BYTES);   // [NS][SCAN_STAGE] candidate keys of this item
-    unsigned int* tab = (unsigned int*)(stage + NS * SCAN_STAGE);  // [NS][E]
+    unsigned int* stage = (unsigned int*)(smem + C::LUT_BYTES);    // [NS][SCAN_STAGE] candidates of this item: S << 16 | index in segment
+    unsigned int* tab = stage + NS * SCAN_STAGE;                   // [NS][E]
     unsigned int* s_thr = tab + NS * a.E;                          // [32]
     int* s_q = (int*)(s_thr + 32);                                 // [32] query of the slot, -1 = empty
     unsigned int* s_posbase = (unsigned int*)(s_q + 32);           // [32]
@@ -249,23 +249,31 @@ k_scan_pk(ScanArgs a) {
         }
 
         int it = 0, gen = 0;
-        // candidates are staged per slot in shared memory (one shared-memory atomic each) and moved to the query's
+        // candidates are staged per slot in shared memory (one shared-memory atomic, 4 bytes each) and moved to the query's
         // global list once per work item; only a full staging buffer falls back to the direct global append
         auto append = [&](unsigned int v, int sl, int idx) {
-            const unsigned long long key = ((unsigned long long)v << 32) | (unsigned long long)(s_posbase[sl] + (unsigned)idx);
             const unsigned int n = atomicAdd(&s_nst[sl], 1u);
-            if (n < SCAN_STAGE) stage[sl * SCAN_STAGE + n] = key;
+            if (n < SCAN_STAGE) stage[sl * SCAN_STAGE + n] = (v << 16) | (unsigned int)idx;      // S < 2^16, idx < segc <= 2^14
             else {
                 const int q = s_q[sl];
                 const unsigned int gn = atomicAdd(&a.cand_cnt[q], 1u);
-                if (gn < SCAN_CAND_CAP) a.cand[(size_t)q * SCAN_CAND_CAP + gn] = key;
+                if (gn < SCAN_CAND_CAP)
+                    a.cand[(size_t)q * SCAN_CAND_CAP + gn] = ((unsigned long long)v << 32) | (unsigned long long)(s_posbase[sl] + (unsigned)idx);
             }
         };
-        auto eval_chunk = [&](const uint32_t (&w)[U][W], int c) {
+        const uint8_t* lane_src = src0 + (size_t)jl * MP;
+        auto load_chunk = [&](uint32_t (&w)[U][W], int c) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) load_row<W>(lane_src + ((size_t)c * CHUNK + u * MP) * MP, w[u]);
+        };
+        // One chunk: the table sums, then -- as soon as the code registers are dead -- the loads of the warp's next chunk,
+        // whose latency hides behind the bound / candidate logic below (three blocks per SM cover the rest).
+        auto eval_chunk = [&](uint32_t (&w)[U][W], int c) {
             const unsigned int t0 = s_thr[sl0], t1 = s_thr[sl1], t2 = s_thr[sl2], t3 = s_thr[sl3];
             uint32_t a0[U], a1[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) adc_block_pk<MP>(w[u], cc, a0[u], a1[u]);
+            if (c + SCAN_WARPS < nchunk) load_chunk(w, c + SCAN_WARPS);
             const int base = c * CHUNK + jl;
             unsigned int v0[U], v1[U], v2[U], v3[U];
 #pragma unroll
@@ -300,22 +308,9 @@ k_scan_pk(ScanArgs a) {
             }
             ++it;
         };
-        const uint8_t* lane_src = src0 + (size_t)jl * MP;
-        auto load_chunk = [&](uint32_t (&w)[U][W], int c) {
-#pragma unroll
-            for (int u = 0; u < U; ++u) load_row<W>(lane_src + ((size_t)c * CHUNK + u * MP) * MP, w[u]);
-        };
-        uint32_t wa[U][W], wb[U][W];
+        uint32_t wa[U][W];
         if (warp < nchunk) load_chunk(wa, warp);
-        for (int c = warp; c < nchunk; c += 2 * SCAN_WARPS) {
-            const bool more = c + SCAN_WARPS < nchunk;
-            if (more) load_chunk(wb, c + SCAN_WARPS);
-            eval_chunk(wa, c);
-            if (more) {
-                if (c + 2 * SCAN_WARPS < nchunk) load_chunk(wa, c + 2 * SCAN_WARPS);
-                eval_chunk(wb, c + SCAN_WARPS);
-            }
-        }
+        for (int c = warp; c < nchunk; c += SCAN_WARPS) eval_chunk(wa, c);
         if (warp < nchunk) {
             const int e = ent + C::LPS * (gen & (a.GEN - 1));
             tab0[e] = min(tab0[e], mn0); tab1[e] = min(tab1[e], mn1); tab2[e] = min(tab2[e], mn2); tab3[e] = min(tab3[e], mn3);
@@ -331,7 +326,11 @@ k_scan_pk(ScanArgs a) {
             if (lane == 0) gbase = atomicAdd(&a.cand_cnt[q], n);
             gbase = __shfl_sync(0xffffffffu, gbase, 0);
             for (unsigned int i = lane; i < n; i += 32)
-                if (gbase + i < SCAN_CAND_CAP) a.cand[(size_t)q * SCAN_CAND_CAP + gbase + i] = stage[sl * SCAN_STAGE + i];
+                if (gbase + i < SCAN_CAND_CAP) {
+                    const unsigned int e = stage[sl * SCAN_STAGE + i];
+                    a.cand[(size_t)q * SCAN_CAND_CAP + gbase + i] =
+                        ((unsigned long long)(e >> 16) << 32) | (unsigned long long)(s_posbase[sl] + (e & 0xFFFFu));
+                }
         }
         __syncthreads();
         for (int e = tid; e < NS * a.E; e += SCAN_THREADS) {
