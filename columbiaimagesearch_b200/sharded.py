@@ -139,7 +139,8 @@ class ShardedLOPQSearcher(object):
 
     def search_batch_async(self, X, quota=10, limit=None):
         """Enqueue one batch on the handle's stream (local search -> all-gather -> merge -> one device-to-host copy)
-        and return a pending object; ``.result()`` waits for it.  Up to two batches may be pending at a time, so the
+        and return a pending object; ``.result()`` waits for it and returns arrays that are views of a pinned buffer
+        (copy them if they must outlive the next two ``search_batch_async`` calls).  Up to two batches may be pending at a time, so the
         host-side launch work of batch i+1 overlaps the device work of batch i.  Every rank must call this (and
         ``result``) in the same order."""
         import torch
@@ -186,7 +187,8 @@ class ShardedLOPQSearcher(object):
                 X = X[None, :] if X.ndim == 1 else X
                 if X.dtype != np.float32:            # float64 queries: the synchronous path keeps their precision
                     return self._search_batch_sync(X, quota, limit)
-            return self.search_batch_async(X, quota, limit).result()
+            out = self.search_batch_async(X, quota, limit).result()
+            return {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in out.items()}     # owned arrays
         return self._search_batch_sync(X, quota, limit)
 
     def _search_batch_sync(self, X, quota=10, limit=None):
@@ -278,7 +280,8 @@ class _PendingSearch(object):
         b["event"].synchronize()
         raw = b["out_h"].numpy()
         o = b["offs"]
-        view = lambda name, dt, shape: raw[o[name]:o[name] + int(np.prod(shape)) * np.dtype(dt).itemsize].view(dt).reshape(shape).copy()
+        # zero-copy views of the pinned block: valid until this buffer set comes round again (two more batches enqueued)
+        view = lambda name, dt, shape: raw[o[name]:o[name] + int(np.prod(shape)) * np.dtype(dt).itemsize].view(dt).reshape(shape)
         out = dict(rowid=view("rowid", np.int64, (nq, k)), dist=view("dist", np.float64, (nq, k)),
                    coarse=view("coarse", np.int32, (nq, k, 2)), fine=view("fine", np.uint8, (nq, k, M)),
                    count=view("count", np.int32, (nq,)), visited=view("visited", np.int32, (nq,)),
