@@ -365,10 +365,10 @@ def run_b200(a):
         for b in range(first, first + count):
             p = searcher.search_batch_async(batch_of(b), quota=a.quota, limit=k)
             if pend is not None:
-                last = pend.result()
+                last = pend.result(copy=False)
                 redo += (last["exact_queries"], last["rescan_queries"])
             pend = p
-        last = pend.result()
+        last = pend.result(copy=False)
         redo += (last["exact_queries"], last["rescan_queries"])
         return redo, last
 

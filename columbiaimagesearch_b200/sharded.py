@@ -139,8 +139,8 @@ class ShardedLOPQSearcher(object):
 
     def search_batch_async(self, X, quota=10, limit=None):
         """Enqueue one batch on the handle's stream (local search -> all-gather -> merge -> one device-to-host copy)
-        and return a pending object; ``.result()`` waits for it and returns arrays that are views of a pinned buffer
-        (copy them if they must outlive the next two ``search_batch_async`` calls).  Up to two batches may be pending at a time, so the
+        and return a pending object; ``.result()`` waits for it (``result(copy=False)``: zero-copy views of the pinned
+        result block, valid until two more batches have been enqueued).  Up to two batches may be pending at a time, so the
         host-side launch work of batch i+1 overlaps the device work of batch i.  Every rank must call this (and
         ``result``) in the same order."""
         import torch
@@ -187,8 +187,7 @@ class ShardedLOPQSearcher(object):
                 X = X[None, :] if X.ndim == 1 else X
                 if X.dtype != np.float32:            # float64 queries: the synchronous path keeps their precision
                     return self._search_batch_sync(X, quota, limit)
-            out = self.search_batch_async(X, quota, limit).result()
-            return {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in out.items()}     # owned arrays
+            return self.search_batch_async(X, quota, limit).result()
         return self._search_batch_sync(X, quota, limit)
 
     def _search_batch_sync(self, X, quota=10, limit=None):
@@ -272,7 +271,8 @@ class _PendingSearch(object):
         self.s, self.b, self.X, self.nq, self.k, self.quota = searcher, bufs, X, nq, k, quota
         self._out = None
 
-    def result(self):
+    def result(self, copy=True):
+        """copy=False returns views of the pinned result block: valid only until two more batches have been enqueued."""
         if self._out is not None:
             return self._out
         s, b, nq, k = self.s, self.b, self.nq, self.k
@@ -305,5 +305,7 @@ class _PendingSearch(object):
             ids[pad] = -1
             out["dist"][pad] = np.nan
         out["ids"] = ids
+        if copy:
+            out = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in out.items()}
         self._out = out
         return out
