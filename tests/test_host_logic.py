@@ -1,0 +1,64 @@
+"""CPU: host-side pieces that need no GPU -- split / chunk helpers against the oracle and the reference semantics, the
+cell -> rank ownership map, the plugin quota rule, and the LMDB wire format of LOPQSearcherLMDB (search.py:425-443)."""
+import array
+
+import numpy as np
+
+from oracle import lopq_oracle as orc
+from columbiaimagesearch_b200.lopq import utils as gutils
+from columbiaimagesearch_b200.lopq.search import LOPQSearcherLMDB, codes_to_arrays
+from columbiaimagesearch_b200.lopq.model import LOPQCode
+from columbiaimagesearch_b200.sharded import cell_owner
+from columbiaimagesearch_b200 import plugin
+
+
+def test_iterate_splits_matches_oracle():
+    x = np.arange(24.0)
+    for splits in (1, 2, 3, 4, 8):
+        a = [(v.tolist(), s) for v, s in gutils.iterate_splits(x, splits)]
+        b = [(v.tolist(), s) for v, s in orc.iterate_splits(x, splits)]
+        assert a == b
+
+
+def test_chunk_ranges_cover_everything():
+    # utils.py:164-175: contiguous ranges, remainder goes to the first worker
+    for n, p in [(10, 4), (7, 7), (100000, 8), (3, 1)]:
+        r = gutils.get_chunk_ranges(n, p)
+        assert r[0][0] == 0 and r[-1][1] == n and len(r) == p
+        assert all(r[i][1] == r[i + 1][0] for i in range(p - 1))
+        assert r[0][1] - r[0][0] == n // p + (n - p * (n // p))
+
+
+def test_cell_owner_spreads_neighbours():
+    for V, world in [(8, 1), (8, 2), (8, 4), (8, 8), (4, 3)]:
+        own = cell_owner(V, world).reshape(V, V)
+        assert set(np.unique(own).tolist()) == set(range(world))
+        if world > 1:
+            # cells adjacent in multi-sequence order share c0 or c1: their owners differ
+            assert (own[:, :-1] != own[:, 1:]).all() and (own[:-1, :] != own[1:, :]).all()
+        counts = np.bincount(own.ravel(), minlength=world)
+        assert counts.max() - counts.min() <= max(1, V)
+
+
+def test_plugin_quota_rule():
+    # searcher_lopqhbase.py:838: quota = min(1000 * max_returned, 10000)
+    assert plugin.plugin_quota(1) == 1000 and plugin.plugin_quota(5) == 5000
+    assert plugin.plugin_quota(10) == 10000 and plugin.plugin_quota(100) == 10000
+
+
+def test_lmdb_wire_format_matches_reference_encoding():
+    # search.py:425-443: cell = array('H').tostring(), fine = array('B').tostring(); key = cell bytes + str(id)
+    cell, fine = (3, 517), (0, 255, 17, 4)
+    assert LOPQSearcherLMDB.encode_cell(cell) == array.array("H", cell).tobytes()
+    assert LOPQSearcherLMDB.encode_fine_codes(fine) == array.array("B", fine).tobytes()
+    assert LOPQSearcherLMDB.decode_cell(array.array("H", cell).tobytes()) == cell
+    assert LOPQSearcherLMDB.decode_fine_codes(array.array("B", fine).tobytes()) == fine
+
+
+def test_codes_to_arrays_accepts_reference_shapes():
+    codes = [LOPQCode((1, 2), (3, 4, 5, 6)), ((0, 7), (9, 8, 7, 6)), [[5, 5], [1, 1, 1, 1]]]
+    coarse, fine = codes_to_arrays(codes, 4)
+    assert coarse.dtype == np.int32 and fine.dtype == np.uint8
+    assert coarse.tolist() == [[1, 2], [0, 7], [5, 5]] and fine.tolist() == [[3, 4, 5, 6], [9, 8, 7, 6], [1, 1, 1, 1]]
+    c2, f2 = codes_to_arrays((coarse, fine), 4)
+    assert c2 is not None and np.array_equal(c2, coarse) and np.array_equal(f2, fine)
