@@ -482,10 +482,11 @@ def run_b200(a):
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": 1e3 * step_s / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                "dtype": "u16 packed scan (f32 / f64 fallbacks) + f64 re-rank", "data": "synthetic",
+                "dtype": "u16", "data": "synthetic",
                 "config": {"workload": "10M x 128-d dlib-style synthetic (4096-centre GMM, L2-normalised), V=8 M=16 K=256, "
                                        "batch=%d near-duplicate queries (rho=%.2f), quota=%d, top-%d" % (nq, a.rho, a.quota, k),
                            "n_db": n, "batch": nq, "quota": a.quota, "k": k,
+                           "arithmetic": "16-bit packed table sums in the scan (float32-table and float64 fallbacks), float64 tables and re-rank",
                            "l2": "distinct query batch per step; per-step working set (160 MB codes + per-batch LUTs) exceeds the 126 MB L2",
                            "sharding": "cells by (c0+c1) mod N, one all-gather of per-rank top-k" if world > 1 else "single GPU"},
                 "recall@10": r10, "recall@1": r1, "cells_visited_per_query": vis, "codes_ranked_per_query": cand * world if world > 1 else cand,
