@@ -33,7 +33,7 @@
 #define SCAN_THREADS 256
 #define SCAN_WARPS 8
 #define SCAN_CAND_CAP 8192          // candidate keys per query (overflow => the query is re-ranked by the exact path)
-#define SCAN_DRY 4                  // chunks per warp evaluated without appending when a query has no bound yet
+#define SCAN_DRY 8                  // chunks per warp evaluated without appending when a query has no bound yet
 #define SCAN_NO_BOUND 0x7f7f7f7fu   // "no bound yet" (3.39e38), the memset pattern of gthr
 
 struct ScanArgs {
