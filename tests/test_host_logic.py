@@ -62,3 +62,17 @@ def test_codes_to_arrays_accepts_reference_shapes():
     assert coarse.tolist() == [[1, 2], [0, 7], [5, 5]] and fine.tolist() == [[3, 4, 5, 6], [9, 8, 7, 6], [1, 1, 1, 1]]
     c2, f2 = codes_to_arrays((coarse, fine), 4)
     assert c2 is not None and np.array_equal(c2, coarse) and np.array_equal(f2, fine)
+
+
+def test_reconstruct_matches_reference_golden():
+    """LOPQModel.reconstruct (model.py:643-671; host NumPy in the mirror package) against the reference's own output."""
+    import columbiaimagesearch_b200.lopq as lopq
+    from tests.util import load_case
+    for name in ("A", "B", "C"):
+        z, _ = load_case(name)
+        model = lopq.LOPQModel.from_npz(z)
+        for i in range(16):
+            code = (tuple(int(v) for v in z["db_coarse"][i]), tuple(int(v) for v in z["db_fine"][i]))
+            np.testing.assert_allclose(model.reconstruct(code), z["probe_recon"][i], rtol=1e-12, atol=1e-13)
+        assert model.get_cell_id_for_coarse_codes((3, 2)) == 2 + 3 * model.V
+        assert model.get_coarse_codes_for_cell_id(2 + 3 * model.V) == (3, 2)
