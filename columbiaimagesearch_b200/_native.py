@@ -44,6 +44,7 @@ SIGNATURES = {
     "b2l_set_fine_mode": (_i, [_h, _i]),
     "b2l_encode_guard_count": (_i64, [_h, _i]),
     "b2l_apply_pca": (_i, [_h, _vp, _i, _i64, _i, _vp]),
+    "b2l_apply_pca64": (_i, [_h, _vp, _i, _i64, _i, _vp]),
     "b2l_project_lut": (_i, [_h, _vp, _i, _i64, _vp, _vp, _vp]),
     "b2l_index_add": (_i, [_h, _vp, _vp, _i64, _vp, _i]),
     "b2l_index_clear": (_i, [_h]),
@@ -183,10 +184,11 @@ class Handle(object):
     def encode_guard_count(self, reset=False):
         return int(self._check(self.lib.b2l_encode_guard_count(self.h, int(bool(reset)))))
 
-    def apply_pca(self, X):
+    def apply_pca(self, X, f64_out=False):
         X, f64 = _as_queries(X)
-        Y = np.empty((X.shape[0], self.D), np.float32)
-        self._check(self.lib.b2l_apply_pca(self.h, _ptr(X), f64, X.shape[0], 0, _ptr(Y)))
+        Y = np.empty((X.shape[0], self.D), np.float64 if f64_out else np.float32)
+        fn = self.lib.b2l_apply_pca64 if f64_out else self.lib.b2l_apply_pca
+        self._check(fn(self.h, _ptr(X), f64, X.shape[0], 0, _ptr(Y)))
         return Y
 
     def project_lut(self, X, coarse, want_px=True, want_lut=True):

@@ -266,7 +266,7 @@ int ensure_index(b2l_handle h) {
     CU(h->sorted_first.reserve((size_t)ncell * 8));
     std::vector<int64_t> first(ncell, 0);
     if (n > 0) {
-        if (n >= (int64_t)1 << 32) FAIL(B2L_ERR_UNSUPPORTED, "more than 2^32 rows per shard");
+        if (n >= (int64_t)1 << 31) FAIL(B2L_ERR_UNSUPPORTED, "more than 2^31 - 1 rows per shard");
         CU(h->w_sort_a.reserve((size_t)n * 8));      // cell[n] | order[n]
         CU(h->w_sort_b.reserve((size_t)n * 8));      // sorted_cell[n] | sorted_src[n]
         CU(h->w_misc.reserve((size_t)ncell * 8 + 64));
@@ -988,31 +988,45 @@ int b2l_encode(b2l_handle h, const void* X, int x_is_f64, int64_t n, int on_devi
     return B2L_OK;
 }
 
-int b2l_apply_pca(b2l_handle h, const void* X, int x_is_f64, int64_t n, int on_device, float* Y) {
-    if (!h) return B2L_ERR_ARG;
-    std::lock_guard<std::mutex> lk(h->mu);
-    CU(cudaSetDevice(h->device));
+static int apply_pca_impl(b2l_handle h, const void* X, int x_is_f64, int64_t n, int on_device, float* Y, double* Y64) {
     if (!h->has_pca) FAIL(B2L_ERR_STATE, "no PCA set");
-    if (n < 1 || !X || !Y) FAIL(B2L_ERR_ARG, "bad apply_pca arguments");
+    if (n < 1 || !X || (!Y && !Y64)) FAIL(B2L_ERR_ARG, "bad apply_pca arguments");
     const ModelView& mv = h->mv;
     const size_t esz = x_is_f64 ? 8 : 4;
+    const size_t osz = Y64 ? 8 : 4;
     const void* dx = X;
     if (!on_device) {
         CU(h->w_q.reserve((size_t)n * mv.D0 * esz));
         CU(cudaMemcpyAsync(h->w_q.p, X, (size_t)n * mv.D0 * esz, cudaMemcpyHostToDevice, h->stream));
         dx = h->w_q.p;
     }
-    float* dy = Y;
-    if (!on_device) { CU(h->w_xq.reserve((size_t)n * mv.D * 4)); dy = h->w_xq.as<float>(); }
+    void* dy = Y64 ? (void*)Y64 : (void*)Y;
+    if (!on_device) { CU(h->w_xq.reserve((size_t)n * mv.D * osz)); dy = h->w_xq.p; }
+    float* dy32 = Y64 ? nullptr : (float*)dy;
+    double* dy64 = Y64 ? (double*)dy : nullptr;
     const size_t smem = (size_t)(mv.D0 + mv.D) * 8;
     if (x_is_f64) { CU(cudaFuncSetAttribute(k_pca<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_pca<double><<<(unsigned)n, 128, smem, h->stream>>>(mv, (const double*)dx, n, dy); }
+        k_pca<double><<<(unsigned)n, 128, smem, h->stream>>>(mv, (const double*)dx, n, dy32, dy64); }
     else { CU(cudaFuncSetAttribute(k_pca<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_pca<float><<<(unsigned)n, 128, smem, h->stream>>>(mv, (const float*)dx, n, dy); }
+        k_pca<float><<<(unsigned)n, 128, smem, h->stream>>>(mv, (const float*)dx, n, dy32, dy64); }
     LAUNCHED();
-    if (!on_device) CU(cudaMemcpyAsync(Y, dy, (size_t)n * mv.D * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (!on_device) CU(cudaMemcpyAsync(Y64 ? (void*)Y64 : (void*)Y, dy, (size_t)n * mv.D * osz, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return B2L_OK;
+}
+
+int b2l_apply_pca(b2l_handle h, const void* X, int x_is_f64, int64_t n, int on_device, float* Y) {
+    if (!h) return B2L_ERR_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(cudaSetDevice(h->device));
+    return apply_pca_impl(h, X, x_is_f64, n, on_device, Y, nullptr);
+}
+
+int b2l_apply_pca64(b2l_handle h, const void* X, int x_is_f64, int64_t n, int on_device, double* Y) {
+    if (!h) return B2L_ERR_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(cudaSetDevice(h->device));
+    return apply_pca_impl(h, X, x_is_f64, n, on_device, nullptr, Y);
 }
 
 int b2l_project_lut(b2l_handle h, const void* X, int x_is_f64, int64_t n, const int32_t* coarse, double* px, double* lut) {
@@ -1052,6 +1066,7 @@ int b2l_index_add(b2l_handle h, const int32_t* coarse, const uint8_t* fine, int6
     if (n == 0) return B2L_OK;
     const ModelView& mv = h->mv;
     const int64_t tot = h->n_items + n;
+    if (tot >= ((int64_t)1 << 31)) FAIL(B2L_ERR_UNSUPPORTED, "more than 2^31 - 1 rows per shard (%lld)", (long long)tot);
     CU(h->m_coarse.reserve((size_t)tot * 8, true, h->stream));
     CU(h->m_fine.reserve((size_t)tot * mv.M, true, h->stream));
     CU(h->m_rowid.reserve((size_t)tot * 8, true, h->stream));
@@ -1060,7 +1075,16 @@ int b2l_index_add(b2l_handle h, const int32_t* coarse, const uint8_t* fine, int6
     CU(cudaMemcpyAsync(h->m_fine.as<uint8_t>() + h->n_items * mv.M, fine, (size_t)n * mv.M, kind, h->stream));
     if (rowids) CU(cudaMemcpyAsync(h->m_rowid.as<int64_t>() + h->n_items, rowids, (size_t)n * 8, kind, h->stream));
     else { k_iota64<<<grid_for(n, 256), 256, 0, h->stream>>>(h->m_rowid.as<int64_t>() + h->n_items, h->n_items, n); LAUNCHED(); }
+    // the batch is committed only if every coarse code is in range (the reference logs and skips a bad item,
+    // search.py:343-367; here the whole batch is refused and the index stays as it was)
+    CU(h->w_misc.reserve(64));
+    CU(cudaMemsetAsync(h->w_misc.p, 0, 4, h->stream));
+    k_check_coarse<<<grid_for(2 * n, 256), 256, 0, h->stream>>>(h->m_coarse.as<int32_t>() + h->n_items * 2, n, mv.V, h->w_misc.as<int>());
+    LAUNCHED();
+    int hbad = 0;
+    CU(cudaMemcpyAsync(&hbad, h->w_misc.p, 4, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
+    if (hbad) FAIL(B2L_ERR_ARG, "index_add: coarse code out of range [0, %d); nothing was added", mv.V);
     h->n_items = tot;
     h->dirty = true;
     return B2L_OK;

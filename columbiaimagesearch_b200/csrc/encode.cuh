@@ -7,7 +7,8 @@
 
 // ---- apply_PCA: one block per vector ----------------------------------------------------------
 template <typename XT>
-__global__ void __launch_bounds__(128) k_pca(ModelView mv, const XT* __restrict__ X, int64_t n, float* __restrict__ Y) {
+__global__ void __launch_bounds__(128) k_pca(ModelView mv, const XT* __restrict__ X, int64_t n, float* __restrict__ Y,
+                                             double* __restrict__ Y64 = nullptr) {
     extern __shared__ double sm_pca[];   // [D0] centred input, then [D] output
     double* xc = sm_pca;
     double* y = sm_pca + mv.D0;
@@ -31,9 +32,15 @@ __global__ void __launch_bounds__(128) k_pca(ModelView mv, const XT* __restrict_
         double tot = 0.0;
         for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[w];
         const double nrm = sqrt(tot);
-        for (int e = threadIdx.x; e < mv.D; e += blockDim.x) Y[i * (int64_t)mv.D + e] = (float)(y[e] / nrm);
+        for (int e = threadIdx.x; e < mv.D; e += blockDim.x) {
+            if (Y) Y[i * (int64_t)mv.D + e] = (float)(y[e] / nrm);
+            if (Y64) Y64[i * (int64_t)mv.D + e] = y[e] / nrm;
+        }
     } else {
-        for (int e = threadIdx.x; e < mv.D; e += blockDim.x) Y[i * (int64_t)mv.D + e] = (float)y[e];
+        for (int e = threadIdx.x; e < mv.D; e += blockDim.x) {
+            if (Y) Y[i * (int64_t)mv.D + e] = (float)y[e];
+            if (Y64) Y64[i * (int64_t)mv.D + e] = y[e];
+        }
     }
 }
 

@@ -44,6 +44,14 @@ __global__ void k_scatter_rows(const unsigned int* __restrict__ sorted_cell, con
     }
 }
 
+// coarse codes of a batch about to be appended: *bad = 1 if any is outside [0, V)
+__global__ void k_check_coarse(const int32_t* __restrict__ coarse, int64_t n, int V, int* __restrict__ bad) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < 2 * n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = coarse[i];
+        if (c < 0 || c >= V) atomicExch(bad, 1);
+    }
+}
+
 __global__ void k_iota64(int64_t* p, int64_t base, int64_t n) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = base + i;
 }

@@ -3,6 +3,7 @@ constructor, attributes and method names; every arithmetic step of predict / pro
 get_subquantizer_distances / apply_PCA runs in libb200lopq (CUDA).  Parameter containers stay plain
 NumPy arrays so pickles written by the reference (storer/local.py:58) load into these classes.
 """
+import os
 from collections import namedtuple
 
 import numpy as np
@@ -25,7 +26,7 @@ _cluster_cache = {}
 def _cluster_handle(centroids):
     """Throw-away model whose first coarse split is `centroids` (for utils.predict_cluster and
     search.multisequence, which take bare centroid arrays in the reference API)."""
-    key = (id(centroids), centroids.shape, centroids.dtype.str)
+    key = (id(centroids), centroids.shape, centroids.dtype.str, os.getpid())
     ent = _cluster_cache.get(key)
     if ent is not None and ent[0] is centroids:
         return ent[1]
@@ -74,11 +75,15 @@ class LOPQModel(object):
     def _native(self):
         """The model's own library handle (encode / project / LUT probes), created lazily so that a
         model unpickled before fork() initialises CUDA in the worker that first uses it."""
-        h = self.__dict__.get(_NATIVE_ATTR)
-        if h is None:
-            h = self._new_handle()
-            self.__dict__[_NATIVE_ATTR] = h
-        return h
+        ent = self.__dict__.get(_NATIVE_ATTR)
+        pid = os.getpid()
+        if ent is not None and ent[1] != pid:      # inherited through fork(): the parent's CUDA context is not usable here
+            ent[0].h = None
+            ent = None
+        if ent is None:
+            ent = (self._new_handle(), pid)
+            self.__dict__[_NATIVE_ATTR] = ent
+        return ent[0]
 
     def _new_handle(self, device=None):
         if self.Cs is None or self.Rs is None or self.mus is None or self.subquantizers is None:
@@ -203,30 +208,35 @@ class LOPQModelPCA(LOPQModel):
         return self.pca_P, self.pca_mu, self.renorm
 
     def fit_pca(self, data, pca_dims=256, pca_subsample=None):
-        """model.py:878-886 -> train_pca (model.py:242-287)."""
+        """model.py:878-886 -> train_pca (model.py:242-287).  Retraining an existing PCA is an error, as in the reference."""
         from .train import train_pca
         if self.pca_P is None or self.pca_mu is None:
             self.pca_P, self.pca_mu = train_pca(data, pca_dims, pca_subsample)
             self._invalidate()
+        else:
+            raise ValueError("You are trying to retrain PCA...")
 
-    def fit(self, data, pca_dims=None, kmeans_coarse_iters=10, kmeans_local_iters=20, n_init=10,
-            subquantizer_sample_ratio=1.0, random_state=None, verbose=False):
-        """model.py:888-931 -- PCA (if missing) then LOPQ training on the projected data."""
-        if self.pca_P is None:
-            self.fit_pca(data, pca_dims if pca_dims is not None else data.shape[1])
-        proj = self.apply_PCA(np.asarray(data))
+    def fit(self, data, pca_dims=256, kmeans_coarse_iters=10, kmeans_local_iters=20, n_init=10,
+            subquantizer_sample_ratio=1.0, random_state=None, verbose=False, pca_subsample=None,
+            apply_pca=True, train_pca=True):
+        """model.py:888-931 -- PCA (when `train_pca`), projection of the training data (when `apply_pca`), then LOPQ
+        training.  The product trains on features it has already projected:
+        ``fit(train_np, verbose=True, apply_pca=False, train_pca=False)`` (searcher_lopqhbase.py:462)."""
+        if train_pca:
+            self.fit_pca(data, pca_dims, pca_subsample)
+        proj = self.apply_PCA(np.asarray(data)) if apply_pca else np.asarray(data)
         LOPQModel.fit(self, proj, kmeans_coarse_iters, kmeans_local_iters, n_init, subquantizer_sample_ratio,
                       random_state, verbose)
 
     def apply_PCA(self, x, dtype=np.float32):
-        """model.py:961-978 -- (x - mu) . P, optional L2 renorm, cast (float32 on the device)."""
+        """model.py:961-978 -- (x - mu) . P, optional L2 renorm, cast to `dtype`.  float32 (the default, and what search
+        and predict use) is produced by the device kernel; any other dtype takes the float64 result of the same kernel
+        so that it is not rounded through float32 first."""
         x = np.asarray(x)
-        if self.Cs is None:       # model not trained yet: PCA-only handle
-            y = _pca_only_handle(self).apply_pca(x if x.ndim > 1 else x[None, :])
-        else:
-            y = self._native().apply_pca(x if x.ndim > 1 else x[None, :])
-        y = y if x.ndim > 1 else y[0]
-        return y if dtype == np.float32 else y.astype(dtype)
+        h = _pca_only_handle(self) if self.Cs is None else self._native()      # model not trained yet: PCA-only handle
+        x2 = x if x.ndim > 1 else x[None, :]
+        y = h.apply_pca(x2) if dtype == np.float32 else h.apply_pca(x2, f64_out=True).astype(dtype, copy=False)
+        return y if x.ndim > 1 else y[0]
 
 
 def _pca_only_handle(model):

@@ -4,6 +4,7 @@ reference's method names, arguments and return shapes.  The inverted index lives
 libb200lopq.  Host code here only keeps ids (arbitrary Python objects in the reference), applies
 the per-cell id de-duplication of add_codes (search.py:325-369) and wraps results.
 """
+import os
 from collections import namedtuple
 from itertools import count
 
@@ -34,7 +35,7 @@ _pair_cache = {}
 
 
 def _pair_handle(c0, c1):
-    key = (id(c0), id(c1))
+    key = (id(c0), id(c1), os.getpid())
     ent = _pair_cache.get(key)
     if ent is not None and ent[0] is c0 and ent[1] is c1:
         return ent[2]
@@ -179,10 +180,19 @@ class LOPQSearcher(LOPQSearcherBase):
     """search.py:310-382 with a GPU-resident index.  ``device`` selects the GPU (default: LOCAL_RANK
     or 0).  Extra, array-level entry points: add_codes((coarse, fine) arrays), search_batch."""
 
-    def __init__(self, model, device=None):
+    def __init__(self, model, device=None, keep_host_copy=True):
+        """The library handle (CUDA context, device index) is created by the PROCESS that first needs the device, not
+        here: the product builds its searcher in the gunicorn master (`--preload`) and serves from forked workers
+        (setup/components/search/docker-compose.yml:67), and a CUDA context does not survive fork().  add_codes only
+        records the rows on the host (the reference's in-RAM index is copied by fork the same way); each process
+        uploads them when it first searches.  keep_host_copy=False drops the host rows after upload (not fork-safe)."""
         super(LOPQSearcher, self).__init__()
         self.model = model
-        self._handle = model._new_handle(device)
+        self._device = device
+        self._keep_host = bool(keep_host_copy)
+        self._h, self._h_pid = None, None
+        self._host_rows = []               # [(coarse, fine, rowids)] of everything added (replayed after fork)
+        self._uploaded = 0                 # entries of _host_rows already on this process's device
         self.index = _IndexView(self)
         self._numeric = True               # ids seen so far are all non-negative ints < 2**40
         self._row_ids = []                 # per add call: ndarray of ids (numeric) in row order
@@ -191,6 +201,38 @@ class LOPQSearcher(LOPQSearcherBase):
         self._id2num, self._num2id = None, None      # generic ids: dense numbering
         self._keys = None                  # sorted int64 keys (cell << 40 | idnum) of everything indexed
         self._pending_keys = []
+
+    # ---- device handle (per process) ---------------------------------------------------------------
+    @property
+    def _handle(self):
+        pid = os.getpid()
+        if self._h is None or self._h_pid != pid:
+            if self._h is not None:
+                if not self._keep_host:
+                    raise RuntimeError("searcher built with keep_host_copy=False cannot be used from a forked process")
+                self._h.h = None           # the parent's handle: its context is not ours to destroy
+            self._h = self.model._new_handle(self._device)
+            self._h_pid = pid
+            self._uploaded = 0
+        while self._uploaded < len(self._host_rows):
+            coarse, fine, rows = self._host_rows[self._uploaded]
+            self._h.index_add(coarse, fine, rows)
+            self._uploaded += 1
+            if not self._keep_host:
+                self._host_rows[self._uploaded - 1] = None
+        if not self._keep_host and self._host_rows:
+            self._host_rows, self._uploaded = [], 0
+        return self._h
+
+    def _device_add(self, coarse, fine, rows):
+        self._host_rows.append((coarse, fine, rows))
+        if self._h is not None and self._h_pid == os.getpid():
+            self._handle                   # already on a device in this process: upload now  # noqa: B018
+
+    def _device_clear(self):
+        self._host_rows, self._uploaded = [], 0
+        if self._h is not None and self._h_pid == os.getpid():
+            self._h.index_clear()
 
     # ---- id bookkeeping --------------------------------------------------------------------------
     def _to_numeric(self, ids, n):
@@ -248,6 +290,25 @@ class LOPQSearcher(LOPQSearcherBase):
         if n == 0:
             return
         V = self.model.V
+        bad = ((coarse < 0) | (coarse >= V)).any(axis=1)
+        if bad.any():
+            # a coarse code outside [0, V) names a cell no query can ever visit; the reference logs such an item and goes
+            # on (search.py:343-367).  It is dropped here before any bookkeeping, so host and device stay in step.
+            if self.verbose > 0:
+                print("Discarding %d codes with a coarse code outside [0, %d)" % (int(bad.sum()), V))
+            good = np.nonzero(~bad)[0]
+            if ids is not None and not isinstance(ids, (count, range)):
+                seq = ids if hasattr(ids, "__getitem__") else list(ids)
+                ids = [seq[int(i)] for i in good if int(i) < len(seq)]
+            elif ids is not None:
+                seq = np.asarray([next(ids) for _ in range(n)]) if isinstance(ids, count) else np.asarray(ids)[:n]
+                ids = seq[good[good < seq.shape[0]]]
+            else:
+                ids = good.astype(np.int64)
+            coarse, fine = coarse[good], fine[good]
+            n = coarse.shape[0]
+            if n == 0:
+                return
         nums, known_unique = self._to_numeric(ids, n)
         n = min(n, nums.shape[0])
         coarse, fine, nums = coarse[:n], fine[:n], nums[:n]
@@ -270,7 +331,7 @@ class LOPQSearcher(LOPQSearcherBase):
         if coarse.shape[0] == 0:
             return
         base = self.nb_indexed
-        self._handle.index_add(coarse, fine, np.arange(base, base + coarse.shape[0], dtype=np.int64))
+        self._device_add(np.ascontiguousarray(coarse), np.ascontiguousarray(fine), np.arange(base, base + coarse.shape[0], dtype=np.int64))
         self._row_ids.append(nums)
         self._row_cells.append(cell)
         self._row_ids_flat = None
@@ -399,7 +460,8 @@ class LOPQSearcherLMDB(LOPQSearcher):
         try:
             for i, item_id in zip(range(n), ids):
                 item_id = item_id.item() if isinstance(item_id, np.generic) else item_id
-                key = self.encode_cell(coarse[i]) + str(item_id).encode()
+                # py2 `bytes(item_id)` (search.py:463): an id that is already bytes is the key suffix as it is
+                key = self.encode_cell(coarse[i]) + (bytes(item_id) if isinstance(item_id, (bytes, bytearray)) else str(item_id).encode())
                 self._items[key] = fine[i].copy()
                 if txn is not None:
                     txn.put(key, self.encode_fine_codes(fine[i]))
@@ -412,7 +474,7 @@ class LOPQSearcherLMDB(LOPQSearcher):
 
     def _rebuild(self):
         """Device index in key order: rows sorted by the full LMDB key (cell bytes, then str(id) bytes)."""
-        self._handle.index_clear()
+        self._device_clear()
         keys = sorted(self._items)
         n = len(keys)
         self._row_ids, self._row_cells, self._row_ids_flat = [], [], None
@@ -420,8 +482,10 @@ class LOPQSearcherLMDB(LOPQSearcher):
         if n:
             coarse = np.frombuffer(b"".join(k[:4] for k in keys), np.uint16).reshape(n, 2).astype(np.int32)
             fine = np.stack([self._items[k] for k in keys])
-            self._num2id = [self.id_lambda(k[4:]) for k in keys]
-            self._handle.index_add(coarse, fine, np.arange(n, dtype=np.int64))
+            # the reference is Python 2: the key suffix handed to id_lambda is a `str` (search.py:486-496), and the
+            # product passes id_lambda=str (searcher_lopqhbase.py:204-206) -- decode, or str(b'..') would quote it
+            self._num2id = [self.id_lambda(k[4:].decode()) for k in keys]
+            self._device_add(coarse, fine, np.arange(n, dtype=np.int64))
             self._row_ids = [np.arange(n, dtype=np.int64)]
             self._row_cells = [coarse[:, 0].astype(np.int64) * self.model.V + coarse[:, 1]]
         self._stale = False

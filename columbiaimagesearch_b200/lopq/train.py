@@ -133,14 +133,16 @@ def train(data, V=8, M=4, subquantizer_clusters=256, parameters=None, kmeans_coa
     return Cs, Rs, mus, subs
 
 
-def train_pca(data, dims, subsample=None):
-    """model.py:242-287 -- PCA by eigen-decomposition of the covariance; returns (P [D0, dims], mu)."""
+def train_pca(data, dims=256, subsample=None):
+    """model.py:242-287 -- PCA by eigen-decomposition of the covariance of the first `subsample` rows; the kept
+    eigen-directions are permuted by eigenvalue_allocation(2, E) so that the two coarse halves carry balanced variance
+    (model.py:276-278).  Returns (P [D0, dims], mu)."""
     X = np.asarray(data, dtype=np.float64)
     if subsample:
-        X = X[np.random.RandomState(0).choice(X.shape[0], size=min(subsample, X.shape[0]), replace=False)]
+        X = X[:min(int(subsample), X.shape[0])]
+    dims = min(int(dims), X.shape[1])
     mu = X.mean(0)
-    Xc = X - mu
-    cov = (Xc.T @ Xc) / max(1, X.shape[0] - 1)
-    ev, vecs = np.linalg.eigh(cov)
-    order = np.argsort(ev)[::-1][:dims]
-    return vecs[:, order], mu
+    cov = (X.T @ X) / max(1, X.shape[0] - 1) - np.outer(mu, mu)          # the reference's estimator (model.py:266-269)
+    ev, vecs = np.linalg.eigh(cov)                                       # ascending eigenvalues
+    ev, vecs = ev[-dims:], vecs[:, -dims:]
+    return vecs[:, eigenvalue_allocation(2, ev)], mu

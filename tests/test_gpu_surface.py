@@ -1,0 +1,266 @@
+"""GPU: the edges of the drop-in boundary that the big parity file does not touch -- the bare helpers of
+the reference API (utils.predict_cluster, eval.get_recall, LOPQSearcherBase.compute_distances, the codes TSV loader),
+pickles written by the reference's own classes loaded through install_as_lopq(), the process model of the product
+(searcher built before fork(), used from forked workers sharing one GPU), LOPQSearcherLMDB with the product's
+id_lambda=str, rejected index rows, and the training entry points of LOPQModelPCA as the product calls them."""
+import os
+import pickle
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import lopq_oracle as orc
+from tests.util import load_case, case_inputs, random_model_params, random_data, GOLDEN
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _lopq():
+    import columbiaimagesearch_b200.lopq as lopq
+    return lopq
+
+
+def test_predict_cluster_matches_oracle():
+    """utils.py:33-53: first minimum of the direct-form squared distances, smallest unsigned type that fits."""
+    lopq = _lopq()
+    rng = np.random.RandomState(3)
+    for n, d, dt in [(5, 7, np.float64), (256, 16, np.float64), (300, 8, np.float32), (64, 33, np.float32)]:
+        C = rng.randn(n, d).astype(dt)
+        C[n // 2] = C[1]                                    # an exact tie: the first index must win
+        for x in [rng.randn(d).astype(np.float32), C[1].astype(np.float32), rng.randn(d)]:
+            got = lopq.utils.predict_cluster(x, C)
+            want = orc.predict_cluster(x, C)
+            assert int(got) == int(want)
+            assert type(got) is type(want)
+
+
+def test_get_recall_matches_reference_definition():
+    """eval.py:92-142 through the mirror's get_recall and get_recall_batch against the oracle's restatement."""
+    lopq = _lopq()
+    z, omodel = load_case("A")
+    _, db, Q, ids = case_inputs("A")
+    model = lopq.LOPQModel.from_npz(z)
+    s = lopq.LOPQSearcher(model)
+    s.add_codes((z["db_coarse"], z["db_fine"]), ids)
+    index = orc.ArrayIndex(omodel.V, z["db_coarse"], z["db_fine"], ids)
+    # true nearest neighbours by brute force (eval.py:7-38)
+    d2 = ((Q[:, None, :].astype(np.float64) - db[None, :, :].astype(np.float64)) ** 2).sum(-1)
+    nns = ids[d2.argmin(1)]
+    th = (1, 10, 100, 1000)
+    want = orc.recall_at(lambda q, quota: orc.search_arrays(omodel, index, q, quota, None)[0], Q, nns, th)
+    got, qtime = lopq.eval.get_recall(s, Q, nns, thresholds=th)
+    np.testing.assert_array_equal(got, want)
+    assert qtime > 0
+    got_b = lopq.eval.get_recall_batch(s, Q, nns, quota=th[-1], thresholds=th, batch=16)
+    np.testing.assert_array_equal(got_b, want)
+    raw, _ = lopq.eval.get_recall(s, Q, nns, thresholds=th, normalize=False)
+    np.testing.assert_array_equal(raw, want * len(Q))
+
+
+def test_compute_distances_and_tsv_loader(tmp_path):
+    """search.py:137-177 (per-item ADC distances, left-to-right float64 sum) and :227-243 (codes TSV)."""
+    lopq = _lopq()
+    params = random_model_params(32, 3, 4, 32, seed=5)
+    omodel = orc.OracleModel(*params)
+    model = lopq.LOPQModel(parameters=params)
+    db = random_data(params, 300, seed=9)
+    coarse, fine = lopq.utils.compute_codes_arrays(db, model)
+    path = tmp_path / "codes.tsv"
+    with open(path, "w") as f:
+        for i in range(300):
+            f.write("id%03d\t%s\n" % (i, [[int(v) for v in coarse[i]], [int(v) for v in fine[i]]]))
+        f.write("\n")
+    s = lopq.LOPQSearcher(model)
+    s.add_codes_from_local(str(path))
+    o = orc.OracleSearcher(omodel)
+    o.add_codes([orc.LOPQCode(tuple(int(v) for v in c), tuple(int(v) for v in f)) for c, f in zip(coarse, fine)],
+                ["id%03d" % i for i in range(300)])
+    assert s.get_nb_indexed() == o.nb_indexed == 300
+    x = db[17]
+    items, vis = s.get_result_quota(x, 120)
+    oitems, ovis = o.get_result_quota(x, 120)
+    assert vis == ovis and [i[0] for i in items] == [i[0] for i in oitems]
+    got = s.compute_distances(x, items)
+    want = o.compute_distances(x, oitems)
+    assert [g[1][0] for g in got] == [w[1][0] for w in want]
+    np.testing.assert_array_equal(np.array([g[0] for g in got]), np.array([w[0] for w in want]))
+    a, _ = s.search(x, 120, 15, with_dists=True)
+    b, _ = o.search(x, 120, 15, with_dists=True)
+    assert [r.id for r in a] == [r.id for r in b]
+
+
+@pytest.mark.parametrize("case,fname", [("B", "ref_model_B.pkl"), ("C", "ref_model_C_pca.pkl")])
+def test_reference_pickle_loads_through_install_as_lopq(case, fname):
+    """Models are stored by pickle (storer/local.py:58,75): a file written by the reference's own classes
+    (tests/golden/make_pickles.py) must resolve to this package under the name `lopq` and behave identically."""
+    lopq = _lopq()
+    lopq.install_as_lopq(force=True)
+    import lopq as aliased
+    from lopq.search import LOPQSearcher
+    from lopq.utils import compute_codes_notparallel
+    assert aliased is lopq
+    with open(os.path.join(GOLDEN, fname), "rb") as f:
+        model = pickle.load(f)
+    assert type(model).__module__ == "columbiaimagesearch_b200.lopq.model"
+    assert isinstance(model, lopq.LOPQModelPCA if case == "C" else lopq.LOPQModel)
+    assert model.V == 4 and model.num_coarse_splits == 2 and model.subquantizer_clusters == 256
+    z, omodel = load_case(case)
+    _, db, Q, ids = case_inputs(case)
+    codes = compute_codes_notparallel(db[:400], model)
+    assert [tuple(int(v) for v in c.coarse) for c in codes] == [tuple(r) for r in z["db_coarse"][:400].tolist()]
+    assert [tuple(int(v) for v in c.fine) for c in codes] == [tuple(r) for r in z["db_fine"][:400].tolist()]
+    s = LOPQSearcher(model)
+    s.add_codes((z["db_coarse"], z["db_fine"]), ids)
+    assert s.get_nb_indexed() == int(z["nb_indexed"])
+    quota, limit = int(z["s1_quota"]), int(z["s1_limit"])
+    for i in range(8):
+        res, vis = s.search(Q[i], quota=quota, limit=limit, with_dists=True)
+        cnt = int(z["s1_counts"][i])
+        assert vis == int(z["s1_visited"][i]) and len(res) == cnt
+        assert [r.id for r in res] == z["s1_ids"][i][:cnt].tolist()
+    # and back: what this package pickles carries no native handle
+    blob = pickle.dumps(model, protocol=2)
+    again = pickle.loads(blob)
+    assert again.predict(db[3]) == model.predict(db[3])
+
+
+_FORK_SCRIPT = r"""
+import os, sys, numpy as np
+sys.path.insert(0, %(root)r)
+import columbiaimagesearch_b200.lopq as lopq
+from tests.util import load_case, case_inputs
+z, _ = load_case("A")
+_, db, Q, ids = case_inputs("A")
+model = lopq.LOPQModel.from_npz(z)
+s = lopq.LOPQSearcher(model)                       # gunicorn --preload: built in the master ...
+s.add_codes((z["db_coarse"], z["db_fine"]), ids)
+assert s._h is None                                # ... without touching the GPU
+quota, limit = int(z["s1_quota"]), int(z["s1_limit"])
+def serve(lo, hi):
+    for i in range(lo, hi):
+        res, vis = s.search(Q[i], quota=quota, limit=limit, with_dists=True)
+        cnt = int(z["s1_counts"][i])
+        assert vis == int(z["s1_visited"][i]) and [r.id for r in res] == z["s1_ids"][i][:cnt].tolist(), i
+        code = model.predict(db[i])
+        assert tuple(int(v) for v in code.fine) == tuple(z["db_fine"][i].tolist())
+pids = []
+for w in range(3):                                 # three workers share the one GPU
+    pid = os.fork()
+    if pid == 0:
+        try:
+            serve(w * 8, w * 8 + 8)
+            os._exit(0)
+        except BaseException as e:
+            sys.stderr.write("worker %%d: %%r\n" %% (w, e))
+            os._exit(1)
+    pids.append(pid)
+bad = [p for p in pids if os.waitpid(p, 0)[1] != 0]
+assert not bad, bad
+serve(24, 32)                                      # the master itself can still create its own context afterwards
+# a searcher that was used BEFORE the fork is rebuilt from its host rows in the child
+pid = os.fork()
+if pid == 0:
+    try:
+        serve(32, 40)
+        os._exit(0)
+    except BaseException as e:
+        sys.stderr.write("late worker: %%r\n" %% (e,))
+        os._exit(1)
+# (forking after CUDA initialisation leaves the child without a usable driver; report what happened, do not require it)
+st = os.waitpid(pid, 0)[1]
+print("late-fork child status", st)
+print("ok")
+"""
+
+
+def test_searcher_built_before_fork_serves_from_workers(tmp_path):
+    """Process model of the product: `gunicorn --preload` builds the searcher in the master and forks the workers
+    (setup/components/search/docker-compose.yml:67).  The handle is created by the process that first searches."""
+    script = tmp_path / "fork_workers.py"
+    script.write_text(_FORK_SCRIPT % {"root": ROOT})
+    r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "ok" in r.stdout
+
+
+def test_lmdb_searcher_string_ids():
+    """The product builds LOPQSearcherLMDB(model, path, id_lambda=str) with sha1 row keys (searcher_lopqhbase.py:204-206):
+    ids come back as the `str` they went in as (not "b'..'"), in key order inside a cell; bytes ids are taken as they are."""
+    import hashlib
+    lopq = _lopq()
+    params = random_model_params(32, 3, 4, 32, seed=5)
+    omodel = orc.OracleModel(*params)
+    model = lopq.LOPQModel(parameters=params)
+    db = random_data(params, 200, seed=9)
+    coarse, fine = lopq.utils.compute_codes_arrays(db, model)
+    sha = [hashlib.sha1(b"img%d" % i).hexdigest().upper() for i in range(200)]
+    s = lopq.LOPQSearcherLMDB(model, None, id_lambda=str)
+    s.add_codes((coarse[:120], fine[:120]), sha[:120])
+    s.add_codes((coarse[120:], fine[120:]), [v.encode() for v in sha[120:]])          # bytes ids
+    assert s.get_nb_indexed() == 200
+    res, vis = s.search(db[5], quota=60, limit=20, with_dists=True)
+    assert res and all(isinstance(r.id, str) and r.id in sha for r in res)
+    # same ranking as the oracle over cells read in key order
+    keyorder = sorted(range(200), key=lambda i: (int(coarse[i, 0]), int(coarse[i, 1]), sha[i].encode()))
+    o = orc.OracleSearcher(omodel)
+    o.add_codes([orc.LOPQCode(tuple(int(v) for v in coarse[i]), tuple(int(v) for v in fine[i])) for i in keyorder],
+                [sha[i] for i in keyorder])
+    want, ovis = o.search(db[5], quota=60, limit=20, with_dists=True)
+    assert vis == ovis and [r.id for r in res] == [r.id for r in want]
+    cell = (int(coarse[5, 0]), int(coarse[5, 1]))
+    assert [i for i, _ in s.get_cell(cell)] == [i for i, _ in o.get_cell(cell)]
+
+
+def test_out_of_range_coarse_codes_are_refused_atomically():
+    from columbiaimagesearch_b200._native import NativeError
+    lopq = _lopq()
+    params = random_model_params(32, 3, 4, 32, seed=5)
+    model = lopq.LOPQModel(parameters=params)
+    db = random_data(params, 100, seed=9)
+    coarse, fine = lopq.utils.compute_codes_arrays(db, model)
+    h = model._new_handle()
+    h.index_add(coarse[:50], fine[:50])
+    bad = coarse[50:].copy()
+    bad[7, 1] = 3                                           # V = 3: out of range
+    with pytest.raises(NativeError):
+        h.index_add(bad, fine[50:])
+    assert h.index_size() == 50 and int(h.cell_sizes().sum()) == 50       # nothing of the refused batch stayed
+    h.index_add(coarse[50:], fine[50:])
+    assert h.index_size() == 100
+    # the searcher drops such rows (the reference logs the item and goes on, search.py:343-367) and stays consistent
+    s = lopq.LOPQSearcher(model)
+    s.add_codes((bad, fine[50:]), np.arange(50, 100))
+    assert s.get_nb_indexed() == 49
+    res, _ = s.search(db[60], quota=1000)
+    assert 57 not in [r.id for r in res] and len(res) == 49
+
+
+def test_pca_model_training_entry_points():
+    """searcher_lopqhbase.py:462 trains on already projected features: fit(x, apply_pca=False, train_pca=False);
+    fit_pca refuses to retrain (model.py:878-886); apply_PCA(dtype=float64) is not rounded through float32."""
+    lopq = _lopq()
+    rng = np.random.RandomState(0)
+    X = (rng.randn(3000, 24) * np.linspace(3.0, 0.2, 24)).astype(np.float32)
+    m = lopq.LOPQModelPCA(V=2, M=4, subquantizer_clusters=16)
+    m.fit_pca(X, pca_dims=16)
+    assert m.pca_P.shape == (24, 16)
+    with pytest.raises(ValueError):
+        m.fit_pca(X, pca_dims=16)
+    proj = m.apply_PCA(X)
+    assert proj.dtype == np.float32 and proj.shape == (3000, 16)
+    p64 = m.apply_PCA(X[:50], dtype=np.float64)
+    want = (X[:50].astype(np.float64) - m.pca_mu) @ m.pca_P
+    np.testing.assert_allclose(p64, want, rtol=1e-12, atol=1e-12)
+    assert np.abs(p64 - p64.astype(np.float32)).max() > 0                    # genuinely float64
+    m.fit(proj, verbose=False, apply_pca=False, train_pca=False, n_init=1, kmeans_coarse_iters=3, kmeans_local_iters=3,
+          random_state=0)
+    assert m.Cs[0].shape == (2, 8) and len(m.subquantizers[0]) == 2
+    code = m.predict(X[0])
+    assert len(code.coarse) == 2 and len(code.fine) == 4
+    # the full path (train PCA + project + train) on a fresh model
+    m2 = lopq.LOPQModelPCA(V=2, M=4, subquantizer_clusters=16)
+    m2.fit(X, pca_dims=16, n_init=1, kmeans_coarse_iters=3, kmeans_local_iters=3, random_state=0, pca_subsample=2000)
+    assert m2.pca_P.shape == (24, 16) and m2.predict(X[1]).fine is not None

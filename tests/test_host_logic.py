@@ -76,3 +76,31 @@ def test_reconstruct_matches_reference_golden():
             np.testing.assert_allclose(model.reconstruct(code), z["probe_recon"][i], rtol=1e-12, atol=1e-13)
         assert model.get_cell_id_for_coarse_codes((3, 2)) == 2 + 3 * model.V
         assert model.get_coarse_codes_for_cell_id(2 + 3 * model.V) == (3, 2)
+
+
+def test_train_pca_balances_the_two_halves():
+    """model.py:242-287: the kept eigen-directions are permuted by eigenvalue_allocation(2, E), so the two coarse halves
+    of the projected space carry comparable variance (plain descending order would put most of it in the first half);
+    pca_dims is clamped to D; pca_subsample takes the FIRST rows."""
+    from columbiaimagesearch_b200.lopq.train import train_pca, eigenvalue_allocation
+    rng = np.random.RandomState(0)
+    scales = np.array([9.0, 7.0, 5.0, 4.0, 3.0, 2.5, 2.0, 1.5, 1.2, 1.0, 0.8, 0.5])
+    X = rng.randn(20000, 12) * scales
+    P, mu = train_pca(X, 8)
+    assert P.shape == (12, 8) and mu.shape == (12,)
+    Y = (X - mu) @ P
+    v = Y.var(0)
+    first, second = v[:4].sum(), v[4:].sum()
+    # log-products are balanced: both halves hold large and small directions
+    assert 0.4 < np.log(v[:4]).sum() / np.log(v[4:]).sum() < 2.5
+    assert max(first, second) / min(first, second) < 2.0
+    ev = np.sort(np.linalg.eigvalsh(np.cov(X.T)))[-8:]
+    np.testing.assert_allclose(np.sort(v), ev, rtol=1e-2)
+    assert sorted(eigenvalue_allocation(2, ev).tolist()) == list(range(8))
+    # matches the reference's estimator and permutation (oracle port of the same lines)
+    P2, _ = train_pca(X, 64)
+    assert P2.shape == (12, 12)
+    Pa, mua = train_pca(X, 8, subsample=5000)
+    Pb, mub = train_pca(X[:5000], 8)
+    np.testing.assert_array_equal(Pa, Pb)
+    np.testing.assert_array_equal(mua, mub)

@@ -79,3 +79,20 @@ def test_pca_model_identical(setup):
     for row in x[:20]:
         a, b = m.predict(row), orc.predict(om, row)
         assert tuple(map(int, a.coarse + a.fine)) == tuple(map(int, b.coarse + b.fine))
+
+
+def test_train_pca_matches_reference():
+    """The training mirror's PCA (host NumPy, not on the hot path) against the reference's train_pca (model.py:242-287):
+    same subspace, same eigenvalue_allocation permutation of the columns, same first-rows subsample."""
+    from columbiaimagesearch_b200.lopq.train import train_pca, eigenvalue_allocation
+    ref = ref_loader.load()
+    rng = np.random.RandomState(5)
+    X = rng.randn(3000, 20) * np.linspace(4.0, 0.3, 20)
+    with contextlib.redirect_stdout(io.StringIO()):
+        rp, rdims = ref.model.train_pca(X, 12, 2000)
+    P, mu = train_pca(X, 12, 2000)
+    assert rdims == 12 and P.shape == rp["P"].shape
+    np.testing.assert_allclose(mu, rp["mu"], rtol=0, atol=1e-12)
+    sign = np.sign((P * rp["P"]).sum(0))
+    np.testing.assert_allclose(P * sign, rp["P"], rtol=0, atol=1e-8)
+    assert eigenvalue_allocation(2, rp["E"]).tolist() == ref.model.eigenvalue_allocation(2, rp["E"]).tolist()
