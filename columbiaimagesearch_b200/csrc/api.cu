@@ -74,7 +74,7 @@ struct b2l_ctx {
     // model
     bool has_model = false, has_pca = false;
     ModelView mv = {};
-    DevBuf dCs, dmus, dRt, dsubs, dsubs32, dc2max, dP, dpmu;
+    DevBuf dCs, dmus, dRt, dsubs, dsubs32, dsubs32T, dc2max, dP, dpmu;
     // index: master copy in insertion order
     int64_t n_items = 0;
     DevBuf m_coarse, m_fine, m_rowid;
@@ -85,7 +85,7 @@ struct b2l_ctx {
     std::vector<int64_t> h_lsize, h_gsize, h_cell_start;
     // workspaces
     DevBuf w_q, w_xq, w_px, w_coarse, w_fine, w_lut32, w_lut64, w_p64, w_cellq, w_cand, w_gtab, w_lut16, w_quant, w_plan, w_sort_a, w_sort_b,
-        w_sort_tmp, w_rec, w_rec2, w_out, w_out2, w_misc;
+        w_sort_tmp, w_rec, w_rec2, w_out, w_out2, w_misc, w_bkt, w_perm;
     PlanView pv = {};
     unsigned int* gthr = nullptr;      // [nq] per-query pruning bound shared by the scan blocks
     unsigned int* cand_cnt = nullptr;  // [nq] candidates the scan appended
@@ -188,7 +188,7 @@ int encode_device(b2l_handle h, const void* dX, int x_is_f64, int64_t n, const i
     const unsigned blocks = (unsigned)((n + ENC_WARPS - 1) / ENC_WARPS);
     const size_t smem = (size_t)ENC_WARPS * mv.h * 8;
     // batch encode of the common shape: coarse assignment, then the rotation as a grouped float64 tensor-core GEMM
-    const bool gemm = d_fine && !d_coarse_in && d_coarse && mv.h == ROT_H && n >= 2048 && n < ((int64_t)1 << 31);
+    const bool gemm = d_fine && !d_coarse_in && d_coarse && mv.h % 64 == 0 && n >= 2048 && n < ((int64_t)1 << 31);
     double* px_out = gemm ? nullptr : h->w_px.as<double>();
     if (gemm && mv.h % 8 == 0 && mv.h <= 128) {
         if (xf64) k_coarse_assign<double><<<blocks, ENC_WARPS * 32, 0, h->stream>>>(mv, (const double*)x, n, d_coarse);
@@ -214,6 +214,13 @@ int encode_device(b2l_handle h, const void* dX, int x_is_f64, int64_t n, const i
         LAUNCHED();
         const unsigned tiles = (unsigned)(2 * ((n + 63) / 64) + nb);       // upper bound; surplus blocks leave at once
         const size_t smr = (size_t)2 * ROT_H * ROT_LD * 8 + 64 * 4;
+        if (mv.h != ROT_H) {             // large models (2048-d: h = 1024): 64 x 64 output tiles, contraction in chunks of 64
+            const dim3 g2(tiles, (unsigned)(mv.h / 64));
+            if (xf64) { CU(cudaFuncSetAttribute(k_rotate_dmma_g<double, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr));
+                k_rotate_dmma_g<double, 0><<<g2, 128, smr, h->stream>>>(mv, (const double*)x, n, cnt, base, tile_base, perm, nullptr, h->w_px.as<double>()); }
+            else { CU(cudaFuncSetAttribute(k_rotate_dmma_g<float, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr));
+                k_rotate_dmma_g<float, 0><<<g2, 128, smr, h->stream>>>(mv, (const float*)x, n, cnt, base, tile_base, perm, nullptr, h->w_px.as<double>()); }
+        } else
         if (xf64) { CU(cudaFuncSetAttribute(k_rotate_dmma<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr));
             k_rotate_dmma<double><<<tiles, 128, smr, h->stream>>>(mv, (const double*)x, n, cnt, base, tile_base, perm, h->w_px.as<double>()); }
         else { CU(cudaFuncSetAttribute(k_rotate_dmma<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr));
@@ -233,6 +240,7 @@ int encode_device(b2l_handle h, const void* dX, int x_is_f64, int64_t n, const i
 #define FINE32(DSV)                                                                                             \
     do {                                                                                                        \
         const size_t sm3 = (size_t)mv.K * DSV * 4;                                                              \
+        if (sm3 > 48 * 1024) CU(cudaFuncSetAttribute(k_fine_argmin32<DSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3)); \
         k_fine_argmin32<DSV><<<b2, FINE_THREADS, sm3, h->stream>>>(mv, h->w_px.as<double>(), n, d_fine, h->d_nguard); \
     } while (0)
         const bool f32stage = h->fine_mode == 0 && n >= 2048;    // float32 first stage + float64 guard (same codes)
@@ -241,6 +249,8 @@ int encode_device(b2l_handle h, const void* dX, int x_is_f64, int64_t n, const i
             case 4: if (f32stage) FINE32(4); else FINE(4); break;
             case 8: if (f32stage) FINE32(8); else FINE(8); break;
             case 16: if (f32stage) FINE32(16); else FINE(16); break;
+            case 32: if (f32stage) FINE32(32); else FINE(0); break;
+            case 64: if (f32stage) FINE32(64); else FINE(0); break;
             default:
                 if (mv.ds > 128) FAIL(B2L_ERR_UNSUPPORTED, "sub-vector length D/M = %d > 128 not supported", mv.ds);
                 FINE(0);
@@ -519,7 +529,10 @@ int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_
         unsigned char* qb = h->w_quant.as<unsigned char>();
         qv.qmin = (unsigned int*)(qb + o_qmin); qv.qmax = (unsigned int*)(qb + o_qmax);
         qv.B = (double*)(qb + o_B); qv.delta = (double*)(qb + o_dl); qv.slack = (double*)(qb + o_sl); qv.qmax_code = 65535 / mv.M;
-        qv.ds = mv.ds; qv.c2m = h->c2m; qv.f32_entries = (mv.ds == 8 && mv.m == 8 && mv.K <= 256) ? 1 : 0;
+        qv.ds = mv.ds; qv.c2m = h->c2m;
+        // float32 table entries (their error is part of the certification bound): the register-resident kernel of the
+        // headline shape, or the generic one behind the grouped rotation GEMM of large models
+        qv.f32_entries = ((mv.ds == 8 && mv.m == 8) || (mv.h % 64 == 0 && mv.h > 64)) ? 1 : 0;
         iv.qmin = qv.qmin; iv.qmax = qv.qmax; iv.M = mv.M;
     }
     {
@@ -574,7 +587,44 @@ int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_
         case 16: LUTK(XT, 16); break;             \
         default: LUTK(XT, 0);                     \
     }
-        if (packed && qv.f32_entries) {
+        if (mv.h % 64 == 0 && mv.h > 64) {
+            // large models (2048-d: R[c] is 8 MB): the projections of all slots as ONE grouped float64 tensor-core GEMM
+            // (slots bucketed by (split, coarse code)), then the table entries from the finished projections
+            const int nb2 = 2 * mv.V;
+            CU(h->w_perm.reserve((size_t)2 * cap_lut * 4));                    // perm[2][cap_lut]
+            CU(h->w_bkt.reserve((size_t)(4 * nb2 + 4) * 4));
+            unsigned int* bc = h->w_bkt.as<unsigned int>();
+            unsigned int* bbase = bc + nb2; unsigned int* bcur = bbase + nb2; unsigned int* btile = bcur + nb2;
+            unsigned int* perm = h->w_perm.as<unsigned int>();
+            CU(cudaMemsetAsync(bc, 0, (size_t)nb2 * 4, h->stream));
+            const unsigned sg = (unsigned)std::min<size_t>((cap_lut + 255) / 256, 1024);
+            k_slot_hist<<<sg, 256, 0, h->stream>>>(pv.lut_desc, &pv.cnt->n_lut, mv.V, bc);
+            LAUNCHED();
+            k_enc_offsets<<<1, 32, 0, h->stream>>>(mv.V, bc, bbase, bcur, btile);
+            LAUNCHED();
+            k_slot_scatter<<<sg, 256, 0, h->stream>>>(pv.lut_desc, &pv.cnt->n_lut, mv.V, cap_lut, bbase, bcur, perm);
+            LAUNCHED();
+            const dim3 g2((unsigned)(cap_lut / 64 + nb2), (unsigned)(mv.h / 64));
+            const size_t smr = (size_t)2 * 64 * ROT_LD * 8 + 64 * 4;
+            if (xf64) { CU(cudaFuncSetAttribute(k_rotate_dmma_g<double, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr));
+                k_rotate_dmma_g<double, 1><<<g2, 128, smr, h->stream>>>(mv, (const double*)x, (int64_t)cap_lut, bc, bbase, btile, perm, pv.lut_desc, h->w_p64.as<double>()); }
+            else { CU(cudaFuncSetAttribute(k_rotate_dmma_g<float, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr));
+                k_rotate_dmma_g<float, 1><<<g2, 128, smr, h->stream>>>(mv, (const float*)x, (int64_t)cap_lut, bc, bbase, btile, perm, pv.lut_desc, h->w_p64.as<double>()); }
+            LAUNCHED();
+            if (packed) {
+                constexpr int SB = 4;
+                const size_t sme = (size_t)SB * mv.h * 4;
+                CU(cudaFuncSetAttribute(k_lut_entries_f32<SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sme));
+                const unsigned eg = (unsigned)std::min<size_t>(cap_lut / SB + 2, (size_t)h->num_sms * 4);
+                k_lut_entries_f32<SB><<<eg, 256, sme, h->stream>>>(mv, h->w_p64.as<double>(), perm, bbase, bc, cap_lut, lut32);
+            } else if (xf64) {
+                CU(cudaFuncSetAttribute(k_lut<double, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                k_lut<double, 0><<<lgrid, LUT_THREADS, smem, h->stream>>>(mv, (const double*)x, pv.lut_desc, pv.cnt, h->w_p64.as<double>(), lut32, lut64, 1);
+            } else {
+                CU(cudaFuncSetAttribute(k_lut<float, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                k_lut<float, 0><<<lgrid, LUT_THREADS, smem, h->stream>>>(mv, (const float*)x, pv.lut_desc, pv.cnt, h->w_p64.as<double>(), lut32, lut64, 1);
+            }
+        } else if (packed && qv.f32_entries) {
             // headline shape, packed scan: float64 projection, table entries in float32 from the register-resident float32
             // codebook (their evaluation error is part of the certification bound), column ranges reduced on the way
             const size_t sm32 = (size_t)(2 * mv.h + 256) * 8 + (size_t)mv.h * 4;
@@ -786,10 +836,10 @@ int b2l_destroy(b2l_handle h) {
     if (!h) return B2L_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    DevBuf* bufs[] = {&h->dCs, &h->dmus, &h->dRt, &h->dsubs, &h->dsubs32, &h->dc2max, &h->dP, &h->dpmu, &h->m_coarse, &h->m_fine, &h->m_rowid, &h->codes,
+    DevBuf* bufs[] = {&h->dCs, &h->dmus, &h->dRt, &h->dsubs, &h->dsubs32, &h->dsubs32T, &h->dc2max, &h->dP, &h->dpmu, &h->m_coarse, &h->m_fine, &h->m_rowid, &h->codes,
                       &h->rowids, &h->cell_start, &h->lsize, &h->gsize, &h->sorted_first, &h->w_q, &h->w_xq, &h->w_px,
                       &h->w_coarse, &h->w_fine, &h->w_lut32, &h->w_lut64, &h->w_p64, &h->w_cellq, &h->w_cand, &h->w_gtab, &h->w_lut16, &h->w_quant, &h->w_plan,
-                      &h->w_sort_a, &h->w_sort_b, &h->w_sort_tmp, &h->w_rec, &h->w_rec2, &h->w_out, &h->w_out2, &h->w_misc};
+                      &h->w_sort_a, &h->w_sort_b, &h->w_sort_tmp, &h->w_rec, &h->w_rec2, &h->w_out, &h->w_out2, &h->w_misc, &h->w_bkt, &h->w_perm};
     for (DevBuf* b : bufs) b->release();
     if (h->h_out) cudaFreeHost(h->h_out);
     if (h->d_nguard) cudaFree(h->d_nguard);
@@ -925,11 +975,16 @@ int b2l_set_model(b2l_handle h, int D, int V, int M, int K, int coarse_is_f32, c
         c2[j] = (float)(mx * 1.001 + 1e-30);
         h->c2m = std::max(j ? h->c2m : 0.0f, c2[j]);
     }
-    CU(h->dsubs32.reserve(nS * 4)); CU(h->dc2max.reserve((size_t)M * 4));
+    std::vector<float> s32t(nS);
+    for (int j = 0; j < M; ++j)
+        for (int k = 0; k < K; ++k)
+            for (int d = 0; d < mv.ds; ++d) s32t[((size_t)j * mv.ds + d) * K + k] = s32[((size_t)j * K + k) * mv.ds + d];
+    CU(h->dsubs32.reserve(nS * 4)); CU(h->dsubs32T.reserve(nS * 4)); CU(h->dc2max.reserve((size_t)M * 4));
+    CU(cudaMemcpyAsync(h->dsubs32T.p, s32t.data(), nS * 4, cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(h->dsubs32.p, s32.data(), nS * 4, cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(h->dc2max.p, c2.data(), (size_t)M * 4, cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    mv.subs32 = h->dsubs32.as<float>(); mv.c2max = h->dc2max.as<float>();
+    mv.subs32 = h->dsubs32.as<float>(); mv.subs32T = h->dsubs32T.as<float>(); mv.c2max = h->dc2max.as<float>();
     mv.Cs = h->dCs.as<double>(); mv.mus = h->dmus.as<double>(); mv.Rt = h->dRt.as<double>(); mv.subs = h->dsubs.as<double>();
     h->has_model = true; h->has_pca = false; h->dirty = true; h->global_set = false;
     return B2L_OK;

@@ -21,6 +21,7 @@ struct ModelView {
     const double* Rt;          // [2][V][h(d)][h(t)] : Rt[s][c][d][t] = R[s][c][t][d]  (coalesced mat-vec)
     const double* subs;        // [M][K][ds]
     const float* subs32;       // [M][K][ds] the same, rounded to float32 (first stage of the fine argmin)
+    const float* subs32T;      // [M][ds][K] float32, centroid index fastest (coalesced one-thread-per-centroid reads)
     const float* c2max;        // [M] upper bound on max_k |subs[j][k]|^2
     // PCA (LOPQModelPCA)
     int D0, renorm;

@@ -370,3 +370,93 @@ k_rotate_dmma(ModelView mv, const XT* __restrict__ X, int64_t n, const unsigned 
         for (int nt = 0; nt < 8; ++nt) *(double2*)(o + 8 * nt) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
     }
 }
+
+
+// ---- the same grouped GEMM for any h that is a multiple of 64 (2048-d models: h = 1024) -------------------------------
+// grid = (64-row tiles, h / 64 column blocks).  A block produces a 64 x 64 tile of P = Resid . R[c]^T, walking the
+// contraction index in chunks of 64: the R chunk [64 d][64 t] and the residual chunk [64 rows][64 d] (recomputed from
+// the raw rows: x - C - mu) are staged in shared memory, 16 DMMA k-steps per chunk.  Every R[c] (8 MB at h = 1024) is
+// thus read once per 64 rows instead of once per row.
+// MODE 0 (batch encode): tile rows are database rows i = perm[s][.], input X[i], output PX[i][s*h + t].
+// MODE 1 (distance tables of a query batch): tile rows are LUT slots = perm[s][.], input Xq[desc[slot].q], output P64[slot][t];
+//         `n` is then the slot capacity (row stride of perm).
+template <typename XT, int MODE>
+__global__ void __launch_bounds__(128)
+k_rotate_dmma_g(ModelView mv, const XT* __restrict__ X, int64_t n, const unsigned int* __restrict__ cnt,
+                const unsigned int* __restrict__ base, const unsigned int* __restrict__ tile_base, const unsigned int* __restrict__ perm,
+                const int32_t* __restrict__ desc, double* __restrict__ OUT) {
+    extern __shared__ double sm_rot[];
+    double* Rs = sm_rot;                       // Rs[d][t]
+    double* Es = sm_rot + 64 * ROT_LD;         // Es[row][d]
+    int* rows = (int*)(Es + 64 * ROT_LD);
+    const int V = mv.V, nb = 2 * V, h = mv.h;
+    const unsigned int tile = blockIdx.x;
+    if (tile >= tile_base[nb]) return;
+    int lo = 0, hi = nb;
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (tile_base[mid] <= tile) lo = mid; else hi = mid; }
+    const int b = lo, s = b / V;
+    const unsigned int row0 = (tile - tile_base[b]) * 64u;
+    const int nrow = (int)min(64u, cnt[b] - row0);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int t0 = blockIdx.y * 64;
+    const double* Rt = mv.Rt + (int64_t)b * h * (int64_t)h;
+    const double* C = mv.Cs + (int64_t)b * h;
+    const double* mu = mv.mus + (int64_t)b * h;
+    if (tid < 64) rows[tid] = tid < nrow ? (int)perm[(size_t)s * n + base[b] + row0 + tid] : -1;
+    double acc[2][8][2];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) { acc[mt][nt][0] = 0.0; acc[mt][nt][1] = 0.0; }
+    const int ar = lane >> 2, ak = lane & 3;
+    for (int d0 = 0; d0 < h; d0 += 64) {
+        __syncthreads();                       // rows[] published / previous chunk consumed
+        for (int e = tid; e < 64 * 64; e += 128) Rs[(e >> 6) * ROT_LD + (e & 63)] = Rt[(int64_t)(d0 + (e >> 6)) * h + t0 + (e & 63)];
+        for (int e = tid; e < 64 * 64; e += 128) {
+            const int r = e >> 6, d = d0 + (e & 63);
+            const int i = rows[r];
+            double v = 0.0;
+            if (i >= 0) {
+                const XT* x = MODE == 0 ? X + (int64_t)i * mv.D + s * h : X + (int64_t)desc[3 * i] * mv.D + s * h;
+                v = coarse_residual<XT>(x[d], C[d], mu[d], mv.coarse_f32);
+            }
+            Es[r * ROT_LD + (e & 63)] = v;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int k0 = 0; k0 < 64; k0 += 4) {
+            double a[2], bb[8];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) a[mt] = Es[(16 * warp + 8 * mt + ar) * ROT_LD + k0 + ak];
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) bb[nt] = Rs[(k0 + ak) * ROT_LD + 8 * nt + ar];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], a[mt], bb[nt]);
+        }
+    }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+        const int i = rows[16 * warp + 8 * mt + ar];
+        if (i < 0) continue;
+        double* o = (MODE == 0 ? OUT + (int64_t)i * mv.D + s * h : OUT + (int64_t)i * h) + t0 + 2 * ak;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) *(double2*)(o + 8 * nt) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+    }
+}
+
+// bucketing of LUT slots by (split, coarse code) for MODE 1: desc [slot][3] = (q, split, c); nslot read from the device
+__global__ void k_slot_hist(const int32_t* __restrict__ desc, const unsigned int* __restrict__ nslot_p, int V, unsigned int* __restrict__ cnt) {
+    const unsigned int nslot = *nslot_p;
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < nslot; i += gridDim.x * blockDim.x)
+        atomicAdd(&cnt[desc[3 * i + 1] * V + desc[3 * i + 2]], 1u);
+}
+__global__ void k_slot_scatter(const int32_t* __restrict__ desc, const unsigned int* __restrict__ nslot_p, int V, size_t cap,
+                               const unsigned int* __restrict__ base, unsigned int* __restrict__ cursor, unsigned int* __restrict__ perm) {
+    const unsigned int nslot = *nslot_p;
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < nslot; i += gridDim.x * blockDim.x) {
+        const int s = desc[3 * i + 1], b = s * V + desc[3 * i + 2];
+        perm[(size_t)s * cap + base[b] + atomicAdd(&cursor[b], 1u)] = i;
+    }
+}

@@ -257,7 +257,7 @@ __global__ void k_fill(PlanView pv) {
 template <typename XT, int DS>
 __global__ void __launch_bounds__(LUT_THREADS)
 k_lut(ModelView mv, const XT* __restrict__ Xq, const int32_t* __restrict__ lut_desc, const PlanCounters* __restrict__ cnt,
-      double* __restrict__ P64, float* __restrict__ lut32, double* __restrict__ lut64) {
+      double* __restrict__ P64, float* __restrict__ lut32, double* __restrict__ lut64, int have_p = 0) {
     extern __shared__ double sm_lut[];
     const int h = mv.h, m = mv.m, V = mv.V;
     const int ds = DS ? DS : mv.ds;
@@ -272,6 +272,9 @@ k_lut(ModelView mv, const XT* __restrict__ Xq, const int32_t* __restrict__ lut_d
     const XT* x = Xq + (int64_t)q * mv.D + s * h;
     const double* C = mv.Cs + ((int64_t)s * V + c) * h;
     const double* mu = mv.mus + ((int64_t)s * V + c) * h;
+    if (have_p) {          // the projection was produced by the grouped GEMM (k_rotate_dmma_g, large h)
+        for (int d = tid; d < h; d += LUT_THREADS) p[d] = P64[(int64_t)slot * h + d];
+    } else
     for (int d = tid; d < h; d += LUT_THREADS) r[d] = coarse_residual<XT>(x[d], C[d], mu[d], mv.coarse_f32);
     __syncthreads();
     // rotation p[t] = sum_d Rt[d][t] r[d]: `parts` threads share one output (contiguous d ranges, summed in order)
@@ -281,7 +284,7 @@ k_lut(ModelView mv, const XT* __restrict__ Xq, const int32_t* __restrict__ lut_d
     const int tw = LUT_THREADS / parts;                                       // outputs handled per sweep
     const int part = tid / tw, tl = tid - part * tw;
     const int dlen = h / parts, d0 = part * dlen;
-    for (int t0 = 0; t0 < h; t0 += tw) {
+    for (int t0 = 0; t0 < (have_p ? 0 : h); t0 += tw) {
         const int t = t0 + tl;
         double acc = 0.0;
         if (t < h) {
@@ -511,6 +514,67 @@ k_lut_f32(ModelView mv, const XT* __restrict__ Xq, const int32_t* __restrict__ l
         __syncthreads();
         if (tid < MJ) atomicMin(&qmin[(size_t)q * mv.M + s * MJ + tid], s_cmin[tid]);
         if (tid == 0) atomicMax(&qmax[q], s_cmax);
+    }
+}
+
+// ---- LUT entries in float32 for any sub-vector length (packed scan, large models) ----------------------------------
+// Same contract as k_lut_f32 (entries within Emax of the float64 value, folded into the certification bound by
+// k_lut_quant), for shapes whose codebook does not fit a thread's registers (2048-d: ds = 64).  The projection comes
+// from the grouped GEMM.  Block = 256 threads = centroids; it takes SB slots of one coarse split at a time (perm lists
+// the slots split by split), so a codebook element read once (subs32T: centroid index fastest, coalesced) serves SB
+// tables.  dynamic smem: p32[SB][h] floats
+template <int SB>
+__global__ void __launch_bounds__(256)
+k_lut_entries_f32(ModelView mv, const double* __restrict__ P64, const unsigned int* __restrict__ perm, const unsigned int* __restrict__ base,
+                  const unsigned int* __restrict__ bcnt, size_t cap, float* __restrict__ lut32) {
+    extern __shared__ float sm_le[];
+    __shared__ unsigned int s_slot[SB];
+    const int h = mv.h, m = mv.m, ds = mv.ds, V = mv.V, K = mv.K;
+    const int k = threadIdx.x;
+    const bool live = k < K;
+    const unsigned int nr0 = base[V - 1] + bcnt[V - 1], nr1 = base[2 * V - 1] + bcnt[2 * V - 1];
+    const unsigned int g0 = (nr0 + SB - 1) / SB, g1 = (nr1 + SB - 1) / SB;
+    for (unsigned int g = blockIdx.x; g < g0 + g1; g += gridDim.x) {
+        const int s = g >= g0;
+        const unsigned int r0 = (g - (s ? g0 : 0u)) * SB, nr = s ? nr1 : nr0;
+        const int ns = (int)min((unsigned int)SB, nr - r0);
+        __syncthreads();
+        if (k < SB) s_slot[k] = k < ns ? perm[(size_t)s * cap + r0 + k] : 0u;
+        __syncthreads();
+        for (int e = k; e < SB * h; e += 256) {
+            const int i = e / h;
+            sm_le[e] = i < ns ? (float)P64[(int64_t)s_slot[i] * h + (e - i * h)] : 0.0f;
+        }
+        __syncthreads();
+        for (int j0 = 0; j0 < m; j0 += 4) {
+            float out[SB][4];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const int j = j0 + jj;
+                float acc[SB];
+#pragma unroll
+                for (int i = 0; i < SB; ++i) acc[i] = 0.0f;
+                if (j < m) {
+                    const float* c = mv.subs32T + ((int64_t)(s * m + j) * ds) * K + (live ? k : 0);
+                    const float* pj = sm_le + j * ds;
+#pragma unroll 4
+                    for (int t = 0; t < ds; ++t) {
+                        const float cv = c[(int64_t)t * K];
+#pragma unroll
+                        for (int i = 0; i < SB; ++i) { const float df = pj[i * h + t] - cv; acc[i] = fmaf(df, df, acc[i]); }
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < SB; ++i) out[i][jj] = live ? acc[i] : 0.0f;
+            }
+#pragma unroll
+            for (int i = 0; i < SB; ++i) {
+                if (i >= ns) break;
+                float* o = lut32 + ((int64_t)s_slot[i] * B2L_LUT_ROWS + k) * m + j0;
+                if (j0 + 4 <= m && (m & 3) == 0) *(float4*)o = make_float4(out[i][0], out[i][1], out[i][2], out[i][3]);
+                else for (int jj = 0; jj < 4 && j0 + jj < m; ++jj) o[jj] = out[i][jj];
+            }
+        }
     }
 }
 

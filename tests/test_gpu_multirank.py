@@ -45,6 +45,7 @@ class EmulatedShards(object):
         nq = Q.shape[0]
         nb = h0.records_bytes(nq, k)
         allrec = torch.zeros(nb * self.world, dtype=torch.uint8, device="cuda:%d" % h0.device)
+        torch.cuda.synchronize()                             # the handles launch on their own non-blocking streams
         for r, s in enumerate(self.ranks):
             s._handle.search_local(Q, quota, k, allrec.data_ptr() + r * nb, exact=exact)
         outs = [s._handle.search_merge(allrec.data_ptr(), self.world, nq, k) for s in self.ranks]
@@ -69,11 +70,16 @@ def test_merge_over_ranks_matches_oracle(world, shape):
     lopq = _lopq()
     D, V, M, K, n = shape
     Cs, Rs, mus, subs = random_model_params(D, V, M, K, seed=D + world)
-    # coarse clusters 0 and 1 of split 0 share centroid, rotation and mean: cells (0, c1) and (1, c1) have identical
-    # tables, are adjacent in the cell order (equal coarse distance, index order) and live on different ranks
-    Cs[0][1] = Cs[0][0]
+    # Coarse clusters 0 and 1 of split 0 get the SAME local frame seen from two different centroids: C1 = C0 + 1/4 and
+    # mu1 = mu0 - 1/4 on the 2^-10 lattice, so x - C - mu is evaluated exactly and is bit-identical for both, and with
+    # R1 = R0 the cells (0, c1) and (1, c1) have identical distance tables -- but different coarse distances (exactly
+    # tied coarse distances would make the reference's own cell order depend on NumPy's unstable argsort) -- and they
+    # are owned by different ranks.
+    Cs[0][0] = np.round(Cs[0][0] * 1024.0) / 1024.0
+    mus[0][0] = np.round(mus[0][0] * 1024.0) / 1024.0
+    Cs[0][1] = Cs[0][0] + 0.25
+    mus[0][1] = mus[0][0] - 0.25
     Rs[0][1] = Rs[0][0]
-    mus[0][1] = mus[0][0]
     params = (Cs, Rs, mus, subs)
     omodel = orc.OracleModel(*params)
     model = lopq.LOPQModel(parameters=params)
@@ -81,6 +87,7 @@ def test_merge_over_ranks_matches_oracle(world, shape):
     coarse, fine = lopq.utils.compute_codes_arrays(db, model)
     ocoarse, ofine = orc.encode_batch(omodel, db)
     assert np.array_equal(coarse, ocoarse) and np.array_equal(fine, ofine)
+    assert (coarse[:, 0] == 0).sum() > 100 and (coarse[:, 0] == 1).sum() > 100
     # mirror a third of cluster 0's rows into cluster 1 (same fine codes): exact distance ties across two ranks
     twin = np.nonzero(coarse[:, 0] == 0)[0][::3]
     tc = coarse[twin].copy()
