@@ -11,7 +11,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200lopq.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class NativeError(RuntimeError):
@@ -59,6 +59,13 @@ SIGNATURES = {
     "b2l_search_merge": (_i, [_h, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b2l_merge_block_bytes": (_i64, [_h, _i, _i]),
     "b2l_search_merge_block": (_i, [_h, _vp, _i, _i, _i, _vp, _i]),
+    "b2l_comm_init": (_i, [_h, _i, _i, _i, _i, _i]),
+    "b2l_comm_handle_bytes": (_i, []),
+    "b2l_comm_get_handle": (_i, [_h, _vp, C.POINTER(_vp)]),
+    "b2l_comm_connect": (_i, [_h, _vp, _i]),
+    "b2l_sharded_block_bytes": (_i64, [_h, _i, _i]),
+    "b2l_search_sharded": (_i, [_h, _vp, _i, _i, _i, _i64, _i, _vp, _i]),
+    "b2l_comm_error": (_i, [_h]),
     "b2l_get_stats": (_i, [_h, C.POINTER(Stats)]),
     "b2l_reset_stats": (_i, [_h]),
     "b2l_set_scan_mode": (_i, [_h, _i]),
@@ -300,6 +307,44 @@ class Handle(object):
         """Merge into one packed block (layout: include/b200lopq.h); asynchronous when set_async(True)."""
         self._check(self.lib.b2l_search_merge_block(self.h, _ptr(int(records_all_ptr)), int(nranks), int(nq), int(k),
                                                     _ptr(int(block_ptr)), int(on_device)))
+
+    # ---- multi-GPU exchange inside the library ---------------------------------------------------------
+    def comm_init(self, world, rank, max_nq_home, max_k, f64=False):
+        self._check(self.lib.b2l_comm_init(self.h, int(world), int(rank), int(max_nq_home), int(max_k), int(bool(f64))))
+
+    def comm_handle(self):
+        """(64-byte IPC handle of this rank's window, its local device address)."""
+        buf = C.create_string_buffer(self.lib.b2l_comm_handle_bytes())
+        ptr = _vp()
+        self._check(self.lib.b2l_comm_get_handle(self.h, buf, C.byref(ptr)))
+        return buf.raw, int(ptr.value)
+
+    def comm_local_ptr(self):
+        ptr = _vp()
+        self._check(self.lib.b2l_comm_get_handle(self.h, None, C.byref(ptr)))
+        return int(ptr.value)
+
+    def comm_connect(self, handles=None, pointers=None):
+        """handles: list of `world` 64-byte IPC handles (one process per GPU); pointers: list of `world` window addresses
+        (ranks that are handles of this process)."""
+        if pointers is not None:
+            arr = (C.c_void_p * len(pointers))(*[C.c_void_p(int(p)) for p in pointers])
+            self._check(self.lib.b2l_comm_connect(self.h, C.cast(arr, _vp), 1))
+        else:
+            blob = b"".join(handles)
+            self._check(self.lib.b2l_comm_connect(self.h, C.c_char_p(blob), 0))
+
+    def sharded_block_bytes(self, nq_home, k):
+        return int(self._check(self.lib.b2l_sharded_block_bytes(self.h, int(nq_home), int(k))))
+
+    def search_sharded(self, Qhome, nq_home, quota, k, block_ptr, on_device=False, block_on_device=False, f64=False):
+        """Qhome: host ndarray (float32, C-contiguous, pinned when asynchronous) or a device pointer (on_device)."""
+        q = _ptr(int(Qhome)) if on_device else _ptr(Qhome)
+        self._check(self.lib.b2l_search_sharded(self.h, q, int(f64), int(nq_home), int(on_device), int(quota), int(k),
+                                                _ptr(int(block_ptr)), int(block_on_device)))
+
+    def comm_error(self):
+        return int(self._check(self.lib.b2l_comm_error(self.h)))
 
     def stats(self):
         s = Stats()

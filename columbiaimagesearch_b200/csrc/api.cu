@@ -13,6 +13,7 @@
 
 #include "../../include/b200lopq.h"
 #include "common.cuh"
+#include "comm.cuh"
 #include "encode.cuh"
 #include "exact.cuh"
 #include "index.cuh"
@@ -21,7 +22,7 @@
 #include "scan_pk.cuh"
 #include "select.cuh"
 
-#define B2L_ABI_VERSION 2
+#define B2L_ABI_VERSION 3
 
 namespace {
 
@@ -101,6 +102,22 @@ struct b2l_ctx {
     int scan_mode = 0;                 // 0: packed 16-bit tables first (default), 1: float32 tables only
     void* h_out = nullptr;             // pinned staging of the search outputs
     size_t h_out_cap = 0;
+    // multi-GPU exchange (comm.cuh): this rank's window and the peers' windows
+    struct Comm {
+        int world = 0, rank = 0;
+        int64_t max_home = 0;          // largest home slice (queries per rank and batch)
+        int max_k = 0;
+        size_t qrow = 0;               // bytes of one query row (float32 or float64, D0 wide)
+        size_t q_region = 0, r_region = 0;
+        DevBuf window;
+        unsigned char* peer[COMM_MAX_WORLD] = {};
+        bool opened[COMM_MAX_WORLD] = {};
+        bool connected = false;
+        unsigned long long seq = 0;
+        int* d_err = nullptr;          // device word set by a wait that timed out
+        unsigned int* d_unc = nullptr; // queries of the current batch this rank could not certify
+        DevBuf cnt_out;                // [world] payloads gathered by the last wait of a batch
+    } comm;
 };
 
 namespace {
@@ -436,7 +453,7 @@ int finish_stats(b2l_handle h) {
 
 // finish = false: return with the work queued on the stream (the caller synchronises and calls finish_stats)
 int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_device, int64_t quota, int k, int exact,
-                      void* d_records, bool finish = true) {
+                      void* d_records, bool finish = true, const RecRoute* route_in = nullptr) {
     if (!h->has_model) FAIL(B2L_ERR_STATE, "no model set");
     if (nq < 1 || k < 1 || !Q || !d_records) FAIL(B2L_ERR_ARG, "bad search arguments (nq=%d k=%d)", nq, k);
     if (h->mv.V > B2L_MAX_V) FAIL(B2L_ERR_UNSUPPORTED, "V=%d > %d: large-V multi-index traversal is not implemented", h->mv.V, B2L_MAX_V);
@@ -490,6 +507,7 @@ int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_
     // exact: 0 = default fast scan (16-bit packed tables unless the handle is set to float32), 1 = float64 full sort,
     // 2 = fast scan with float32 tables
     const bool fast = exact != 1 && mv.G > 0 && KP <= 512;
+    if (route_in && !fast) FAIL(B2L_ERR_UNSUPPORTED, "the in-library exchange needs the fast scan (M <= 32, k <= 504)");
     const bool packed = fast && exact == 0 && h->scan_mode == 0 && 65535 / mv.M >= 255;
     const int NS = (packed ? 4 : 2) * mv.G;
     // segment length: a multiple of 64 codes, sized so the batch yields enough work items
@@ -689,8 +707,10 @@ int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_
         const double eps_rel = (double)(mv.M + 4) * 2.0 * ldexp(1.0, -24);
         const size_t smem = select_smem_bytes(KP);
         CU(cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RecRoute route = {};
+        if (route_in) route = *route_in; else { route.base[0] = (unsigned char*)d_records; route.nq_home = nq; }
         k_select<<<nq, SEL_THREADS, smem, h->stream>>>(mv, ix, pv, h->w_cand.as<unsigned long long>(), h->cand_cnt, h->gthr,
-                                                       SCAN_CAND_CAP, h->w_p64.as<double>(), KP, k, eps_rel, d_records,
+                                                       SCAN_CAND_CAP, h->w_p64.as<double>(), KP, k, eps_rel, route,
                                                        packed ? 1 : 0, qv.B, qv.delta, qv.slack);
         LAUNCHED();
         h->cr->st.packed = packed ? 1 : 0;
@@ -746,7 +766,8 @@ int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_
 
 // single-rank copy-out of records (any k); multi-rank merge through k_final
 int merge_impl(b2l_handle h, const void* d_recs, int nranks, int nq, int k, int on_device, int64_t* rowid, double* dist,
-               int32_t* coarse, uint8_t* fine, int32_t* count, int32_t* visited, uint8_t* certified, bool finish = true) {
+               int32_t* coarse, uint8_t* fine, int32_t* count, int32_t* visited, uint8_t* certified, bool finish = true,
+               unsigned int* d_unc = nullptr) {
     if (!h->has_model) FAIL(B2L_ERR_STATE, "no model set");
     if (nranks < 1 || nq < 1 || k < 1 || !count) FAIL(B2L_ERR_ARG, "bad merge arguments");
     const ModelView& mv = h->mv;
@@ -769,7 +790,7 @@ int merge_impl(b2l_handle h, const void* d_recs, int nranks, int nq, int k, int 
     }
     CU(cudaFuncSetAttribute(k_final, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_final<<<nq, 128, smem, h->stream>>>(mv.V, mv.M, d_recs, nranks, nq, k, n, d_rowid, d_dist, d_coarse, d_fine, d_count,
-                                          d_visited, d_cert);
+                                          d_visited, d_cert, d_unc);
     LAUNCHED();
     if (!on_device) {
         const size_t nk = (size_t)nq * k;
@@ -843,6 +864,10 @@ int b2l_destroy(b2l_handle h) {
     for (DevBuf* b : bufs) b->release();
     if (h->h_out) cudaFreeHost(h->h_out);
     if (h->d_nguard) cudaFree(h->d_nguard);
+    for (int r = 0; r < COMM_MAX_WORLD; ++r) if (h->comm.opened[r]) cudaIpcCloseMemHandle(h->comm.peer[r]);
+    h->comm.window.release(); h->comm.cnt_out.release();
+    if (h->comm.d_err) cudaFree(h->comm.d_err);
+    if (h->comm.d_unc) cudaFree(h->comm.d_unc);
     for (int r = 0; r < b2l_ctx::NREC; ++r) {
         for (int i = 0; i < 5; ++i) if (h->ring[r].ev[i]) cudaEventDestroy(h->ring[r].ev[i]);
         if (h->ring[r].h_pc) cudaFreeHost(h->ring[r].h_pc);
@@ -1397,6 +1422,172 @@ int b2l_search(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_device,
         if (visited) memcpy(visited, hb + o6, (size_t)nq * 4);
     }
     return B2L_OK;
+}
+
+// ---- multi-GPU exchange inside the library (comm.cuh) -------------------------------------------------------------
+static size_t comm_slot_q_off(const b2l_ctx::Comm& c, int slot) { return COMM_FLAG_BYTES + (size_t)slot * (c.q_region + c.r_region); }
+static size_t comm_slot_r_off(const b2l_ctx::Comm& c, int slot) { return comm_slot_q_off(c, slot) + c.q_region; }
+static size_t comm_flag_off(const b2l_ctx::Comm& c, int slot, int kind) { return ((size_t)(slot * 3 + kind) * COMM_MAX_WORLD) * 8; }
+
+int b2l_comm_init(b2l_handle h, int world, int rank, int max_nq_home, int max_k, int q_is_f64) {
+    if (!h) return B2L_ERR_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(cudaSetDevice(h->device));
+    if (!h->has_model) FAIL(B2L_ERR_STATE, "set the model before b2l_comm_init");
+    if (world < 1 || world > COMM_MAX_WORLD || rank < 0 || rank >= world || max_nq_home < 1 || max_k < 1)
+        FAIL(B2L_ERR_ARG, "bad comm arguments (world=%d rank=%d)", world, rank);
+    b2l_ctx::Comm& c = h->comm;
+    if (c.connected || c.window.p) FAIL(B2L_ERR_STATE, "the exchange is already initialised on this handle");
+    const ModelView& mv = h->mv;
+    c.world = world; c.rank = rank; c.max_home = max_nq_home; c.max_k = max_k;
+    c.qrow = (size_t)(h->has_pca ? mv.D0 : mv.D) * (q_is_f64 ? 8 : 4);
+    c.q_region = align256((size_t)world * max_nq_home * c.qrow);
+    c.r_region = (size_t)world * rec_bytes(max_nq_home, max_k, mv.M);
+    const size_t total = COMM_FLAG_BYTES + (size_t)COMM_SLOTS * (c.q_region + c.r_region);
+    CU(c.window.reserve(total));
+    CU(cudaMemsetAsync(c.window.p, 0, COMM_FLAG_BYTES, h->stream));
+    if (!c.d_err) { CU(cudaMalloc((void**)&c.d_err, 4)); CU(cudaMalloc((void**)&c.d_unc, 4)); }
+    CU(cudaMemsetAsync(c.d_err, 0, 4, h->stream));
+    CU(c.cnt_out.reserve(256));
+    CU(cudaStreamSynchronize(h->stream));
+    c.peer[rank] = c.window.as<unsigned char>();
+    c.seq = 0;
+    return B2L_OK;
+}
+
+int b2l_comm_handle_bytes(void) { return (int)sizeof(cudaIpcMemHandle_t); }
+
+int b2l_comm_get_handle(b2l_handle h, void* ipc_handle_out, void** local_ptr_out) {
+    if (!h) return B2L_ERR_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(cudaSetDevice(h->device));
+    if (!h->comm.window.p) FAIL(B2L_ERR_STATE, "b2l_comm_init first");
+    if (local_ptr_out) *local_ptr_out = h->comm.window.p;
+    if (ipc_handle_out) {
+        cudaIpcMemHandle_t mh;
+        CU(cudaIpcGetMemHandle(&mh, h->comm.window.p));
+        memcpy(ipc_handle_out, &mh, sizeof mh);
+    }
+    return B2L_OK;
+}
+
+int b2l_comm_connect(b2l_handle h, const void* handles, int same_process) {
+    if (!h || !handles) return B2L_ERR_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(cudaSetDevice(h->device));
+    b2l_ctx::Comm& c = h->comm;
+    if (!c.window.p) FAIL(B2L_ERR_STATE, "b2l_comm_init first");
+    for (int r = 0; r < c.world; ++r) {
+        if (r == c.rank) continue;
+        if (same_process) {
+            c.peer[r] = (unsigned char*)((void* const*)handles)[r];
+            cudaPointerAttributes at;
+            CU(cudaPointerGetAttributes(&at, c.peer[r]));
+            if (at.device != h->device) {                       // another GPU of this process: map it
+                int can = 0;
+                CU(cudaDeviceCanAccessPeer(&can, h->device, at.device));
+                if (!can) FAIL(B2L_ERR_UNSUPPORTED, "device %d cannot access device %d", h->device, at.device);
+                cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CU(e);
+                cudaGetLastError();
+            }
+        } else {
+            cudaIpcMemHandle_t mh;
+            memcpy(&mh, (const char*)handles + (size_t)r * sizeof mh, sizeof mh);
+            void* p = nullptr;
+            CU(cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess));
+            c.peer[r] = (unsigned char*)p; c.opened[r] = true;
+        }
+    }
+    c.connected = true;
+    return B2L_OK;
+}
+
+int64_t b2l_sharded_block_bytes(b2l_handle h, int nq_home, int k) {
+    const int64_t b = b2l_merge_block_bytes(h, nq_home, k);
+    return b < 0 ? b : b + 256;
+}
+
+/* One batch of the cell-sharded search with the exchange inside the library.  Every rank passes ITS home slice of the
+ * batch (nq_home queries, the same number on every rank); the global batch is rank-major.  Asynchronous: everything is
+ * enqueued on the handle's stream; `block` (pinned host, or device) receives the merge block of the home queries followed by
+ * [world] int32 counts of queries each rank could not certify (all zero: the results are final). */
+int b2l_search_sharded(b2l_handle h, const void* Qhome, int q_is_f64, int nq_home, int on_device, int64_t quota, int k,
+                       void* block, int block_on_device) {
+    if (!h || !Qhome || !block) return B2L_ERR_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(cudaSetDevice(h->device));
+    b2l_ctx::Comm& c = h->comm;
+    if (!c.connected && c.world != 1) FAIL(B2L_ERR_STATE, "b2l_comm_connect first");
+    if (!c.window.p) FAIL(B2L_ERR_STATE, "b2l_comm_init first");
+    const ModelView& mv = h->mv;
+    const size_t qrow = (size_t)(h->has_pca ? mv.D0 : mv.D) * (q_is_f64 ? 8 : 4);
+    if (nq_home < 1 || nq_home > c.max_home || k < 1 || k > c.max_k || qrow != c.qrow)
+        FAIL(B2L_ERR_ARG, "search_sharded: nq_home=%d k=%d outside what b2l_comm_init reserved (%lld, %d) or query type changed",
+             nq_home, k, (long long)c.max_home, c.max_k);
+    if ((nq_home * qrow) % 16) FAIL(B2L_ERR_ARG, "home slice of %zu bytes is not a multiple of 16", nq_home * qrow);
+    const unsigned long long seq = ++c.seq;
+    const int slot = (int)(seq % COMM_SLOTS), W = c.world, nq = nq_home * W;
+    PeerPtrs peers;
+    for (int r = 0; r < COMM_MAX_WORLD; ++r) peers.p[r] = r < W ? c.peer[r] : nullptr;
+    unsigned char* win = c.window.as<unsigned char>();
+    // 1. queries: my slice into everybody's query mailbox
+    const size_t slice = (size_t)nq_home * qrow;
+    const uint4* src = (const uint4*)Qhome;
+    if (!on_device) {
+        CU(h->w_q.reserve(slice));
+        CU(cudaMemcpyAsync(h->w_q.p, Qhome, slice, cudaMemcpyHostToDevice, h->stream));
+        src = h->w_q.as<uint4>();
+    }
+    k_comm_put<<<std::min<unsigned>(h->num_sms, (unsigned)(slice / 16 / 256 + 1)), 256, 0, h->stream>>>(
+        peers, W, comm_slot_q_off(c, slot) + (size_t)c.rank * slice, src, slice);
+    LAUNCHED();
+    k_comm_signal<<<1, 32, 0, h->stream>>>(peers, W, c.rank, comm_flag_off(c, slot, 0), seq, nullptr);
+    LAUNCHED();
+    k_comm_wait<<<1, 32, 0, h->stream>>>(win, W, comm_flag_off(c, slot, 0), seq, c.d_err, nullptr);
+    LAUNCHED();
+    // 2. rank the whole batch on the local cells; records go straight to the home ranks' mailboxes
+    RecRoute route = {};
+    route.nq_home = nq_home;
+    const size_t rb = rec_bytes(nq_home, k, mv.M);
+    for (int r = 0; r < W; ++r) route.base[r] = c.peer[r] + comm_slot_r_off(c, slot) + (size_t)c.rank * rb;
+    int rc = search_local_impl(h, win + comm_slot_q_off(c, slot), q_is_f64, nq, 1, quota, k, 0, win /*unused*/, false, &route);
+    if (rc) return rc;
+    k_comm_signal<<<1, 32, 0, h->stream>>>(peers, W, c.rank, comm_flag_off(c, slot, 1), seq, nullptr);
+    LAUNCHED();
+    k_comm_wait<<<1, 32, 0, h->stream>>>(win, W, comm_flag_off(c, slot, 1), seq, c.d_err, nullptr);
+    LAUNCHED();
+    // 3. merge my home queries
+    const size_t nk = (size_t)nq_home * k;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes); return o; };
+    const size_t o1 = take(nk * 8), o2 = take(nk * 8), o3 = take(nk * 8), o4 = take(nk * mv.M), o5 = take((size_t)nq_home * 4),
+                 o6 = take((size_t)nq_home * 4), o7 = take((size_t)nq_home);
+    const size_t o8 = off; off += 256;
+    unsigned char* b = (unsigned char*)block;
+    if (!block_on_device) { CU(h->w_out.reserve(off)); b = h->w_out.as<unsigned char>(); }
+    CU(cudaMemsetAsync(c.d_unc, 0, 4, h->stream));
+    rc = merge_impl(h, win + comm_slot_r_off(c, slot), W, nq_home, k, 1, (int64_t*)(b + o1), (double*)(b + o2), (int32_t*)(b + o3), b + o4,
+                    (int32_t*)(b + o5), (int32_t*)(b + o6), b + o7, false, c.d_unc);
+    if (rc) return rc;
+    k_comm_signal<<<1, 32, 0, h->stream>>>(peers, W, c.rank, comm_flag_off(c, slot, 2), seq, c.d_unc);
+    LAUNCHED();
+    k_comm_wait<<<1, 32, 0, h->stream>>>(win, W, comm_flag_off(c, slot, 2), seq, c.d_err, (int32_t*)(b + o8));
+    LAUNCHED();
+    if (!block_on_device) CU(cudaMemcpyAsync(block, b, off, cudaMemcpyDeviceToHost, h->stream));
+    if (!h->async_mode) { CU(cudaStreamSynchronize(h->stream)); return finish_stats(h); }
+    return B2L_OK;
+}
+
+/* 0 = no wait of the exchange has timed out; r + 1 = the wait for rank r did */
+int b2l_comm_error(b2l_handle h) {
+    if (!h) return B2L_ERR_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(cudaSetDevice(h->device));
+    if (!h->comm.d_err) return 0;
+    int e = 0;
+    CU(cudaMemcpy(&e, h->comm.d_err, 4, cudaMemcpyDeviceToHost));
+    return e;
 }
 
 }  // extern "C"

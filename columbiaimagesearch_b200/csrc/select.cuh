@@ -37,6 +37,14 @@ __host__ __device__ inline RecView rec_view(void* base, int nq, int k, int M) {
     return r;
 }
 
+// Where k_select puts the records of query q: block q / nq_home (the query's HOME rank in the multi-GPU exchange, whose
+// record mailbox base[] points into -- a peer-mapped window -- at this rank's block), entry q % nq_home.  Single GPU and the
+// host-driven (all-gather) protocol: nq_home = nq, base[0] = the record buffer.
+struct RecRoute {
+    unsigned char* base[8];
+    int nq_home;
+};
+
 struct IndexView {
     const uint8_t* codes;        // [rows][MP]
     const int64_t* rowids;       // [rows]
@@ -104,7 +112,7 @@ __device__ __forceinline__ int sel_bucket(unsigned int dbits, unsigned int lo_bi
 __global__ void __launch_bounds__(SEL_THREADS, 8)
 k_select(ModelView mv, IndexView ix, PlanView pv, const unsigned long long* __restrict__ cand,
          const unsigned int* __restrict__ cand_cnt, const unsigned int* __restrict__ gthr, int cand_cap,
-         const double* __restrict__ P64, int KP, int k, double eps_rel, void* recbuf,
+         const double* __restrict__ P64, int KP, int k, double eps_rel, RecRoute route,
          int packed, const double* __restrict__ qB, const double* __restrict__ qDelta, const double* __restrict__ qSlack) {
     extern __shared__ __align__(16) unsigned char sm_sel[];
     unsigned long long* keys = (unsigned long long*)sm_sel;
@@ -119,11 +127,12 @@ k_select(ModelView mv, IndexView ix, PlanView pv, const unsigned long long* __re
     __shared__ unsigned int s_scan[SEL_THREADS / 32];
     __shared__ int s_n, s_bstar;
     const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    RecView rv = rec_view(recbuf, pv.nq, k, mv.M);
+    const int qh = q / route.nq_home, ql = q - qh * route.nq_home;       // home block, index inside it
+    RecView rv = rec_view(route.base[qh], route.nq_home, k, mv.M);
     if (pv.ncand_local[q] == 0) {                     // nothing of this query is stored on this rank (uniform exit)
         if (tid == 0) {
-            rv.lb[q] = __longlong_as_double(0x7FF0000000000000ll);
-            rv.count[q] = 0; rv.visited[q] = pv.nvis[q]; rv.ncand[q] = pv.ncand[q];
+            rv.lb[ql] = __longlong_as_double(0x7FF0000000000000ll);
+            rv.count[ql] = 0; rv.visited[ql] = pv.nvis[q]; rv.ncand[ql] = pv.ncand[q];
         }
         return;
     }
@@ -259,7 +268,7 @@ k_select(ModelView mv, IndexView ix, PlanView pv, const unsigned long long* __re
         const int sidx = idx[i];
         const int64_t row = rows[sidx];
         const int v = visv[sidx];
-        const int64_t e = (int64_t)q * k + i;
+        const int64_t e = (int64_t)ql * k + i;
         rv.d64[e] = __longlong_as_double((long long)dk[i]);
         rv.pos[e] = pk[i];
         rv.rowid[e] = ix.rowids[row];
@@ -275,10 +284,10 @@ k_select(ModelView mv, IndexView ix, PlanView pv, const unsigned long long* __re
             if (packed) lb = (qB[q] + qDelta[q] * ((double)kb - 1.0) - qSlack[q]) * (1.0 - 1e-6) - 1e-300;      // see plan.cuh (k_lut_quant)
             else lb = (double)__uint_as_float(kb) * (1.0 - eps_rel) - 1e-300;
         }
-        rv.lb[q] = lb;
-        rv.count[q] = nout;
-        rv.visited[q] = nv;
-        rv.ncand[q] = pv.ncand[q];
+        rv.lb[ql] = lb;
+        rv.count[ql] = nout;
+        rv.visited[ql] = nv;
+        rv.ncand[ql] = pv.ncand[q];
     }
 }
 
@@ -287,7 +296,8 @@ k_select(ModelView mv, IndexView ix, PlanView pv, const unsigned long long* __re
 __global__ void __launch_bounds__(128)
 k_final(int V, int M, const void* __restrict__ recs_all, int nranks, int nq, int k, int n,
         int64_t* __restrict__ rowid, double* __restrict__ dist, int32_t* __restrict__ coarse, uint8_t* __restrict__ fine,
-        int32_t* __restrict__ count, int32_t* __restrict__ visited, uint8_t* __restrict__ certified) {
+        int32_t* __restrict__ count, int32_t* __restrict__ visited, uint8_t* __restrict__ certified,
+        unsigned int* __restrict__ n_uncertified = nullptr) {
     extern __shared__ __align__(16) unsigned char sm_fin[];
     unsigned long long* dk = (unsigned long long*)sm_fin;
     unsigned int* pk = (unsigned int*)(dk + n);
@@ -339,5 +349,6 @@ k_final(int V, int M, const void* __restrict__ recs_all, int nranks, int nq, int
         if (nout == k && k > 0) ok = __longlong_as_double((long long)dk[k - 1]) < lbmin;
         else ok = !(lbmin < __longlong_as_double(0x7FF0000000000000ll));
         if (certified) certified[q] = ok ? 1 : 0;
+        if (!ok && n_uncertified) atomicAdd(n_uncertified, 1u);
     }
 }

@@ -89,6 +89,113 @@ class ShardedLOPQSearcher(object):
         self._handle.set_global_cell_sizes(t.cpu().numpy())
         self._dirty = False
 
+    # ---- exchange inside the library (peer-mapped windows, csrc/comm.cuh) ---------------------------------
+    def enable_peer_exchange(self, max_nq_home, max_k=16, peers=None):
+        """Switch the search to b2l_search_sharded: queries and per-rank top-k records travel through peer-mapped device
+        windows (CUDA IPC between the processes of the group), the record all-to-all is fused into the selection kernel,
+        and no NCCL call or host round trip remains on the search path.  Collective over the group (the 64-byte IPC
+        handles are exchanged once, on the host).  `peers`: the other ShardedLOPQSearcher objects when the ranks are
+        handles of ONE process (emulation / tests), listed in rank order; then call it on every one of them."""
+        h = self._handle
+        world = self.world if peers is None else len(peers)
+        for p in ([self] if peers is None else peers):          # (one process: every window must exist before connecting)
+            if not getattr(p, "_peer_init", False):
+                p._handle.comm_init(world, p.rank, int(max_nq_home), int(max_k))
+                p._peer_init = True
+        if peers is not None:
+            h.comm_connect(pointers=[p._handle.comm_local_ptr() for p in peers])
+        elif world > 1:
+            mine, _ = h.comm_handle()
+            allh = [None] * world
+            self.dist.all_gather_object(allh, mine, group=self.group)
+            h.comm_connect(handles=allh)
+            self.dist.barrier(group=self.group)
+        self._peer = True
+        self._peer_world = world
+        h.set_async(True)
+        if self._stream is None and self._pipelined:
+            import torch
+            self._stream = torch.cuda.ExternalStream(h.stream(), device=self._tdev)
+
+    def _home_buffers(self, nq_home, k, D):
+        import torch
+        key = ("home", nq_home, k, D)
+        sets = self._pool.get(key)
+        if sets is None:
+            nbytes = self._handle.sharded_block_bytes(nq_home, k)
+            sets = [dict(out_h=torch.zeros(nbytes, dtype=torch.uint8).pin_memory(),
+                         q_h=torch.empty((nq_home, D), dtype=torch.float32).pin_memory(),
+                         event=torch.cuda.Event()) for _ in range(3)]
+            self._pool[key] = sets
+        self._pool_next = (self._pool_next + 1) % 3
+        return sets[self._pool_next]
+
+    def search_home_async(self, Xhome, quota=10, limit=None):
+        """One batch through the in-library exchange.  Xhome [nq_home, D0] float32 (host ndarray or CUDA tensor) is THIS
+        rank's slice of the global batch (global query index = rank * nq_home + i; the same nq_home on every rank).
+        Returns a pending object whose result() holds the final top-k of the home queries."""
+        import torch
+        assert getattr(self, "_peer", False), "enable_peer_exchange() first"
+        if self._dirty:
+            self.finalize()
+        if limit is None:
+            limit = quota
+        k = int(max(1, min(int(limit), max(1, self.nb_indexed))))
+        h = self._handle
+        on_dev = hasattr(Xhome, "data_ptr")
+        nq_home, D = int(Xhome.shape[0]), int(Xhome.shape[1])
+        b = self._home_buffers(nq_home, k, D)
+        if on_dev:
+            assert Xhome.is_contiguous() and Xhome.dtype == torch.float32
+            self._stream.wait_stream(torch.cuda.current_stream(Xhome.device))
+            h.search_sharded(Xhome.data_ptr(), nq_home, quota, k, b["out_h"].data_ptr(), on_device=True)
+        else:
+            qh = b["q_h"].numpy()
+            np.copyto(qh, Xhome, casting="same_kind")
+            h.search_sharded(qh, nq_home, quota, k, b["out_h"].data_ptr())
+        b["event"].record(self._stream)
+        return _PendingHome(self, b, Xhome, nq_home, k, quota)
+
+    def _redo_home(self, out, Xhome, quota, k, mine):
+        """Fallback chain for the queries of a batch that some rank could not certify.  Collective: every rank brings the
+        home rows it could not certify (possibly none); all ranks re-run the union with float32 tables, then exactly, over
+        the host-driven all-gather protocol, and each rank patches its own rows."""
+        D = int(Xhome.shape[1])
+        rows = (Xhome[mine].cpu().numpy() if hasattr(Xhome, "data_ptr") else np.asarray(Xhome)[mine]).astype(np.float32).reshape(-1, D)
+        if self._peer_world > 1:
+            parts = [None] * self._peer_world
+            self.dist.all_gather_object(parts, (self.rank, mine.tolist(), rows), group=self.group)
+            parts = sorted(parts, key=lambda p: p[0])
+        else:
+            parts = [(self.rank, mine.tolist(), rows)]
+        owner = np.concatenate([np.full(len(p[1]), p[0], np.int64) for p in parts])
+        local = np.concatenate([np.asarray(p[1], np.int64) for p in parts])
+        Xall = np.concatenate([np.asarray(p[2], np.float32).reshape(-1, D) for p in parts])
+        if not local.size:
+            return 0, 0
+        h = self._handle
+        h.sync()
+        h.set_async(False)
+        try:
+            n32 = nex = 0
+            todo = np.arange(local.size)
+            for mode in (2, 1):
+                if not todo.size:
+                    break
+                sub = self._gather_merge(np.ascontiguousarray(Xall[todo]), quota, k, mode, int(todo.size))
+                sel = owner[todo] == self.rank
+                for key in ("rowid", "dist", "coarse", "fine", "count"):
+                    out[key][local[todo][sel]] = sub[key][sel]
+                if mode == 2:
+                    n32 += int(todo.size)
+                    todo = todo[sub["certified"] == 0]
+                else:
+                    nex += int(todo.size)
+                    todo = todo[:0]
+        finally:
+            h.set_async(True)
+        return n32, nex
+
     # ---- search -----------------------------------------------------------------------------------
     def _gather_merge(self, Q, quota, k, exact, nq, q_ptr=None):
         import torch
@@ -307,5 +414,53 @@ class _PendingSearch(object):
         out["ids"] = ids
         if copy:
             out = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in out.items()}
+        self._out = out
+        return out
+
+
+class _PendingHome(object):
+    """A batch enqueued by ShardedLOPQSearcher.search_home_async."""
+
+    def __init__(self, searcher, bufs, X, nq, k, quota):
+        self.s, self.b, self.X, self.nq, self.k, self.quota = searcher, bufs, X, nq, k, quota
+        self._out = None
+
+    def result(self, copy=True):
+        if self._out is not None:
+            return self._out
+        s, b, nq, k = self.s, self.b, self.nq, self.k
+        M = s.model.M
+        b["event"].synchronize()
+        raw = b["out_h"].numpy()
+        a256 = lambda n: (n + 255) & ~255
+        nk = nq * k
+        o, off = {}, 0
+        for name, nbytes in (("rowid", nk * 8), ("dist", nk * 8), ("coarse", nk * 8), ("fine", nk * M), ("count", nq * 4),
+                             ("visited", nq * 4), ("certified", nq)):
+            o[name] = off
+            off += a256(nbytes)
+        view = lambda name, dt, shape: raw[o[name]:o[name] + int(np.prod(shape)) * np.dtype(dt).itemsize].view(dt).reshape(shape)
+        out = dict(rowid=view("rowid", np.int64, (nq, k)), dist=view("dist", np.float64, (nq, k)),
+                   coarse=view("coarse", np.int32, (nq, k, 2)), fine=view("fine", np.uint8, (nq, k, M)),
+                   count=view("count", np.int32, (nq,)), visited=view("visited", np.int32, (nq,)),
+                   certified=view("certified", np.uint8, (nq,)))
+        tail = raw[off:off + 36].view(np.int32)
+        if int(tail[8]) != 0:
+            raise RuntimeError("multi-GPU exchange: the wait for rank %d timed out" % (int(tail[8]) - 1))
+        unc = tail[:s._peer_world]
+        n32 = nex = 0
+        if int(unc.sum()) > 0:                               # somebody needs the fallback chain: every rank takes part
+            mine = np.nonzero(out["certified"] == 0)[0]
+            n32, nex = s._redo_home(out, self.X, self.quota, k, mine)
+        out["exact_queries"], out["rescan_queries"] = nex, n32
+        ids = out["rowid"]
+        if nq and int(out["count"].min()) < k:
+            pad = np.arange(k)[None, :] >= out["count"][:, None]
+            ids = ids.copy()
+            ids[pad] = -1
+            out["dist"][pad] = np.nan
+        out["ids"] = ids
+        if copy:
+            out = {k_: (v.copy() if isinstance(v, np.ndarray) else v) for k_, v in out.items()}
         self._out = out
         return out

@@ -145,6 +145,31 @@ int b2l_search_merge(b2l_handle h, const void* d_records_all, int nranks, int nq
 int64_t b2l_merge_block_bytes(b2l_handle h, int nq, int k);
 int b2l_search_merge_block(b2l_handle h, const void* d_records_all, int nranks, int nq, int k, void* block, int on_device);
 
+/* ---- multi-GPU exchange inside the library ------------------------------------------------------------------------
+ * The reference has no multi-GPU path; SURVEY.md 8(e) defines it: inverted lists sharded by coarse cell, queries
+ * replicated, one exchange of per-rank top-k records, merge.  These calls run that exchange without NCCL and without the
+ * host: every rank owns a device "window" (query and record mailboxes + flags) that the other ranks map through CUDA IPC
+ * (one process per GPU) or plain pointers (handles of one process: same_process = 1); queries are put into every rank's
+ * mailbox, the selection kernel writes the k records of a query directly into the mailbox of the query's HOME rank over
+ * NVLink, and release/acquire flags at system scope order it (csrc/comm.cuh).
+ *   b2l_comm_init        reserve the window for home slices of <= max_nq_home queries, top-<= max_k, queries float32/64
+ *   b2l_comm_get_handle  the 64-byte IPC handle of the window (b2l_comm_handle_bytes) and/or its local address
+ *   b2l_comm_connect     handles = [world] IPC handles (64 bytes each), or [world] window addresses when same_process
+ *   b2l_search_sharded   one batch: Qhome [nq_home][D0 or D] is THIS rank's slice of the global batch (rank-major, the same
+ *                        nq_home on every rank); block receives b2l_sharded_block_bytes(nq_home, k) bytes: the merge block
+ *                        of the home queries (layout of b2l_search_merge_block) followed, 256-byte aligned, by [world] int32 =
+ *                        queries each rank could not certify (any non-zero: rerun those through the fallback chain).
+ *                        Honours b2l_set_async.  Every rank must call it the same number of times.
+ *   b2l_comm_error       0, or 1 + the rank a bounded device-side wait gave up on */
+int     b2l_comm_init(b2l_handle h, int world, int rank, int max_nq_home, int max_k, int q_is_f64);
+int     b2l_comm_handle_bytes(void);
+int     b2l_comm_get_handle(b2l_handle h, void* ipc_handle_out, void** local_ptr_out);
+int     b2l_comm_connect(b2l_handle h, const void* handles, int same_process);
+int64_t b2l_sharded_block_bytes(b2l_handle h, int nq_home, int k);
+int     b2l_search_sharded(b2l_handle h, const void* Qhome, int q_is_f64, int nq_home, int on_device, int64_t quota, int k,
+                           void* block, int block_on_device);
+int     b2l_comm_error(b2l_handle h);
+
 /* ---- introspection (counters of the most recent b2l_search / b2l_search_local) ------------------ */
 typedef struct b2l_stats {
     double  scan_ms;          /* device time of the ADC scan kernel (CUDA events)            */

@@ -146,3 +146,68 @@ def test_rank_without_any_cell_of_the_query():
     outx = sh.search(db[:16], 1, 5, exact=1)
     for i in range(16):
         _check(outx, i, orc.search_arrays(omodel, index, db[i], 1, 5))
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_in_library_exchange_on_emulated_ranks(world):
+    """b2l_search_sharded (csrc/comm.cuh): queries put into every rank's mailbox, k_select writing each query's records
+    straight into the HOME rank's record mailbox, release/acquire flags, merge of the home slice -- on `world` handles of
+    one process whose windows are connected by plain pointers.  One host thread per rank (a rank's device-side wait needs
+    the other ranks' work to be enqueued).  Several batches back to back reuse the mailbox slots."""
+    import threading
+    lopq = _lopq()
+    params = random_model_params(128, 8, 16, 256, seed=31 + world)
+    omodel = orc.OracleModel(*params)
+    model = lopq.LOPQModel(parameters=params)
+    n, nq_home, k = 30000, 16, 10
+    db = random_data(params, n, seed=5)
+    coarse, fine = lopq.utils.compute_codes_arrays(db, model)
+    sh = EmulatedShards(model, world)
+    sh.add(coarse, fine)
+    for s in sh.ranks:
+        s.enable_peer_exchange(nq_home, 16, peers=sh.ranks)
+    index = orc.ArrayIndex(8, coarse, fine, np.arange(n, dtype=np.int64))
+    rng = np.random.RandomState(3)
+    nbatch = 7                                   # > COMM_SLOTS: the slots wrap around
+    batches = []
+    for b in range(nbatch):
+        qi = rng.randint(0, n, size=nq_home * world)
+        batches.append((db[qi].astype(np.float64) + 0.02 * rng.randn(len(qi), 128)).astype(np.float32))
+    results = [[None] * nbatch for _ in range(world)]
+    errors = []
+
+    def run(r):
+        try:
+            s = sh.ranks[r]
+            pend = []
+            for b in range(nbatch):
+                quota = (n // 25, n // 4, 3)[b % 3]
+                pend.append(s.search_home_async(batches[b][r * nq_home:(r + 1) * nq_home], quota=quota, limit=k))
+                if len(pend) == 2:
+                    results[r][b - 1] = pend.pop(0).result()
+            results[r][nbatch - 1] = pend.pop(0).result()
+        except BaseException as e:                 # noqa: BLE001
+            errors.append((r, repr(e)))
+
+    # emulated ranks have no process group: the fallback chain of uncertified queries is covered by the multi-process run
+    for s in sh.ranks:
+        s._redo_home = lambda out, X, quota, kk, mine: (0, 0)
+    th = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=120)
+    assert not errors, errors
+    assert all(not t.is_alive() for t in th)
+    assert all(s._handle.comm_error() == 0 for s in sh.ranks)
+    ncheck = 0
+    for b in range(nbatch):
+        quota = (n // 25, n // 4, 3)[b % 3]
+        for r in range(world):
+            out = results[r][b]
+            out["rowid"] = out["ids"]
+            for i in range(nq_home):
+                if out["certified"][i]:
+                    _check(out, i, orc.search_arrays(omodel, index, batches[b][r * nq_home + i], quota, k))
+                    ncheck += 1
+    assert ncheck > nbatch * world * nq_home * 0.8
