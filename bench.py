@@ -1,13 +1,18 @@
 #!/usr/bin/env python
-"""LOPQ search benchmark: queries/s at recall@10 on a 10M x 128-d synthetic database, V=8 M=16 K=256
-(BASELINE.json metric).
+"""LOPQ hot-path benchmark (BASELINE.json).
 
-    python bench.py --gpus 1 --steps 20 --warmup 3              # this repo (CUDA path through the C-ABI)
-    python bench.py --impl reference --gpus 1 --steps 3 --warmup 1   # reference CPU algorithm on the host cores
-    torchrun --nproc-per-node N bench.py --gpus N ...            # index sharded by coarse cell over N GPUs
+    python bench.py --gpus 1 --steps 20 --warmup 3                   # headline: config 4 (10M x 128-d, V=8 M=16) on this repo
+    python bench.py --impl reference --gpus 1 --steps 3 --warmup 1   # the reference's CPU algorithm on the host cores
+    torchrun --nproc-per-node N bench.py --gpus N ...                # index sharded by coarse cell over N GPUs
+    python bench.py --config c2|c3|c5                                # the other BASELINE configs (see CONFIGS)
 
-One step = one batch of `--batch` queries through the whole hot path (cell order, LUT build, ADC scan,
-top-k, float64 re-rank).  Prints ONE JSON line (rank 0).
+One step = one batch of queries through the whole hot path (cell order, LUT build, ADC scan, top-k, float64 re-rank); for
+--config c5 one step = one encode pass over this rank's rows.  Prints ONE JSON line (rank 0).
+
+Multi-GPU (N > 1): the inverted lists are sharded by coarse cell; every rank brings a HOME slice of `--batch` queries per
+step, so a step ranks N x batch queries and the per-GPU scan work stays what it is at N = 1 ("scaling": "weak"; the
+database is fixed).  The exchange runs inside the library (peer-mapped windows, csrc/comm.cuh).  The fixed-batch figure
+(the same `--batch` queries split over the ranks, strong scaling) is reported next to it as `strong`.
 """
 import argparse
 import json
@@ -22,8 +27,19 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-METRIC = "LOPQ queries/sec @ recall@10, 10Mx128-d, V=8 M=16"
-MODEL_NPZ = os.path.join(ROOT, "bench_models", "dlib128_V8_M16.npz")
+CONFIGS = {
+    # BASELINE.json configs[3] (headline metric) and configs[1]
+    "c4": dict(metric="LOPQ queries/sec @ recall@10, 10Mx128-d, V=8 M=16", n_db=10_000_000, D=128, V=8, M=16,
+               model="dlib128_V8_M16.npz", quota=210_000, style="dlib"),
+    "c2": dict(metric="LOPQ queries/sec @ recall@10, 1Mx128-d, V=8 M=16, batch=1024", n_db=1_000_000, D=128, V=8, M=16,
+               model="dlib128_V8_M16.npz", quota=21_000, style="dlib"),
+    # configs[2]: DeepSentibank-style 2048-d; the model is trained at start-up (134 MB of rotations: not a fixture)
+    "c3": dict(metric="LOPQ queries/sec @ recall@10, 10Mx2048-d, V=8 M=32", n_db=10_000_000, D=2048, V=8, M=32,
+               model=None, quota=210_000, style="sentibank"),
+    # configs[4]: batch encode
+    "c5": dict(metric="LOPQ compute_codes codes/sec, 50Mx128-d, V=8 M=16", n_db=50_000_000, D=128, V=8, M=16,
+               model="dlib128_V8_M16.npz", style="dlib"),
+}
 
 
 def parse():
@@ -32,17 +48,29 @@ def parse():
     p.add_argument("--steps", type=int, default=20)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    p.add_argument("--n-db", type=int, default=10_000_000)
-    p.add_argument("--batch", type=int, default=1024)
-    p.add_argument("--quota", type=int, default=210_000)
+    p.add_argument("--config", default="c4", choices=sorted(CONFIGS))
+    p.add_argument("--n-db", type=int, default=0, help="override the database size of the config")
+    p.add_argument("--batch", type=int, default=1024, help="queries per rank and step")
+    p.add_argument("--quota", type=int, default=0)
     p.add_argument("--k", type=int, default=10)
     p.add_argument("--rho", type=float, default=0.1)
     p.add_argument("--seed", type=int, default=1234)
     p.add_argument("--cpu-queries", type=int, default=6, help="queries of the bounded CPU-baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--sustain-s", type=float, default=2.0, help="length of the sustained run reported as value_sustained")
+    p.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="N > 1: in-library exchange or NCCL all-gather")
     p.add_argument("--emulate-shard", type=int, default=0, help="profiling aid (1 process): act as rank 0 of an N-way cell-sharded index")
     p.add_argument("--sweep", default="", help="comma-separated quotas: print recall/QPS per quota and exit")
-    return p.parse_args()
+    p.add_argument("--ntrain", type=int, default=20000, help="c3: training vectors of the 2048-d model")
+    a = p.parse_args()
+    cfg = dict(CONFIGS[a.config])
+    if a.n_db:
+        cfg["quota"] = int(cfg.get("quota", 0) * a.n_db / cfg["n_db"]) or cfg.get("quota", 0)
+        cfg["n_db"] = a.n_db
+    if a.quota:
+        cfg["quota"] = a.quota
+    a.cfg = cfg
+    return a
 
 
 # ------------------------------------------------------------------------------------------------
@@ -89,11 +117,12 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def ncu_traffic():
-    """DRAM bytes per launch of the scan kernel from the committed ncu --set full capture (profiles/scan_traffic.json)."""
+def ncu_traffic(name):
+    """DRAM bytes per launch of a kernel from the committed ncu --set full captures (profiles/scan_traffic.json)."""
     try:
         with open(os.path.join(ROOT, "profiles", "scan_traffic.json")) as f:
             j = json.load(f)
+        j = j.get(name, j) if isinstance(j.get(name), dict) else j
         return j["dram_bytes_per_launch"], j["source"]
     except Exception:
         return None, None
@@ -157,6 +186,7 @@ def prep_encode_fine(omodel, X, coarse):
 
 
 _G_SEARCHER = None          # inherited by the forked replica workers (never pickled)
+_G_MODEL = None
 
 
 def _worker(args):
@@ -164,30 +194,71 @@ def _worker(args):
     return time_oracle_queries(_G_SEARCHER, queries, quota, k)[0]
 
 
+def _enc_worker(X):
+    from oracle import lopq_oracle as orc
+    t0 = time.perf_counter()
+    orc.compute_codes(_G_MODEL, X)
+    return time.perf_counter() - t0
+
+
 # ------------------------------------------------------------------------------------------------
 def run_reference(a):
     """Reference arm: the reference's algorithm (oracle port of LOPQSearcher.search: per-item Python ADC loop,
-    stable sorted) on the host cores, pure CPU, same config.  Replica processes (one query stream per core) are
-    the only parallelism the reference has (gunicorn workers)."""
+    stable sorted; c5: compute_codes_notparallel, one model.predict per row) on the host cores, pure CPU, same config.
+    Replica processes (one stream per core) are the only parallelism the reference has (gunicorn workers / parmap).
+    `kind` is "port": the reference's own files are Python 2 and only exist in the build container (oracle/ref_loader.py
+    pins the port against them there); /root/reference is absent on the GPU box."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if a.config == "c3":
+        print(json.dumps({"impl": "reference", "unavailable": "c3 reference arm not built: the 2048-d model is trained on the GPU at start-up; see cpu_baseline of the b200 line"}))
+        return
     import multiprocessing as mp
     from oracle import lopq_oracle as orc
-    from columbiaimagesearch_b200 import synth
-    z = np.load(MODEL_NPZ)
+    cfg = a.cfg
+    z = np.load(os.path.join(ROOT, "bench_models", cfg["model"]))
     omodel = orc.OracleModel.from_npz(z)
     V = omodel.V
+    ncores = max(1, min(os.cpu_count() or 1, 16))
+    ctx = mp.get_context("fork")
+    if a.config == "c5":
+        from columbiaimagesearch_b200 import synth
+        global _G_MODEL
+        _G_MODEL = omodel
+        rows = 1500                                        # per core and step (about 0.3 s of model.predict calls)
+        X = synth.dlib_style(rows * ncores * 2, 128, seed=a.seed)
+        times = []
+        with ctx.Pool(ncores) as pool:
+            for it in range(a.warmup + a.steps):
+                off = (it % 2) * rows * ncores
+                jobs = [X[off + w * rows: off + (w + 1) * rows] for w in range(ncores)]
+                t0 = time.perf_counter()
+                pool.map(_enc_worker, jobs)
+                dt = time.perf_counter() - t0
+                if it >= a.warmup:
+                    times.append(dt)
+        total = sum(times)
+        cps = a.steps * ncores * rows / total
+        line = {"impl": "reference", "metric": cfg["metric"], "value": cps, "unit": "codes/s", "n_gpus": a.gpus, "steps": a.steps,
+                "warmup": a.warmup, "ms_per_step": 1e3 * total / a.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "compute_codes on 128-d dlib-style synthetic vectors, V=8 M=16 K=256", "rows_per_step": ncores * rows},
+                "cpu_baseline": {"value": cps, "unit": "codes/s", "cores": ncores, "kind": "port",
+                                 "sample": "%d rows per step on %d processes (compute_codes_parallel's row-chunk fan-out, utils.py:178-200)" % (ncores * rows, ncores)},
+                "e2e": {"value": cps, "unit": "codes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line))
+        return
     t_prep = time.perf_counter()
     # database: same recipe (NumPy generator), coarse cells of all rows, fine codes only where needed
     rng = np.random.default_rng(a.seed + 1)
     C = np.random.RandomState(a.seed).randn(4096, 128).astype(np.float32)
-    n = a.n_db
+    n = cfg["n_db"]
+    quota = cfg["quota"]
     cell = np.empty(n, np.int32)
     chunk = 1 << 20
     h = 64
     cn = [(omodel.Cs[s].astype(np.float64) ** 2).sum(1) for s in (0, 1)]
-    ncores = max(1, min(os.cpu_count() or 1, 16))
     nq_total = max(2, a.cpu_queries) * ncores
     blocks = []
     for s0 in range(0, n, chunk):
@@ -218,7 +289,7 @@ def run_reference(a):
         for _, c in orc.multisequence(q, omodel.Cs):
             need.add(int(c[0]) * V + int(c[1]))
             got += int(sizes[int(c[0]) * V + int(c[1])])
-            if got >= a.quota:
+            if got >= quota:
                 break
     s = orc.OracleSearcher(omodel)
     for cid in sorted(need):
@@ -235,7 +306,6 @@ def run_reference(a):
     qstep = max(1, per // max(1, a.steps + a.warmup))
     global _G_SEARCHER
     _G_SEARCHER = s
-    ctx = mp.get_context("fork")
     times = []
     with ctx.Pool(ncores) as pool:
         pos = 0
@@ -243,7 +313,7 @@ def run_reference(a):
             jobs = []
             for w in range(ncores):
                 qs = [Q[(pos + w * qstep + j) % len(Q)] for j in range(qstep)]
-                jobs.append((qs, a.quota, a.k))
+                jobs.append((qs, quota, a.k))
             pos += ncores * qstep
             t0 = time.perf_counter()
             pool.map(_worker, jobs)
@@ -252,58 +322,190 @@ def run_reference(a):
                 times.append(dt)
     total = sum(times)
     qps = a.steps * ncores * qstep / total
-    line = {"impl": "reference", "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": a.gpus, "steps": a.steps,
-            "warmup": a.warmup, "ms_per_step": 1e3 * total / a.steps, "higher_is_better": True, "scaling": "strong",
+    line = {"impl": "reference", "metric": cfg["metric"], "value": qps, "unit": "queries/s", "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": 1e3 * total / a.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "10M x 128-d dlib-style synthetic, V=8 M=16 K=256, quota=%d, top-%d" % (a.quota, a.k),
+            "config": {"workload": "%dM x 128-d dlib-style synthetic, V=8 M=16 K=256, quota=%d, top-%d" % (n // 1_000_000, quota, a.k),
                        "n_db": n, "queries_per_step": ncores * qstep, "index": "python dict, visited cells only",
+                       "query_sample": "near-duplicates of rows of one median-sized cell (only the visited cells are materialised as "
+                                       "Python objects); cost per query is linear in the codes ranked, as for any query",
                        "prep_s": round(prep_s, 1)},
             "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": ncores, "kind": "port",
-                             "sample": "%d queries per step on %d replica processes (reference search is single-threaded)" % (ncores * qstep, ncores)},
+                             "sample": "%d queries per step on %d replica processes (reference search is single-threaded); oracle port: the "
+                                       "reference's Python-2 files exist only in the build container" % (ncores * qstep, ncores)},
             "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------------
-def run_b200(a):
-    import torch
-    import torch.distributed as dist
+class Env(object):
+    """torch / torch.distributed plumbing shared by the b200 configs."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device (this implementation has no CPU fallback)")
+        torch.cuda.set_device(self.local)
+        self.dev = "cuda:%d" % self.local
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=torch.device(self.dev))
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, *vals):
+        t = self.torch.tensor(list(vals), dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(v) for v in t]
+
+    def sum_over_ranks(self, *vals):
+        t = self.torch.tensor(list(vals), dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return [float(v) for v in t]
+
+    def all_gather_rows(self, t, counts):
+        """concatenate per-rank row blocks (rank r holds counts[r] rows) on every rank"""
+        torch = self.torch
+        if self.world == 1:
+            return t
+        mx = max(counts)
+        pad = torch.zeros((mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        pad[:t.shape[0]] = t
+        out = torch.empty((self.world * mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        self.dist.all_gather_into_tensor(out, pad)
+        return torch.cat([out[r * mx:r * mx + counts[r]] for r in range(self.world)])
+
+
+# ------------------------------------------------------------------------------------------------
+def train_model_c3(env, a, cfg, lopq, synth):
+    """DATA PREPARATION (c3): a 2048-d V=8 M=32 model is 134 MB of float64 rotations, too large for a fixture, so it is
+    trained here with the package's own trainer (lopq/train.py: the reference's algorithm, batched) on `ntrain` seeded
+    vectors, identically on every rank.  Models are inputs of the hot path: not timed, not part of parity."""
+    X = synth.dlib_style_torch(a.ntrain, cfg["D"], seed=a.seed + 5, device=env.dev, relu=True).cpu().numpy().astype(np.float64)
+    m = lopq.LOPQModel(V=cfg["V"], M=cfg["M"], subquantizer_clusters=256)
+    t0 = time.perf_counter()
+    m.fit(X, n_init=1, kmeans_coarse_iters=8, kmeans_local_iters=8, random_state=0)
+    return m, time.perf_counter() - t0
+
+
+def build_database(env, a, cfg, model, synth):
+    """Synthesize the database on the device and encode it with the library, ROW-SHARDED over the ranks (each rank encodes
+    its contiguous block of chunks, no communication: compute_codes_parallel's decomposition, utils.py:178-200), then
+    all-gather the codes (18-40 bytes per row) so that every rank can pick the rows of its cells.
+    Returns coarse_t [n,2], fine_t [n,M] (full, on every rank), the query batches, ground truth, encode statistics."""
+    torch = env.torch
+    n, D, M = cfg["n_db"], cfg["D"], cfg["M"]
+    relu = cfg["style"] == "sentibank"
+    nb = a.warmup + a.steps
+    nq_tot = nb * a.batch * env.world
+    nrec = min(nb, 4) * a.batch * env.world                      # recall is evaluated on the first batches
+    enc = model._new_handle(env.local)
+    chunk = 1 << 20 if D <= 256 else 1 << 17
+    nchunks = (n + chunk - 1) // chunk
+    C = torch.from_numpy(np.random.RandomState(a.seed).randn(4096, D)).to(device=env.dev, dtype=torch.float32)
+
+    def gen_chunk(c):
+        """chunk c of the database: same values on whichever rank generates it"""
+        g = torch.Generator(device=env.dev)
+        g.manual_seed(a.seed * 1000003 + c)
+        rows = min(chunk, n - c * chunk)
+        idx = torch.randint(0, 4096, (rows,), generator=g, device=env.dev)
+        X = C[idx] + 0.35 * torch.randn((rows, D), generator=g, device=env.dev, dtype=torch.float32)
+        if relu:
+            X = torch.clamp_min(X, 0.0)
+            X[:, 0] += 1e-3
+        return X / X.norm(dim=1, keepdim=True)
+
+    # queries: near-duplicates of rows of chunk 0 (so that they exist before the rest of the database is generated)
+    X0 = gen_chunk(0)
+    Qall, _ = synth.near_duplicate_queries_torch(X0, nq_tot, rho=a.rho, seed=a.seed + 77)
+    Qrec = Qall[:nrec]
+    best = torch.full((nrec,), float("inf"), device=env.dev)
+    arg = torch.zeros((nrec,), dtype=torch.int64, device=env.dev)
+    qn = (Qrec * Qrec).sum(1)
+    # this rank's chunks: a contiguous range
+    per = (nchunks + env.world - 1) // env.world
+    c_lo, c_hi = min(nchunks, env.rank * per), min(nchunks, (env.rank + 1) * per)
+    my_rows = max(0, min(n, c_hi * chunk) - c_lo * chunk)
+    coarse_loc = torch.empty((max(my_rows, 1), 2), dtype=torch.int32, device=env.dev)
+    fine_loc = torch.empty((max(my_rows, 1), M), dtype=torch.uint8, device=env.dev)
+    stream = torch.cuda.ExternalStream(enc.stream(), device=env.dev)
+    enc_ms = 0.0
+    torch.backends.cuda.matmul.allow_tf32 = False
+    for c in range(c_lo, c_hi):
+        X = X0 if c == 0 else gen_chunk(c)
+        rows = X.shape[0]
+        o = (c - c_lo) * chunk
+        if c == c_lo:                                             # warm-up call (allocations), then the timed passes
+            enc.encode_device(X.data_ptr(), min(rows, 1 << 16), coarse_loc[o:].data_ptr(), fine_loc[o:].data_ptr())
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        enc.encode_device(X.data_ptr(), rows, coarse_loc[o:].data_ptr(), fine_loc[o:].data_ptr())
+        ev1.record(stream)
+        torch.cuda.synchronize()
+        enc_ms += ev0.elapsed_time(ev1)
+        # exact ground truth for the recall queries (eval.py:7-38 compute_all_neighbors), chunk by chunk
+        for a0 in range(0, rows, 1 << 18):
+            xb = X[a0:a0 + (1 << 18)]
+            xn = (xb * xb).sum(1)
+            for q0 in range(0, nrec, 4096):
+                sl = slice(q0, min(nrec, q0 + 4096))
+                d = qn[sl, None] - 2.0 * (Qrec[sl] @ xb.T) + xn[None, :]
+                v, i = d.min(dim=1)
+                upd = v < best[sl]
+                best[sl] = torch.where(upd, v, best[sl])
+                arg[sl] = torch.where(upd, i + (c * chunk + a0), arg[sl])
+        del X
+    if env.world > 1:                                             # combine the ground truth of the row blocks
+        allb = [torch.empty_like(best) for _ in range(env.world)]
+        alla = [torch.empty_like(arg) for _ in range(env.world)]
+        env.dist.all_gather(allb, best)
+        env.dist.all_gather(alla, arg)
+        sb, sa = torch.stack(allb), torch.stack(alla)
+        win = sb.argmin(0)
+        arg = sa.gather(0, win[None, :])[0]
+    counts = [max(0, min(n, min(nchunks, (r + 1) * per) * chunk) - min(nchunks, r * per) * chunk) for r in range(env.world)]
+    coarse_t = env.all_gather_rows(coarse_loc[:my_rows], counts)
+    fine_t = env.all_gather_rows(fine_loc[:my_rows], counts)
+    assert coarse_t.shape[0] == n
+    enc_s = env.max_over_ranks(enc_ms * 1e-3)[0]
+    enc_stats = {"codes_per_s": n / max(enc_s, 1e-9), "n": n, "rows_per_rank": counts, "seconds_max_over_ranks": enc_s,
+                 "guard_subvectors": enc.encode_guard_count(),
+                 "note": "b2l_encode on device-resident float32 rows, row-sharded over the ranks (no communication), CUDA events per chunk, "
+                         "first call warmed on a prefix; float64 arithmetic"}
+    enc.close()
+    return coarse_t, fine_t, Qall, arg.cpu().numpy(), enc_stats
+
+
+def run_search(a):
+    env = Env()
+    torch, dist = env.torch, env.dist
     from columbiaimagesearch_b200 import synth
     import columbiaimagesearch_b200.lopq as lopq
     from columbiaimagesearch_b200.sharded import ShardedLOPQSearcher
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device (this implementation has no CPU fallback)")
-    torch.cuda.set_device(local)
-    dev = "cuda:%d" % local
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device(dev))
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    z = np.load(MODEL_NPZ)
-    model = lopq.LOPQModel.from_npz(z)
-    M = model.M
-    n = a.n_db
-
-    # ---- database: synthesize on the device, encode with the library (timed: the C5 encode figure) ----
-    X = synth.dlib_style_torch(n, 128, seed=a.seed, device=dev)
-    enc = model._new_handle(local)
-    coarse_t = torch.empty((n, 2), dtype=torch.int32, device=dev)
-    fine_t = torch.empty((n, M), dtype=torch.uint8, device=dev)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    enc.encode_device(X.data_ptr(), n, coarse_t.data_ptr(), fine_t.data_ptr())
-    enc_s = time.perf_counter() - t0
+    cfg = a.cfg
+    world, rank, local, dev = env.world, env.rank, env.local, env.dev
+    train_s = None
+    if cfg["model"]:
+        z = np.load(os.path.join(ROOT, "bench_models", cfg["model"]))
+        model = lopq.LOPQModel.from_npz(z)
+    else:
+        model, train_s = train_model_c3(env, a, cfg, lopq, synth)
+    M, D, n, quota, k, nq = model.M, cfg["D"], cfg["n_db"], cfg["quota"], a.k, a.batch
+    coarse_t, fine_t, Qall, gt, enc_stats = build_database(env, a, cfg, model, synth)
 
     # one searcher class for every N: the inverted lists are sharded by coarse cell over the ranks (N = 1: one shard)
     if a.emulate_shard > 1 and world == 1:
@@ -316,54 +518,60 @@ def run_b200(a):
         searcher.add_codes_device(coarse_t, fine_t)
         searcher.finalize()
     handle = searcher._handle
-
-    # ---- queries: (warmup + steps) distinct batches of near-duplicates, exact ground truth for recall ----
+    peer = world > 1 and a.exchange == "peer"
+    if peer:
+        searcher.enable_peer_exchange(nq, max(16, k))
     nb = a.warmup + a.steps
-    nq = a.batch
-    Qall, qidx = synth.near_duplicate_queries_torch(X, nb * nq, rho=a.rho, seed=a.seed + 77)
-    nrec = min(nb, 4) * nq                                   # recall is evaluated on the first batches
-    gt = synth.exact_nn_torch(X, Qall[:nrec]).cpu().numpy()
-    k = a.k
+    G = nq * world                                             # queries per step, all ranks
 
-    def recall_of(quota, nbatches):
-        hits10 = hits1 = 0
+    def global_batch(b):
+        return Qall[b * G:(b + 1) * G]
+
+    def home_batch(b):
+        return Qall[b * G + rank * nq: b * G + (rank + 1) * nq]
+
+    def recall_of(q_quota, nbatches):
+        """eval.get_recall's definition (eval.py:92-142) on whole batches, through the synchronous host-driven API"""
+        rec = np.zeros(2)
         vis = cand = 0
         for b in range(nbatches):
-            q = Qall[b * nq:(b + 1) * nq].cpu().numpy()
-            o = searcher.search_batch(q, quota=quota, limit=k)
-            g = gt[b * nq:(b + 1) * nq]
-            hit = (o["ids"] == g[:, None]) & (np.arange(k)[None, :] < o["count"][:, None])
-            hits10 += int(hit.any(1).sum())
-            hits1 += int(hit[:, 0].sum())
-            vis += int(o["visited"].sum())
+            q = global_batch(b).cpu().numpy()
+            r = lopq.eval.get_recall_batch(_Fixed(searcher, handle), q, gt[b * G:(b + 1) * G], quota=q_quota, thresholds=(1, k), batch=G)
+            rec += r * G
+            vis += _Fixed.last_visited
             cand += handle.stats()["codes_scanned"]
-        tot = nbatches * nq
-        return hits10 / tot, hits1 / tot, vis / tot, cand / tot
+        tot = nbatches * G
+        return rec[1] / tot, rec[0] / tot, vis / tot, cand / tot
 
     if a.sweep:
-        for quota in [int(v) for v in a.sweep.split(",")]:
-            r10, r1, vis, cand = recall_of(quota, min(nb, 2))
+        for qv in [int(v) for v in a.sweep.split(",")]:
+            r10, r1, vis, cand = recall_of(qv, min(nb, 2))
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             reps = 5
             for b in range(reps):
-                searcher.search_batch(Qall[(b % nb) * nq:((b % nb) + 1) * nq], quota=quota, limit=k)
+                searcher.search_batch(global_batch(b % nb), quota=qv, limit=k)
             dt = (time.perf_counter() - t0) / reps
             st = handle.stats()
-            app, bnd = handle.debug_candidates(nq)
-            st["cand_appended"] = {"mean": float(app.mean()), "p50": float(np.median(app)), "p99": float(np.percentile(app, 99)),
-                                   "max": int(app.max()), "sum": int(app.sum())}
             if rank == 0:
-                print(json.dumps({"quota": quota, "recall@10": r10, "recall@1": r1, "cells_visited": vis, "codes_per_query_local": cand,
-                                  "qps": nq / dt, "ms_per_batch": dt * 1e3, "stats": st}))
+                print(json.dumps({"quota": qv, "recall@10": r10, "recall@1": r1, "cells_visited": vis, "codes_per_query_local": cand,
+                                  "qps": G / dt, "ms_per_batch": dt * 1e3, "stats": st}))
         return
+
+    # recall first: it runs the host-driven protocol, which also sizes every workspace before the exchange is used
+    r10, r1, vis, cand = recall_of(quota, min(nb, 4))
+
+    def enqueue(batch_of, b):
+        if peer:
+            return searcher.search_home_async(batch_of(b), quota=quota, limit=k)
+        return searcher.search_batch_async(batch_of(b), quota=quota, limit=k)
 
     def run_pipelined(batch_of, first, count):
         """`count` batches through the public asynchronous API, two in flight: the host-side launch work of batch i+1
         overlaps the device work of batch i.  Every batch's results are read (and certified) on the host."""
         pend, redo, last = None, np.zeros(2, np.int64), None
         for b in range(first, first + count):
-            p = searcher.search_batch_async(batch_of(b), quota=a.quota, limit=k)
+            p = enqueue(batch_of, b)
             if pend is not None:
                 last = pend.result(copy=False)
                 redo += (last["exact_queries"], last["rescan_queries"])
@@ -372,10 +580,10 @@ def run_b200(a):
         redo += (last["exact_queries"], last["rescan_queries"])
         return redo, last
 
-    dev_batch = lambda b: Qall[b * nq:(b + 1) * nq]
+    dev_batch = home_batch if peer else global_batch
     # ---- warm-up -----------------------------------------------------------------------------------
     run_pipelined(dev_batch, 0, a.warmup)
-    barrier()
+    env.barrier()
 
     # ---- timed region 1: device-resident inputs ("value") ------------------------------------------
     sampler = ClockSampler(local)
@@ -383,132 +591,303 @@ def run_b200(a):
     stream = torch.cuda.ExternalStream(handle.stream(), device=dev)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     handle.reset_stats()
-    barrier()
+    env.barrier()
     ev0.record(stream)
     t0 = time.perf_counter()
-    redo_q, _ = run_pipelined(dev_batch, a.warmup, a.steps)
+    redo_q, last = run_pipelined(dev_batch, a.warmup, a.steps)
     exact_q, rescan_q = int(redo_q[0]), int(redo_q[1])
     ev1.record(stream)
-    barrier()
+    env.barrier()
     wall = time.perf_counter() - t0
-    dev_ms = ev0.elapsed_time(ev1)
-    t = torch.tensor([max(dev_ms * 1e-3, 0.0), wall], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_s, wall_s = float(t[0]), float(t[1])
+    dev_s, wall_s = env.max_over_ranks(max(ev0.elapsed_time(ev1) * 1e-3, 0.0), wall)
     st = handle.stats()                                       # per-call CUDA-event times of the timed steps, summed
     scan_ms, plan_ms, sel_ms = st["acc_scan_ms"], st["acc_plan_ms"], st["acc_select_ms"]
     scan_bytes, items = st["acc_scan_bytes"], st["acc_work_items"]
-    launches = st["acc_kernel_launches"] + st["acc_calls"]    # + the merge kernel of every step
-    timed_calls = st["acc_calls"]
+    timed_calls = max(1, st["acc_calls"])
+    # kernels of the library per step: the search kernels + merge (+ put / 3 signals / 3 waits of the exchange)
+    launches = st["acc_kernel_launches"] + st["acc_calls"] * (8 if peer else 1)
     step_s = max(dev_s, 1e-9)
-    value = a.steps * nq / step_s
+    value = a.steps * G / step_s
+    # parity spot-check at N > 1 (rank 0, first queries of the last timed batch against the oracle)
+    parity = None
+    if rank == 0 and world > 1 and not a.no_cpu_baseline:
+        parity = oracle_spot_check(a, cfg, model, coarse_t, fine_t, dev_batch(a.warmup + a.steps - 1), last, quota, k)
+
+    # ---- sustained run (>= sustain_s seconds of back-to-back batches, device-resident inputs) --------------------
+    sustained = None
+    if a.sustain_s > 0:
+        nsteps = max(a.steps, int(a.sustain_s / (step_s / a.steps)) + 1)
+        env.barrier()
+        ev0.record(stream)
+        run_pipelined(lambda b: dev_batch(b % nb), 0, nsteps)
+        ev1.record(stream)
+        env.barrier()
+        sus_s = env.max_over_ranks(ev0.elapsed_time(ev1) * 1e-3)[0]
+        sustained = {"value": nsteps * G / sus_s, "steps": nsteps, "seconds": sus_s}
 
     # ---- timed region 2: end to end through the public API with host buffers ("e2e") -----------------
-    Qhost = torch.empty((a.steps * nq, 128), dtype=torch.float32).pin_memory()
-    Qhost.copy_(Qall[a.warmup * nq:nb * nq])
+    Qhost = torch.empty((a.steps * (nq if peer else G), D), dtype=torch.float32).pin_memory()
+    for b in range(a.steps):
+        w = nq if peer else G
+        Qhost[b * w:(b + 1) * w].copy_(dev_batch(a.warmup + b))
     Qh = Qhost.numpy()
-    host_batch = lambda b: Qh[(b % a.steps) * nq:((b % a.steps) + 1) * nq]
+    w = nq if peer else G
+    host_batch = lambda b: Qh[(b % a.steps) * w:((b % a.steps) + 1) * w]
     run_pipelined(host_batch, 0, a.warmup)                   # warm-up of the host-buffer path
-    barrier()
+    env.barrier()
     t0 = time.perf_counter()
     redo_e2e, _ = run_pipelined(host_batch, 0, a.steps)
-    barrier()
-    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t[0])
+    env.barrier()
+    e2e_s = env.max_over_ranks(time.perf_counter() - t0)[0]
     # the same, one synchronous call at a time (what the unmodified plugin loop does per request batch)
-    barrier()
+    env.barrier()
     t0 = time.perf_counter()
     for b in range(a.steps):
-        searcher.search_batch(host_batch(b), quota=a.quota, limit=k)
-    barrier()
-    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_sync_s = float(t[0])
+        if peer:
+            searcher.search_home_async(host_batch(b), quota=quota, limit=k).result(copy=False)
+        else:
+            searcher.search_batch(host_batch(b), quota=quota, limit=k)
+    env.barrier()
+    e2e_sync_s = env.max_over_ranks(time.perf_counter() - t0)[0]
     clocks = sampler.stop()                                  # sampled through the timed regions
-    h2d = nq * 128 * 4
-    d2h = nq * k * (8 + 8 + 8 + M) + nq * 9
+    h2d = w * D * 4                                           # per rank
+    d2h = w * k * (8 + 8 + 8 + M) + w * 9 + (256 if peer else 0)
 
-    # ---- recall@10 (eval.get_recall definition) on the first batches ---------------------------------
-    r10, r1, vis, cand = recall_of(a.quota, min(nb, 4))
+    # ---- strong scaling figure at N > 1: the same `batch` queries split over the ranks ------------------------------
+    strong = None
+    if peer and nq % world == 0 and (nq // world) * D * 4 % 16 == 0:
+        nh = nq // world
+        sb = lambda b: Qall[b * nq + rank * nh: b * nq + (rank + 1) * nh]
+        run_pipelined_n = lambda first, count: _run_home(searcher, sb, first, count, quota, k)
+        run_pipelined_n(0, a.warmup)
+        env.barrier()
+        ev0.record(stream)
+        run_pipelined_n(a.warmup, a.steps)
+        ev1.record(stream)
+        env.barrier()
+        s_s = env.max_over_ranks(ev0.elapsed_time(ev1) * 1e-3)[0]
+        strong = {"value": a.steps * nq / s_s, "ms_per_step": 1e3 * s_s / a.steps, "queries_per_step": nq,
+                  "note": "fixed global batch of %d queries (%d per rank), device-resident inputs" % (nq, nh)}
 
     # ---- roofline of the dominant kernel (ADC scan) ----------------------------------------------------
     peak, peak_src = measured_peak()
-    ach = scan_bytes / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0
-    traffic, traffic_src = ncu_traffic()
-    roofline = {"bound": "hbm", "kernel": "k_scan_pk<%d>" % M, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": scan_bytes / max(1, timed_calls), "scan_ms_per_launch": scan_ms / max(1, timed_calls),
-                "launches_timed": timed_calls,
-                "note": "algorithmic bytes = M x codes ranked, summed over the batch's queries, on this rank (no credit for cross-query "
-                        "reuse: a code tile read once from HBM/L2 serves every query of the batch that visits the cell, which is why "
-                        "`traffic` is far below it and frac can exceed 1); the resource that actually bounds the kernel is the "
-                        "shared-memory gather pipe, see `gather`"}
-    # secondary roofline: shared-memory LUT gathers.  One conflict-free LDS wavefront serves 32 lanes x 2 packed queries.
+    alg = scan_bytes / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0
+    kname = "k_scan_pk<%d>" % max(4, 1 << (M - 1).bit_length())
+    traffic, traffic_src = ncu_traffic(a.config)
     nsm = torch.cuda.get_device_properties(local).multi_processor_count
     sm_hz = 1e6 * float(clocks["sm_mhz"] or clocks["sm_max_mhz"] or 1965)
-    lookups = scan_bytes                                   # one table look-up per code byte ranked
-    wf_min = lookups / 64.0
-    roofline["gather"] = {"bound": "shared-memory wavefronts (1 per clock per SM)", "lookups_per_launch": lookups / max(1, timed_calls),
-                          "min_wavefronts_per_launch": wf_min / max(1, timed_calls),
-                          "achieved": wf_min / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0, "peak": nsm * sm_hz / 1e9,
-                          "unit": "Gwavefront/s", "frac": (wf_min / (scan_ms * 1e-3)) / (nsm * sm_hz) if scan_ms > 0 else 0.0}
+    wf_min = scan_bytes / 64.0                                  # one conflict-free LDS wavefront serves 32 lanes x 2 packed queries
+    g_ach = wf_min / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0
+    g_peak = nsm * sm_hz / 1e9
+    roofline = {"bound": "smem-gather", "kernel": kname, "achieved": g_ach, "peak": g_peak, "unit": "Gwavefront/s", "frac": g_ach / g_peak,
+                "traffic": traffic, "traffic_source": traffic_src,
+                "lookups_per_launch": scan_bytes / timed_calls, "min_wavefronts_per_launch": wf_min / timed_calls,
+                "scan_ms_per_launch": scan_ms / timed_calls, "launches_timed": timed_calls,
+                "hbm": {"algorithmic_GBps": alg, "algorithmic_frac_of_peak": alg / peak, "peak_GBps": peak, "peak_source": peak_src,
+                        "algorithmic_bytes_per_launch": scan_bytes / timed_calls,
+                        "dram_GBps": (traffic / (scan_ms / timed_calls * 1e-3) / 1e9) if traffic and scan_ms > 0 else None,
+                        "dram_frac_of_peak": (traffic / (scan_ms / timed_calls * 1e-3) / 1e9 / peak) if traffic and scan_ms > 0 else None},
+                "note": "The batched scan is bound by shared-memory LUT gathers, not HBM: one code row read from HBM/L2 serves every query "
+                        "of the batch that visits the cell.  `frac` = minimum conflict-free LDS wavefronts (one per 32 lanes x 2 packed "
+                        "queries = 64 look-ups) per second over the pipe's 1 wavefront/clock/SM at the sampled SM clock.  `hbm` keeps the "
+                        "SURVEY 8d accounting (M x codes ranked, no credit for reuse: may exceed the HBM peak) and the measured DRAM "
+                        "traffic of the committed ncu capture.  The HBM-bound regime (single query, no reuse) is measured by "
+                        "--config c3 / profiles/*latency*."}
 
     # ---- CPU baseline (rank 0, N = 1): the reference's per-item Python loop on a bounded sample ---------
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        from oracle import lopq_oracle as orc
-        omodel = orc.OracleModel.from_npz(z)
-        co = coarse_t.cpu().numpy()
-        fi = fine_t.cpu().numpy()
-        cellid = co[:, 0].astype(np.int64) * model.V + co[:, 1]
-        order = np.argsort(cellid, kind="stable")
-        sizes = np.bincount(cellid, minlength=model.V ** 2)
-        starts = np.concatenate([[0], np.cumsum(sizes)])
-        qs = Qall[:a.cpu_queries].cpu().numpy()
-        s = oracle_index_for(omodel, orc, co, fi, sizes, starts, order, qs, a.quota)
-        dt, res = time_oracle_queries(s, qs, a.quota, k)
-        g = searcher.search_batch(qs, quota=a.quota, limit=k)
-        same = all([r.id for r in res[i][0]] == g["ids"][i][:len(res[i][0])].tolist() and res[i][1] == int(g["visited"][i])
-                   for i in range(len(qs)))
-        maxd = max(float(np.max(np.abs(np.array([r.dist for r in res[i][0]]) - g["dist"][i][:len(res[i][0])]))) for i in range(len(qs)))
-        cpu = {"value": len(qs) / dt, "unit": "queries/s", "cores": 1, "kind": "port",
-               "sample": "%d queries of the same 10M workload, reference algorithm (per-item Python ADC loop, oracle port), %0.1f s" % (len(qs), dt),
-               "ids_match_gpu": bool(same), "max_abs_dist_diff": maxd, "host_cores": os.cpu_count()}
+        cpu = cpu_baseline_search(a, cfg, model, coarse_t, fine_t, Qall, searcher, quota, k)
 
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-                "ms_per_step": 1e3 * step_s / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        line = {"metric": cfg["metric"], "value": value, "unit": "queries/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": 1e3 * step_s / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u16", "data": "synthetic",
-                "config": {"workload": "10M x 128-d dlib-style synthetic (4096-centre GMM, L2-normalised), V=8 M=16 K=256, "
-                                       "batch=%d near-duplicate queries (rho=%.2f), quota=%d, top-%d" % (nq, a.rho, a.quota, k),
-                           "n_db": n, "batch": nq, "quota": a.quota, "k": k,
+                "config": {"workload": "%s: %dM x %d-d %s-style synthetic (4096-centre GMM, L2-normalised), V=%d M=%d K=256, "
+                                       "%d near-duplicate queries per rank and step (rho=%.2f), quota=%d, top-%d"
+                                       % (a.config, n // 1_000_000, D, cfg["style"], model.V, M, nq, a.rho, quota, k),
+                           "n_db": n, "batch_per_rank": nq, "queries_per_step": G, "quota": quota, "k": k,
+                           "recall@10": r10, "recall@1": r1,
                            "arithmetic": "16-bit packed table sums in the scan (float32-table and float64 fallbacks), float64 tables and re-rank",
-                           "l2": "distinct query batch per step; per-step working set (160 MB codes + per-batch LUTs) exceeds the 126 MB L2",
-                           "sharding": "cells by (c0+c1) mod N, one all-gather of per-rank top-k" if world > 1 else "single GPU"},
+                           "l2": "distinct query batch per step; per-step working set (%d MB codes + per-batch LUTs) exceeds the 126 MB L2"
+                                 % (n * max(4, 1 << (M - 1).bit_length()) // 1_000_000),
+                           "sharding": ("cells by (c0+c1) mod N; every rank brings %d home queries per step (weak scaling over a fixed "
+                                        "database); exchange = %s" % (nq, "peer-mapped windows inside the library" if peer else "NCCL all-gather"))
+                           if world > 1 else "single GPU",
+                           "model_train_s": train_s},
                 "recall@10": r10, "recall@1": r1, "cells_visited_per_query": vis, "codes_ranked_per_query": cand * world if world > 1 else cand,
-                "wall_s_timed_region": wall_s,
-                "e2e": {"value": a.steps * nq / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "api": "search_batch_async, 2 batches in flight, pinned host queries in / host results out every step",
-                        "sync_api_value": a.steps * nq / e2e_sync_s,
+                "wall_s_timed_region": wall_s, "value_sustained": sustained, "strong": strong,
+                "e2e": {"value": a.steps * G / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
+                        "api": "%s, 2 batches in flight, pinned host queries in / host results out every step"
+                               % ("search_home_async" if peer else "search_batch_async"),
+                        "sync_api_value": a.steps * G / e2e_sync_s,
                         "exact_fallback_queries": int(redo_e2e[0]), "float32_rescan_queries": int(redo_e2e[1])},
                 "gpu_launches": int(launches), "exact_fallback_queries": int(exact_q), "float32_rescan_queries": int(rescan_q),
-                "time_split_ms_per_step": {"plan+lut": plan_ms / max(1, timed_calls), "scan": scan_ms / max(1, timed_calls),
-                                           "select": sel_ms / max(1, timed_calls)},
-                "work_items_per_step": items / max(1, timed_calls),
-                "encode": {"codes_per_s": n / enc_s, "n": n, "note": "b2l_encode on device-resident float32 vectors (C5 path), float64 arithmetic"},
-                "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks}
+                "time_split_ms_per_step": {"plan+lut": plan_ms / timed_calls, "scan": scan_ms / timed_calls, "select": sel_ms / timed_calls,
+                                           "total_local": st["acc_total_ms"] / timed_calls},
+                "work_items_per_step": items / timed_calls, "parity_spot_check": parity,
+                "encode": enc_stats, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks}
         print(json.dumps(line))
+    searcher.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+
+
+def _run_home(searcher, batch_of, first, count, quota, k):
+    pend = None
+    for b in range(first, first + count):
+        p = searcher.search_home_async(batch_of(b), quota=quota, limit=k)
+        if pend is not None:
+            pend.result(copy=False)
+        pend = p
+    pend.result(copy=False)
+
+
+class _Fixed(object):
+    """adapter: get_recall_batch calls searcher.search_batch(X, quota=, limit=); route it to the synchronous entry point"""
+    last_visited = 0
+
+    def __init__(self, searcher, handle):
+        self.s = searcher
+
+    def search_batch(self, X, quota, limit):
+        o = self.s._search_batch_sync(X, quota, limit)
+        _Fixed.last_visited = int(o["visited"].sum())
+        return o
+
+
+def _host_index(model, coarse_t, fine_t):
+    co = coarse_t.cpu().numpy()
+    fi = fine_t.cpu().numpy()
+    cellid = co[:, 0].astype(np.int64) * model.V + co[:, 1]
+    order = np.argsort(cellid, kind="stable")
+    sizes = np.bincount(cellid, minlength=model.V ** 2)
+    starts = np.concatenate([[0], np.cumsum(sizes)])
+    return co, fi, order, sizes, starts
+
+
+def _oracle_model(model):
+    from oracle import lopq_oracle as orc
+    return orc, orc.OracleModel(model.Cs, model.Rs, model.mus, model.subquantizers)
+
+
+def oracle_spot_check(a, cfg, model, coarse_t, fine_t, Qdev, out, quota, k, nqs=3):
+    """N > 1: the first queries of a timed batch against the oracle (ids, visited, distances)"""
+    orc, omodel = _oracle_model(model)
+    co, fi, order, sizes, starts = _host_index(model, coarse_t, fine_t)
+    qs = Qdev[:nqs].cpu().numpy()
+    s = oracle_index_for(omodel, orc, co, fi, sizes, starts, order, qs, quota)
+    _, res = time_oracle_queries(s, qs, quota, k)
+    same = all([r.id for r in res[i][0]] == out["ids"][i][:len(res[i][0])].tolist() and res[i][1] == int(out["visited"][i]) for i in range(nqs))
+    maxd = max(float(np.max(np.abs(np.array([r.dist for r in res[i][0]]) - out["dist"][i][:len(res[i][0])]))) for i in range(nqs))
+    return {"queries": nqs, "ids_match_oracle": bool(same), "max_abs_dist_diff": maxd}
+
+
+def cpu_baseline_search(a, cfg, model, coarse_t, fine_t, Qall, searcher, quota, k):
+    orc, omodel = _oracle_model(model)
+    co, fi, order, sizes, starts = _host_index(model, coarse_t, fine_t)
+    qs = Qall[:a.cpu_queries].cpu().numpy()
+    s = oracle_index_for(omodel, orc, co, fi, sizes, starts, order, qs, quota)
+    dt, res = time_oracle_queries(s, qs, quota, k)
+    g = searcher.search_batch(qs, quota=quota, limit=k)
+    same = all([r.id for r in res[i][0]] == g["ids"][i][:len(res[i][0])].tolist() and res[i][1] == int(g["visited"][i])
+               for i in range(len(qs)))
+    maxd = max(float(np.max(np.abs(np.array([r.dist for r in res[i][0]]) - g["dist"][i][:len(res[i][0])]))) for i in range(len(qs)))
+    return {"value": len(qs) / dt, "unit": "queries/s", "cores": 1, "kind": "port",
+            "sample": "%d queries of the same workload, reference algorithm (per-item Python ADC loop, oracle port), %0.1f s" % (len(qs), dt),
+            "ids_match_gpu": bool(same), "max_abs_dist_diff": maxd, "host_cores": os.cpu_count()}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_encode(a):
+    """--config c5: compute_codes over 50M x 128-d rows, row-sharded over the ranks (utils.py:178-200's decomposition, no
+    communication).  One step = one encode pass over this rank's resident block of rows; the 50M rows are visited block
+    by block (device-resident figure = `value`); `e2e` times the same call with PINNED HOST rows in and host codes out."""
+    env = Env()
+    torch = env.torch
+    from columbiaimagesearch_b200 import synth
+    import columbiaimagesearch_b200.lopq as lopq
+    cfg = a.cfg
+    z = np.load(os.path.join(ROOT, "bench_models", cfg["model"]))
+    model = lopq.LOPQModel.from_npz(z)
+    M, D, n = model.M, cfg["D"], cfg["n_db"]
+    per_rank = n // env.world
+    block = min(per_rank, 1 << 22)                              # rows resident per step (2 GB of float32 at 128-d)
+    nblocks = (per_rank + block - 1) // block
+    h = model._new_handle(env.local)
+    stream = torch.cuda.ExternalStream(h.stream(), device=env.dev)
+    X = synth.dlib_style_torch(block, D, seed=a.seed + 31 * env.rank, device=env.dev)
+    coarse_t = torch.empty((block, 2), dtype=torch.int32, device=env.dev)
+    fine_t = torch.empty((block, M), dtype=torch.uint8, device=env.dev)
+    for _ in range(max(1, a.warmup)):
+        h.encode_device(X.data_ptr(), block, coarse_t.data_ptr(), fine_t.data_ptr())
+    sampler = ClockSampler(env.local)
+    sampler.start()
+    env.barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(a.steps):
+        h.encode_device(X.data_ptr(), block, coarse_t.data_ptr(), fine_t.data_ptr())
+    ev1.record(stream)
+    env.barrier()
+    dev_s = env.max_over_ranks(ev0.elapsed_time(ev1) * 1e-3)[0]
+    value = a.steps * block * env.world / dev_s
+    # end to end: pinned host rows in, host codes out (H2D-bound: 512 B in, 24 B out per row)
+    eb = min(block, 1 << 20)
+    Xh = torch.empty((eb, D), dtype=torch.float32).pin_memory()
+    Xh.copy_(X[:eb])
+    xh = Xh.numpy()
+    h.encode(xh)
+    env.barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        co, fi = h.encode(xh)
+    env.barrier()
+    e2e_s = env.max_over_ranks(time.perf_counter() - t0)[0]
+    clocks = sampler.stop()
+    guards = h.encode_guard_count()
+    # parity + CPU baseline on rank 0: the reference's compute_codes_notparallel (one model.predict per row) on a bounded sample
+    cpu = None
+    if env.rank == 0 and not a.no_cpu_baseline:
+        orc, omodel = _oracle_model(model)
+        ns = 3000
+        t0 = time.perf_counter()
+        oc = orc.compute_codes(omodel, xh[:ns])
+        dt = time.perf_counter() - t0
+        same = all(tuple(int(v) for v in c.coarse) == tuple(co[i]) and tuple(int(v) for v in c.fine) == tuple(fi[i]) for i, c in enumerate(oc))
+        cpu = {"value": ns / dt, "unit": "codes/s", "cores": 1, "kind": "port",
+               "sample": "%d rows, compute_codes_notparallel (model.predict per row, utils.py:203-218), %.1f s" % (ns, dt),
+               "codes_match_gpu": bool(same), "host_cores": os.cpu_count()}
+    flops_row = 3 * model.V * D + D * D + 3 * 256 * D           # SURVEY 8d: coarse + rotation + fine
+    if env.rank == 0:
+        line = {"metric": cfg["metric"], "value": value, "unit": "codes/s", "n_gpus": env.world, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": 1e3 * dev_s / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "c5: compute_codes, %dM x %d-d dlib-style rows row-sharded over %d rank(s): %d rows per rank in %d resident "
+                                       "block(s) of %d rows; one step = one pass over a resident block" % (n // 1_000_000, D, env.world, per_rank, nblocks, block),
+                           "rows_per_step": block * env.world, "seconds_for_all_rows_at_this_rate": n / value,
+                           "l2": "a resident block (%d MB) exceeds the 126 MB L2" % (block * D * 4 // 1_000_000)},
+                "e2e": {"value": a.steps * eb * env.world / e2e_s, "unit": "codes/s", "h2d_bytes_per_step": eb * D * 4 * env.world,
+                        "d2h_bytes_per_step": eb * (8 + M) * env.world, "api": "Handle.encode (b2l_encode, pinned host rows in, host codes out)"},
+                "gpu_launches": int(h.stats()["kernel_launches"]) * a.steps,
+                "roofline": {"bound": "tensor", "kernel": "b2l_encode pipeline (k_coarse_assign, k_rotate_dmma, k_fine_argmin32)",
+                             "achieved": value / env.world * flops_row / 1e12, "peak": 75.0, "unit": "TFLOP/s",
+                             "frac": value / env.world * flops_row / 1e12 / 75.0, "traffic": None,
+                             "note": "SURVEY 8d flops per row (3VD + D^2 + 3KD = %d) over the fp32 FFMA peak of the part (~75 TFLOP/s: the fine "
+                                     "argmin, 83%% of the flops, runs in float32 with a float64 guard; the rotation on the float64 tensor cores)" % flops_row},
+                "guard_subvectors_total": guards, "cpu_baseline": cpu, "clocks": clocks}
+        print(json.dumps(line))
+    if env.world > 1:
+        env.dist.barrier()
+        env.dist.destroy_process_group()
 
 
 if __name__ == "__main__":
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.config == "c5":
+        run_encode(args)
     else:
-        run_b200(args)
+        run_search(args)

@@ -164,6 +164,9 @@ def test_in_library_exchange_on_emulated_ranks(world):
     coarse, fine = lopq.utils.compute_codes_arrays(db, model)
     sh = EmulatedShards(model, world)
     sh.add(coarse, fine)
+    # size every workspace first (host-driven protocol, same batch shape): on ONE device a cudaFree of a growing workspace
+    # would wait for the other emulated ranks' spinning wait kernels -- separate processes / GPUs have no such coupling
+    sh.search(db[:nq_home * world], n // 4, k)
     for s in sh.ranks:
         s.enable_peer_exchange(nq_home, 16, peers=sh.ranks)
     index = orc.ArrayIndex(8, coarse, fine, np.arange(n, dtype=np.int64))
@@ -211,3 +214,18 @@ def test_in_library_exchange_on_emulated_ranks(world):
                     _check(out, i, orc.search_arrays(omodel, index, batches[b][r * nq_home + i], quota, k))
                     ncheck += 1
     assert ncheck > nbatch * world * nq_home * 0.8
+
+
+def test_two_processes_two_gpus():
+    """The real thing when the box has >= 2 GPUs: tests/mp_sharded_check.py under torchrun (NCCL + CUDA IPC)."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29517", os.path.join(root, "tests", "mp_sharded_check.py")],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and r.stdout.count("MP_SHARDED_OK") == 2, r.stdout[-3000:] + r.stderr[-3000:]
