@@ -20,6 +20,7 @@
 #include "plan.cuh"
 #include "scan.cuh"
 #include "scan_pk.cuh"
+#include "scan1.cuh"
 #include "select.cuh"
 
 #define B2L_ABI_VERSION 3
@@ -169,6 +170,19 @@ template <int MP> int launch_scan_pk(b2l_handle h, const ScanArgs& a) {
     if (occ < 1) occ = 1;
     const unsigned grid = (unsigned)(h->num_sms * occ);
     k_scan_pk<MP><<<grid, SCAN_THREADS, smem, h->stream>>>(a);
+    LAUNCHED();
+    return B2L_OK;
+}
+
+template <int MP> int launch_scan1(b2l_handle h, const ScanArgs& a) {
+    const size_t smem = scan1_smem_bytes<MP>(a.E);
+    if (smem > 227 * 1024) FAIL(B2L_ERR_UNSUPPORTED, "scan shared memory %zu too large", smem);
+    CU(cudaFuncSetAttribute(k_scan1<MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 1;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_scan1<MP>, SCAN_THREADS, smem));
+    if (occ < 1) occ = 1;
+    const unsigned grid = (unsigned)(h->num_sms * occ);
+    k_scan1<MP><<<grid, SCAN_THREADS, smem, h->stream>>>(a);
     LAUNCHED();
     return B2L_OK;
 }
@@ -328,7 +342,7 @@ int ensure_index(b2l_handle h) {
         acc += h->h_lsize[c];
         start += (h->h_lsize[c] + 15) & ~(int64_t)15;
     }
-    h->rows_padded = start + 64;
+    h->rows_padded = start + 256;          // the scans read whole chunks (up to 128 rows) past the end of the last cell
     CU(h->codes.reserve((size_t)h->rows_padded * mv.MP));
     CU(h->rowids.reserve((size_t)h->rows_padded * 8));
     CU(cudaMemsetAsync(h->codes.p, 0, (size_t)h->rows_padded * mv.MP, h->stream));
@@ -502,14 +516,18 @@ int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_
     }
     // fast path eligibility: the bound table of the scan needs >= KP entries per slot
     const int KP = std::max(16, next_pow2(k + 8));
-    const int LPS = mv.MP * SCAN_WARPS;
+    const bool lowb_shape = nq <= SCAN1_MAX_NQ && h->scan_mode != 1 && h->scan_mode != 2 && exact == 0 && mv.MP >= 8 && mv.G > 0;
+    const int LPS = lowb_shape ? 32 * SCAN_WARPS : mv.MP * SCAN_WARPS;
     const int GEN = std::max(1, KP / std::max(1, LPS));
     // exact: 0 = default fast scan (16-bit packed tables unless the handle is set to float32), 1 = float64 full sort,
     // 2 = fast scan with float32 tables
     const bool fast = exact != 1 && mv.G > 0 && KP <= 512;
     if (route_in && !fast) FAIL(B2L_ERR_UNSUPPORTED, "the in-library exchange needs the fast scan (M <= 32, k <= 504)");
-    const bool packed = fast && exact == 0 && h->scan_mode == 0 && 65535 / mv.M >= 255;
-    const int NS = (packed ? 4 : 2) * mv.G;
+    // low-batch regime (a handful of queries: no cross-query reuse of a code row, the scan is HBM-bound): one query per
+    // work item, float32 tables, 32 rows per warp step (scan1.cuh)
+    const bool lowb = fast && exact != 2 && nq <= SCAN1_MAX_NQ && h->scan_mode != 1 && h->scan_mode != 2 && mv.MP >= 8;
+    const bool packed = fast && !lowb && exact == 0 && h->scan_mode == 0 && 65535 / mv.M >= 255;
+    const int NS = lowb ? 1 : (packed ? 4 : 2) * mv.G;
     // segment length: a multiple of 64 codes, sized so the batch yields enough work items
     int64_t maxcell = 0;
     for (int c = 0; c < ncell; ++c) maxcell = std::max(maxcell, h->h_lsize[c]);
@@ -517,13 +535,24 @@ int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_
     // enough items (few queries, or a small shard of a multi-GPU index: shorter segments) -- results do not depend on it.
     int segc = 16 * 1024;
     if (fast && h->fb_nq == nq && h->fb_segc > 0) {
-        const int64_t grid = (int64_t)h->num_sms * 2;
         segc = h->fb_segc;
+        if (lowb) {
+            // one query per item, tables prefetched: ~2 items per block (3 blocks per SM) keeps the tail short
+            const int64_t grid = (int64_t)h->num_sms * 3;
+            if (h->fb_items < grid * 3 / 2 || h->fb_items > 4 * grid) {
+                const double want = (double)segc * (double)h->fb_items / (2.0 * (double)grid);
+                int s2 = 2048;
+                while (s2 * 2 <= want * 1.42 && s2 < 64 * 1024) s2 *= 2;
+                segc = s2;
+            }
+        } else {
+        const int64_t grid = (int64_t)h->num_sms * 2;
         if (h->fb_items < 3 * grid || h->fb_items > 24 * grid) {           // aim at ~6 items per block, in one jump
             const double want = (double)segc * (double)h->fb_items / (6.0 * (double)grid);
             int s2 = 2048;
             while (s2 * 2 <= want * 1.42 && s2 < 16 * 1024) s2 *= 2;        // nearest power of two
             segc = s2;
+        }
         }
     }
     if (maxcell > 0 && maxcell < segc) segc = (int)(((maxcell + 63) / 64) * 64);
@@ -680,7 +709,8 @@ int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_
     CU(cudaEventRecord(h->cr->ev[1], h->stream));
     if (fast) {
         CU(h->w_cellq.reserve(cap_pairs * 8));
-        CU(h->w_cand.reserve((size_t)nq * SCAN_CAND_CAP * 8));
+        const int cand_cap = lowb ? SCAN1_CAND_CAP : SCAN_CAND_CAP;
+        CU(h->w_cand.reserve((size_t)nq * cand_cap * 8));
 
         pv.cellq = h->w_cellq.as<int2>();
         k_fill<<<(nq + 255) / 256, 256, 0, h->stream>>>(pv);
@@ -694,6 +724,15 @@ int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_
             a.GEN = GEN; a.E = LPS * GEN;
             a.gthr = h->gthr; a.gtab = h->w_gtab.as<float>();
             a.lut16 = packed ? h->w_lut16.as<unsigned short>() : nullptr; a.qfill = (unsigned)qv.qmax_code;
+            a.cand_cap = cand_cap;
+            if (lowb) {
+                switch (mv.MP) {
+                    case 8: rc = launch_scan1<8>(h, a); break;
+                    case 16: rc = launch_scan1<16>(h, a); break;
+                    case 32: rc = launch_scan1<32>(h, a); break;
+                    default: FAIL(B2L_ERR_UNSUPPORTED, "no low-batch scan for code stride %d", mv.MP);
+                }
+            } else
             switch (mv.MP) {
                 case 4: rc = packed ? launch_scan_pk<4>(h, a) : launch_scan<4>(h, a); break;
                 case 8: rc = packed ? launch_scan_pk<8>(h, a) : launch_scan<8>(h, a); break;
@@ -710,7 +749,7 @@ int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_
         RecRoute route = {};
         if (route_in) route = *route_in; else { route.base[0] = (unsigned char*)d_records; route.nq_home = nq; }
         k_select<<<nq, SEL_THREADS, smem, h->stream>>>(mv, ix, pv, h->w_cand.as<unsigned long long>(), h->cand_cnt, h->gthr,
-                                                       SCAN_CAND_CAP, h->w_p64.as<double>(), KP, k, eps_rel, route,
+                                                       cand_cap, h->w_p64.as<double>(), KP, k, eps_rel, route,
                                                        packed ? 1 : 0, qv.B, qv.delta, qv.slack);
         LAUNCHED();
         h->cr->st.packed = packed ? 1 : 0;
@@ -938,7 +977,7 @@ int64_t b2l_encode_guard_count(b2l_handle h, int reset) {
 }
 
 int b2l_set_scan_mode(b2l_handle h, int mode) {
-    if (!h || mode < 0 || mode > 1) return B2L_ERR_ARG;
+    if (!h || mode < 0 || mode > 2) return B2L_ERR_ARG;
     std::lock_guard<std::mutex> lk(h->mu);
     h->scan_mode = mode;
     return B2L_OK;

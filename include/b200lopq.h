@@ -194,8 +194,10 @@ typedef struct b2l_stats {
 /* waits for searches still in flight on the handle, then returns the statistics */
 int b2l_get_stats(b2l_handle h, b2l_stats* out);
 int b2l_reset_stats(b2l_handle h);
-/* Table precision of the fast scan.  0 (default): 16-bit quantised tables, two queries per shared-memory word; queries
- * whose float64 order cannot be proven from them are re-run with float32 tables, then exactly.  1: float32 tables only. */
+/* Kernel choice of the fast scan.  0 (default): batches of <= 8 queries take the one-query-per-item scan with float32 tables
+ * (scan1.cuh: no cross-query reuse, HBM-bound); larger batches take 16-bit quantised tables, two queries per shared-memory
+ * word; queries whose float64 order cannot be proven are re-run with float32 tables, then exactly.  1: float32 tables only
+ * (batched kernel).  2: as 0 without the low-batch kernel. */
 int b2l_set_scan_mode(b2l_handle h, int mode);
 /* Asynchronous mode (pipelined / multi-GPU searches).  While enabled, b2l_search_local and b2l_search_merge only
  * enqueue their work (including the copies from / to host buffers, which must then be PINNED and stay alive) on the

@@ -134,6 +134,7 @@ sys.path.insert(0, %(root)r)
 import columbiaimagesearch_b200.lopq as lopq
 from tests.util import load_case, case_inputs
 z, _ = load_case("A")
+z = {k: z[k] for k in z.files}                     # read everything now: a lazily read .npz shares one file offset across fork()
 _, db, Q, ids = case_inputs("A")
 model = lopq.LOPQModel.from_npz(z)
 s = lopq.LOPQSearcher(model)                       # gunicorn --preload: built in the master ...
