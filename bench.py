@@ -30,12 +30,12 @@ if ROOT not in sys.path:
 CONFIGS = {
     # BASELINE.json configs[3] (headline metric) and configs[1]
     "c4": dict(metric="LOPQ queries/sec @ recall@10, 10Mx128-d, V=8 M=16", n_db=10_000_000, D=128, V=8, M=16,
-               model="dlib128_V8_M16.npz", quota=210_000, style="dlib"),
+               model="dlib128_V8_M16.npz", quota=330_000, style="dlib"),
     "c2": dict(metric="LOPQ queries/sec @ recall@10, 1Mx128-d, V=8 M=16, batch=1024", n_db=1_000_000, D=128, V=8, M=16,
-               model="dlib128_V8_M16.npz", quota=21_000, style="dlib"),
+               model="dlib128_V8_M16.npz", quota=33_000, style="dlib"),
     # configs[2]: DeepSentibank-style 2048-d; the model is trained at start-up (134 MB of rotations: not a fixture)
     "c3": dict(metric="LOPQ queries/sec @ recall@10, 10Mx2048-d, V=8 M=32", n_db=10_000_000, D=2048, V=8, M=32,
-               model=None, quota=210_000, style="sentibank"),
+               model=None, quota=330_000, style="sentibank"),
     # configs[4]: batch encode
     "c5": dict(metric="LOPQ compute_codes codes/sec, 50Mx128-d, V=8 M=16", n_db=50_000_000, D=128, V=8, M=16,
                model="dlib128_V8_M16.npz", style="dlib"),

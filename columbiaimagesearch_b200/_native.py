@@ -53,6 +53,7 @@ SIGNATURES = {
     "b2l_index_set_global_cell_sizes": (_i, [_h, _vp]),
     "b2l_index_get_cell": (_i64, [_h, _i, _i, _i64, _vp, _vp]),
     "b2l_cell_order": (_i, [_h, _vp, _i, _i, _i64, _vp, _vp, _vp]),
+    "b2l_cell_order_prefix": (_i, [_h, _vp, _i, _i, _i64, _i, _vp, _vp, _vp]),
     "b2l_search": (_i, [_h, _vp, _i, _i, _i, _i64, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b2l_records_bytes": (_i64, [_h, _i, _i]),
     "b2l_search_local": (_i, [_h, _vp, _i, _i, _i, _i64, _i, _i, _vp]),
@@ -255,6 +256,18 @@ class Handle(object):
         nvis = np.empty(nq, np.int32)
         q = np.iinfo(np.int64).max if quota is None else int(quota)
         self._check(self.lib.b2l_cell_order(self.h, _ptr(X), f64, nq, q, _ptr(cells), _ptr(dists), _ptr(nvis)))
+        return cells, dists, nvis
+
+    def cell_order_prefix(self, X, quota=None, max_cells=1024):
+        """V > 64: the first min(visited, max_cells) cells of the multi-sequence traversal (quota cut applied)."""
+        X, f64 = _as_queries(X)
+        nq = X.shape[0]
+        assert X.shape[1] == self.D
+        cells = np.empty((nq, max_cells), np.int32)
+        dists = np.empty((nq, max_cells), np.float64)
+        nvis = np.empty(nq, np.int32)
+        q = np.iinfo(np.int64).max if quota is None else int(quota)
+        self._check(self.lib.b2l_cell_order_prefix(self.h, _ptr(X), f64, nq, q, int(max_cells), _ptr(cells), _ptr(dists), _ptr(nvis)))
         return cells, dists, nvis
 
     def search(self, Q, quota, k):

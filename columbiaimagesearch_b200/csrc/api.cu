@@ -21,6 +21,7 @@
 #include "scan.cuh"
 #include "scan_pk.cuh"
 #include "scan1.cuh"
+#include "largev.cuh"
 #include "select.cuh"
 
 #define B2L_ABI_VERSION 3
@@ -85,6 +86,10 @@ struct b2l_ctx {
     int64_t rows_padded = 0;
     DevBuf codes, rowids, cell_start, lsize, gsize, sorted_first;
     std::vector<int64_t> h_lsize, h_gsize, h_cell_start;
+    // large V (V > B2L_MAX_V): sparse cell directory instead of the dense per-cell arrays (largev.cuh)
+    DevBuf d_ucell, d_ustart, d_hkeys, d_hvals, w_walk, w_walk2;
+    std::vector<unsigned int> h_ucell, h_ustart;
+    unsigned int nu = 0, hmask = 0, max_run = 0;
     // workspaces
     DevBuf w_q, w_xq, w_px, w_coarse, w_fine, w_lut32, w_lut64, w_p64, w_cellq, w_cand, w_gtab, w_lut16, w_quant, w_plan, w_sort_a, w_sort_b,
         w_sort_tmp, w_rec, w_rec2, w_out, w_out2, w_misc, w_bkt, w_perm;
@@ -294,8 +299,82 @@ int encode_device(b2l_handle h, const void* dX, int x_is_f64, int64_t n, const i
 }
 
 // ---- (re)build the cell-major layout ---------------------------------------------------------------
+// large V: rows sorted by cell, run-length encoded into the sparse directory (no dense V*V array anywhere)
+int ensure_index_sparse(b2l_handle h) {
+    const ModelView& mv = h->mv;
+    const int64_t n = h->n_items;
+    h->nu = 0; h->max_run = 0; h->hmask = 0;
+    h->h_ucell.clear(); h->h_ustart.assign(1, 0u);
+    h->rows_padded = n + 256;
+    CU(h->codes.reserve((size_t)h->rows_padded * mv.MP));
+    CU(h->rowids.reserve((size_t)h->rows_padded * 8));
+    CU(cudaMemsetAsync(h->codes.p, 0, (size_t)h->rows_padded * mv.MP, h->stream));
+    if (n > 0) {
+        if (n >= (int64_t)1 << 31) FAIL(B2L_ERR_UNSUPPORTED, "more than 2^31 - 1 rows per shard");
+        CU(h->w_sort_a.reserve((size_t)n * 8));
+        CU(h->w_sort_b.reserve((size_t)n * 8));
+        CU(h->w_misc.reserve(64));
+        unsigned int* cell = h->w_sort_a.as<unsigned int>();
+        unsigned int* order = cell + n;
+        unsigned int* scell = h->w_sort_b.as<unsigned int>();
+        unsigned int* ssrc = scell + n;
+        int* bad = h->w_misc.as<int>();
+        CU(cudaMemsetAsync(bad, 0, 64, h->stream));
+        k_cell_ids<<<grid_for(n, 256), 256, 0, h->stream>>>(h->m_coarse.as<int32_t>(), n, mv.V, cell, order, nullptr, bad);
+        LAUNCHED();
+        int bits = 1;
+        while (((int64_t)1 << bits) < (int64_t)mv.V * mv.V) ++bits;
+        size_t tmp = 0;
+        CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp, cell, scell, order, ssrc, (int)n, 0, bits, h->stream));
+        CU(h->w_sort_tmp.reserve(tmp));
+        CU(cub::DeviceRadixSort::SortPairs(h->w_sort_tmp.p, tmp, cell, scell, order, ssrc, (int)n, 0, bits, h->stream));
+        ++h->launches;
+        // runs of equal cell ids: unique cells + counts (the unsorted cell / order arrays are free now)
+        unsigned int* ucell_tmp = cell;
+        unsigned int* counts = order;
+        int* d_nruns = bad + 4;
+        size_t t2 = 0;
+        CU(cub::DeviceRunLengthEncode::Encode(nullptr, t2, scell, ucell_tmp, counts, d_nruns, (int)n, h->stream));
+        CU(h->w_sort_tmp.reserve(t2));
+        CU(cub::DeviceRunLengthEncode::Encode(h->w_sort_tmp.p, t2, scell, ucell_tmp, counts, d_nruns, (int)n, h->stream));
+        ++h->launches;
+        int hb[8] = {};
+        CU(cudaMemcpyAsync(hb, bad, 32, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        if (hb[0]) FAIL(B2L_ERR_ARG, "coarse code out of range [0, V) in the index");
+        const unsigned int nu = (unsigned int)hb[4];
+        CU(h->d_ucell.reserve((size_t)nu * 4));
+        CU(h->d_ustart.reserve((size_t)(nu + 1) * 4));
+        CU(cudaMemcpyAsync(h->d_ucell.p, ucell_tmp, (size_t)nu * 4, cudaMemcpyDeviceToDevice, h->stream));
+        k_run_starts<<<1, 1024, 0, h->stream>>>(counts, nu, h->d_ustart.as<unsigned int>());
+        LAUNCHED();
+        unsigned int hs = 64;
+        while (hs < 2 * nu) hs <<= 1;
+        CU(h->d_hkeys.reserve((size_t)hs * 4));
+        CU(h->d_hvals.reserve((size_t)hs * 4));
+        CU(cudaMemsetAsync(h->d_hkeys.p, 0xFF, (size_t)hs * 4, h->stream));
+        k_dir_build<<<grid_for(nu, 256), 256, 0, h->stream>>>(h->d_ucell.as<unsigned int>(), nu, h->d_hkeys.as<unsigned int>(),
+                                                               h->d_hvals.as<unsigned int>(), hs - 1);
+        LAUNCHED();
+        k_scatter_runs<<<grid_for(nu, 128), 128, 0, h->stream>>>(ssrc, h->d_ustart.as<unsigned int>(), nu, h->m_fine.as<uint8_t>(),
+                                                                  h->m_rowid.as<int64_t>(), mv.M, mv.MP, mv.SW, h->codes.as<uint8_t>(),
+                                                                  h->rowids.as<int64_t>());
+        LAUNCHED();
+        h->h_ucell.resize(nu);
+        h->h_ustart.resize(nu + 1);
+        CU(cudaMemcpyAsync(h->h_ucell.data(), h->d_ucell.p, (size_t)nu * 4, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaMemcpyAsync(h->h_ustart.data(), h->d_ustart.p, (size_t)(nu + 1) * 4, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        h->nu = nu; h->hmask = hs - 1;
+        for (unsigned int r = 0; r < nu; ++r) h->max_run = std::max(h->max_run, h->h_ustart[r + 1] - h->h_ustart[r]);
+    }
+    h->dirty = false;
+    return B2L_OK;
+}
+
 int ensure_index(b2l_handle h) {
     if (!h->dirty) return B2L_OK;
+    if (h->mv.V > B2L_MAX_V) return ensure_index_sparse(h);
     const ModelView& mv = h->mv;
     const int ncell = mv.V * mv.V;
     const int64_t n = h->n_items;
@@ -465,18 +544,197 @@ int finish_stats(b2l_handle h) {
     return B2L_OK;
 }
 
+// carve the per-sub-batch arrays of the large-V plan out of w_walk
+int setup_walk(b2l_handle h, int nqc, int segcap, size_t desc_cap, int viscap, WalkView& wv) {
+    const ModelView& mv = h->mv;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes); return o; };
+    const size_t o_cnt = take(sizeof(WalkCounters)), o_nvis = take((size_t)nqc * 4), o_nseg = take((size_t)nqc * 4),
+                 o_ncand = take((size_t)nqc * 4), o_seg = take((size_t)nqc * segcap * 16), o_s0 = take((size_t)nqc * mv.V * 4),
+                 o_s1 = take((size_t)nqc * mv.V * 4), o_desc = take(desc_cap * 12),
+                 o_vc = take((size_t)nqc * viscap * 4), o_vd = take((size_t)nqc * viscap * 8);
+    CU(h->w_walk.reserve(off));
+    unsigned char* b = h->w_walk.as<unsigned char>();
+    wv = WalkView();
+    wv.nq = nqc; wv.segcap = segcap;
+    wv.cnt = (WalkCounters*)(b + o_cnt);
+    wv.nvis = (int32_t*)(b + o_nvis); wv.nseg = (int32_t*)(b + o_nseg); wv.ncand = (unsigned int*)(b + o_ncand);
+    wv.seg = (uint4*)(b + o_seg); wv.slot0 = (int32_t*)(b + o_s0); wv.slot1 = (int32_t*)(b + o_s1);
+    wv.lut_desc = (int32_t*)(b + o_desc);
+    wv.viscap = viscap;
+    wv.vis_cells = viscap ? (int32_t*)(b + o_vc) : nullptr;
+    wv.vis_dists = viscap ? (double*)(b + o_vd) : nullptr;
+    wv.max_visit = ((long long)1) << 62;
+    CU(cudaMemsetAsync(wv.cnt, 0, sizeof(WalkCounters), h->stream));
+    return B2L_OK;
+}
+
+SparseDir sparse_dir(b2l_handle h) {
+    SparseDir d;
+    d.hkeys = h->d_hkeys.as<unsigned int>(); d.hvals = h->d_hvals.as<unsigned int>(); d.hmask = h->hmask;
+    d.ustart = h->d_ustart.as<unsigned int>(); d.ucell = h->d_ucell.as<unsigned int>(); d.nu = h->nu;
+    return d;
+}
+
+int launch_walk(b2l_handle h, const void* x, int xf64, int nqc, int64_t quota, const WalkView& wv) {
+    const ModelView& mv = h->mv;
+    const size_t smem = walk_smem_bytes(mv.V);
+    if (smem > 227 * 1024) FAIL(B2L_ERR_UNSUPPORTED, "V=%d too large for the traversal kernel", mv.V);
+    SparseDir dir = sparse_dir(h);
+    if (h->nu == 0) {           // empty index: a one-entry empty hash table
+        CU(h->d_hkeys.reserve(256)); CU(h->d_hvals.reserve(256)); CU(h->d_ustart.reserve(256)); CU(h->d_ucell.reserve(256));
+        CU(cudaMemsetAsync(h->d_hkeys.p, 0xFF, 256, h->stream));
+        dir = sparse_dir(h);
+        dir.hmask = 63;
+    }
+    if (xf64) { CU(cudaFuncSetAttribute(k_walk<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_walk<double><<<nqc, WALK_THREADS, smem, h->stream>>>(mv, (const double*)x, quota, dir, wv); }
+    else { CU(cudaFuncSetAttribute(k_walk<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_walk<float><<<nqc, WALK_THREADS, smem, h->stream>>>(mv, (const float*)x, quota, dir, wv); }
+    LAUNCHED();
+    return B2L_OK;
+}
+
+// Large-V search (V > B2L_MAX_V): traversal by k_walk, projections by the grouped GEMM, exact float64 ADC of every
+// retrieved code, stable segmented sort, records.  Synchronous planning (two small read-backs per sub-batch).
+int search_large_impl(b2l_handle h, const void* x, int xf64, int nq, int64_t quota, int k, void* d_records) {
+    const ModelView& mv = h->mv;
+    if (h->global_set) FAIL(B2L_ERR_UNSUPPORTED, "a cell-sharded index is not supported at V > %d", B2L_MAX_V);
+    const size_t esz = xf64 ? 8 : 4;
+    const int64_t nu = h->nu;
+    const int segcap = (int)std::min<int64_t>(std::max<int64_t>(quota, 1), nu) + 2;
+    // sub-batches: bound the segment lists (16 bytes per non-empty visited cell) to ~2 GB
+    const int qchunk = (int)std::max<int64_t>(1, std::min<int64_t>(nq, ((int64_t)2 << 30) / ((int64_t)segcap * 16 + (int64_t)mv.V * 8 + 64)));
+    CU(cudaEventRecord(h->cr->ev[1], h->stream));
+    CU(cudaEventRecord(h->cr->ev[2], h->stream));
+    int64_t cand_sum = 0, lut_sum = 0;
+    for (int qa0 = 0; qa0 < nq; qa0 += qchunk) {
+        const int nqc = std::min(qchunk, nq - qa0);
+        const void* xs = (const char*)x + (size_t)qa0 * mv.D * esz;
+        WalkView wv;
+        const size_t desc_cap = (size_t)nqc * 2 * (size_t)std::min<int64_t>(mv.V, segcap);
+        int rc = setup_walk(h, nqc, segcap, desc_cap, 0, wv);
+        if (rc) return rc;
+        if ((rc = launch_walk(h, xs, xf64, nqc, quota, wv))) return rc;
+        WalkCounters wc;
+        std::vector<unsigned int> ncand(nqc);
+        CU(cudaMemcpyAsync(&wc, wv.cnt, sizeof wc, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaMemcpyAsync(ncand.data(), wv.ncand, (size_t)nqc * 4, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        if (wc.err == 1) FAIL(B2L_ERR_UNSUPPORTED, "more than %d cells at one and the same coarse distance: the traversal order is degenerate", WALK_CAP);
+        if (wc.err) FAIL(B2L_ERR_STATE, "internal: segment list overflow in the traversal");
+        cand_sum += (int64_t)wc.cand_total; lut_sum += wc.n_lut;
+        // ---- projections of every (query, split, coarse code) in use
+        const size_t nl = wc.n_lut;
+        CU(h->w_p64.reserve(std::max<size_t>(1, nl) * mv.h * 8));
+        if (nl) {
+            if (mv.h % 64 == 0) {
+                const int nb2 = 2 * mv.V;
+                CU(h->w_perm.reserve((size_t)2 * nl * 4));
+                CU(h->w_bkt.reserve((size_t)(4 * nb2 + 4) * 4));
+                unsigned int* bc = h->w_bkt.as<unsigned int>();
+                unsigned int* bbase = bc + nb2; unsigned int* bcur = bbase + nb2; unsigned int* btile = bcur + nb2;
+                unsigned int* perm = h->w_perm.as<unsigned int>();
+                CU(cudaMemsetAsync(bc, 0, (size_t)nb2 * 4, h->stream));
+                const unsigned sg = (unsigned)std::min<size_t>((nl + 255) / 256, 2048);
+                k_slot_hist<<<sg, 256, 0, h->stream>>>(wv.lut_desc, &wv.cnt->n_lut, mv.V, bc);
+                LAUNCHED();
+                k_enc_offsets<<<1, 32, 0, h->stream>>>(mv.V, bc, bbase, bcur, btile);
+                LAUNCHED();
+                k_slot_scatter<<<sg, 256, 0, h->stream>>>(wv.lut_desc, &wv.cnt->n_lut, mv.V, nl, bbase, bcur, perm);
+                LAUNCHED();
+                const dim3 g2((unsigned)(nl / 64 + nb2), (unsigned)(mv.h / 64));
+                const size_t smr = (size_t)2 * 64 * ROT_LD * 8 + 64 * 4;
+                if (xf64) { CU(cudaFuncSetAttribute(k_rotate_dmma_g<double, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr));
+                    k_rotate_dmma_g<double, 1><<<g2, 128, smr, h->stream>>>(mv, (const double*)xs, (int64_t)nl, bc, bbase, btile, perm, wv.lut_desc, h->w_p64.as<double>()); }
+                else { CU(cudaFuncSetAttribute(k_rotate_dmma_g<float, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr));
+                    k_rotate_dmma_g<float, 1><<<g2, 128, smr, h->stream>>>(mv, (const float*)xs, (int64_t)nl, bc, bbase, btile, perm, wv.lut_desc, h->w_p64.as<double>()); }
+                LAUNCHED();
+            } else {
+                // shapes without the grouped GEMM: one block per slot computes the projection (k_lut with no table output)
+                CU(h->w_misc.reserve(sizeof(PlanCounters) + 64));
+                PlanCounters pcs = {};
+                pcs.n_lut = (unsigned)nl;
+                CU(cudaMemcpyAsync(h->w_misc.p, &pcs, sizeof pcs, cudaMemcpyHostToDevice, h->stream));
+                const size_t smem = (size_t)(2 * mv.h + LUT_THREADS) * 8;
+                const unsigned lgrid = (unsigned)std::min<size_t>(nl, (size_t)h->num_sms * 8);
+                if (xf64) { CU(cudaFuncSetAttribute(k_lut<double, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    k_lut<double, 0><<<lgrid, LUT_THREADS, smem, h->stream>>>(mv, (const double*)xs, wv.lut_desc, (const PlanCounters*)h->w_misc.p, h->w_p64.as<double>(), nullptr, nullptr, 2); }
+                else { CU(cudaFuncSetAttribute(k_lut<float, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    k_lut<float, 0><<<lgrid, LUT_THREADS, smem, h->stream>>>(mv, (const float*)xs, wv.lut_desc, (const PlanCounters*)h->w_misc.p, h->w_p64.as<double>(), nullptr, nullptr, 2); }
+                LAUNCHED();
+                CU(cudaStreamSynchronize(h->stream));     // pcs is a local
+            }
+        }
+        // ---- groups of queries with at most ~48M candidates: exact distances, stable segmented sort, emit
+        const int64_t budget = (int64_t)48 << 20;
+        for (int ga = 0; ga < nqc;) {
+            int gb = ga;
+            int64_t tot = 0;
+            while (gb < nqc && (gb == ga || tot + ncand[gb] <= budget)) { tot += ncand[gb]; ++gb; }
+            const int ng = gb - ga;
+            if (tot >= ((int64_t)1 << 31)) FAIL(B2L_ERR_UNSUPPORTED, "a single query retrieves %lld codes (>= 2^31)", (long long)tot);
+            std::vector<unsigned long long> qoff(ng + 1, 0ull);
+            for (int g = 0; g < ng; ++g) qoff[g + 1] = qoff[g] + ncand[ga + g];
+            const size_t T = (size_t)std::max<int64_t>(tot, 1);
+            size_t woff = 0;
+            auto wt = [&](size_t bytes) { size_t o = woff; woff += align256(bytes); return o; };
+            const size_t o_k1 = wt(T * 8), o_k2 = wt(T * 8), o_v1 = wt(T * 4), o_v2 = wt(T * 4), o_qo = wt((size_t)(ng + 1) * 8);
+            CU(h->w_walk2.reserve(woff));
+            unsigned char* wb = h->w_walk2.as<unsigned char>();
+            unsigned long long* k1 = (unsigned long long*)(wb + o_k1); unsigned long long* k2 = (unsigned long long*)(wb + o_k2);
+            unsigned int* v1 = (unsigned int*)(wb + o_v1); unsigned int* v2 = (unsigned int*)(wb + o_v2);
+            unsigned long long* dqo = (unsigned long long*)(wb + o_qo);
+            CU(cudaMemcpyAsync(dqo, qoff.data(), (size_t)(ng + 1) * 8, cudaMemcpyHostToDevice, h->stream));
+            const unsigned long long* kout = k1;
+            const unsigned int* vout = v1;
+            if (tot > 0) {
+                k_cand_dist<<<grid_for(tot, 256, h->num_sms * 16), 256, 0, h->stream>>>(mv, h->codes.as<uint8_t>(), wv, ga, ng, dqo,
+                                                                                          h->w_p64.as<double>(), k1, v1);
+                LAUNCHED();
+                size_t tmp = 0;
+                CU(cub::DeviceSegmentedRadixSort::SortPairs(nullptr, tmp, k1, k2, v1, v2, (int)tot, ng, dqo, dqo + 1, 0, 64, h->stream));
+                CU(h->w_sort_tmp.reserve(tmp));
+                CU(cub::DeviceSegmentedRadixSort::SortPairs(h->w_sort_tmp.p, tmp, k1, k2, v1, v2, (int)tot, ng, dqo, dqo + 1, 0, 64, h->stream));
+                ++h->launches;
+                kout = k2; vout = v2;
+            }
+            k_emit_sorted<<<ng, 128, 0, h->stream>>>(mv, h->codes.as<uint8_t>(), h->rowids.as<int64_t>(), wv, ga, dqo, kout, vout, k,
+                                                     d_records, nq, qa0);
+            LAUNCHED();
+            CU(cudaStreamSynchronize(h->stream));         // qoff is a local; the work buffers are reused by the next group
+            ga = gb;
+        }
+    }
+    CU(cudaEventRecord(h->cr->ev[3], h->stream));
+    CU(cudaEventRecord(h->cr->ev[4], h->stream));
+    h->cr->has_pc = false;
+    h->cr->st.lut_slots = lut_sum;
+    h->cr->st.codes_scanned = cand_sum;
+    h->cr->st.scan_bytes = cand_sum * mv.M;
+    h->cr->st.work_items = 0;
+    h->cr->st.exact_queries = nq;
+    h->cr->st.kernel_launches = h->launches - h->cr->launch0;
+    h->cr->pending = true;
+    CU(cudaStreamSynchronize(h->stream));
+    return finish_stats(h);
+}
+
 // finish = false: return with the work queued on the stream (the caller synchronises and calls finish_stats)
 int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_device, int64_t quota, int k, int exact,
                       void* d_records, bool finish = true, const RecRoute* route_in = nullptr) {
     if (!h->has_model) FAIL(B2L_ERR_STATE, "no model set");
     if (nq < 1 || k < 1 || !Q || !d_records) FAIL(B2L_ERR_ARG, "bad search arguments (nq=%d k=%d)", nq, k);
-    if (h->mv.V > B2L_MAX_V) FAIL(B2L_ERR_UNSUPPORTED, "V=%d > %d: large-V multi-index traversal is not implemented", h->mv.V, B2L_MAX_V);
+    if (h->mv.V > B2L_MAX_V_SPARSE) FAIL(B2L_ERR_UNSUPPORTED, "V=%d > %d", h->mv.V, B2L_MAX_V_SPARSE);
+    const bool largev = h->mv.V > B2L_MAX_V;
+    if (largev && route_in) FAIL(B2L_ERR_UNSUPPORTED, "the in-library exchange is not available at V > %d", B2L_MAX_V);
     int rc = ensure_index(h);
     if (rc) return rc;
     const ModelView& mv = h->mv;
-    const int ncell = mv.V * mv.V;
+    const int ncell = largev ? 1 : mv.V * mv.V;
     int64_t gtotal = 0;
-    for (int c = 0; c < ncell; ++c) gtotal += h->h_gsize[c];
+    if (largev) gtotal = h->n_items;
+    else for (int c = 0; c < ncell; ++c) gtotal += h->h_gsize[c];
     if (gtotal >= ((int64_t)1 << 32)) FAIL(B2L_ERR_UNSUPPORTED, "more than 2^32 indexed codes");
 
     { cudaError_t pre = cudaGetLastError(); if (pre != cudaSuccess) FAIL(B2L_ERR_CUDA, "stale CUDA error at search entry: %s", cudaGetErrorString(pre)); }
@@ -514,6 +772,7 @@ int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_
         LAUNCHED();
         x = h->w_xq.p; xf64 = 0;
     }
+    if (largev) return search_large_impl(h, x, xf64, nq, quota, k, d_records);
     // fast path eligibility: the bound table of the scan needs >= KP entries per slot
     const int KP = std::max(16, next_pow2(k + 8));
     const bool lowb_shape = nq <= SCAN1_MAX_NQ && h->scan_mode != 1 && h->scan_mode != 2 && exact == 0 && mv.MP >= 8 && mv.G > 0;
@@ -526,7 +785,7 @@ int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_
     // low-batch regime (a handful of queries: no cross-query reuse of a code row, the scan is HBM-bound): one query per
     // work item, float32 tables, 32 rows per warp step (scan1.cuh)
     const bool lowb = fast && exact != 2 && nq <= SCAN1_MAX_NQ && h->scan_mode != 1 && h->scan_mode != 2 && mv.MP >= 8;
-    const bool packed = fast && !lowb && exact == 0 && h->scan_mode == 0 && 65535 / mv.M >= 255;
+    const bool packed = fast && !lowb && exact == 0 && h->scan_mode != 1 && 65535 / mv.M >= 255;
     const int NS = lowb ? 1 : (packed ? 4 : 2) * mv.G;
     // segment length: a multiple of 64 codes, sized so the batch yields enough work items
     int64_t maxcell = 0;
@@ -537,14 +796,7 @@ int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_
     if (fast && h->fb_nq == nq && h->fb_segc > 0) {
         segc = h->fb_segc;
         if (lowb) {
-            // one query per item, tables prefetched: ~2 items per block (3 blocks per SM) keeps the tail short
-            const int64_t grid = (int64_t)h->num_sms * 3;
-            if (h->fb_items < grid * 3 / 2 || h->fb_items > 4 * grid) {
-                const double want = (double)segc * (double)h->fb_items / (2.0 * (double)grid);
-                int s2 = 2048;
-                while (s2 * 2 <= want * 1.42 && s2 < 64 * 1024) s2 *= 2;
-                segc = s2;
-            }
+            segc = 16 * 1024;          // (set below from the expected candidate count, no feedback needed)
         } else {
         const int64_t grid = (int64_t)h->num_sms * 2;
         if (h->fb_items < 3 * grid || h->fb_items > 24 * grid) {           // aim at ~6 items per block, in one jump
@@ -554,6 +806,13 @@ int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_
             segc = s2;
         }
         }
+    }
+    if (lowb) {
+        // one query per item and the next item's tables prefetched: short items are cheap, so aim at ~4 items per resident
+        // block for a short tail; a multiple of 1024 codes keeps the 8 warps of a block (128 codes per step) in step
+        const int64_t est = (int64_t)nq * std::min<int64_t>(gtotal, (quota < gtotal ? quota : gtotal) + maxcell / 2);
+        const int64_t want = est / ((int64_t)h->num_sms * 3 * 4);
+        segc = (int)std::min<int64_t>(64 * 1024, std::max<int64_t>(1024, ((want + 1023) / 1024) * 1024));
     }
     if (maxcell > 0 && maxcell < segc) segc = (int)(((maxcell + 63) / 64) * 64);
     const int nsegmax = (int)std::max<int64_t>(1, (maxcell + segc - 1) / segc);
@@ -899,7 +1158,7 @@ int b2l_destroy(b2l_handle h) {
     DevBuf* bufs[] = {&h->dCs, &h->dmus, &h->dRt, &h->dsubs, &h->dsubs32, &h->dsubs32T, &h->dc2max, &h->dP, &h->dpmu, &h->m_coarse, &h->m_fine, &h->m_rowid, &h->codes,
                       &h->rowids, &h->cell_start, &h->lsize, &h->gsize, &h->sorted_first, &h->w_q, &h->w_xq, &h->w_px,
                       &h->w_coarse, &h->w_fine, &h->w_lut32, &h->w_lut64, &h->w_p64, &h->w_cellq, &h->w_cand, &h->w_gtab, &h->w_lut16, &h->w_quant, &h->w_plan,
-                      &h->w_sort_a, &h->w_sort_b, &h->w_sort_tmp, &h->w_rec, &h->w_rec2, &h->w_out, &h->w_out2, &h->w_misc, &h->w_bkt, &h->w_perm};
+                      &h->w_sort_a, &h->w_sort_b, &h->w_sort_tmp, &h->w_rec, &h->w_rec2, &h->w_out, &h->w_out2, &h->w_misc, &h->w_bkt, &h->w_perm, &h->d_ucell, &h->d_ustart, &h->d_hkeys, &h->d_hvals, &h->w_walk, &h->w_walk2};
     for (DevBuf* b : bufs) b->release();
     if (h->h_out) cudaFreeHost(h->h_out);
     if (h->d_nguard) cudaFree(h->d_nguard);
@@ -1225,6 +1484,11 @@ int b2l_index_cell_sizes(b2l_handle h, int64_t* sizes) {
     if (!h->has_model) FAIL(B2L_ERR_STATE, "no model set");
     int rc = ensure_index(h);
     if (rc) return rc;
+    if (h->mv.V > B2L_MAX_V) {             // sparse directory -> the dense array the caller asked for
+        memset(sizes, 0, (size_t)h->mv.V * h->mv.V * 8);
+        for (unsigned int r = 0; r < h->nu; ++r) sizes[h->h_ucell[r]] = (int64_t)(h->h_ustart[r + 1] - h->h_ustart[r]);
+        return B2L_OK;
+    }
     memcpy(sizes, h->h_lsize.data(), h->h_lsize.size() * 8);
     return B2L_OK;
 }
@@ -1234,6 +1498,7 @@ int b2l_index_set_global_cell_sizes(b2l_handle h, const int64_t* sizes) {
     std::lock_guard<std::mutex> lk(h->mu);
     CU(cudaSetDevice(h->device));
     if (!h->has_model) FAIL(B2L_ERR_STATE, "no model set");
+    if (h->mv.V > B2L_MAX_V) FAIL(B2L_ERR_UNSUPPORTED, "a cell-sharded index is not supported at V > %d", B2L_MAX_V);
     const int ncell = h->mv.V * h->mv.V;
     h->h_gsize.assign(sizes, sizes + ncell);
     h->global_set = true;
@@ -1254,9 +1519,16 @@ int64_t b2l_index_get_cell(b2l_handle h, int c0, int c1, int64_t cap, int64_t* r
     int rc = ensure_index(h);
     if (rc) return rc;
     const int cell = c0 * mv.V + c1;
-    const int64_t n = h->h_lsize[cell], take = std::min(n, cap);
+    int64_t n, s0 = 0;
+    if (mv.V > B2L_MAX_V) {
+        auto it = std::lower_bound(h->h_ucell.begin(), h->h_ucell.end(), (unsigned int)cell);
+        if (it == h->h_ucell.end() || *it != (unsigned int)cell) return 0;
+        const size_t r = it - h->h_ucell.begin();
+        s0 = h->h_ustart[r]; n = (int64_t)h->h_ustart[r + 1] - s0;
+    } else { n = h->h_lsize[cell]; s0 = n ? h->h_cell_start[cell] : 0; }
+    const int64_t take = std::min(n, cap);
     if (take > 0) {
-        const int64_t s = h->h_cell_start[cell];
+        const int64_t s = s0;
         if (rowids) CU(cudaMemcpyAsync(rowids, h->rowids.as<int64_t>() + s, (size_t)take * 8, cudaMemcpyDeviceToHost, h->stream));
         if (fine) {
             CU(h->w_fine.reserve((size_t)take * mv.M));
@@ -1276,7 +1548,7 @@ int b2l_cell_order(b2l_handle h, const void* Q, int q_is_f64, int nq, int64_t qu
     CU(cudaSetDevice(h->device));
     if (!h->has_model) FAIL(B2L_ERR_STATE, "no model set");
     if (nq < 1 || !Q || !nvis) FAIL(B2L_ERR_ARG, "bad cell_order arguments");
-    if (h->mv.V > B2L_MAX_V) FAIL(B2L_ERR_UNSUPPORTED, "V=%d > %d: large-V multi-index traversal is not implemented", h->mv.V, B2L_MAX_V);
+    if (h->mv.V > B2L_MAX_V) FAIL(B2L_ERR_UNSUPPORTED, "V=%d > %d: use b2l_cell_order_prefix (the full V*V order is not materialised)", h->mv.V, B2L_MAX_V);
     int rc = ensure_index(h);
     if (rc) return rc;
     const ModelView& mv = h->mv;
@@ -1298,6 +1570,37 @@ int b2l_cell_order(b2l_handle h, const void* Q, int q_is_f64, int nq, int64_t qu
     CU(cudaMemcpyAsync(nvis, pv.nvis, (size_t)nq * 4, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     pv.vis_dist = nullptr;
+    return B2L_OK;
+}
+
+int b2l_cell_order_prefix(b2l_handle h, const void* Q, int q_is_f64, int nq, int64_t quota, int max_cells,
+                          int32_t* cells, double* dists, int32_t* nvis) {
+    if (!h) return B2L_ERR_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(cudaSetDevice(h->device));
+    if (!h->has_model) FAIL(B2L_ERR_STATE, "no model set");
+    if (nq < 1 || !Q || !nvis || max_cells < 1) FAIL(B2L_ERR_ARG, "bad cell_order_prefix arguments");
+    const ModelView& mv = h->mv;
+    if (mv.V > B2L_MAX_V_SPARSE) FAIL(B2L_ERR_UNSUPPORTED, "V=%d > %d", mv.V, B2L_MAX_V_SPARSE);
+    if (h->global_set) FAIL(B2L_ERR_UNSUPPORTED, "b2l_cell_order_prefix works on an unsharded index");
+    if (mv.V <= B2L_MAX_V) FAIL(B2L_ERR_UNSUPPORTED, "V=%d <= %d: use b2l_cell_order", mv.V, B2L_MAX_V);
+    int rc = ensure_index(h);
+    if (rc) return rc;
+    const size_t esz = q_is_f64 ? 8 : 4;
+    CU(h->w_q.reserve((size_t)nq * mv.D * esz));
+    CU(cudaMemcpyAsync(h->w_q.p, Q, (size_t)nq * mv.D * esz, cudaMemcpyHostToDevice, h->stream));
+    WalkView wv;
+    const int segcap = (int)std::min<int64_t>(std::min<int64_t>(std::max<int64_t>(quota, 1), (int64_t)h->nu), (int64_t)max_cells) + 2;
+    if ((rc = setup_walk(h, nq, segcap, (size_t)nq * 2 * std::min(mv.V, segcap), max_cells, wv))) return rc;
+    wv.max_visit = max_cells;
+    if ((rc = launch_walk(h, h->w_q.p, q_is_f64, nq, quota, wv))) return rc;
+    WalkCounters wc;
+    CU(cudaMemcpyAsync(&wc, wv.cnt, sizeof wc, cudaMemcpyDeviceToHost, h->stream));
+    if (cells) CU(cudaMemcpyAsync(cells, wv.vis_cells, (size_t)nq * max_cells * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (dists) CU(cudaMemcpyAsync(dists, wv.vis_dists, (size_t)nq * max_cells * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(nvis, wv.nvis, (size_t)nq * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (wc.err == 1) FAIL(B2L_ERR_UNSUPPORTED, "more than %d cells at one and the same coarse distance: the traversal order is degenerate", WALK_CAP);
     return B2L_OK;
 }
 

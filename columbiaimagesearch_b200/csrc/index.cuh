@@ -20,6 +20,7 @@ __global__ void k_cell_ids(const int32_t* __restrict__ coarse, int64_t n, int V,
             cell[i] = c;
             order[i] = (unsigned int)i;
         }
+        if (!hist) continue;                 // large V: no dense per-cell histogram (sparse directory, largev.cuh)
         const unsigned int peers = __match_any_sync(0xffffffffu, c);
         if (live && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[c], (unsigned long long)__popc(peers));
     }

@@ -272,7 +272,7 @@ k_lut(ModelView mv, const XT* __restrict__ Xq, const int32_t* __restrict__ lut_d
     const XT* x = Xq + (int64_t)q * mv.D + s * h;
     const double* C = mv.Cs + ((int64_t)s * V + c) * h;
     const double* mu = mv.mus + ((int64_t)s * V + c) * h;
-    if (have_p) {          // the projection was produced by the grouped GEMM (k_rotate_dmma_g, large h)
+    if (have_p == 1) {     // the projection was produced by the grouped GEMM (k_rotate_dmma_g, large h)
         for (int d = tid; d < h; d += LUT_THREADS) p[d] = P64[(int64_t)slot * h + d];
     } else
     for (int d = tid; d < h; d += LUT_THREADS) r[d] = coarse_residual<XT>(x[d], C[d], mu[d], mv.coarse_f32);
@@ -284,7 +284,7 @@ k_lut(ModelView mv, const XT* __restrict__ Xq, const int32_t* __restrict__ lut_d
     const int tw = LUT_THREADS / parts;                                       // outputs handled per sweep
     const int part = tid / tw, tl = tid - part * tw;
     const int dlen = h / parts, d0 = part * dlen;
-    for (int t0 = 0; t0 < (have_p ? 0 : h); t0 += tw) {
+    for (int t0 = 0; t0 < (have_p == 1 ? 0 : h); t0 += tw) {
         const int t = t0 + tl;
         double acc = 0.0;
         if (t < h) {
@@ -304,6 +304,7 @@ k_lut(ModelView mv, const XT* __restrict__ Xq, const int32_t* __restrict__ lut_d
         }
     }
     __syncthreads();
+    if (have_p == 2) continue;             // projection only (large-V search evaluates table entries on the fly)
     for (int k = tid; k < B2L_LUT_ROWS; k += LUT_THREADS) {
         const bool live = k < mv.K;
         float* o32 = lut32 ? lut32 + ((int64_t)slot * B2L_LUT_ROWS + k) * m : nullptr;

@@ -125,7 +125,10 @@ class LOPQModel(object):
 
     def predict_coarse(self, x):
         """model.py:563-573 (x is the D-dim, post-PCA vector)."""
-        cells, _, _ = self._native().cell_order(np.asarray(x)[None, :], quota=0)
+        if self.V > 64:
+            cells, _, _ = self._native().cell_order_prefix(np.asarray(x)[None, :], quota=0, max_cells=1)
+        else:
+            cells, _, _ = self._native().cell_order(np.asarray(x)[None, :], quota=0)
         ct = _uint_type(self.V)
         return (ct(cells[0, 0] // self.V), ct(cells[0, 0] % self.V))
 

@@ -14,7 +14,8 @@ from .. import _native
 from .model import LOPQCode, LOPQModelPCA, _cluster_handle
 from .utils import compute_codes_arrays
 
-_ID_BITS = 40       # fast de-dup key = cell << 40 | id  (non-negative integer ids below 2**40)
+_ID_BITS = 39       # fast de-dup key = cell << 39 | id  (non-negative integer ids below 2**39; cell < 2**24 at V = 4096)
+_DENSE_V = 64       # up to this V the library materialises the whole V x V cell order; above it, prefixes of the traversal
 
 
 def multisequence(x, centroids):
@@ -24,8 +25,23 @@ def multisequence(x, centroids):
     c0, c1 = np.asarray(centroids[0]), np.asarray(centroids[1])
     V = c0.shape[0]
     h = _pair_handle(c0, c1)
-    cells, dists, nvis = h.cell_order(x[None, :])
     f32 = x.dtype == np.float32 and c0.dtype == np.float32 and c1.dtype == np.float32
+    if V > _DENSE_V:
+        # large V: the traversal is produced in growing prefixes (the generator is usually abandoned after a few cells)
+        done, cap = 0, 1024
+        while done < V * V:
+            cap = min(cap, V * V)
+            cells, dists, nvis = h.cell_order_prefix(x[None, :], quota=None, max_cells=cap)
+            n = int(nvis[0])
+            for i in range(done, n):
+                d = np.float32(dists[0, i]) if f32 else np.float64(dists[0, i])
+                yield d, (int(cells[0, i]) // V, int(cells[0, i]) % V)
+            done = n
+            if n < cap:
+                break
+            cap *= 8
+        return
+    cells, dists, nvis = h.cell_order(x[None, :])
     for i in range(int(nvis[0])):
         d = np.float32(dists[0, i]) if f32 else np.float64(dists[0, i])
         yield d, (int(cells[0, i]) // V, int(cells[0, i]) % V)
@@ -129,8 +145,16 @@ class LOPQSearcherBase(object):
     def get_result_quota(self, x, quota=10):
         """search.py:110-135 -- (items of whole cells in multisequence order until >= quota, visited).
         x is the D-dim (post-PCA) vector, as in the reference."""
-        cells, _, nvis = self._handle.cell_order(np.asarray(x)[None, :], quota=quota)
         V = self.model.V
+        if V > _DENSE_V:
+            cap = 4096
+            while True:
+                cells, _, nvis = self._handle.cell_order_prefix(np.asarray(x)[None, :], quota=quota, max_cells=cap)
+                if int(nvis[0]) < cap or cap >= V * V:
+                    break
+                cap = min(V * V, cap * 8)
+        else:
+            cells, _, nvis = self._handle.cell_order(np.asarray(x)[None, :], quota=quota)
         retrieved = []
         for i in range(int(nvis[0])):
             retrieved += self.get_cell((int(cells[0, i]) // V, int(cells[0, i]) % V))

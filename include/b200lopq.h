@@ -107,6 +107,12 @@ int64_t b2l_index_get_cell(b2l_handle h, int c0, int c1, int64_t cap, int64_t* r
 int b2l_cell_order(b2l_handle h, const void* Q, int q_is_f64, int nq, int64_t quota,
                    int32_t* cells, double* dists, int32_t* nvis);
 
+/* The same for V > 64 (the product's V = 2048 / 4096 models), where the V*V order is never materialised: the first
+ * min(visited, max_cells) cells of the traversal of every query, stopping at the quota cut or after max_cells cells.
+ *   cells [nq][max_cells], dists [nq][max_cells] (either may be NULL), nvis [nq]. */
+int b2l_cell_order_prefix(b2l_handle h, const void* Q, int q_is_f64, int nq, int64_t quota, int max_cells,
+                          int32_t* cells, double* dists, int32_t* nvis);
+
 /* ---- search ------------------------------------------------------------------------------------
  * LOPQSearcherBase.search (search.py:179-224) for a batch of queries:
  *   multisequence cell order (search.py:13-82) -> whole cells until >= quota (110-135) ->
@@ -115,7 +121,9 @@ int b2l_cell_order(b2l_handle h, const void* Q, int q_is_f64, int nq, int64_t qu
  *   rowid int64, dist float64, coarse [nq][k][2] int32, fine [nq][k][M] uint8,
  *   count [nq] int32 (= min(k, retrieved)), visited [nq] int32 (cells visited, incl. empty).
  * Any output pointer except count may be NULL.  Queries: [nq][D0 or D] float32/float64, host.
- * on_device = 1: Q and all outputs are device pointers. */
+ * on_device = 1: Q and all outputs are device pointers.
+ * V <= 64: dense V*V plan, quantised ADC scan + certified float64 re-rank.  64 < V <= 4096: sparse cell directory, the
+ * multi-sequence traversal on the device, every retrieved code ranked in float64 (csrc/largev.cuh). */
 int b2l_search(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_device,
                int64_t quota, int k,
                int64_t* rowid, double* dist, int32_t* coarse, uint8_t* fine,
