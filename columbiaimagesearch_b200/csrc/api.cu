@@ -225,8 +225,10 @@ int encode_device(b2l_handle h, const void* dX, int x_is_f64, int64_t n, const i
     const size_t smem = (size_t)ENC_WARPS * mv.h * 8;
     // batch encode of the common shape: coarse assignment, then the rotation as a grouped float64 tensor-core GEMM
     const bool gemm = d_fine && !d_coarse_in && d_coarse && mv.h % 64 == 0 && n >= 2048 && n < ((int64_t)1 << 31);
-    double* px_out = gemm ? nullptr : h->w_px.as<double>();
-    if (gemm && mv.h % 8 == 0 && mv.h <= 128) {
+    // coarse assignment only (utils.predict_cluster over rows; the assignment step of k-means training): no projection
+    const bool coarse_only = !d_fine && !d_coarse_in && d_coarse;
+    double* px_out = (gemm || coarse_only) ? nullptr : h->w_px.as<double>();
+    if ((gemm || coarse_only) && mv.h % 8 == 0 && mv.h <= 128) {
         if (xf64) k_coarse_assign<double><<<blocks, ENC_WARPS * 32, 0, h->stream>>>(mv, (const double*)x, n, d_coarse);
         else k_coarse_assign<float><<<blocks, ENC_WARPS * 32, 0, h->stream>>>(mv, (const float*)x, n, d_coarse);
     } else if (xf64) { CU(cudaFuncSetAttribute(k_coarse_project<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -808,11 +810,20 @@ int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_
         }
     }
     if (lowb) {
-        // one query per item and the next item's tables prefetched: short items are cheap, so aim at ~4 items per resident
-        // block for a short tail; a multiple of 1024 codes keeps the 8 warps of a block (128 codes per step) in step
-        const int64_t est = (int64_t)nq * std::min<int64_t>(gtotal, (quota < gtotal ? quota : gtotal) + maxcell / 2);
-        const int64_t want = est / ((int64_t)h->num_sms * 3 * 4);
-        segc = (int)std::min<int64_t>(64 * 1024, std::max<int64_t>(1024, ((want + 1023) / 1024) * 1024));
+        // One query per item, the next item's tables prefetched.  The items of a query all compete for the resident blocks
+        // (3 per SM) at once, so the segment length decides the tail: pick the multiple of 1024 codes (8 warps x 128 codes per
+        // step) that minimises  waves x (segment + per-item overhead)  for the expected share of the index a query ranks.
+        const int64_t est = std::min<int64_t>(gtotal, (quota < gtotal ? quota : gtotal) + maxcell / 2);
+        const double frac = gtotal > 0 ? (double)est / (double)gtotal : 1.0;
+        const double grid = (double)h->num_sms * 3.0;
+        double best_cost = 1e300;
+        for (int sc = 1024; sc <= 64 * 1024; sc += 1024) {
+            double items = 0.0;
+            for (int c = 0; c < ncell; ++c) items += (double)((h->h_lsize[c] + sc - 1) / sc);
+            items = std::max(1.0, items * frac * nq);
+            const double cost = std::ceil(items / grid) * ((double)sc + 3072.0);
+            if (cost <= best_cost) { best_cost = cost; segc = sc; }
+        }
     }
     if (maxcell > 0 && maxcell < segc) segc = (int)(((maxcell + 63) / 64) * 64);
     const int nsegmax = (int)std::max<int64_t>(1, (maxcell + segc - 1) / segc);

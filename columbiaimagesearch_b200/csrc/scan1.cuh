@@ -76,7 +76,7 @@ k_scan1(ScanArgs a) {
     const int ent = warp * 32 + lane;                // entry of this lane in the bound table (generation 0)
     const int LPS = 32 * SCAN_WARPS;
 
-    for (int e = tid; e < B2L_LUT_ROWS * 64; e += SCAN_THREADS) lut[e] = 0.0f;   // padding columns of both buffers stay zero
+    if (a.M < MP) for (int e = tid; e < B2L_LUT_ROWS * 64; e += SCAN_THREADS) lut[e] = 0.0f;   // padding columns of both buffers stay zero
     const unsigned int n_items = pv.cnt->n_items;
     if (tid == 0) { s_misc[2] = atomicAdd(&pv.cnt->next_item, 1u); s_misc[3] = 0xFFFFFFFFu; }
     __syncthreads();
@@ -114,12 +114,14 @@ k_scan1(ScanArgs a) {
 
     Item1 cur;
     unsigned int item = s_misc[2];
-    int buf = 0;
+    int buf = 0, tab_q = -1;                          // tab_q: the query whose lane minima the block's bound table holds
     if (item < n_items) { decode(item, cur); fetch_lut(cur, 0); }
     while (item < n_items) {
         if (tid == 0) s_misc[3] = atomicAdd(&pv.cnt->next_item, 1u);
-        // bound table of the query as finished items left it; bound as published so far
-        for (int e = tid; e < a.E; e += SCAN_THREADS) tab[e] = a.gtab[(size_t)cur.q * a.E + e];
+        // bound table: what finished items of the query left in gtab -- unless the block's previous item was the same query
+        // (then its own table, which only gets better, stays: hundreds of blocks share one query in this regime, and a
+        // read-modify-write of the query's global table per item would serialise them on the same 256 addresses)
+        if (tab_q != cur.q) for (int e = tid; e < a.E; e += SCAN_THREADS) tab[e] = a.gtab[(size_t)cur.q * a.E + e];
         if (tid == 0) { s_misc[0] = *(volatile unsigned int*)&a.gthr[cur.q]; s_misc[1] = 0u; }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();                                                  // tables of `cur` landed; s_misc published
@@ -250,12 +252,16 @@ k_scan1(ScanArgs a) {
                 gb = __shfl_sync(0xffffffffu, gb, 0) + __popc(bal & ((1u << lane) - 1u));
                 if (keep && gb < (unsigned)a.cand_cap) a.cand[(size_t)cur.q * a.cand_cap + gb] = stage[i] + cur.posbase;
             }
-            for (int e = tid; e < a.E; e += SCAN_THREADS) {
-                const float v = tab[e];
-                if (__float_as_uint(v) <= thr) atomicMin((unsigned int*)&a.gtab[(size_t)cur.q * a.E + e], __float_as_uint(v));
+            // leave the table to other blocks only when this block moves on to another query (or stops)
+            if (!(nxt < n_items && nx.q == cur.q)) {
+                for (int e = tid; e < a.E; e += SCAN_THREADS) {
+                    const float v = tab[e];
+                    if (__float_as_uint(v) <= thr) atomicMin((unsigned int*)&a.gtab[(size_t)cur.q * a.E + e], __float_as_uint(v));
+                }
             }
         }
         __syncthreads();                                                   // stage / tab / s_misc free for the next item
+        tab_q = cur.q;
         item = nxt;
         cur = nx;
         buf ^= 1;

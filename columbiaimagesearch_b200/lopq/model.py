@@ -98,12 +98,13 @@ class LOPQModel(object):
 
     # ---- training ("next" row; statistical parity only) -------------------------------------------
     def fit(self, data, kmeans_coarse_iters=10, kmeans_local_iters=20, n_init=10, subquantizer_sample_ratio=1.0,
-            random_state=None, verbose=False):
-        """model.py:495-519 -> train (model.py:339-437)."""
+            random_state=None, verbose=False, device=None):
+        """model.py:495-519 -> train (model.py:339-437).  The nearest-centroid assignments (every k-means iteration,
+        compute_residuals) run on the GPU; `device=False` keeps them on the host."""
         from .train import train
         self.Cs, self.Rs, self.mus, self.subquantizers = train(
             data, self.V, self.M, self.subquantizer_clusters, (self.Cs, self.Rs, self.mus, self.subquantizers),
-            kmeans_coarse_iters, kmeans_local_iters, n_init, subquantizer_sample_ratio, random_state, verbose)
+            kmeans_coarse_iters, kmeans_local_iters, n_init, subquantizer_sample_ratio, random_state, verbose, device)
         self._invalidate()
 
     def get_split_parameters(self, split):

@@ -29,7 +29,28 @@ def eigenvalue_allocation(num_buckets, eigenvalues):
     return perm.reshape(D)
 
 
-def _assign(X, C, chunk=65536):
+def _assign_device(X, C):
+    """Nearest centroid of every row on the GPU: utils.predict_cluster (utils.py:33-53, direct-form squared distances,
+    first minimum, float64) over all rows in one b2l_encode call -- the O(n k d) step of every Lloyd iteration and of
+    compute_residuals (model.py:236-239).  The centroids are wrapped as the first coarse split of a throw-away model."""
+    from .model import _cluster_handle
+    C = np.ascontiguousarray(C, dtype=np.float64)
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    h = _cluster_handle(C)
+    coarse, _ = h.encode(np.concatenate([X, X], axis=1), want_fine=False)
+    return coarse[:, 0].astype(np.int64)
+
+
+def _use_device(device):
+    """device=None means the GPU, like every other arithmetic step of this package (no silent host fallback: without a
+    CUDA device the library fails loudly).  device=False keeps the assignments on the host (NumPy) -- training has no
+    parity contract (models are inputs of the hot path), and the flag exists for comparisons."""
+    return True if device is None else bool(device)
+
+
+def _assign(X, C, chunk=65536, device=False):
+    if device:
+        return _assign_device(X, C)
     out = np.empty(X.shape[0], dtype=np.int64)
     cn = (C * C).sum(1)
     for a in range(0, X.shape[0], chunk):
@@ -38,19 +59,20 @@ def _assign(X, C, chunk=65536):
     return out
 
 
-def kmeans(X, k, iters, rng, n_init=1):
-    """Seeded Lloyd k-means (random distinct initial points; empty clusters re-seeded)."""
+def kmeans(X, k, iters, rng, n_init=1, device=False):
+    """Seeded Lloyd k-means (random distinct initial points; empty clusters re-seeded).  device=True: the assignment step
+    runs on the GPU (_assign_device); the centroid update is a segmented sum on the host."""
     X = np.asarray(X, dtype=np.float64)
     best, best_cost = None, np.inf
     for _ in range(max(1, n_init)):
         C = X[rng.choice(X.shape[0], size=k, replace=X.shape[0] < k)].copy()
         for _it in range(iters):
-            a = _assign(X, C)
+            a = _assign(X, C, device=device)
             cnt = np.bincount(a, minlength=k)
             S = _segment_sum(X, a, k)
             empty = cnt == 0
             C = np.where(empty[:, None], X[rng.randint(0, X.shape[0], size=k)], S / np.maximum(cnt, 1)[:, None])
-        a = _assign(X, C)
+        a = _assign(X, C, device=device)
         cost = ((X - C[a]) ** 2).sum()
         if cost < best_cost:
             best, best_cost = C, cost
@@ -68,11 +90,11 @@ def _segment_sum(X, a, k):
     return S
 
 
-def compute_local_rotations(data, C, num_buckets):
+def compute_local_rotations(data, C, num_buckets, device=False):
     """model.py:74-206 -- per-cluster residual mean, covariance, eigenvectors permuted by
     eigenvalue_allocation.  Returns (R [V,D,D], mu [V,D], assignments, residuals)."""
     V, D = C.shape
-    a = _assign(data, C)
+    a = _assign(data, C, device=device)
     residuals = data - C[a]
     R = np.zeros((V, D, D))
     mu = np.zeros((V, D))
@@ -101,20 +123,22 @@ def project_residuals_to_local(residuals, assignments, Rs, mu):
 
 
 def train(data, V=8, M=4, subquantizer_clusters=256, parameters=None, kmeans_coarse_iters=10, kmeans_local_iters=20,
-          n_init=10, subquantizer_sample_ratio=1.0, random_state=None, verbose=False):
-    """model.py:339-437 -- returns (Cs, Rs, mus, subquantizers); existing parameters are kept."""
+          n_init=10, subquantizer_sample_ratio=1.0, random_state=None, verbose=False, device=None):
+    """model.py:339-437 -- returns (Cs, Rs, mus, subquantizers); existing parameters are kept.  device: True / False / None
+    (= the GPU when one is present) for the nearest-centroid assignments."""
     rng = np.random.RandomState(random_state)
+    device = _use_device(device)
     data = np.asarray(data, dtype=np.float64)
     Cs, Rs, mus, subs = parameters if parameters is not None else (None, None, None, None)
     h = data.shape[1] // 2
     halves = (data[:, :h], data[:, h:2 * h])
     if Cs is None:
-        Cs = tuple(kmeans(x, V, kmeans_coarse_iters, rng, n_init) for x in halves)
+        Cs = tuple(kmeans(x, V, kmeans_coarse_iters, rng, n_init, device) for x in halves)
         if verbose:
             print("coarse quantizers trained")
     m = M // 2
     if Rs is None or mus is None or subs is None:
-        rot = [compute_local_rotations(x, C, m) for x, C in zip(halves, Cs)]
+        rot = [compute_local_rotations(x, C, m, device) for x, C in zip(halves, Cs)]
         if Rs is None or mus is None:
             Rs, mus = tuple(r[0] for r in rot), tuple(r[1] for r in rot)
         if subs is None:
@@ -125,7 +149,7 @@ def train(data, V=8, M=4, subquantizer_clusters=256, parameters=None, kmeans_coa
                     n = int(proj.shape[0] * subquantizer_sample_ratio)
                     proj = proj[rng.choice(proj.shape[0], size=n, replace=False)]
                 ds = h // m
-                out.append([kmeans(proj[:, j * ds:(j + 1) * ds], subquantizer_clusters, kmeans_local_iters, rng, n_init)
+                out.append([kmeans(proj[:, j * ds:(j + 1) * ds], subquantizer_clusters, kmeans_local_iters, rng, n_init, device)
                             for j in range(m)])
                 if verbose:
                     print("subquantizers of one split trained")

@@ -266,3 +266,47 @@ def test_pca_model_training_entry_points():
     m2 = lopq.LOPQModelPCA(V=2, M=4, subquantizer_clusters=16)
     m2.fit(X, pca_dims=16, n_init=1, kmeans_coarse_iters=3, kmeans_local_iters=3, random_state=0, pca_subsample=2000)
     assert m2.pca_P.shape == (24, 16) and m2.predict(X[1]).fine is not None
+
+
+def test_training_on_the_gpu_statistical_parity():
+    """Training (model.py:339-437) with the nearest-centroid assignments on the GPU: same algorithm as the reference's
+    trainer, so on the training data of golden case A the quantisation error (eval.py:145-161's distortion: squared error
+    of reconstruct(predict(x))) must be on a par with the reference-trained model's, and GPU- and host-assigned training
+    from the same seed must agree closely."""
+    lopq = _lopq()
+    from columbiaimagesearch_b200.lopq import train as T
+    z, omodel = load_case("A")
+    train, db, Q, ids = case_inputs("A")
+    ref_model = lopq.LOPQModel.from_npz(z)
+
+    def distortion(model, X):
+        coarse, fine = lopq.utils.compute_codes_arrays(X, model)
+        rec = np.stack([model.reconstruct((tuple(c), tuple(f))) for c, f in zip(coarse, fine)])
+        return float(((X.astype(np.float64) - rec) ** 2).sum(1).mean())
+
+    sample = db[:1500]
+    d_ref = distortion(ref_model, sample)
+    m_gpu = lopq.LOPQModel(V=8, M=16, subquantizer_clusters=256)
+    m_gpu.fit(train[:12000].astype(np.float64), n_init=1, kmeans_coarse_iters=10, kmeans_local_iters=10, random_state=0)
+    d_gpu = distortion(m_gpu, sample)
+    assert d_gpu < 1.25 * d_ref, (d_gpu, d_ref)
+    # the device assignment is utils.predict_cluster over rows: identical to the oracle's on every row
+    X = train[:4000, :64].astype(np.float64)
+    C = np.asarray(m_gpu.Cs[0], dtype=np.float64)
+    a_dev = T._assign_device(X, C)
+    a_orc = np.array([int(orc.predict_cluster(x, C)) for x in X[:600]])
+    assert np.array_equal(a_dev[:600], a_orc)
+    a_host = T._assign(X, C, device=False)
+    assert (a_dev != a_host).mean() < 1e-3              # matmul-form host distances can only differ in near ties
+    m_host = lopq.LOPQModel(V=8, M=16, subquantizer_clusters=256)
+    m_host.fit(train[:12000].astype(np.float64), n_init=1, kmeans_coarse_iters=10, kmeans_local_iters=10, random_state=0, device=False)
+    d_host = distortion(m_host, sample)
+    assert abs(d_gpu - d_host) < 0.1 * d_host, (d_gpu, d_host)
+    # recall of a searcher built on the GPU-trained model (eval.get_recall_batch) is on a par with the reference-trained one
+    def recall(model):
+        s = lopq.LOPQSearcher(model)
+        s.add_data(db)
+        d2 = ((Q[:, None, :].astype(np.float64) - db[None, :, :].astype(np.float64)) ** 2).sum(-1)
+        return lopq.eval.get_recall_batch(s, Q, d2.argmin(1), quota=2000, thresholds=(1, 10), batch=64)
+    r_ref, r_gpu = recall(ref_model), recall(m_gpu)
+    assert r_gpu[1] >= r_ref[1] - 0.1, (r_gpu, r_ref)
