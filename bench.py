@@ -36,6 +36,9 @@ CONFIGS = {
     # configs[2]: DeepSentibank-style 2048-d; the model is trained at start-up (134 MB of rotations: not a fixture)
     "c3": dict(metric="LOPQ queries/sec @ recall@10, 10Mx2048-d, V=8 M=32", n_db=10_000_000, D=2048, V=8, M=32,
                model=None, quota=330_000, style="sentibank"),
+    # the product's shipped shape (conf/conf_search_dlibface_release.json:12-16): V=2048, M=8, 128-d, quota = min(1000 x 100, 10000)
+    "pv": dict(metric="LOPQ queries/sec @ recall@10, 4Mx128-d, V=2048 M=8 (product-shaped), quota=10000 top-100", n_db=4_000_000,
+               D=128, V=2048, M=8, model=None, quota=10_000, style="dlib"),
     # configs[4]: batch encode
     "c5": dict(metric="LOPQ compute_codes codes/sec, 50Mx128-d, V=8 M=16", n_db=50_000_000, D=128, V=8, M=16,
                model="dlib128_V8_M16.npz", style="dlib"),
@@ -211,7 +214,7 @@ def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    if a.config == "c3":
+    if a.config in ("c3", "pv"):
         print(json.dumps({"impl": "reference", "unavailable": "c3 reference arm not built: the 2048-d model is trained on the GPU at start-up; see cpu_baseline of the b200 line"}))
         return
     import multiprocessing as mp
@@ -800,6 +803,106 @@ def cpu_baseline_search(a, cfg, model, coarse_t, fine_t, Qall, searcher, quota, 
 
 
 # ------------------------------------------------------------------------------------------------
+def run_product(a):
+    """--config pv: the product-shaped configuration (V = 2048, M = 8, 128-d, quota 10000, top-100) on one GPU through the
+    large-V path (csrc/largev.cuh).  One step = one batch of `--batch` queries through b2l_search."""
+    env = Env()
+    torch = env.torch
+    from columbiaimagesearch_b200 import synth
+    import columbiaimagesearch_b200.lopq as lopq
+    cfg = a.cfg
+    assert env.world == 1, "the large-V path is single-GPU"
+    D, V, M, n, quota, k, nq = cfg["D"], cfg["V"], cfg["M"], cfg["n_db"], cfg["quota"], max(a.k, 100), a.batch
+    # model: trained here with the package's trainer on seeded vectors (data preparation; models are inputs)
+    Xt = synth.dlib_style_torch(a.ntrain * 5, D, seed=a.seed + 5, device=env.dev).cpu().numpy().astype(np.float64)
+    model = lopq.LOPQModel(V=V, M=M, subquantizer_clusters=256)
+    t0 = time.perf_counter()
+    model.fit(Xt, n_init=1, kmeans_coarse_iters=8, kmeans_local_iters=8, random_state=0)
+    train_s = time.perf_counter() - t0
+    coarse_t, fine_t, Qall, gt, enc_stats = build_database(env, a, cfg, model, synth)
+    s = lopq.LOPQSearcher(model, device=env.local, keep_host_copy=False)
+    h = s._handle
+    h.index_add_device(coarse_t.data_ptr(), fine_t.data_ptr(), n)
+    s.nb_indexed = n
+    s._row_ids = [np.arange(n, dtype=np.int64)]
+    nb = a.warmup + a.steps
+    outs = dict(rowid=torch.empty((nq, k), dtype=torch.int64, device=env.dev), dist=torch.empty((nq, k), dtype=torch.float64, device=env.dev),
+                coarse=torch.empty((nq, k, 2), dtype=torch.int32, device=env.dev), fine=torch.empty((nq, k, M), dtype=torch.uint8, device=env.dev),
+                count=torch.empty(nq, dtype=torch.int32, device=env.dev), visited=torch.empty(nq, dtype=torch.int32, device=env.dev))
+
+    def dev_step(b):
+        q = Qall[b * nq:(b + 1) * nq]
+        h.search_device(q.data_ptr(), nq, quota, k, outs["rowid"].data_ptr(), outs["dist"].data_ptr(), outs["coarse"].data_ptr(),
+                        outs["fine"].data_ptr(), outs["count"].data_ptr(), outs["visited"].data_ptr())
+
+    # recall (eval.get_recall definition) on the first batches, through the host API
+    nrec = min(nb, 4)
+    rec = np.zeros(2)
+    vis = 0
+    for b in range(nrec):
+        q = Qall[b * nq:(b + 1) * nq].cpu().numpy()
+        o = s.search_batch(q, quota=quota, limit=k)
+        hit = (o["ids"] == gt[b * nq:(b + 1) * nq, None]) & (np.arange(k)[None, :] < o["count"][:, None])
+        rank = np.where(hit.any(1), hit.argmax(1), k)
+        rec += [np.count_nonzero(rank < 1), np.count_nonzero(rank < 10)]
+        vis += int(o["visited"].sum())
+    st0 = h.stats()
+    for b in range(a.warmup):
+        dev_step(b)
+    sampler = ClockSampler(env.local)
+    sampler.start()
+    stream = torch.cuda.ExternalStream(h.stream(), device=env.dev)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    h.reset_stats()
+    env.barrier()
+    ev0.record(stream)
+    for b in range(a.warmup, nb):
+        dev_step(b)
+    ev1.record(stream)
+    env.barrier()
+    dev_s = ev0.elapsed_time(ev1) * 1e-3
+    st = h.stats()
+    Qh = torch.empty((a.steps * nq, D), dtype=torch.float32).pin_memory()
+    Qh.copy_(Qall[a.warmup * nq:nb * nq])
+    qh = Qh.numpy()
+    s.search_batch(qh[:nq], quota=quota, limit=k)
+    t0 = time.perf_counter()
+    for b in range(a.steps):
+        s.search_batch(qh[b * nq:(b + 1) * nq], quota=quota, limit=k)
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()
+    cpu = None
+    if not a.no_cpu_baseline:
+        orc, omodel = _oracle_model(model)
+        co, fi = coarse_t.cpu().numpy(), fine_t.cpu().numpy()
+        index = orc.ArrayIndex(V, co, fi, np.arange(n, dtype=np.int64))
+        qs = Qall[:a.cpu_queries].cpu().numpy()
+        t0 = time.perf_counter()
+        res = [orc.search_arrays(omodel, index, q, quota, k) for q in qs]
+        dt = time.perf_counter() - t0
+        g = s.search_batch(qs, quota=quota, limit=k)
+        same = all(np.array_equal(g["ids"][i][:len(r[0])], r[0]) and int(g["visited"][i]) == r[4] for i, r in enumerate(res))
+        maxd = max(float(np.max(np.abs(r[1] - g["dist"][i][:len(r[1])]))) for i, r in enumerate(res))
+        cpu = {"value": len(qs) / dt, "unit": "queries/s", "cores": 1, "kind": "port",
+               "sample": "%d queries, reference algorithm (Python heap multi-sequence walk, memoised LUTs; ADC sums vectorised over a cell), %.1f s" % (len(qs), dt),
+               "ids_match_gpu": bool(same), "max_abs_dist_diff": maxd, "host_cores": os.cpu_count()}
+    tot = nrec * nq
+    line = {"metric": cfg["metric"], "value": a.steps * nq / dev_s, "unit": "queries/s", "n_gpus": 1, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": 1e3 * dev_s / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "pv: %dM x %d-d dlib-style synthetic, V=%d M=%d K=256 (model trained at start-up, %d vectors), batch=%d near-duplicate "
+                                   "queries (rho=%.2f), quota=%d, top-%d" % (n // 1_000_000, D, V, M, Xt.shape[0], nq, a.rho, quota, k),
+                       "recall@10": rec[1] / tot, "recall@1": rec[0] / tot, "cells_visited_per_query": vis / tot, "model_train_s": train_s,
+                       "arithmetic": "float64 throughout: device multi-sequence traversal, grouped-GEMM projections, exact ADC of every retrieved code"},
+            "recall@10": rec[1] / tot, "codes_ranked_per_query": st["acc_codes_scanned"] / max(1, st["acc_calls"]) / nq,
+            "projection_slots_per_query": st0["lut_slots"] / nq,
+            "e2e": {"value": a.steps * nq / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": nq * D * 4, "d2h_bytes_per_step": nq * k * (24 + M) + nq * 9,
+                    "api": "LOPQSearcher.search_batch (b2l_search, host queries in / host results out)"},
+            "gpu_launches": int(st["acc_kernel_launches"]), "encode": enc_stats, "cpu_baseline": cpu, "clocks": clocks,
+            "roofline": None}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
 def run_encode(a):
     """--config c5: compute_codes over 50M x 128-d rows, row-sharded over the ranks (utils.py:178-200's decomposition, no
     communication).  One step = one encode pass over this rank's resident block of rows; the 50M rows are visited block
@@ -889,5 +992,7 @@ if __name__ == "__main__":
         run_reference(args)
     elif args.config == "c5":
         run_encode(args)
+    elif args.config == "pv":
+        run_product(args)
     else:
         run_search(args)

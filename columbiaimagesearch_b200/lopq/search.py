@@ -72,11 +72,11 @@ def codes_to_arrays(codes, M):
         return np.ascontiguousarray(codes[0], dtype=np.int32), np.ascontiguousarray(codes[1], dtype=np.uint8)
     codes = list(codes)
     n = len(codes)
-    coarse = np.empty((n, 2), np.int32)
-    fine = np.empty((n, M), np.uint8)
-    for i, c in enumerate(codes):
-        coarse[i] = c[0]
-        fine[i] = c[1]
+    if n == 0:
+        return np.zeros((0, 2), np.int32), np.zeros((0, M), np.uint8)
+    # bulk conversion (the per-update code dicts the product pickles hold ~10^4..10^6 entries, searcher_lopqhbase.py:506-522)
+    coarse = np.asarray([c[0] for c in codes], dtype=np.int32).reshape(n, 2)
+    fine = np.asarray([c[1] for c in codes], dtype=np.uint8).reshape(n, M)
     return coarse, fine
 
 
