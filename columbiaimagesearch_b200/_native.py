@@ -36,6 +36,7 @@ _vp, _i, _i64, _h = C.c_void_p, C.c_int, C.c_int64, C.c_void_p
 SIGNATURES = {
     "b2l_create": (_i, [_i, C.POINTER(_h)]),
     "b2l_destroy": (_i, [_h]),
+    "b2l_create_sibling": (_i, [_h, C.POINTER(_h)]),
     "b2l_last_error": (C.c_char_p, [_h]),
     "b2l_version": (_i, []),
     "b2l_set_model": (_i, [_h, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
@@ -134,6 +135,16 @@ class Handle(object):
         self.h = h
         self.device = int(device)
         self.D = self.V = self.M = self.K = self.D0 = None
+
+    def create_sibling(self):
+        """A handle sharing this one's model and index with its own stream and workspaces (b2l_create_sibling)."""
+        h = _h()
+        self._check(self.lib.b2l_create_sibling(self.h, C.byref(h)))
+        s = Handle.__new__(Handle)
+        s.lib, s.h, s.device = self.lib, h, self.device
+        s.D, s.V, s.M, s.K, s.D0 = self.D, self.V, self.M, self.K, self.D0
+        s._parent = self                        # keeps the parent alive for as long as the sibling lives
+        return s
 
     def close(self):
         if getattr(self, "h", None):

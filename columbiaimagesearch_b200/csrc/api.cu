@@ -33,8 +33,11 @@ std::string g_create_error;
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
+    bool borrowed = false;             // a sibling handle's view of its parent's buffer: never freed or grown here
+    void borrow(const DevBuf& o) { p = o.p; cap = o.cap; borrowed = true; }
     cudaError_t reserve(size_t bytes, bool keep = false, cudaStream_t st = 0) {
         if (bytes <= cap) return cudaSuccess;
+        if (borrowed) return cudaErrorInvalidValue;
         size_t ncap = std::max(bytes, cap + cap / 2);
         ncap = (ncap + 255) & ~(size_t)255;
         void* np = nullptr;
@@ -49,7 +52,7 @@ struct DevBuf {
         p = np; cap = ncap;
         return cudaSuccess;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    void release() { if (p && !borrowed) cudaFree(p); p = nullptr; cap = 0; borrowed = false; }
     template <typename T> T* as() const { return (T*)p; }
 };
 
@@ -108,6 +111,9 @@ struct b2l_ctx {
     int scan_mode = 0;                 // 0: packed 16-bit tables first (default), 1: float32 tables only
     void* h_out = nullptr;             // pinned staging of the search outputs
     size_t h_out_cap = 0;
+    // sibling handles (b2l_create_sibling): own stream and workspaces, the parent's model and index
+    b2l_ctx* parent = nullptr;
+    int n_siblings = 0;
     // multi-GPU exchange (comm.cuh): this rank's window and the peers' windows
     struct Comm {
         int world = 0, rank = 0;
@@ -1166,6 +1172,7 @@ int b2l_destroy(b2l_handle h) {
     if (!h) return B2L_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    if (h->parent) { std::lock_guard<std::mutex> lk(h->parent->mu); --h->parent->n_siblings; }
     DevBuf* bufs[] = {&h->dCs, &h->dmus, &h->dRt, &h->dsubs, &h->dsubs32, &h->dsubs32T, &h->dc2max, &h->dP, &h->dpmu, &h->m_coarse, &h->m_fine, &h->m_rowid, &h->codes,
                       &h->rowids, &h->cell_start, &h->lsize, &h->gsize, &h->sorted_first, &h->w_q, &h->w_xq, &h->w_px,
                       &h->w_coarse, &h->w_fine, &h->w_lut32, &h->w_lut64, &h->w_p64, &h->w_cellq, &h->w_cand, &h->w_gtab, &h->w_lut16, &h->w_quant, &h->w_plan,
@@ -1183,6 +1190,41 @@ int b2l_destroy(b2l_handle h) {
     }
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
+    return B2L_OK;
+}
+
+/* A second handle on the same device that SHARES the parent's model and (finalised) index but has its own stream and
+ * workspaces: batches issued alternately on a handle and its siblings overlap on the GPU (the plan / table / selection
+ * kernels and the exchange waits of one batch run under the scan of another).  While siblings exist, model and index of
+ * the family are frozen (mutating calls fail with B2L_ERR_STATE).  Destroy siblings before the parent. */
+int b2l_create_sibling(b2l_handle p, b2l_handle* out) {
+    if (!p || !out) return B2L_ERR_ARG;
+    *out = nullptr;
+    b2l_handle h = p;                                           // (error macros report on the parent)
+    std::lock_guard<std::mutex> lk(p->mu);
+    CU(cudaSetDevice(p->device));
+    if (!p->has_model) FAIL(B2L_ERR_STATE, "no model set");
+    if (p->parent) FAIL(B2L_ERR_STATE, "create siblings from the parent handle");
+    int rc = ensure_index(p);
+    if (rc) return rc;
+    b2l_handle s = nullptr;
+    rc = b2l_create(p->device, &s);
+    if (rc) { p->err = g_create_error; return rc; }
+    s->has_model = true; s->has_pca = p->has_pca; s->mv = p->mv; s->c2m = p->c2m;
+    s->fine_mode = p->fine_mode; s->scan_mode = p->scan_mode;
+    DevBuf* src[] = {&p->dCs, &p->dmus, &p->dRt, &p->dsubs, &p->dsubs32, &p->dsubs32T, &p->dc2max, &p->dP, &p->dpmu, &p->m_coarse, &p->m_fine,
+                     &p->m_rowid, &p->codes, &p->rowids, &p->cell_start, &p->lsize, &p->gsize, &p->sorted_first, &p->d_ucell, &p->d_ustart,
+                     &p->d_hkeys, &p->d_hvals};
+    DevBuf* dst[] = {&s->dCs, &s->dmus, &s->dRt, &s->dsubs, &s->dsubs32, &s->dsubs32T, &s->dc2max, &s->dP, &s->dpmu, &s->m_coarse, &s->m_fine,
+                     &s->m_rowid, &s->codes, &s->rowids, &s->cell_start, &s->lsize, &s->gsize, &s->sorted_first, &s->d_ucell, &s->d_ustart,
+                     &s->d_hkeys, &s->d_hvals};
+    for (size_t i = 0; i < sizeof(src) / sizeof(src[0]); ++i) dst[i]->borrow(*src[i]);
+    s->n_items = p->n_items; s->rows_padded = p->rows_padded; s->dirty = false; s->global_set = p->global_set;
+    s->h_lsize = p->h_lsize; s->h_gsize = p->h_gsize; s->h_cell_start = p->h_cell_start;
+    s->h_ucell = p->h_ucell; s->h_ustart = p->h_ustart; s->nu = p->nu; s->hmask = p->hmask; s->max_run = p->max_run;
+    s->parent = p;
+    ++p->n_siblings;
+    *out = s;
     return B2L_OK;
 }
 
@@ -1279,6 +1321,7 @@ int b2l_set_model(b2l_handle h, int D, int V, int M, int K, int coarse_is_f32, c
     if (K > B2L_MAX_K) FAIL(B2L_ERR_UNSUPPORTED, "subquantizer_clusters=%d > 256 (fine codes are bytes)", K);
     if (V > 65536) FAIL(B2L_ERR_UNSUPPORTED, "V=%d > 65536", V);
     if (h->n_items) FAIL(B2L_ERR_STATE, "clear the index before changing the model");
+    if (h->parent || h->n_siblings) FAIL(B2L_ERR_STATE, "the model is shared with sibling handles: destroy them first");
     ModelView& mv = h->mv;
     mv = ModelView();
     mv.D = D; mv.V = V; mv.M = M; mv.K = K; mv.h = D / 2; mv.m = M / 2; mv.ds = D / M; mv.coarse_f32 = coarse_is_f32 ? 1 : 0;
@@ -1329,6 +1372,7 @@ int b2l_set_pca(b2l_handle h, int D0, const double* P, const double* mu, int ren
     std::lock_guard<std::mutex> lk(h->mu);
     CU(cudaSetDevice(h->device));
     if (!h->has_model) FAIL(B2L_ERR_STATE, "set the model before the PCA");
+    if (h->parent || h->n_siblings) FAIL(B2L_ERR_STATE, "the model is shared with sibling handles: destroy them first");
     if (D0 < 1 || !P || !mu) FAIL(B2L_ERR_ARG, "bad PCA arguments");
     if ((size_t)(D0 + h->mv.D) * 8 > 200 * 1024) FAIL(B2L_ERR_UNSUPPORTED, "PCA input dimension %d too large", D0);
     CU(h->dP.reserve((size_t)D0 * h->mv.D * 8)); CU(h->dpmu.reserve((size_t)D0 * 8));
@@ -1452,6 +1496,7 @@ int b2l_index_add(b2l_handle h, const int32_t* coarse, const uint8_t* fine, int6
     CU(cudaSetDevice(h->device));
     if (!h->has_model) FAIL(B2L_ERR_STATE, "no model set");
     if (n < 0 || (n && (!coarse || !fine))) FAIL(B2L_ERR_ARG, "bad index_add arguments");
+    if (h->parent || h->n_siblings) FAIL(B2L_ERR_STATE, "the index is shared with sibling handles: destroy them first");
     if (n == 0) return B2L_OK;
     const ModelView& mv = h->mv;
     const int64_t tot = h->n_items + n;
@@ -1482,6 +1527,7 @@ int b2l_index_add(b2l_handle h, const int32_t* coarse, const uint8_t* fine, int6
 int b2l_index_clear(b2l_handle h) {
     if (!h) return B2L_ERR_ARG;
     std::lock_guard<std::mutex> lk(h->mu);
+    if (h->parent || h->n_siblings) FAIL(B2L_ERR_STATE, "the index is shared with sibling handles: destroy them first");
     h->n_items = 0; h->dirty = true; h->global_set = false;
     return B2L_OK;
 }
@@ -1510,6 +1556,7 @@ int b2l_index_set_global_cell_sizes(b2l_handle h, const int64_t* sizes) {
     CU(cudaSetDevice(h->device));
     if (!h->has_model) FAIL(B2L_ERR_STATE, "no model set");
     if (h->mv.V > B2L_MAX_V) FAIL(B2L_ERR_UNSUPPORTED, "a cell-sharded index is not supported at V > %d", B2L_MAX_V);
+    if (h->parent || h->n_siblings) FAIL(B2L_ERR_STATE, "the index is shared with sibling handles: destroy them first");
     const int ncell = h->mv.V * h->mv.V;
     h->h_gsize.assign(sizes, sizes + ncell);
     h->global_set = true;

@@ -23,11 +23,14 @@
 #define SCAN1_STAGE 1024          // staged candidates per item (8 bytes each); overflow: direct global append
 #define SCAN1_CAND_CAP (1 << 18)  // candidate keys per query in the low-batch regime (nq <= SCAN1_MAX_NQ)
 #define SCAN1_MAX_NQ 8
+#define SCAN1_PF 4                // L2 prefetch distance, in chunks of the warp
 
 template <int MP>
 size_t scan1_smem_bytes(int E) {
     return (size_t)B2L_LUT_ROWS * 256 + (size_t)SCAN1_STAGE * 8 + (size_t)E * 4 + 64 * 4 + 256;
 }
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 template <int MP, int OFF>
 __device__ __forceinline__ float adc_row1(const uint32_t (&w)[MP / 4], const uint32_t (&cc)[MP / 4]) {
@@ -180,6 +183,12 @@ k_scan1(ScanArgs a) {
                 for (int u = 0; u < U; ++u) d[u] = adc_row1<MP, 0>(w[u], cc);
             }
             if (c + SCAN_WARPS < nchunk) load_chunk(w, c + SCAN_WARPS);   // registers are dead: next chunk's rows in flight
+            // ... and the warp's chunks after that are pulled into L2 (one 128-byte line per lane), so that the register loads
+            // above find them there: with one chunk per warp in flight a single query would be bound by the HBM latency
+            {
+                const int cp = c + SCAN1_PF * SCAN_WARPS;
+                if (cp < nchunk && lane * 128 < CHUNK * MP) prefetch_l2(cur.src + (size_t)cp * CHUNK * MP + lane * 128);
+            }
             const int base = c * CHUNK + lane;
             if (c * CHUNK + CHUNK > count) {
 #pragma unroll
@@ -215,6 +224,11 @@ k_scan1(ScanArgs a) {
         };
         uint32_t wa[U][W];
         if (warp < nchunk) load_chunk(wa, warp);
+#pragma unroll
+        for (int pf = 1; pf < SCAN1_PF; ++pf) {
+            const int cp = warp + pf * SCAN_WARPS;
+            if (cp < nchunk && lane * 128 < CHUNK * MP) prefetch_l2(cur.src + (size_t)cp * CHUNK * MP + lane * 128);
+        }
         if (s_misc[0] >= SCAN_NO_BOUND) {                                  // (block-uniform: read after the barrier above)
             // no bound yet (the first items of a query all start at once): lane minima of the warp's first chunk only, then a
             // first bound; the chunk is evaluated again by the main loop, which then appends against that bound

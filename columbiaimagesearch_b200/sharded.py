@@ -40,6 +40,39 @@ class ShardedLOPQSearcher(object):
         self._stream = None
         self._pool = {}
         self._pool_next = 0
+        # lanes: the handle and its siblings (own stream + workspaces, shared model and index); asynchronous batches go
+        # round-robin over them, so the kernels and exchange waits of one batch overlap the scan of another
+        self._lanes = []
+        self._rr = 0
+        self.active_lanes = 0           # 0 = all lanes; n = only the first n (measurement passes that need un-overlapped kernels)
+
+    def _lane(self):
+        """(handle, torch stream) of the next asynchronous batch."""
+        import torch
+        if not self._lanes:
+            self._lanes = [[self._handle, None]]
+        n = len(self._lanes) if not self.active_lanes else max(1, min(len(self._lanes), int(self.active_lanes)))
+        lane = self._lanes[self._rr % n]
+        self._rr += 1
+        if lane[1] is None:
+            lane[1] = torch.cuda.ExternalStream(lane[0].stream(), device=self._tdev)
+            lane[0].set_async(True)
+        if self._stream is None:
+            self._stream = lane[1]                # (also the flag "the asynchronous pipeline has been used")
+        return lane
+
+    def enable_pipelining(self, lanes=2):
+        """Create `lanes - 1` sibling handles (b2l_create_sibling).  Call after the index is complete (finalize())."""
+        if self._dirty:
+            self.finalize()
+        if not self._lanes:
+            self._lanes = [[self._handle, None]]
+        while len(self._lanes) < lanes:
+            self._lanes.append([self._handle.create_sibling(), None])
+
+    def _sync_lanes(self):
+        for h, _ in (self._lanes or [[self._handle, None]]):
+            h.sync()
 
     # ---- index ------------------------------------------------------------------------------------
     def add_codes_arrays(self, coarse, fine, row_base=None):
@@ -96,26 +129,32 @@ class ShardedLOPQSearcher(object):
         and no NCCL call or host round trip remains on the search path.  Collective over the group (the 64-byte IPC
         handles are exchanged once, on the host).  `peers`: the other ShardedLOPQSearcher objects when the ranks are
         handles of ONE process (emulation / tests), listed in rank order; then call it on every one of them."""
-        h = self._handle
         world = self.world if peers is None else len(peers)
-        for p in ([self] if peers is None else peers):          # (one process: every window must exist before connecting)
-            if not getattr(p, "_peer_init", False):
-                p._handle.comm_init(world, p.rank, int(max_nq_home), int(max_k))
-                p._peer_init = True
-        if peers is not None:
-            h.comm_connect(pointers=[p._handle.comm_local_ptr() for p in peers])
-        elif world > 1:
-            mine, _ = h.comm_handle()
-            allh = [None] * world
-            self.dist.all_gather_object(allh, mine, group=self.group)
-            h.comm_connect(handles=allh)
-            self.dist.barrier(group=self.group)
+        if self._dirty:
+            self.finalize()
+        if not self._lanes:
+            self._lanes = [[self._handle, None]]
+        if peers is not None:                 # one process: every window must exist before connecting (single lane)
+            for p in peers:
+                if not getattr(p, "_peer_init", False):
+                    p._handle.comm_init(world, p.rank, int(max_nq_home), int(max_k))
+                    p._peer_init = True
+            self._handle.comm_connect(pointers=[p._handle.comm_local_ptr() for p in peers])
+        else:
+            mine = []
+            for h, _ in self._lanes:
+                h.comm_init(world, self.rank, int(max_nq_home), int(max_k))
+                mine.append(h.comm_handle()[0])
+            if world > 1:
+                allh = [None] * world
+                self.dist.all_gather_object(allh, mine, group=self.group)
+                for li, (h, _) in enumerate(self._lanes):
+                    h.comm_connect(handles=[allh[r][li] for r in range(world)])
+                self.dist.barrier(group=self.group)
         self._peer = True
         self._peer_world = world
-        h.set_async(True)
-        if self._stream is None and self._pipelined:
-            import torch
-            self._stream = torch.cuda.ExternalStream(h.stream(), device=self._tdev)
+        for h, _ in self._lanes:
+            h.set_async(True)
 
     def _home_buffers(self, nq_home, k, D):
         import torch
@@ -141,19 +180,19 @@ class ShardedLOPQSearcher(object):
         if limit is None:
             limit = quota
         k = int(max(1, min(int(limit), max(1, self.nb_indexed))))
-        h = self._handle
+        h, stream = self._lane()
         on_dev = hasattr(Xhome, "data_ptr")
         nq_home, D = int(Xhome.shape[0]), int(Xhome.shape[1])
         b = self._home_buffers(nq_home, k, D)
         if on_dev:
             assert Xhome.is_contiguous() and Xhome.dtype == torch.float32
-            self._stream.wait_stream(torch.cuda.current_stream(Xhome.device))
+            stream.wait_stream(torch.cuda.current_stream(Xhome.device))
             h.search_sharded(Xhome.data_ptr(), nq_home, quota, k, b["out_h"].data_ptr(), on_device=True)
         else:
             qh = b["q_h"].numpy()
             np.copyto(qh, Xhome, casting="same_kind")
             h.search_sharded(qh, nq_home, quota, k, b["out_h"].data_ptr())
-        b["event"].record(self._stream)
+        b["event"].record(stream)
         return _PendingHome(self, b, Xhome, nq_home, k, quota)
 
     def _redo_home(self, out, Xhome, quota, k, mine):
@@ -174,7 +213,7 @@ class ShardedLOPQSearcher(object):
         if not local.size:
             return 0, 0
         h = self._handle
-        h.sync()
+        self._sync_lanes()
         h.set_async(False)
         try:
             n32 = nex = 0
@@ -256,10 +295,7 @@ class ShardedLOPQSearcher(object):
         if limit is None:
             limit = quota
         k = int(max(1, min(int(limit), max(1, self.nb_indexed))))
-        h = self._handle
-        if self._stream is None:
-            self._stream = torch.cuda.ExternalStream(h.stream(), device=self._tdev)
-            h.set_async(True)
+        h, stream = self._lane()
         on_dev = hasattr(X, "data_ptr")
         nq, D = int(X.shape[0]), int(X.shape[1])
         b = self._buffers(nq, k, D)
@@ -269,20 +305,20 @@ class ShardedLOPQSearcher(object):
         # torch only sees that stream for the all-gather and the completion event.
         if on_dev:
             assert X.is_contiguous() and X.dtype == torch.float32
-            self._stream.wait_stream(torch.cuda.current_stream(X.device))
+            stream.wait_stream(torch.cuda.current_stream(X.device))
             h.search_local(X.data_ptr(), quota, k, b["rec"].data_ptr(), exact=False, on_device=True, nq=nq)
         else:
             qh = b["q_h"].numpy()
             np.copyto(qh, X, casting="same_kind")
             h.search_local(qh, quota, k, b["rec"].data_ptr(), exact=False)
         if self.world > 1:
-            with torch.cuda.stream(self._stream):
+            with torch.cuda.stream(stream):
                 self.dist.all_gather_into_tensor(b["allrec"], b["rec"], group=self.group)
             allrec = b["allrec"]
         else:
             allrec = b["rec"]
         h.search_merge_block(allrec.data_ptr(), self.world, nq, k, base, on_device=False)      # one copy, same layout as `offs`
-        b["event"].record(self._stream)
+        b["event"].record(stream)
         return _PendingSearch(self, b, X, nq, k, quota)
 
     def search_batch(self, X, quota=10, limit=None):
@@ -304,7 +340,7 @@ class ShardedLOPQSearcher(object):
             limit = quota
         k = int(max(1, min(int(limit), max(1, self.nb_indexed))))
         if self._stream is not None:
-            self._handle.sync()
+            self._sync_lanes()
             self._handle.set_async(False)
         try:
             return self._search_batch_sync_impl(X, quota, k)
@@ -334,6 +370,14 @@ class ShardedLOPQSearcher(object):
     def stats(self):
         return self._handle.stats()
 
+    def lane_stats(self):
+        """statistics of every lane (the handle and its siblings)"""
+        return [h.stats() for h, _ in (self._lanes or [[self._handle, None]])]
+
+    def reset_stats(self):
+        for h, _ in (self._lanes or [[self._handle, None]]):
+            h.reset_stats()
+
     def _redo_chain(self, out, Xsel, redo, quota, k):
         """Uncertified queries (the same set on every rank: the flags come from the gathered buffers) are re-run with
         float32 tables, and what is still uncertified with the float64 full sort; rows of `out` are patched.  `Xsel(idx)`
@@ -358,11 +402,17 @@ class ShardedLOPQSearcher(object):
         h = getattr(self, "_handle", None)
         if h is not None and self._stream is not None:
             try:
-                h.sync()
+                self._sync_lanes()
             except Exception:
                 pass
         self._pool = {}
         self._stream = None
+        for sib, _ in getattr(self, "_lanes", [])[1:]:          # siblings go before the parent handle
+            try:
+                sib.close()
+            except Exception:
+                pass
+        self._lanes = self._lanes[:1] if getattr(self, "_lanes", None) else []
 
     def __del__(self):
         try:
@@ -398,7 +448,7 @@ class _PendingSearch(object):
         if redo.size:
             X = self.X
             sel = (lambda idx: X[idx].cpu().numpy()) if hasattr(X, "data_ptr") else (lambda idx: np.asarray(X)[idx])
-            s._handle.sync()
+            s._sync_lanes()
             s._handle.set_async(False)
             try:
                 n32, nex = s._redo_chain(out, sel, redo, self.quota, k)

@@ -38,6 +38,10 @@ typedef struct b2l_ctx* b2l_handle;
 /* ---- lifecycle ---------------------------------------------------------------------------- */
 int         b2l_create(int device, b2l_handle* out);
 int         b2l_destroy(b2l_handle h);
+/* A second handle on the same device sharing the parent's model and (finalised) index, with its own stream and workspaces:
+ * batches issued alternately on a handle and its siblings overlap on the GPU.  While siblings exist the family's model and
+ * index are frozen (mutating calls return B2L_ERR_STATE).  Destroy siblings before the parent. */
+int         b2l_create_sibling(b2l_handle parent, b2l_handle* out);
 /* h may be NULL: returns the text of the last failure of b2l_create. */
 const char* b2l_last_error(b2l_handle h);
 /* library ABI version (bumped on any signature change) */
