@@ -558,7 +558,16 @@ def run_search(a):
             for b in range(reps):
                 searcher.search_batch(global_batch(b % nb), quota=qv, limit=k)
             dt = (time.perf_counter() - t0) / reps
+            handle.set_async(False)
+            import torch as _t
+            rec = _t.empty(handle.records_bytes(G, k), dtype=_t.uint8, device=dev)
+            handle.search_local(global_batch(0).cpu().numpy(), qv, k, rec.data_ptr(), exact=0)      # one plain fast-path pass: its statistics
             st = handle.stats()
+            app, bnd = handle.debug_candidates(G)
+            cert = handle.search_merge(rec.data_ptr(), 1, G, k)["certified"] if world == 1 else None
+            st["cand_appended"] = {"mean": float(app.mean()), "p50": float(np.median(app)), "p99": float(np.percentile(app, 99)),
+                                   "max": int(app.max()), "over_cap": int((app > 8192).sum())}
+            st["uncertified_first_pass"] = None if cert is None else int((cert == 0).sum())
             if rank == 0:
                 print(json.dumps({"quota": qv, "recall@10": r10, "recall@1": r1, "cells_visited": vis, "codes_per_query_local": cand,
                                   "qps": G / dt, "ms_per_batch": dt * 1e3, "stats": st}))
@@ -734,7 +743,8 @@ def run_search(a):
                                         "database); exchange = %s" % (nq, "peer-mapped windows inside the library" if peer else "NCCL all-gather"))
                            if world > 1 else "single GPU",
                            "lanes": a.lanes, "model_train_s": train_s},
-                "recall@10": r10, "recall@1": r1, "cells_visited_per_query": vis, "codes_ranked_per_query": cand * world if world > 1 else cand,
+                "recall@10": r10, "recall@1": r1, "cells_visited_per_query": vis,
+                "codes_ranked_per_query": scan_bytes / timed_calls / M / G * world,
                 "wall_s_timed_region": wall_s, "value_sustained": sustained, "strong": strong,
                 "e2e": {"value": a.steps * G / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                         "api": "%s, 2 batches in flight, pinned host queries in / host results out every step"

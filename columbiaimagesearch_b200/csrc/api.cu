@@ -188,10 +188,15 @@ template <int MP> int launch_scan_pk(b2l_handle h, const ScanArgs& a) {
 template <int MP> int launch_scan1(b2l_handle h, const ScanArgs& a) {
     const size_t smem = scan1_smem_bytes<MP>(a.E);
     if (smem > 227 * 1024) FAIL(B2L_ERR_UNSUPPORTED, "scan shared memory %zu too large", smem);
-    CU(cudaFuncSetAttribute(k_scan1<MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int occ = 1;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_scan1<MP>, SCAN_THREADS, smem));
-    if (occ < 1) occ = 1;
+    static thread_local size_t cfg_smem = 0;          // attribute + occupancy query once per shared-memory size (host latency
+    static thread_local int cfg_occ = 0, cfg_dev = -1; //  in front of a single-query scan is comparable to the scan itself)
+    if (cfg_smem != smem || cfg_dev != h->device) {
+        CU(cudaFuncSetAttribute(k_scan1<MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int o = 1;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_scan1<MP>, SCAN_THREADS, smem));
+        cfg_occ = o < 1 ? 1 : o; cfg_smem = smem; cfg_dev = h->device;
+    }
+    const int occ = cfg_occ;
     const unsigned grid = (unsigned)(h->num_sms * occ);
     k_scan1<MP><<<grid, SCAN_THREADS, smem, h->stream>>>(a);
     LAUNCHED();

@@ -267,7 +267,9 @@ k_scan1(ScanArgs a) {
                 if (keep && gb < (unsigned)a.cand_cap) a.cand[(size_t)cur.q * a.cand_cap + gb] = stage[i] + cur.posbase;
             }
             // leave the table to other blocks only when this block moves on to another query (or stops)
-            if (!(nxt < n_items && nx.q == cur.q)) {
+            // (and only if some item can still start later: with at most one item per resident block nobody would read it,
+            //  and hundreds of blocks finishing together would queue up on the query's 256 table words)
+            if (!(nxt < n_items && nx.q == cur.q) && n_items > gridDim.x) {
                 for (int e = tid; e < a.E; e += SCAN_THREADS) {
                     const float v = tab[e];
                     if (__float_as_uint(v) <= thr) atomicMin((unsigned int*)&a.gtab[(size_t)cur.q * a.E + e], __float_as_uint(v));
