@@ -65,6 +65,7 @@ def parse():
     p.add_argument("--emulate-shard", type=int, default=0, help="profiling aid (1 process): act as rank 0 of an N-way cell-sharded index")
     p.add_argument("--sweep", default="", help="comma-separated quotas: print recall/QPS per quota and exit")
     p.add_argument("--ntrain", type=int, default=20000, help="c3: training vectors of the 2048-d model")
+    p.add_argument("--kp", type=int, default=0, help="b2l_set_preselect: minimum width of the float64 re-rank (0 = default)")
     p.add_argument("--lanes", type=int, default=2, help="handles (own stream + workspaces, shared index) the batches alternate over")
     a = p.parse_args()
     cfg = dict(CONFIGS[a.config])
@@ -523,6 +524,9 @@ def run_search(a):
         searcher.finalize()
     handle = searcher._handle
     peer = world > 1 and a.exchange == "peer"
+    kp = a.kp if a.kp else cfg.get("kp", 0)
+    if kp:
+        handle.set_preselect(kp)                            # (before the siblings are created: they inherit it)
     if a.lanes > 1:
         searcher.enable_pipelining(a.lanes)
     if peer:
@@ -742,7 +746,7 @@ def run_search(a):
                            "sharding": ("cells by (c0+c1) mod N; every rank brings %d home queries per step (weak scaling over a fixed "
                                         "database); exchange = %s" % (nq, "peer-mapped windows inside the library" if peer else "NCCL all-gather"))
                            if world > 1 else "single GPU",
-                           "lanes": a.lanes, "model_train_s": train_s},
+                           "lanes": a.lanes, "preselect_kp_min": kp, "model_train_s": train_s},
                 "recall@10": r10, "recall@1": r1, "cells_visited_per_query": vis,
                 "codes_ranked_per_query": scan_bytes / timed_calls / M / G * world,
                 "wall_s_timed_region": wall_s, "value_sustained": sustained, "strong": strong,

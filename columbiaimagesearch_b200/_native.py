@@ -71,6 +71,7 @@ SIGNATURES = {
     "b2l_get_stats": (_i, [_h, C.POINTER(Stats)]),
     "b2l_reset_stats": (_i, [_h]),
     "b2l_set_scan_mode": (_i, [_h, _i]),
+    "b2l_set_preselect": (_i, [_h, _i]),
     "b2l_set_async": (_i, [_h, _i]),
     "b2l_sync": (_i, [_h]),
     "b2l_debug_force_redo": (_i, [_h, _i]),
@@ -381,6 +382,10 @@ class Handle(object):
     def set_scan_mode(self, mode):
         """0: 16-bit packed tables first (default); 1: float32 tables only."""
         self._check(self.lib.b2l_set_scan_mode(self.h, int(mode)))
+
+    def set_preselect(self, kp_min):
+        """at least kp_min candidates per query re-ranked in float64 (0: default k + 8 rounded up to a power of two)"""
+        self._check(self.lib.b2l_set_preselect(self.h, int(kp_min)))
 
     def set_async(self, enabled):
         self._check(self.lib.b2l_set_async(self.h, int(bool(enabled))))

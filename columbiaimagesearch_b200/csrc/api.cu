@@ -109,6 +109,7 @@ struct b2l_ctx {
     int fine_mode = 0;                 // 0: float32 first stage + float64 guard in the fine argmin, 1: float64 only
     unsigned long long* d_nguard = nullptr;   // sub-vectors the guard re-evaluated in float64 (device counter)
     int scan_mode = 0;                 // 0: packed 16-bit tables first (default), 1: float32 tables only
+    int kp_min = 0;                    // lower limit of the preselection width KP (0: k + 8 rounded up to a power of two)
     void* h_out = nullptr;             // pinned staging of the search outputs
     size_t h_out_cap = 0;
     // sibling handles (b2l_create_sibling): own stream and workspaces, the parent's model and index
@@ -787,7 +788,11 @@ int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_
     }
     if (largev) return search_large_impl(h, x, xf64, nq, quota, k, d_records);
     // fast path eligibility: the bound table of the scan needs >= KP entries per slot
-    const int KP = std::max(16, next_pow2(k + 8));
+    // KP = how many candidates of the preselection are re-ranked in float64 (power of two >= k + 8).  A wider KP certifies
+    // more queries at the first stage when distances are concentrated (high-dimensional data, coarse 16-bit tables at
+    // M = 32) at the price of a longer selection; b2l_set_preselect overrides the default.
+    int KP = std::max(16, next_pow2(k + 8));
+    if (h->kp_min > 0) KP = std::min(512, std::max(KP, next_pow2(h->kp_min)));
     const bool lowb_shape = nq <= SCAN1_MAX_NQ && h->scan_mode != 1 && h->scan_mode != 2 && exact == 0 && mv.MP >= 8 && mv.G > 0;
     const int LPS = lowb_shape ? 32 * SCAN_WARPS : mv.MP * SCAN_WARPS;
     const int GEN = std::max(1, KP / std::max(1, LPS));
@@ -1216,7 +1221,7 @@ int b2l_create_sibling(b2l_handle p, b2l_handle* out) {
     rc = b2l_create(p->device, &s);
     if (rc) { p->err = g_create_error; return rc; }
     s->has_model = true; s->has_pca = p->has_pca; s->mv = p->mv; s->c2m = p->c2m;
-    s->fine_mode = p->fine_mode; s->scan_mode = p->scan_mode;
+    s->fine_mode = p->fine_mode; s->scan_mode = p->scan_mode; s->kp_min = p->kp_min;
     DevBuf* src[] = {&p->dCs, &p->dmus, &p->dRt, &p->dsubs, &p->dsubs32, &p->dsubs32T, &p->dc2max, &p->dP, &p->dpmu, &p->m_coarse, &p->m_fine,
                      &p->m_rowid, &p->codes, &p->rowids, &p->cell_start, &p->lsize, &p->gsize, &p->sorted_first, &p->d_ucell, &p->d_ustart,
                      &p->d_hkeys, &p->d_hvals};
@@ -1297,6 +1302,13 @@ int b2l_set_scan_mode(b2l_handle h, int mode) {
     if (!h || mode < 0 || mode > 2) return B2L_ERR_ARG;
     std::lock_guard<std::mutex> lk(h->mu);
     h->scan_mode = mode;
+    return B2L_OK;
+}
+
+int b2l_set_preselect(b2l_handle h, int kp_min) {
+    if (!h || kp_min < 0 || kp_min > 512) return B2L_ERR_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->kp_min = kp_min;
     return B2L_OK;
 }
 

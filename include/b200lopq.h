@@ -211,6 +211,10 @@ int b2l_reset_stats(b2l_handle h);
  * word; queries whose float64 order cannot be proven are re-run with float32 tables, then exactly.  1: float32 tables only
  * (batched kernel).  2: as 0 without the low-batch kernel. */
 int b2l_set_scan_mode(b2l_handle h, int mode);
+/* Width of the preselection: at least kp_min (<= 512) candidates per query are re-ranked in float64 (default 0: k + 8 rounded
+ * up to a power of two).  Results do not depend on it; a wider preselection certifies more queries at the first stage when
+ * distances are concentrated (few go down the fallback chain) and costs a longer selection kernel. */
+int b2l_set_preselect(b2l_handle h, int kp_min);
 /* Asynchronous mode (pipelined / multi-GPU searches).  While enabled, b2l_search_local and b2l_search_merge only
  * enqueue their work (including the copies from / to host buffers, which must then be PINNED and stay alive) on the
  * handle's stream and return; the caller orders other work against that stream (b2l_stream) and waits for it
