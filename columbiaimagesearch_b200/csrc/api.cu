@@ -95,7 +95,7 @@ struct b2l_ctx {
     unsigned int nu = 0, hmask = 0, max_run = 0;
     // workspaces
     DevBuf w_q, w_xq, w_px, w_coarse, w_fine, w_lut32, w_lut64, w_p64, w_cellq, w_cand, w_gtab, w_lut16, w_quant, w_plan, w_sort_a, w_sort_b,
-        w_sort_tmp, w_rec, w_rec2, w_out, w_out2, w_misc, w_bkt, w_perm;
+        w_sort_tmp, w_rec, w_rec2, w_out, w_out2, w_misc, w_bkt, w_perm, w_need2;
     PlanView pv = {};
     unsigned int* gthr = nullptr;      // [nq] per-query pruning bound shared by the scan blocks
     unsigned int* cand_cnt = nullptr;  // [nq] candidates the scan appended
@@ -1034,10 +1034,20 @@ int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_
         CU(cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         RecRoute route = {};
         if (route_in) route = *route_in; else { route.base[0] = (unsigned char*)d_records; route.nq_home = nq; }
+        CU(h->w_need2.reserve((size_t)nq));
         k_select<<<nq, SEL_THREADS, smem, h->stream>>>(mv, ix, pv, h->w_cand.as<unsigned long long>(), h->cand_cnt, h->gthr,
                                                        cand_cap, h->w_p64.as<double>(), KP, k, eps_rel, route,
-                                                       packed ? 1 : 0, qv.B, qv.delta, qv.slack);
+                                                       packed ? 1 : 0, qv.B, qv.delta, qv.slack, h->w_need2.as<uint8_t>());
         LAUNCHED();
+        if (k <= SEL2_LIST) {
+            // second chance of the queries the KP best could not certify (near-ties): every appended candidate, exactly
+            const size_t sm2 = select2_smem_bytes();
+            CU(cudaFuncSetAttribute(k_select2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+            k_select2<<<nq, 256, sm2, h->stream>>>(mv, ix, pv, h->w_cand.as<unsigned long long>(), h->cand_cnt, h->gthr, cand_cap,
+                                                   h->w_p64.as<double>(), k, eps_rel, route, packed ? 1 : 0, qv.B, qv.delta, qv.slack,
+                                                   h->w_need2.as<uint8_t>());
+            LAUNCHED();
+        }
         h->cr->st.packed = packed ? 1 : 0;
         CU(cudaEventRecord(h->cr->ev[4], h->stream));
     } else {
@@ -1186,7 +1196,7 @@ int b2l_destroy(b2l_handle h) {
     DevBuf* bufs[] = {&h->dCs, &h->dmus, &h->dRt, &h->dsubs, &h->dsubs32, &h->dsubs32T, &h->dc2max, &h->dP, &h->dpmu, &h->m_coarse, &h->m_fine, &h->m_rowid, &h->codes,
                       &h->rowids, &h->cell_start, &h->lsize, &h->gsize, &h->sorted_first, &h->w_q, &h->w_xq, &h->w_px,
                       &h->w_coarse, &h->w_fine, &h->w_lut32, &h->w_lut64, &h->w_p64, &h->w_cellq, &h->w_cand, &h->w_gtab, &h->w_lut16, &h->w_quant, &h->w_plan,
-                      &h->w_sort_a, &h->w_sort_b, &h->w_sort_tmp, &h->w_rec, &h->w_rec2, &h->w_out, &h->w_out2, &h->w_misc, &h->w_bkt, &h->w_perm, &h->d_ucell, &h->d_ustart, &h->d_hkeys, &h->d_hvals, &h->w_walk, &h->w_walk2};
+                      &h->w_sort_a, &h->w_sort_b, &h->w_sort_tmp, &h->w_rec, &h->w_rec2, &h->w_out, &h->w_out2, &h->w_misc, &h->w_bkt, &h->w_perm, &h->w_need2, &h->d_ucell, &h->d_ustart, &h->d_hkeys, &h->d_hvals, &h->w_walk, &h->w_walk2};
     for (DevBuf* b : bufs) b->release();
     if (h->h_out) cudaFreeHost(h->h_out);
     if (h->d_nguard) cudaFree(h->d_nguard);

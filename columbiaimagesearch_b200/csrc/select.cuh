@@ -113,7 +113,8 @@ __global__ void __launch_bounds__(SEL_THREADS, 8)
 k_select(ModelView mv, IndexView ix, PlanView pv, const unsigned long long* __restrict__ cand,
          const unsigned int* __restrict__ cand_cnt, const unsigned int* __restrict__ gthr, int cand_cap,
          const double* __restrict__ P64, int KP, int k, double eps_rel, RecRoute route,
-         int packed, const double* __restrict__ qB, const double* __restrict__ qDelta, const double* __restrict__ qSlack) {
+         int packed, const double* __restrict__ qB, const double* __restrict__ qDelta, const double* __restrict__ qSlack,
+         uint8_t* __restrict__ need2) {
     extern __shared__ __align__(16) unsigned char sm_sel[];
     unsigned long long* keys = (unsigned long long*)sm_sel;
     unsigned long long* dk = keys + SEL_LIST;
@@ -133,6 +134,7 @@ k_select(ModelView mv, IndexView ix, PlanView pv, const unsigned long long* __re
         if (tid == 0) {
             rv.lb[ql] = __longlong_as_double(0x7FF0000000000000ll);
             rv.count[ql] = 0; rv.visited[ql] = pv.nvis[q]; rv.ncand[ql] = pv.ncand[q];
+            if (need2) need2[q] = 0;
         }
         return;
     }
@@ -288,6 +290,130 @@ k_select(ModelView mv, IndexView ix, PlanView pv, const unsigned long long* __re
         rv.count[ql] = nout;
         rv.visited[ql] = nv;
         rv.ncand[ql] = pv.ncand[q];
+        // Locally not certifiable from the KP best (near-ties between the k-th and the KP-th candidate: concentrated
+        // distances) but nothing was lost: k_select2 re-ranks EVERY appended candidate of the query exactly, which moves the
+        // bound of "everything not looked at" from the KP-th best out to the scan's final bound.
+        if (need2) {
+            const bool okl = (nout == k) ? (__longlong_as_double((long long)dk[k - 1]) < lb)
+                                         : !(lb < __longlong_as_double(0x7FF0000000000000ll));
+            need2[q] = (!okl && !lost) ? 1 : 0;
+        }
+    }
+}
+
+// Second chance for the queries k_select flagged (a handful per batch, or none: every other block leaves at once).
+// All candidates the scan appended with key <= the final bound (at most SEL2_LIST, else the query stays as it is and goes
+// down the fallback chain) are evaluated in float64 and sorted by (dist64, retrieval position); every code that was NOT
+// appended has a key above the bound, so the certification bound is that of the bound itself.
+// dynamic smem: dk[SEL2_LIST] u64 | rows[SEL2_LIST] i64 | part[SEL_PART] f64 | pk[SEL2_LIST] u32 | idx[SEL2_LIST] int | vis[SEL2_LIST] int
+#define SEL2_LIST 1024
+__host__ __device__ inline size_t select2_smem_bytes() { return (size_t)SEL2_LIST * 28 + (size_t)SEL_PART * 8 + 64; }
+
+__global__ void __launch_bounds__(256)
+k_select2(ModelView mv, IndexView ix, PlanView pv, const unsigned long long* __restrict__ cand,
+          const unsigned int* __restrict__ cand_cnt, const unsigned int* __restrict__ gthr, int cand_cap,
+          const double* __restrict__ P64, int k, double eps_rel, RecRoute route,
+          int packed, const double* __restrict__ qB, const double* __restrict__ qDelta, const double* __restrict__ qSlack,
+          const uint8_t* __restrict__ need2) {
+    const int q = blockIdx.x, tid = threadIdx.x;
+    if (!need2[q]) return;
+    extern __shared__ __align__(16) unsigned char sm_sel2[];
+    unsigned long long* dk = (unsigned long long*)sm_sel2;
+    int64_t* rows = (int64_t*)(dk + SEL2_LIST);
+    double* part = (double*)(rows + SEL2_LIST);
+    unsigned int* pk = (unsigned int*)(part + SEL_PART);
+    int* idx = (int*)(pk + SEL2_LIST);
+    int* visv = idx + SEL2_LIST;
+    __shared__ int s_n;
+    const int qh = q / route.nq_home, ql = q - qh * route.nq_home;
+    RecView rv = rec_view(route.base[qh], route.nq_home, k, mv.M);
+    const unsigned int appended = cand_cnt[q];
+    if (appended > (unsigned int)cand_cap) return;                    // (k_select already marked it lost)
+    const int n = (int)appended;
+    const unsigned int bound = gthr[q];
+    const unsigned long long* src = cand + (size_t)q * cand_cap;
+    if (tid == 0) s_n = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += blockDim.x) {
+        const unsigned long long key = src[i];
+        if ((unsigned int)(key >> 32) <= bound) {
+            const int j = atomicAdd(&s_n, 1);
+            if (j < SEL2_LIST) { pk[j] = (unsigned int)(key & 0xFFFFFFFFull); }
+        }
+    }
+    __syncthreads();
+    const int nl = s_n;
+    if (nl > SEL2_LIST || nl < 1) return;                             // too many to take here: the fallback chain handles it
+    int np2 = 1;
+    while (np2 < nl) np2 <<= 1;
+    const int nv = pv.nvis[q];
+    const int64_t o = (int64_t)q * pv.maxvis;
+    for (int i = tid; i < np2; i += blockDim.x) {
+        dk[i] = 0x7FF0000000000000ull;
+        idx[i] = i;
+        rows[i] = -1;
+        visv[i] = -1;
+        if (i >= nl) { pk[i] = 0xFFFFFFFFu; continue; }
+        const unsigned int pos = pk[i];
+        int v = -1;
+        for (int t = 0; t < nv; ++t) {
+            if (pv.vis_pbase[o + t] >= 0) {
+                const int64_t b = pv.vis_base[o + t];
+                if ((int64_t)pos >= b && (int64_t)pos < b + ix.lsize[pv.vis_cell[o + t]]) { v = t; break; }
+            }
+        }
+        if (v < 0) { pk[i] = 0xFFFFFFFFu; continue; }
+        rows[i] = ix.cell_start[pv.vis_cell[o + v]] + ((int64_t)pos - pv.vis_base[o + v]);
+        visv[i] = v;
+    }
+    __syncthreads();
+    const int M = mv.M, CH = SEL_PART / M;
+    for (int i0 = 0; i0 < nl; i0 += CH) {
+        const int nc = min(CH, nl - i0);
+        for (int t = tid; t < nc * M; t += blockDim.x) {
+            const int i = i0 + t / M, j = t % M;
+            if (rows[i] >= 0) {
+                const int v = visv[i];
+                const int64_t incell = (int64_t)pk[i] - pv.vis_base[o + v];
+                const int s = j / mv.m;
+                const double* p = P64 + (int64_t)(s ? pv.vis_lut1[o + v] : pv.vis_lut0[o + v]) * mv.h + (j - s * mv.m) * mv.ds;
+                const double* c = mv.subs + ((int64_t)j * mv.K + code_byte(ix.codes + rows[i] * mv.MP, incell, j, mv.SW)) * mv.ds;
+                part[t] = sqdist_np<double>(p, c, mv.ds);
+            }
+        }
+        __syncthreads();
+        for (int i = i0 + tid; i < i0 + nc; i += blockDim.x) {
+            if (rows[i] >= 0) {
+                const double* e = part + (i - i0) * M;
+                double acc = e[0];
+                for (int j = 1; j < M; ++j) acc = __dadd_rn(acc, e[j]);
+                dk[i] = (unsigned long long)__double_as_longlong(acc);
+            }
+        }
+        __syncthreads();
+    }
+    bitonic_sort_dp(dk, pk, idx, np2);
+    const int nout = min(k, nl);
+    for (int i = tid; i < nout; i += blockDim.x) {
+        const int sidx = idx[i];
+        const int64_t row = rows[sidx];
+        const int v = visv[sidx];
+        const int64_t e = (int64_t)ql * k + i;
+        rv.d64[e] = __longlong_as_double((long long)dk[i]);
+        rv.pos[e] = pk[i];
+        rv.rowid[e] = ix.rowids[row];
+        rv.cell[e] = pv.vis_cell[o + v];
+        const int64_t incell = (int64_t)pk[i] - pv.vis_base[o + v];
+        for (int j = 0; j < mv.M; ++j) rv.fine[e * mv.M + j] = code_byte(ix.codes + row * mv.MP, incell, j, mv.SW);
+    }
+    if (tid == 0) {
+        double lb = __longlong_as_double(0x7FF0000000000000ll);
+        if (pv.ncand_local[q] > (int64_t)nl) {                        // codes that were never appended: key >= bound + 1 (packed) / > bound
+            if (packed) lb = (qB[q] + qDelta[q] * (double)bound - qSlack[q]) * (1.0 - 1e-6) - 1e-300;
+            else lb = (double)__uint_as_float(bound) * (1.0 - eps_rel) - 1e-300;
+        }
+        rv.lb[ql] = lb;
+        rv.count[ql] = nout;
     }
 }
 
