@@ -857,11 +857,13 @@ int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_
     }
     if (packed) {
         const size_t o_qmin = 0, o_qmax = align256((size_t)nq * mv.M * 4), o_B = o_qmax + align256((size_t)nq * 4),
-                     o_dl = o_B + align256((size_t)nq * 8), o_sl = o_dl + align256((size_t)nq * 8), qbytes = o_sl + align256((size_t)nq * 8);
+                     o_dl = o_B + align256((size_t)nq * 8), o_sl = o_dl + align256((size_t)nq * 8), o_mg = o_sl + align256((size_t)nq * 8),
+                     qbytes = o_mg + align256((size_t)nq * 4);
         CU(h->w_quant.reserve(qbytes));
         unsigned char* qb = h->w_quant.as<unsigned char>();
         qv.qmin = (unsigned int*)(qb + o_qmin); qv.qmax = (unsigned int*)(qb + o_qmax);
         qv.B = (double*)(qb + o_B); qv.delta = (double*)(qb + o_dl); qv.slack = (double*)(qb + o_sl); qv.qmax_code = 65535 / mv.M;
+        qv.margin = (unsigned int*)(qb + o_mg);
         qv.ds = mv.ds; qv.c2m = h->c2m;
         // float32 table entries (their error is part of the certification bound): the register-resident kernel of the
         // headline shape, or the generic one behind the grouped rotation GEMM of large models
@@ -1011,6 +1013,7 @@ int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_
             a.gthr = h->gthr; a.gtab = h->w_gtab.as<float>();
             a.lut16 = packed ? h->w_lut16.as<unsigned short>() : nullptr; a.qfill = (unsigned)qv.qmax_code;
             a.cand_cap = cand_cap;
+            a.qmargin = packed ? qv.margin : nullptr;
             if (lowb) {
                 switch (mv.MP) {
                     case 8: rc = launch_scan1<8>(h, a); break;
@@ -1037,7 +1040,8 @@ int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_
         CU(h->w_need2.reserve((size_t)nq));
         k_select<<<nq, SEL_THREADS, smem, h->stream>>>(mv, ix, pv, h->w_cand.as<unsigned long long>(), h->cand_cnt, h->gthr,
                                                        cand_cap, h->w_p64.as<double>(), KP, k, eps_rel, route,
-                                                       packed ? 1 : 0, qv.B, qv.delta, qv.slack, h->w_need2.as<uint8_t>());
+                                                       packed ? 1 : 0, qv.B, qv.delta, qv.slack, h->w_need2.as<uint8_t>(),
+                                                       packed ? qv.margin : nullptr);
         LAUNCHED();
         if (k <= SEL2_LIST) {
             // second chance of the queries the KP best could not certify (near-ties): every appended candidate, exactly
@@ -1045,7 +1049,7 @@ int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_
             CU(cudaFuncSetAttribute(k_select2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
             k_select2<<<nq, 256, sm2, h->stream>>>(mv, ix, pv, h->w_cand.as<unsigned long long>(), h->cand_cnt, h->gthr, cand_cap,
                                                    h->w_p64.as<double>(), k, eps_rel, route, packed ? 1 : 0, qv.B, qv.delta, qv.slack,
-                                                   h->w_need2.as<uint8_t>());
+                                                   h->w_need2.as<uint8_t>(), packed ? qv.margin : nullptr);
             LAUNCHED();
         }
         h->cr->st.packed = packed ? 1 : 0;

@@ -591,6 +591,8 @@ struct QuantView {
     double* B;              // [nq]
     double* delta;          // [nq]
     double* slack;          // [nq] M * (bound on the evaluation error of a table entry); 0 for the float64-built tables
+    unsigned int* margin;   // [nq] the scan appends candidates up to (bound + margin) code units: wide enough that re-ranking
+                            //      every appended candidate exactly always certifies the first k (see k_select2)
     int qmax_code;          // QMAX
     int f32_entries;        // the tables were evaluated in float32 (k_lut_f32)
     int ds;                 // sub-vector length
@@ -654,6 +656,11 @@ k_lut_quant(int m, const int32_t* __restrict__ lut_desc, const PlanCounters* __r
                 slack = (double)M * ((double)(8.0f * 5.9604645e-08f) * ((double)sqrtf(emax * S2) + (double)qv.ds * (double)emax) * 1.01 + 1e-13 * (double)S2);
             }
             qv.slack[q] = slack;
+            // A candidate with code sum S has a float32 table sum in [B + Delta*S, B + Delta*(S + M)) (each floor loses < 1 unit),
+            // known to +-slack.  With every candidate up to bound + margin re-ranked exactly, the KP >= k candidates of smallest
+            // S (all <= bound) have exact distances < B + Delta*(bound + M) + slack, and everything not appended is
+            // > B + Delta*(bound + margin) - slack: margin > M + 2*slack/Delta makes the first k certifiable by construction.
+            qv.margin[q] = (unsigned int)min(8192.0, (double)M + ceil(2.0 * slack / delta) + 2.0);
             s_inv = (float)(1.0 / delta);
         }
         if (threadIdx.x < m) {

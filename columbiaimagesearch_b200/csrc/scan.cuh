@@ -51,6 +51,7 @@ struct ScanArgs {
     int ncell, nflat, KP, m, M;
     int E, GEN;                     // bound table: E = MP*SCAN_WARPS*GEN entries per slot (>= KP), GEN generations per lane
     int cand_cap;                   // capacity of a query's candidate list (k_scan1; the others use SCAN_CAND_CAP)
+    const unsigned int* qmargin;    // [nq] packed scan: candidates are appended up to bound + qmargin[q] (NULL: 0)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

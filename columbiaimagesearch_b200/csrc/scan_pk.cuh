@@ -17,7 +17,7 @@
 template <int MP>
 size_t scan_pk_smem_bytes(int E) {
     typedef ScanCfg<MP> C;
-    return (size_t)C::LUT_BYTES + (size_t)4 * C::G * SCAN_STAGE * 4 + (size_t)4 * C::G * E * 4 + 6 * 32 * 4 + 256;
+    return (size_t)C::LUT_BYTES + (size_t)4 * C::G * SCAN_STAGE * 4 + (size_t)4 * C::G * E * 4 + 7 * 32 * 4 + 256;
 }
 
 template <int OFF> __device__ __forceinline__ uint32_t lds_lut_u(uint32_t o) {
@@ -115,7 +115,8 @@ k_scan_pk(ScanArgs a) {
     int* s_lut0 = (int*)(s_posbase + 32);                          // [32] table of split 0 (-1 = empty)
     int* s_lut1 = s_lut0 + 32;                                     // [32]
     unsigned int* s_nst = (unsigned int*)(s_lut1 + 32);            // [32] keys staged per slot
-    unsigned int* s_item = s_nst + 32;
+    unsigned int* s_mrg = s_nst + 32;                              // [32] append margin of the slot's query (code units)
+    unsigned int* s_item = s_mrg + 32;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane / MP, jl = lane % MP;
@@ -184,9 +185,11 @@ k_scan_pk(ScanArgs a) {
                 s_posbase[tid] = (unsigned int)(pv.vis_base[o] + first);
                 s_q[tid] = qv.x;
                 s_thr[tid] = *(volatile unsigned int*)&a.gthr[qv.x];
+                s_mrg[tid] = a.qmargin ? a.qmargin[qv.x] : 0u;
                 s_nst[tid] = 0u;
             } else {
                 s_nst[tid] = 0u;
+                s_mrg[tid] = 0u;
                 s_lut0[tid] = -1; s_lut1[tid] = -1; s_posbase[tid] = 0; s_q[tid] = -1;
                 s_thr[tid] = 0u;                                   // an empty slot sums to M * QMAX > 0: nothing passes
             }
@@ -286,7 +289,9 @@ k_scan_pk(ScanArgs a) {
         // One chunk: the table sums, then -- as soon as the code registers are dead -- the loads of the warp's next chunk,
         // whose latency hides behind the bound / candidate logic below (three blocks per SM cover the rest).
         auto eval_chunk = [&](uint32_t (&w)[U][W], int c) {
-            const unsigned int t0 = s_thr[sl0], t1 = s_thr[sl1], t2 = s_thr[sl2], t3 = s_thr[sl3];
+            // append threshold = bound + margin (the bounds themselves are refreshed without it)
+            const unsigned int t0 = s_thr[sl0] + s_mrg[sl0], t1 = s_thr[sl1] + s_mrg[sl1], t2 = s_thr[sl2] + s_mrg[sl2],
+                               t3 = s_thr[sl3] + s_mrg[sl3];
             uint32_t a0[U], a1[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) adc_block_pk<MP>(w[u], cc, a0[u], a1[u]);
@@ -304,12 +309,23 @@ k_scan_pk(ScanArgs a) {
             for (int u = 1; u < U; ++u) { c0 = min(c0, v0[u]); c1 = min(c1, v1[u]); c2 = min(c2, v2[u]); c3 = min(c3, v3[u]); }
             mn0 = min(mn0, c0); mn1 = min(mn1, c1); mn2 = min(mn2, c2); mn3 = min(mn3, c3);
             if (__any_sync(0xffffffffu, (c0 <= t0) | (c1 <= t1) | (c2 <= t2) | (c3 <= t3))) {
+                // (some lane passes in about two chunks out of three, but rarely more than one of its four slots does: test
+                //  the slot minimum first, so the warp walks the U codes of a slot only when a lane has a hit there)
+                if (c0 <= t0) {
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    if (v0[u] <= t0) append(v0[u], sl0, base + u * MP);
-                    if (v1[u] <= t1) append(v1[u], sl1, base + u * MP);
-                    if (v2[u] <= t2) append(v2[u], sl2, base + u * MP);
-                    if (v3[u] <= t3) append(v3[u], sl3, base + u * MP);
+                    for (int u = 0; u < U; ++u) if (v0[u] <= t0) append(v0[u], sl0, base + u * MP);
+                }
+                if (c1 <= t1) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) if (v1[u] <= t1) append(v1[u], sl1, base + u * MP);
+                }
+                if (c2 <= t2) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) if (v2[u] <= t2) append(v2[u], sl2, base + u * MP);
+                }
+                if (c3 <= t3) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) if (v3[u] <= t3) append(v3[u], sl3, base + u * MP);
                 }
             }
             const int cx = it + 1, cy = cx & (cx - 1);              // checkpoints after 1, 2, 3, 4, 6, 8, 12, 16, 24, ... chunks

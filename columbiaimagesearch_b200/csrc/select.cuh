@@ -114,7 +114,7 @@ k_select(ModelView mv, IndexView ix, PlanView pv, const unsigned long long* __re
          const unsigned int* __restrict__ cand_cnt, const unsigned int* __restrict__ gthr, int cand_cap,
          const double* __restrict__ P64, int KP, int k, double eps_rel, RecRoute route,
          int packed, const double* __restrict__ qB, const double* __restrict__ qDelta, const double* __restrict__ qSlack,
-         uint8_t* __restrict__ need2) {
+         uint8_t* __restrict__ need2, const unsigned int* __restrict__ qmargin) {
     extern __shared__ __align__(16) unsigned char sm_sel[];
     unsigned long long* keys = (unsigned long long*)sm_sel;
     unsigned long long* dk = keys + SEL_LIST;
@@ -140,7 +140,7 @@ k_select(ModelView mv, IndexView ix, PlanView pv, const unsigned long long* __re
     }
     const unsigned int appended = cand_cnt[q];
     const int n = (int)min(appended, (unsigned int)cand_cap);
-    const unsigned int bound = gthr[q];
+    const unsigned int bound = gthr[q] + ((packed && qmargin) ? qmargin[q] : 0u);     // what the scan appended up to
     const unsigned long long* src = cand + (size_t)q * cand_cap;
 
     // ---- pass 1: range and count of the passing candidates
@@ -306,7 +306,7 @@ k_select(ModelView mv, IndexView ix, PlanView pv, const unsigned long long* __re
 // down the fallback chain) are evaluated in float64 and sorted by (dist64, retrieval position); every code that was NOT
 // appended has a key above the bound, so the certification bound is that of the bound itself.
 // dynamic smem: dk[SEL2_LIST] u64 | rows[SEL2_LIST] i64 | part[SEL_PART] f64 | pk[SEL2_LIST] u32 | idx[SEL2_LIST] int | vis[SEL2_LIST] int
-#define SEL2_LIST 1024
+#define SEL2_LIST 2048
 __host__ __device__ inline size_t select2_smem_bytes() { return (size_t)SEL2_LIST * 28 + (size_t)SEL_PART * 8 + 64; }
 
 __global__ void __launch_bounds__(256)
@@ -314,7 +314,7 @@ k_select2(ModelView mv, IndexView ix, PlanView pv, const unsigned long long* __r
           const unsigned int* __restrict__ cand_cnt, const unsigned int* __restrict__ gthr, int cand_cap,
           const double* __restrict__ P64, int k, double eps_rel, RecRoute route,
           int packed, const double* __restrict__ qB, const double* __restrict__ qDelta, const double* __restrict__ qSlack,
-          const uint8_t* __restrict__ need2) {
+          const uint8_t* __restrict__ need2, const unsigned int* __restrict__ qmargin) {
     const int q = blockIdx.x, tid = threadIdx.x;
     if (!need2[q]) return;
     extern __shared__ __align__(16) unsigned char sm_sel2[];
@@ -330,7 +330,7 @@ k_select2(ModelView mv, IndexView ix, PlanView pv, const unsigned long long* __r
     const unsigned int appended = cand_cnt[q];
     if (appended > (unsigned int)cand_cap) return;                    // (k_select already marked it lost)
     const int n = (int)appended;
-    const unsigned int bound = gthr[q];
+    const unsigned int bound = gthr[q] + ((packed && qmargin) ? qmargin[q] : 0u);
     const unsigned long long* src = cand + (size_t)q * cand_cap;
     if (tid == 0) s_n = 0;
     __syncthreads();
