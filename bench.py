@@ -35,7 +35,7 @@ CONFIGS = {
                model="dlib128_V8_M16.npz", quota=33_000, style="dlib"),
     # configs[2]: DeepSentibank-style 2048-d; the model is trained at start-up (134 MB of rotations: not a fixture)
     "c3": dict(metric="LOPQ queries/sec @ recall@10, 10Mx2048-d, V=8 M=32", n_db=10_000_000, D=2048, V=8, M=32,
-               model=None, quota=480_000, style="sentibank"),
+               model=None, quota=450_000, style="sentibank"),
     # the product's shipped shape (conf/conf_search_dlibface_release.json:12-16): V=2048, M=8, 128-d, quota = min(1000 x 100, 10000)
     "pv": dict(metric="LOPQ queries/sec @ recall@10, 4Mx128-d, V=2048 M=8 (product-shaped), quota=10000 top-100", n_db=4_000_000,
                D=128, V=2048, M=8, model=None, quota=10_000, style="dlib"),

@@ -95,7 +95,7 @@ struct b2l_ctx {
     unsigned int nu = 0, hmask = 0, max_run = 0;
     // workspaces
     DevBuf w_q, w_xq, w_px, w_coarse, w_fine, w_lut32, w_lut64, w_p64, w_cellq, w_cand, w_gtab, w_lut16, w_quant, w_plan, w_sort_a, w_sort_b,
-        w_sort_tmp, w_rec, w_rec2, w_out, w_out2, w_misc, w_bkt, w_perm, w_need2;
+        w_sort_tmp, w_rec, w_rec2, w_out, w_out2, w_misc, w_bkt, w_perm, w_need2, w_segc;
     PlanView pv = {};
     unsigned int* gthr = nullptr;      // [nq] per-query pruning bound shared by the scan blocks
     unsigned int* cand_cnt = nullptr;  // [nq] candidates the scan appended
@@ -510,6 +510,7 @@ int setup_plan(b2l_handle h, int nq, int segc, int nsegmax = 1, int nseg_cap = 1
     pv.vis_pbase = (int32_t*)(b + o_vpb);
     pv.lut_desc = (int32_t*)(b + o_desc);
     pv.cellq = nullptr;
+    pv.cell_segc = nullptr;
     pv.vis_dist = nullptr;
     h->gthr = (unsigned int*)(b + o_gthr);
     h->cand_cnt = (unsigned int*)(b + o_ccnt);
@@ -825,28 +826,54 @@ int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_
         }
         }
     }
+    std::vector<int32_t> cell_segc;
+    int nseg_low = 1;
     if (lowb) {
         // One query per item, the next item's tables prefetched.  The items of a query all compete for the resident blocks
-        // (3 per SM) at once, so the segment length decides the tail: pick the multiple of 1024 codes (8 warps x 128 codes per
-        // step) that minimises  waves x (segment + per-item overhead)  for the expected share of the index a query ranks.
-        const int64_t est = std::min<int64_t>(gtotal, (quota < gtotal ? quota : gtotal) + maxcell / 2);
-        const double frac = gtotal > 0 ? (double)est / (double)gtotal : 1.0;
+        // (3 per SM) at once, so their sizes decide the tail: every cell is cut into n_c equal segments with n_c proportional
+        // to its size, such that the expected number of items is a whole number of waves over the resident blocks and all
+        // items have (nearly) the same length, whatever the sizes of the cells.
+        const int64_t est = std::min<int64_t>(gtotal, (quota < gtotal ? quota : gtotal) + maxcell / 2);   // codes ranked per query
         const double grid = (double)h->num_sms * 3.0;
-        double best_cost = 1e300;
-        for (int sc = 1024; sc <= 64 * 1024; sc += 1024) {
-            double items = 0.0;
-            for (int c = 0; c < ncell; ++c) items += (double)((h->h_lsize[c] + sc - 1) / sc);
-            items = std::max(1.0, items * frac * nq);
-            const double cost = std::ceil(items / grid) * ((double)sc + 3072.0);
-            if (cost <= best_cost) { best_cost = cost; segc = sc; }
+        const double total = (double)est * nq;
+        const double waves = std::max(1.0, std::ceil(total / (grid * 32768.0)));
+        const double tgt = std::max(2048.0, total / (grid * waves));           // codes per item
+        cell_segc.assign(ncell, 1024);
+        std::vector<std::pair<double, int>> rem;
+        int64_t sumn = 0;
+        for (int c = 0; c < ncell; ++c) {
+            const double x = (double)h->h_lsize[c] / tgt;
+            const int64_t n = std::max<int64_t>(h->h_lsize[c] > 0 ? 1 : 0, (int64_t)std::floor(x));
+            cell_segc[c] = (int32_t)n;                                         // (segments for now)
+            sumn += n;
+            if (h->h_lsize[c] > 0) rem.push_back({x - std::floor(x), c});
         }
+        if (est >= gtotal) {                                                   // whole index per query: hit the wave count exactly
+            int64_t want = (int64_t)(grid * waves) / std::max(1, nq) - sumn;  // (items = segments x queries)
+            std::sort(rem.begin(), rem.end(), [](const std::pair<double, int>& a, const std::pair<double, int>& b) { return a.first > b.first; });
+            for (size_t i = 0; i < rem.size() && want > 0; ++i, --want) ++cell_segc[rem[i].second];
+        } else {
+            for (auto& r : rem) if (r.first >= 0.5) ++cell_segc[r.second];
+        }
+        for (int c = 0; c < ncell; ++c) {
+            const int64_t n = std::max<int64_t>(1, cell_segc[c]);
+            nseg_low = (int)std::max<int64_t>(nseg_low, h->h_lsize[c] > 0 ? n : 1);
+            const int64_t len = (h->h_lsize[c] + n - 1) / n;
+            cell_segc[c] = (int32_t)std::max<int64_t>(128, ((len + 127) / 128) * 128);
+        }
+        segc = 16 * 1024;
     }
     if (maxcell > 0 && maxcell < segc) segc = (int)(((maxcell + 63) / 64) * 64);
-    const int nsegmax = (int)std::max<int64_t>(1, (maxcell + segc - 1) / segc);
+    const int nsegmax = lowb ? nseg_low + 1 : (int)std::max<int64_t>(1, (maxcell + segc - 1) / segc);
     rc = setup_plan(h, nq, segc, nsegmax, (int)((maxcell + 2047) / 2048) + 1);
     if (rc) return rc;
     if (fast) h->cr->segc = segc;
     PlanView& pv = h->pv;
+    if (lowb) {
+        CU(h->w_segc.reserve((size_t)ncell * 4));
+        CU(cudaMemcpyAsync(h->w_segc.p, cell_segc.data(), (size_t)ncell * 4, cudaMemcpyHostToDevice, h->stream));   // (pageable: staged at once)
+        pv.cell_segc = h->w_segc.as<int32_t>();
+    }
     // per-query scratch of the fast path (bounds, bound tables, quantiser ranges): initialised by k_coarse_order
     QuantView qv = {};
     InitView iv = {};
@@ -1200,7 +1227,7 @@ int b2l_destroy(b2l_handle h) {
     DevBuf* bufs[] = {&h->dCs, &h->dmus, &h->dRt, &h->dsubs, &h->dsubs32, &h->dsubs32T, &h->dc2max, &h->dP, &h->dpmu, &h->m_coarse, &h->m_fine, &h->m_rowid, &h->codes,
                       &h->rowids, &h->cell_start, &h->lsize, &h->gsize, &h->sorted_first, &h->w_q, &h->w_xq, &h->w_px,
                       &h->w_coarse, &h->w_fine, &h->w_lut32, &h->w_lut64, &h->w_p64, &h->w_cellq, &h->w_cand, &h->w_gtab, &h->w_lut16, &h->w_quant, &h->w_plan,
-                      &h->w_sort_a, &h->w_sort_b, &h->w_sort_tmp, &h->w_rec, &h->w_rec2, &h->w_out, &h->w_out2, &h->w_misc, &h->w_bkt, &h->w_perm, &h->w_need2, &h->d_ucell, &h->d_ustart, &h->d_hkeys, &h->d_hvals, &h->w_walk, &h->w_walk2};
+                      &h->w_sort_a, &h->w_sort_b, &h->w_sort_tmp, &h->w_rec, &h->w_rec2, &h->w_out, &h->w_out2, &h->w_misc, &h->w_bkt, &h->w_perm, &h->w_need2, &h->w_segc, &h->d_ucell, &h->d_ustart, &h->d_hkeys, &h->d_hvals, &h->w_walk, &h->w_walk2};
     for (DevBuf* b : bufs) b->release();
     if (h->h_out) cudaFreeHost(h->h_out);
     if (h->d_nguard) cudaFree(h->d_nguard);

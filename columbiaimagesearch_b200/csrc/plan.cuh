@@ -35,6 +35,7 @@ struct PlanView {                   // per-batch device arrays, maxvis = V*V
     unsigned int item_cap;
     int2* cellq;                    // [n_pairs] (q, visit index), grouped by cell
     PlanCounters* cnt;
+    const int32_t* cell_segc;       // [V*V] per-cell segment length (low-batch scan: items of equal size over all cells); NULL: segc
 };
 
 // per-query scratch the later kernels expect initialised; done by the query's own block of k_coarse_order instead of
@@ -206,7 +207,8 @@ k_plan(int ncell, int nsegmax, int G, int segc, const int64_t* __restrict__ lsiz
     const int f0 = threadIdx.x * per;
     auto items_of = [&](int f) -> unsigned int {
         const int seg = f / ncell, c = f - seg * ncell;
-        const unsigned int nseg = (unsigned)((lsize[c] + segc - 1) / segc);
+        const int sc = pv.cell_segc ? pv.cell_segc[c] : segc;
+        const unsigned int nseg = (unsigned)((lsize[c] + sc - 1) / sc);
         return ((unsigned)seg < nseg) ? (pv.cell_qcount[c] + G - 1) / G : 0u;
     };
     unsigned int ai = 0;

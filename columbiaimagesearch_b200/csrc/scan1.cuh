@@ -97,9 +97,10 @@ k_scan1(ScanArgs a) {
         const unsigned int pi = item - pv.item_base[lo];                  // one query per item
         const int2 qv = pv.cellq[pv.cellq_off[it.cell] + pi];
         const int64_t o = (int64_t)qv.x * pv.maxvis + qv.y;
-        const int64_t first = (int64_t)seg * pv.segc;
+        const int sc = pv.cell_segc ? pv.cell_segc[it.cell] : pv.segc;
+        const int64_t first = (int64_t)seg * sc;
         it.q = qv.x; it.lut0 = pv.vis_lut0[o]; it.lut1 = pv.vis_lut1[o];
-        it.count = (int)min((int64_t)pv.segc, a.lsize[it.cell] - first);
+        it.count = (int)min((int64_t)sc, a.lsize[it.cell] - first);
         it.posbase = (unsigned int)(pv.vis_base[o] + first);
         it.src = a.codes + (a.cell_start[it.cell] + first) * MP;
     };
