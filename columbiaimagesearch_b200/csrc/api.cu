@@ -194,12 +194,12 @@ template <int MP> int launch_scan1(b2l_handle h, const ScanArgs& a) {
     if (cfg_smem != smem || cfg_dev != h->device) {
         CU(cudaFuncSetAttribute(k_scan1<MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int o = 1;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_scan1<MP>, SCAN1_THREADS, smem));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_scan1<MP>, SCAN_THREADS, smem));
         cfg_occ = o < 1 ? 1 : o; cfg_smem = smem; cfg_dev = h->device;
     }
     const int occ = cfg_occ;
     const unsigned grid = (unsigned)(h->num_sms * occ);
-    k_scan1<MP><<<grid, SCAN1_THREADS, smem, h->stream>>>(a);
+    k_scan1<MP><<<grid, SCAN_THREADS, smem, h->stream>>>(a);
     LAUNCHED();
     return B2L_OK;
 }
@@ -795,7 +795,7 @@ int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_
     int KP = std::max(16, next_pow2(k + 8));
     if (h->kp_min > 0) KP = std::min(512, std::max(KP, next_pow2(h->kp_min)));
     const bool lowb_shape = nq <= SCAN1_MAX_NQ && h->scan_mode != 1 && h->scan_mode != 2 && exact == 0 && mv.MP >= 8 && mv.G > 0;
-    const int LPS = lowb_shape ? 32 * SCAN1_WARPS : mv.MP * SCAN_WARPS;
+    const int LPS = lowb_shape ? 32 * SCAN_WARPS : mv.MP * SCAN_WARPS;
     const int GEN = std::max(1, KP / std::max(1, LPS));
     // exact: 0 = default fast scan (16-bit packed tables unless the handle is set to float32), 1 = float64 full sort,
     // 2 = fast scan with float32 tables
@@ -834,7 +834,7 @@ int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_
         // to its size, such that the expected number of items is a whole number of waves over the resident blocks and all
         // items have (nearly) the same length, whatever the sizes of the cells.
         const int64_t est = std::min<int64_t>(gtotal, (quota < gtotal ? quota : gtotal) + maxcell / 2);   // codes ranked per query
-        const double grid = (double)h->num_sms * 2.0;             // resident blocks of k_scan1 (2 per SM x 16 warps)
+        const double grid = (double)h->num_sms * 3.0;
         const double total = (double)est * nq;
         const double waves = std::max(1.0, std::ceil(total / (grid * 32768.0)));
         const double tgt = std::max(2048.0, total / (grid * waves));           // codes per item

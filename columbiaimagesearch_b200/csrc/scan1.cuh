@@ -24,8 +24,6 @@
 #define SCAN1_CAND_CAP (1 << 18)  // candidate keys per query in the low-batch regime (nq <= SCAN1_MAX_NQ)
 #define SCAN1_MAX_NQ 8
 #define SCAN1_PF 4                // L2 prefetch distance, in chunks of the warp
-#define SCAN1_THREADS 512         // 16 warps per block, 2 blocks per SM (64 registers): 32 warps hide the LDS -> FADD latency better
-#define SCAN1_WARPS 16            //   than 24 (3 blocks of 8 warps at 80 registers)
 
 template <int MP>
 size_t scan1_smem_bytes(int E) {
@@ -56,9 +54,9 @@ struct Item1 {                     // decoded work item
 };
 
 template <int MP>
-__global__ void __launch_bounds__(SCAN1_THREADS, 2)
+__global__ void __launch_bounds__(SCAN_THREADS, 3)
 k_scan1(ScanArgs a) {
-    constexpr int W = MP / 4, U = (MP >= 32 ? 2 : 4), CHUNK = U * 32, G = 32 / MP;
+    constexpr int W = MP / 4, U = 4, CHUNK = U * 32, G = 32 / MP;
     extern __shared__ __align__(256) unsigned char smem[];
     float* lut = (float*)smem;                                                   // [256 rows][64 floats]: two interleaved buffers
     unsigned long long* stage = (unsigned long long*)(smem + B2L_LUT_ROWS * 256); // [SCAN1_STAGE] dist bits << 32 | index in segment
@@ -79,9 +77,9 @@ k_scan1(ScanArgs a) {
         cc[T] = v;
     }
     const int ent = warp * 32 + lane;                // entry of this lane in the bound table (generation 0)
-    const int LPS = 32 * SCAN1_WARPS;
+    const int LPS = 32 * SCAN_WARPS;
 
-    if (a.M < MP) for (int e = tid; e < B2L_LUT_ROWS * 64; e += SCAN1_THREADS) lut[e] = 0.0f;   // padding columns of both buffers stay zero
+    if (a.M < MP) for (int e = tid; e < B2L_LUT_ROWS * 64; e += SCAN_THREADS) lut[e] = 0.0f;   // padding columns of both buffers stay zero
     const unsigned int n_items = pv.cnt->n_items;
     if (tid == 0) { s_misc[2] = atomicAdd(&pv.cnt->next_item, 1u); s_misc[3] = 0xFFFFFFFFu; }
     __syncthreads();
@@ -107,7 +105,7 @@ k_scan1(ScanArgs a) {
         it.src = a.codes + (a.cell_start[it.cell] + first) * MP;
     };
     auto fetch_lut = [&](const Item1& it, int buf) {                      // cp.async the item's two half tables into buffer `buf`
-        for (int e = tid; e < B2L_LUT_ROWS * cpr; e += SCAN1_THREADS) {
+        for (int e = tid; e < B2L_LUT_ROWS * cpr; e += SCAN_THREADS) {
             const int row = e / cpr, r = e - row * cpr;
             const int gg = r / (2 * cph), r2 = r - gg * 2 * cph;
             const int half = r2 / cph, part = r2 - half * cph;
@@ -127,7 +125,7 @@ k_scan1(ScanArgs a) {
         // bound table: what finished items of the query left in gtab -- unless the block's previous item was the same query
         // (then its own table, which only gets better, stays: hundreds of blocks share one query in this regime, and a
         // read-modify-write of the query's global table per item would serialise them on the same 256 addresses)
-        if (tab_q != cur.q) for (int e = tid; e < a.E; e += SCAN1_THREADS) tab[e] = a.gtab[(size_t)cur.q * a.E + e];
+        if (tab_q != cur.q) for (int e = tid; e < a.E; e += SCAN_THREADS) tab[e] = a.gtab[(size_t)cur.q * a.E + e];
         if (tid == 0) { s_misc[0] = *(volatile unsigned int*)&a.gthr[cur.q]; s_misc[1] = 0u; }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();                                                  // tables of `cur` landed; s_misc published
@@ -185,11 +183,11 @@ k_scan1(ScanArgs a) {
 #pragma unroll
                 for (int u = 0; u < U; ++u) d[u] = adc_row1<MP, 0>(w[u], cc);
             }
-            if (c + SCAN1_WARPS < nchunk) load_chunk(w, c + SCAN1_WARPS);   // registers are dead: next chunk's rows in flight
+            if (c + SCAN_WARPS < nchunk) load_chunk(w, c + SCAN_WARPS);   // registers are dead: next chunk's rows in flight
             // ... and the warp's chunks after that are pulled into L2 (one 128-byte line per lane), so that the register loads
             // above find them there: with one chunk per warp in flight a single query would be bound by the HBM latency
             {
-                const int cp = c + SCAN1_PF * SCAN1_WARPS;
+                const int cp = c + SCAN1_PF * SCAN_WARPS;
                 if (cp < nchunk && lane * 128 < CHUNK * MP) prefetch_l2(cur.src + (size_t)cp * CHUNK * MP + lane * 128);
             }
             const int base = c * CHUNK + lane;
@@ -229,7 +227,7 @@ k_scan1(ScanArgs a) {
         if (warp < nchunk) load_chunk(wa, warp);
 #pragma unroll
         for (int pf = 1; pf < SCAN1_PF; ++pf) {
-            const int cp = warp + pf * SCAN1_WARPS;
+            const int cp = warp + pf * SCAN_WARPS;
             if (cp < nchunk && lane * 128 < CHUNK * MP) prefetch_l2(cur.src + (size_t)cp * CHUNK * MP + lane * 128);
         }
         if (s_misc[0] >= SCAN_NO_BOUND) {                                  // (block-uniform: read after the barrier above)
@@ -248,7 +246,7 @@ k_scan1(ScanArgs a) {
             refresh();
             __syncthreads();
         }
-        for (int c = warp; c < nchunk; c += SCAN1_WARPS) eval_chunk(wa, c);
+        for (int c = warp; c < nchunk; c += SCAN_WARPS) eval_chunk(wa, c);
         if (warp < nchunk) {
             const int e = ent + LPS * (gen & (a.GEN - 1));
             tab[e] = fminf(tab[e], mn);
@@ -260,7 +258,7 @@ k_scan1(ScanArgs a) {
         {
             const unsigned int thr = s_misc[0];
             const unsigned int ns = min(s_misc[1], (unsigned int)SCAN1_STAGE);
-            for (unsigned int i0 = 0; i0 < ns; i0 += SCAN1_THREADS) {
+            for (unsigned int i0 = 0; i0 < ns; i0 += SCAN_THREADS) {
                 const unsigned int i = i0 + tid;
                 const bool keep = i < ns && (unsigned int)(stage[i] >> 32) <= thr;
                 const unsigned int bal = __ballot_sync(0xffffffffu, keep);
@@ -273,7 +271,7 @@ k_scan1(ScanArgs a) {
             // (and only if some item can still start later: with at most one item per resident block nobody would read it,
             //  and hundreds of blocks finishing together would queue up on the query's 256 table words)
             if (!(nxt < n_items && nx.q == cur.q) && n_items > gridDim.x) {
-                for (int e = tid; e < a.E; e += SCAN1_THREADS) {
+                for (int e = tid; e < a.E; e += SCAN_THREADS) {
                     const float v = tab[e];
                     if (__float_as_uint(v) <= thr) atomicMin((unsigned int*)&a.gtab[(size_t)cur.q * a.E + e], __float_as_uint(v));
                 }
