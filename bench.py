@@ -618,6 +618,7 @@ def run_search(a):
     searcher._sync_lanes()                                    # (the lanes have their own streams: all of them done ...
     ev1.record(stream)                                        #  ... before the closing event on lane 0's stream)
     env.barrier()
+    last = {kk: (v.copy() if isinstance(v, np.ndarray) else v) for kk, v in last.items()}   # (views of a rotating pinned block)
     wall = time.perf_counter() - t0
     dev_s, wall_s = env.max_over_ranks(max(ev0.elapsed_time(ev1) * 1e-3, 0.0), wall)
     lane_st = searcher.lane_stats()

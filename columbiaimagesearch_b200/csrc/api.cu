@@ -1156,7 +1156,7 @@ int merge_impl(b2l_handle h, const void* d_recs, int nranks, int nq, int k, int 
     }
     CU(cudaFuncSetAttribute(k_final, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_final<<<nq, 128, smem, h->stream>>>(mv.V, mv.M, d_recs, nranks, nq, k, n, d_rowid, d_dist, d_coarse, d_fine, d_count,
-                                          d_visited, d_cert, d_unc);
+                                          d_visited, d_cert, d_unc, (h->force_redo & 4) ? 1 : 0);
     LAUNCHED();
     if (!on_device) {
         const size_t nk = (size_t)nq * k;
@@ -1262,7 +1262,7 @@ int b2l_create_sibling(b2l_handle p, b2l_handle* out) {
     rc = b2l_create(p->device, &s);
     if (rc) { p->err = g_create_error; return rc; }
     s->has_model = true; s->has_pca = p->has_pca; s->mv = p->mv; s->c2m = p->c2m;
-    s->fine_mode = p->fine_mode; s->scan_mode = p->scan_mode; s->kp_min = p->kp_min;
+    s->fine_mode = p->fine_mode; s->scan_mode = p->scan_mode; s->kp_min = p->kp_min; s->force_redo = p->force_redo;
     DevBuf* src[] = {&p->dCs, &p->dmus, &p->dRt, &p->dsubs, &p->dsubs32, &p->dsubs32T, &p->dc2max, &p->dP, &p->dpmu, &p->m_coarse, &p->m_fine,
                      &p->m_rowid, &p->codes, &p->rowids, &p->cell_start, &p->lsize, &p->gsize, &p->sorted_first, &p->d_ucell, &p->d_ustart,
                      &p->d_hkeys, &p->d_hvals};
@@ -1315,7 +1315,7 @@ int b2l_reset_stats(b2l_handle h) {
 int b2l_debug_force_redo(b2l_handle h, int mask) {
     if (!h) return B2L_ERR_ARG;
     std::lock_guard<std::mutex> lk(h->mu);
-    h->force_redo = mask & 3;
+    h->force_redo = mask & 7;
     return B2L_OK;
 }
 

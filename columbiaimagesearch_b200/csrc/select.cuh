@@ -423,7 +423,7 @@ __global__ void __launch_bounds__(128)
 k_final(int V, int M, const void* __restrict__ recs_all, int nranks, int nq, int k, int n,
         int64_t* __restrict__ rowid, double* __restrict__ dist, int32_t* __restrict__ coarse, uint8_t* __restrict__ fine,
         int32_t* __restrict__ count, int32_t* __restrict__ visited, uint8_t* __restrict__ certified,
-        unsigned int* __restrict__ n_uncertified = nullptr) {
+        unsigned int* __restrict__ n_uncertified = nullptr, int force_unc = 0) {
     extern __shared__ __align__(16) unsigned char sm_fin[];
     unsigned long long* dk = (unsigned long long*)sm_fin;
     unsigned int* pk = (unsigned int*)(dk + n);
@@ -474,6 +474,7 @@ k_final(int V, int M, const void* __restrict__ recs_all, int nranks, int nq, int
         bool ok = true;
         if (nout == k && k > 0) ok = __longlong_as_double((long long)dk[k - 1]) < lbmin;
         else ok = !(lbmin < __longlong_as_double(0x7FF0000000000000ll));
+        if (force_unc && q % 5 == 0) ok = false;                  // test knob (b2l_debug_force_redo bit 2): exercise the fallback chain
         if (certified) certified[q] = ok ? 1 : 0;
         if (!ok && n_uncertified) atomicAdd(n_uncertified, 1u);
     }

@@ -339,13 +339,16 @@ class ShardedLOPQSearcher(object):
         if limit is None:
             limit = quota
         k = int(max(1, min(int(limit), max(1, self.nb_indexed))))
-        if self._stream is not None:
+        # the handle may be in asynchronous mode (pipelined batches, the in-library exchange): drain every lane and switch
+        # the main handle to synchronous calls for the host-driven protocol below
+        was_async = self._stream is not None or getattr(self, "_peer", False)
+        if was_async:
             self._sync_lanes()
             self._handle.set_async(False)
         try:
             return self._search_batch_sync_impl(X, quota, k)
         finally:
-            if self._stream is not None:
+            if was_async:
                 self._handle.set_async(True)
 
     def _search_batch_sync_impl(self, X, quota, k):

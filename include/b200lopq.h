@@ -222,7 +222,9 @@ int b2l_set_preselect(b2l_handle h, int kp_min);
 int b2l_set_async(b2l_handle h, int enabled);
 int b2l_sync(b2l_handle h);
 /* test knob for b2l_search: bit 0 sends every query of a batch to the second stage of the certification chain
- * (float32 tables) even if the first certified it, bit 1 sends every query of that stage on to the float64 full sort. */
+ * (float32 tables) even if the first certified it, bit 1 sends every query of that stage on to the float64 full sort.
+ * Bit 2 (any merge: b2l_search_merge*, b2l_search_sharded): every fifth query is reported uncertified, so the callers'
+ * fallback chains run. */
 int b2l_debug_force_redo(b2l_handle h, int mask);
 /* diagnostics of the most recent fast-path search: per query, candidates the scan appended and the final
  * pruning bound (float32 bits).  Either pointer may be NULL. */

@@ -62,10 +62,15 @@ def main():
         redo_b += out["exact_queries"] + out["rescan_queries"]
         for i in range(Q.shape[0]):
             check(out, i, Q[i], quotas[b % 3])
-    # (a) in-library exchange, two batches in flight, host and device inputs alternating
+    # (a) in-library exchange over two lanes (sibling handles), two batches in flight, host and device inputs alternating;
+    #     the last batches with every fifth query forced down the collective fallback chain
+    s.enable_pipelining(2)
     s.enable_peer_exchange(nq_home, 16)
     pend, outs = [], []
     for b, Q in enumerate(batches):
+        if b == 3:
+            for h, _ in s._lanes:
+                h.debug_force_redo(4)
         home = Q[rank * nq_home:(rank + 1) * nq_home]
         x = torch.from_numpy(home).cuda() if b % 2 else home
         pend.append(s.search_home_async(x, quota=quotas[b % 3], limit=k))
@@ -78,6 +83,9 @@ def main():
         for i in range(nq_home):
             check(out, i, Q[rank * nq_home + i], quotas[b % 3])
     assert s._handle.comm_error() == 0
+    assert redo_a > 0, "the forced fallback chain did not run"
+    for h, _ in s._lanes:
+        h.debug_force_redo(0)
     t = torch.tensor([redo_a, redo_b], device="cuda:%d" % local)
     dist.all_reduce(t)
     dist.barrier()

@@ -104,3 +104,32 @@ def test_train_pca_balances_the_two_halves():
     Pb, mub = train_pca(X[:5000], 8)
     np.testing.assert_array_equal(Pa, Pb)
     np.testing.assert_array_equal(mua, mub)
+
+
+def test_lmdb_searcher_persistence_branch_with_a_stand_in_module(monkeypatch):
+    """The `lmdb`-backed branch of LOPQSearcherLMDB (the product's default searcher, searcher_lopqhbase.py:198-206) against
+    a stand-in `lmdb` module (tests/fake_lmdb.py; the real one is absent in this image): what add_codes writes is the
+    reference's wire format (key = 2 x native uint16 cell + str(id) bytes, value = M fine-code bytes, search.py:425-470),
+    and a second searcher opened on the same path finds it again, in key order.  No GPU: nothing here searches."""
+    import sys
+    from tests import fake_lmdb
+
+    class _Model(object):
+        V, M = 4, 8
+    monkeypatch.setitem(sys.modules, "lmdb", fake_lmdb)
+    s = LOPQSearcherLMDB(_Model(), "/fake/lmdb_index_x", id_lambda=str)
+    rng = np.random.RandomState(0)
+    coarse = rng.randint(0, 4, size=(50, 2)).astype(np.int32)
+    fine = rng.randint(0, 256, size=(50, 8)).astype(np.uint8)
+    ids = ["sha1_%02d" % i for i in range(50)]
+    s.add_codes((coarse, fine), ids)
+    s.add_codes((coarse[:5], fine[:5][:, ::-1]), ids[:5])              # re-adding an id in its cell overwrites (txn.put)
+    assert s.get_nb_indexed() == 50
+    store = fake_lmdb._STORES["/fake/lmdb_index_x"][b"index"]
+    key0 = array.array("H", [int(coarse[7, 0]), int(coarse[7, 1])]).tobytes() + b"sha1_07"
+    assert store[key0] == array.array("B", fine[7].tolist()).tobytes()   # the reference's encoders, byte for byte
+    s2 = LOPQSearcherLMDB(_Model(), "/fake/lmdb_index_x", id_lambda=str)
+    assert s2.get_nb_indexed() == 50 and s2._stale
+    assert sorted(s2._items) == sorted(store)
+    k5 = array.array("H", [int(coarse[2, 0]), int(coarse[2, 1])]).tobytes() + b"sha1_02"
+    assert s2._items[k5].tolist() == fine[2][::-1].tolist()
