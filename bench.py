@@ -398,10 +398,32 @@ def train_model_c3(env, a, cfg, lopq, synth):
     """DATA PREPARATION (c3): a 2048-d V=8 M=32 model is 134 MB of float64 rotations, too large for a fixture, so it is
     trained here with the package's own trainer (lopq/train.py: the reference's algorithm, batched) on `ntrain` seeded
     vectors, identically on every rank.  Models are inputs of the hot path: not timed, not part of parity."""
-    X = synth.dlib_style_torch(a.ntrain, cfg["D"], seed=a.seed + 5, device=env.dev, relu=True).cpu().numpy().astype(np.float64)
+    torch = env.torch
     m = lopq.LOPQModel(V=cfg["V"], M=cfg["M"], subquantizer_clusters=256)
     t0 = time.perf_counter()
-    m.fit(X, n_init=1, kmeans_coarse_iters=8, kmeans_local_iters=8, random_state=0)
+    if env.rank == 0:                                          # N > 1: rank 0 trains, the parameters are broadcast
+        X = synth.dlib_style_torch(a.ntrain, cfg["D"], seed=a.seed + 5, device=env.dev, relu=True).cpu().numpy().astype(np.float64)
+        try:
+            from threadpoolctl import threadpool_limits         # (torchrun pins OMP_NUM_THREADS=1: the eigh / GEMMs want the cores)
+            with threadpool_limits(limits=max(1, (os.cpu_count() or 8) // 2)):
+                m.fit(X, n_init=1, kmeans_coarse_iters=8, kmeans_local_iters=8, random_state=0)
+        except ImportError:
+            m.fit(X, n_init=1, kmeans_coarse_iters=8, kmeans_local_iters=8, random_state=0)
+    if env.world > 1:
+        V, M, h, K, ds = cfg["V"], cfg["M"], cfg["D"] // 2, 256, cfg["D"] // cfg["M"]
+        shapes = [(2, V, h), (2, V, h, h), (2, V, h), (M, K, ds)]
+        if env.rank == 0:
+            arrs = [np.stack([np.asarray(x, np.float64) for x in m.Cs]), np.stack([np.asarray(x, np.float64) for x in m.Rs]),
+                    np.stack([np.asarray(x, np.float64) for x in m.mus]),
+                    np.stack([np.asarray(x, np.float64) for x in list(m.subquantizers[0]) + list(m.subquantizers[1])])]
+        out = []
+        for i, shp in enumerate(shapes):
+            t = torch.from_numpy(arrs[i]).to(env.dev) if env.rank == 0 else torch.empty(shp, dtype=torch.float64, device=env.dev)
+            env.dist.broadcast(t, 0)
+            out.append(t.cpu().numpy())
+        mm = M // 2
+        m = lopq.LOPQModel(parameters=((out[0][0], out[0][1]), (out[1][0], out[1][1]), (out[2][0], out[2][1]),
+                                       ([out[3][j] for j in range(mm)], [out[3][j] for j in range(mm, M)])))
     return m, time.perf_counter() - t0
 
 
