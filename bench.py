@@ -45,6 +45,16 @@ CONFIGS = {
 }
 
 
+def workload_string(a, cfg, name=None):
+    """The workload, worded identically by both arms (`config.workload` of the b200 line and of the reference line)."""
+    name = name or a.config
+    if name == "c5":
+        return "c5: compute_codes (LOPQModel.predict over rows), %dM x %d-d dlib-style synthetic rows, V=%d M=%d K=256" % (
+            cfg["n_db"] // 1_000_000, cfg["D"], cfg["V"], cfg["M"])
+    return ("%s: %dM x %d-d %s-style synthetic (4096-centre GMM, L2-normalised), V=%d M=%d K=256, near-duplicate queries (rho=%.2f), "
+            "quota=%d, top-%d" % (name, cfg["n_db"] // 1_000_000, cfg["D"], cfg["style"], cfg["V"], cfg["M"], a.rho, cfg.get("quota", 0), a.k))
+
+
 def parse():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
@@ -248,7 +258,7 @@ def run_reference(a):
         line = {"impl": "reference", "metric": cfg["metric"], "value": cps, "unit": "codes/s", "n_gpus": a.gpus, "steps": a.steps,
                 "warmup": a.warmup, "ms_per_step": 1e3 * total / a.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "compute_codes on 128-d dlib-style synthetic vectors, V=8 M=16 K=256", "rows_per_step": ncores * rows},
+                "config": {"workload": workload_string(a, cfg), "n_db": cfg["n_db"], "rows_per_step": ncores * rows},
                 "cpu_baseline": {"value": cps, "unit": "codes/s", "cores": ncores, "kind": "port",
                                  "sample": "%d rows per step on %d processes (compute_codes_parallel's row-chunk fan-out, utils.py:178-200)" % (ncores * rows, ncores)},
                 "e2e": {"value": cps, "unit": "codes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
@@ -330,8 +340,8 @@ def run_reference(a):
     line = {"impl": "reference", "metric": cfg["metric"], "value": qps, "unit": "queries/s", "n_gpus": a.gpus, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": 1e3 * total / a.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "%dM x 128-d dlib-style synthetic, V=8 M=16 K=256, quota=%d, top-%d" % (n // 1_000_000, quota, a.k),
-                       "n_db": n, "queries_per_step": ncores * qstep, "index": "python dict, visited cells only",
+            "config": {"workload": workload_string(a, cfg), "n_db": n, "quota": quota, "k": a.k,
+                       "queries_per_step": ncores * qstep, "index": "python dict, visited cells only",
                        "query_sample": "near-duplicates of rows of one median-sized cell (only the visited cells are materialised as "
                                        "Python objects); cost per query is linear in the codes ranked, as for any query",
                        "prep_s": round(prep_s, 1)},
@@ -758,9 +768,7 @@ def run_search(a):
         line = {"metric": cfg["metric"], "value": value, "unit": "queries/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": 1e3 * step_s / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u16", "data": "synthetic",
-                "config": {"workload": "%s: %dM x %d-d %s-style synthetic (4096-centre GMM, L2-normalised), V=%d M=%d K=256, "
-                                       "%d near-duplicate queries per rank and step (rho=%.2f), quota=%d, top-%d"
-                                       % (a.config, n // 1_000_000, D, cfg["style"], model.V, M, nq, a.rho, quota, k),
+                "config": {"workload": workload_string(a, cfg),
                            "n_db": n, "batch_per_rank": nq, "queries_per_step": G, "quota": quota, "k": k,
                            "recall@10": r10, "recall@1": r1,
                            "arithmetic": "16-bit packed table sums in the scan (float32-table and float64 fallbacks), float64 tables and re-rank",
@@ -1022,8 +1030,9 @@ def run_encode(a):
         line = {"metric": cfg["metric"], "value": value, "unit": "codes/s", "n_gpus": env.world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": 1e3 * dev_s / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "c5: compute_codes, %dM x %d-d dlib-style rows row-sharded over %d rank(s): %d rows per rank in %d resident "
-                                       "block(s) of %d rows; one step = one pass over a resident block" % (n // 1_000_000, D, env.world, per_rank, nblocks, block),
+                "config": {"workload": workload_string(a, cfg), "n_db": n,
+                           "decomposition": "rows row-sharded over %d rank(s): %d rows per rank in %d resident block(s) of %d rows; one step = one "
+                                            "pass over a resident block" % (env.world, per_rank, nblocks, block),
                            "rows_per_step": block * env.world, "seconds_for_all_rows_at_this_rate": n / value,
                            "l2": "a resident block (%d MB) exceeds the 126 MB L2" % (block * D * 4 // 1_000_000)},
                 "e2e": {"value": a.steps * eb * env.world / e2e_s, "unit": "codes/s", "h2d_bytes_per_step": eb * D * 4 * env.world,
