@@ -141,8 +141,18 @@ k_scan1(ScanArgs a) {
         const uint8_t* lane_src = cur.src + (size_t)lane * MP;
 
         auto refresh = [&]() {                                             // whole warp: bound from the lane-minimum table
-            const int E = a.E, gs = E / a.KP, epl = E / 32;
-            const float* t = tab + lane * epl;
+            const int E = a.E, gs = E / a.KP, epl = E / 32;             // epl = 8 * GEN: a multiple of 4
+            // the lane's run of the table comes in with 16-byte loads (scalar loads at a 32-byte lane stride would be 8-way
+            // bank conflicts: as many wavefronts per refresh as 64 rows of look-ups)
+            float tv[16];
+#pragma unroll
+            for (int e4 = 0; e4 < 4; ++e4) {
+                if (e4 * 4 < epl) {
+                    const float4 f = *(const float4*)(tab + lane * epl + e4 * 4);
+                    tv[e4 * 4] = f.x; tv[e4 * 4 + 1] = f.y; tv[e4 * 4 + 2] = f.z; tv[e4 * 4 + 3] = f.w;
+                }
+            }
+            const float* t = tv;
             float v;
             if (gs <= epl) {
                 v = 0.0f;

@@ -55,8 +55,11 @@ __device__ __forceinline__ void refresh_bounds_u(const ScanArgs& a, const unsign
         if (s_q[sl] < 0) continue;             // uniform
         const unsigned int* t = tab + sl * E + lane * epl;
         unsigned int v[16];
-        if (epl == 4) { const uint4 f = *(const uint4*)t; v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w; }
-        else for (int e = 0; e < epl; ++e) v[e] = t[e];
+        if ((epl & 3) == 0) {                  // 16-byte loads (scalar loads at this lane stride are epl-way bank conflicts)
+#pragma unroll
+            for (int e4 = 0; e4 < 4; ++e4)
+                if (e4 * 4 < epl) { const uint4 f = *(const uint4*)(t + e4 * 4); v[e4 * 4] = f.x; v[e4 * 4 + 1] = f.y; v[e4 * 4 + 2] = f.z; v[e4 * 4 + 3] = f.w; }
+        } else for (int e = 0; e < epl; ++e) v[e] = t[e];
         unsigned int lo = 0u, hi = 0x10000u;   // smallest T in [0, 65536] with count(entries <= T) >= KP; 65536: fewer than KP sums
         if (!exact) {
             unsigned int g;
