@@ -65,6 +65,57 @@ __device__ inline double exact_adc(const ModelView& mv, const uint8_t* code, int
     return acc;
 }
 
+// One squared sub-distance by 8 consecutive lanes (n % 8 == 0, n <= 128; every lane of the warp must call it).  NumPy's
+// pairwise leaf is eight strided accumulators r_j = sum_i term(j + 8 i) combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7));
+// lane j builds r_j and an xor butterfly performs exactly those additions (IEEE addition is commutative), so the bits equal
+// sqdist_np's -- with 8 loads in sequence per term instead of n, and 64-byte coalesced reads.
+__device__ __forceinline__ double sqdist_np_lanes8(const double* p, const double* c, int n, int j, bool live) {
+    double r = 0.0;
+    if (live) {
+        for (int i = j; i < n; i += 8) {
+            const double t = __dsub_rn(p[i], c[i]);
+            const double sq = __dmul_rn(t, t);
+            r = (i == j) ? sq : __dadd_rn(r, sq);
+        }
+    }
+    r = __dadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 1));
+    r = __dadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 2));
+    r = __dadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 4));
+    return r;
+}
+
+// part[t] = exact sub-distance of term t = (candidate i0 + t / M, sub-quantizer t % M), t < nterms, by the whole block
+__device__ __forceinline__ void exact_terms(const ModelView& mv, const IndexView& ix, const PlanView& pv, const double* __restrict__ P64,
+                                            int64_t o, const int64_t* rows, const int* visv, const unsigned int* pk, int i0, int nterms,
+                                            double* part) {
+    const int M = mv.M, tid = threadIdx.x, nthr = blockDim.x;
+    auto pointers = [&](int t, const double*& p, const double*& c) -> bool {
+        const int i = i0 + t / M, j = t % M;
+        if (rows[i] < 0) return false;
+        const int v = visv[i];
+        const int64_t incell = (int64_t)pk[i] - pv.vis_base[o + v];
+        const int s = j / mv.m;
+        p = P64 + (int64_t)(s ? pv.vis_lut1[o + v] : pv.vis_lut0[o + v]) * mv.h + (j - s * mv.m) * mv.ds;
+        c = mv.subs + ((int64_t)j * mv.K + code_byte(ix.codes + rows[i] * mv.MP, incell, j, mv.SW)) * mv.ds;
+        return true;
+    };
+    if ((mv.ds & 7) == 0 && mv.ds <= 128) {
+        const int g8 = tid >> 3, j8 = tid & 7, ng = nthr >> 3;               // 8 lanes per term
+        for (int t0 = 0; t0 < nterms; t0 += ng) {                            // (warp-uniform trip count: the shuffles need every lane)
+            const int t = t0 + g8;
+            const double* p = nullptr; const double* c = nullptr;
+            const bool live = t < nterms && pointers(t, p, c);
+            const double d = sqdist_np_lanes8(p, c, mv.ds, j8, live);
+            if (live && j8 == 0) part[t] = d;
+        }
+    } else {
+        for (int t = tid; t < nterms; t += nthr) {
+            const double* p; const double* c;
+            if (pointers(t, p, c)) part[t] = sqdist_np<double>(p, c, mv.ds);
+        }
+    }
+}
+
 // bitonic sort of n (power of two) entries by (dkey, pkey) ascending, payload idx
 __device__ inline void bitonic_sort_dp(unsigned long long* dk, unsigned int* pk, int* idx, int n) {
     for (int k = 2; k <= n; k <<= 1) {
@@ -241,17 +292,7 @@ k_select(ModelView mv, IndexView ix, PlanView pv, const unsigned long long* __re
     const int M = mv.M, CH = SEL_PART / M;
     for (int i0 = 0; i0 < KP; i0 += CH) {
         const int nc = min(CH, KP - i0);
-        for (int t = tid; t < nc * M; t += SEL_THREADS) {
-            const int i = i0 + t / M, j = t % M;
-            if (rows[i] >= 0) {
-                const int v = visv[i];
-                const int64_t incell = (int64_t)pk[i] - pv.vis_base[o + v];
-                const int s = j / mv.m;
-                const double* p = P64 + (int64_t)(s ? pv.vis_lut1[o + v] : pv.vis_lut0[o + v]) * mv.h + (j - s * mv.m) * mv.ds;
-                const double* c = mv.subs + ((int64_t)j * mv.K + code_byte(ix.codes + rows[i] * mv.MP, incell, j, mv.SW)) * mv.ds;
-                part[t] = sqdist_np<double>(p, c, mv.ds);
-            }
-        }
+        exact_terms(mv, ix, pv, P64, o, rows, visv, pk, i0, nc * M, part);
         __syncthreads();
         for (int i = i0 + tid; i < i0 + nc; i += SEL_THREADS) {
             if (rows[i] >= 0) {
@@ -370,17 +411,7 @@ k_select2(ModelView mv, IndexView ix, PlanView pv, const unsigned long long* __r
     const int M = mv.M, CH = SEL_PART / M;
     for (int i0 = 0; i0 < nl; i0 += CH) {
         const int nc = min(CH, nl - i0);
-        for (int t = tid; t < nc * M; t += blockDim.x) {
-            const int i = i0 + t / M, j = t % M;
-            if (rows[i] >= 0) {
-                const int v = visv[i];
-                const int64_t incell = (int64_t)pk[i] - pv.vis_base[o + v];
-                const int s = j / mv.m;
-                const double* p = P64 + (int64_t)(s ? pv.vis_lut1[o + v] : pv.vis_lut0[o + v]) * mv.h + (j - s * mv.m) * mv.ds;
-                const double* c = mv.subs + ((int64_t)j * mv.K + code_byte(ix.codes + rows[i] * mv.MP, incell, j, mv.SW)) * mv.ds;
-                part[t] = sqdist_np<double>(p, c, mv.ds);
-            }
-        }
+        exact_terms(mv, ix, pv, P64, o, rows, visv, pk, i0, nc * M, part);
         __syncthreads();
         for (int i = i0 + tid; i < i0 + nc; i += blockDim.x) {
             if (rows[i] >= 0) {
