@@ -99,7 +99,7 @@ __device__ __forceinline__ void exact_terms(const ModelView& mv, const IndexView
         c = mv.subs + ((int64_t)j * mv.K + code_byte(ix.codes + rows[i] * mv.MP, incell, j, mv.SW)) * mv.ds;
         return true;
     };
-    if ((mv.ds & 7) == 0 && mv.ds <= 128) {
+    if ((mv.ds & 7) == 0 && mv.ds >= 16 && mv.ds <= 128) {                   // (at ds = 8 a term is 8 loads: one thread does it faster)
         const int g8 = tid >> 3, j8 = tid & 7, ng = nthr >> 3;               // 8 lanes per term
         for (int t0 = 0; t0 < nterms; t0 += ng) {                            // (warp-uniform trip count: the shuffles need every lane)
             const int t = t0 + g8;
