@@ -272,6 +272,7 @@ k_scan_pk(ScanArgs a) {
         }
 
         int it = 0, gen = 0;
+        const unsigned int mg0 = s_mrg[sl0], mg1 = s_mrg[sl1], mg2 = s_mrg[sl2], mg3 = s_mrg[sl3];
         // candidates are staged per slot in shared memory (one shared-memory atomic, 4 bytes each) and moved to the query's
         // global list once per work item; only a full staging buffer falls back to the direct global append
         auto append = [&](unsigned int v, int sl, int idx) {
@@ -292,9 +293,11 @@ k_scan_pk(ScanArgs a) {
         // One chunk: the table sums, then -- as soon as the code registers are dead -- the loads of the warp's next chunk,
         // whose latency hides behind the bound / candidate logic below (three blocks per SM cover the rest).
         auto eval_chunk = [&](uint32_t (&w)[U][W], int c) {
-            // append threshold = bound + margin (the bounds themselves are refreshed without it)
-            const unsigned int t0 = s_thr[sl0] + s_mrg[sl0], t1 = s_thr[sl1] + s_mrg[sl1], t2 = s_thr[sl2] + s_mrg[sl2],
-                               t3 = s_thr[sl3] + s_mrg[sl3];
+            // append threshold = bound + margin (the bounds themselves are refreshed without it); the lane's slots are two
+            // adjacent pairs (2g, 2g+1) and (2(G+g), 2(G+g)+1): two 8-byte loads per chunk, the margins ride in registers
+            const uint2 ta = *(const uint2*)&s_thr[sl0];
+            const uint2 tb = *(const uint2*)&s_thr[sl2];
+            const unsigned int t0 = ta.x + mg0, t1 = ta.y + mg1, t2 = tb.x + mg2, t3 = tb.y + mg3;
             uint32_t a0[U], a1[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) adc_block_pk<MP>(w[u], cc, a0[u], a1[u]);
