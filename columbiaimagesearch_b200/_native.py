@@ -68,6 +68,7 @@ SIGNATURES = {
     "b2l_sharded_block_bytes": (_i64, [_h, _i, _i]),
     "b2l_search_sharded": (_i, [_h, _vp, _i, _i, _i, _i64, _i, _vp, _i]),
     "b2l_comm_error": (_i, [_h]),
+    "b2l_kmeans": (_i, [_h, _vp, _i64, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "b2l_get_stats": (_i, [_h, C.POINTER(Stats)]),
     "b2l_reset_stats": (_i, [_h]),
     "b2l_set_scan_mode": (_i, [_h, _i]),
@@ -370,6 +371,18 @@ class Handle(object):
 
     def comm_error(self):
         return int(self._check(self.lib.b2l_comm_error(self.h)))
+
+    def kmeans(self, X, C0, iters, reseed):
+        """Lloyd k-means on the device (b2l_kmeans).  Returns (centroids [k,d] float64, assignments [n] int32, cost)."""
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        Cc = np.ascontiguousarray(C0, dtype=np.float64).copy()
+        n, d = X.shape
+        k = Cc.shape[0]
+        rs = np.ascontiguousarray(reseed, dtype=np.int64).reshape(max(1, iters), k) if iters > 0 else None
+        assign = np.empty(n, np.int32)
+        cost = np.zeros(1, np.float64)
+        self._check(self.lib.b2l_kmeans(self.h, _ptr(X), n, d, k, int(iters), _ptr(Cc), _ptr(rs), _ptr(assign), _ptr(cost)))
+        return Cc, assign, float(cost[0])
 
     def stats(self):
         s = Stats()

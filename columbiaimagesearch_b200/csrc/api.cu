@@ -22,6 +22,7 @@
 #include "scan_pk.cuh"
 #include "scan1.cuh"
 #include "largev.cuh"
+#include "train.cuh"
 #include "select.cuh"
 
 #define B2L_ABI_VERSION 3
@@ -2034,6 +2035,46 @@ int b2l_search_sharded(b2l_handle h, const void* Qhome, int q_is_f64, int nq_hom
     LAUNCHED();
     if (!block_on_device) CU(cudaMemcpyAsync(block, b, off, cudaMemcpyDeviceToHost, h->stream));
     if (!h->async_mode) { CU(cudaStreamSynchronize(h->stream)); return finish_stats(h); }
+    return B2L_OK;
+}
+
+int b2l_kmeans(b2l_handle h, const double* X, int64_t n, int d, int k, int iters, double* C, const int64_t* reseed,
+               int32_t* assign, double* cost) {
+    if (!h) return B2L_ERR_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(cudaSetDevice(h->device));
+    if (!X || !C || n < 1 || d < 1 || k < 1 || iters < 0 || (iters > 0 && !reseed)) FAIL(B2L_ERR_ARG, "bad kmeans arguments");
+    if ((size_t)KM_WARPS * d * 8 > 200 * 1024) FAIL(B2L_ERR_UNSUPPORTED, "kmeans: dimension %d too large", d);
+    DevBuf dX, dC, dS, dN, dA, dR, dCost;
+    auto freeall = [&]() { dX.release(); dC.release(); dS.release(); dN.release(); dA.release(); dR.release(); dCost.release(); };
+#define KM(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { freeall(); char b_[256]; snprintf(b_, sizeof b_, "kmeans: %s", cudaGetErrorString(e_)); h->err = b_; return B2L_ERR_CUDA; } } while (0)
+    KM(dX.reserve((size_t)n * d * 8)); KM(dC.reserve((size_t)k * d * 8)); KM(dS.reserve((size_t)k * d * 8)); KM(dN.reserve((size_t)k * 8));
+    KM(dA.reserve((size_t)n * 4)); KM(dR.reserve((size_t)std::max(1, iters) * k * 8)); KM(dCost.reserve(8));
+    KM(cudaMemcpyAsync(dX.p, X, (size_t)n * d * 8, cudaMemcpyHostToDevice, h->stream));
+    KM(cudaMemcpyAsync(dC.p, C, (size_t)k * d * 8, cudaMemcpyHostToDevice, h->stream));
+    if (iters > 0) KM(cudaMemcpyAsync(dR.p, reseed, (size_t)iters * k * 8, cudaMemcpyHostToDevice, h->stream));
+    const size_t smem = (size_t)KM_WARPS * d * 8;
+    KM(cudaFuncSetAttribute(k_km_assign, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned ablocks = (unsigned)((n + KM_WARPS - 1) / KM_WARPS);
+    for (int it = 0; it <= iters; ++it) {                     // `iters` updates, then the final assignment and cost
+        KM(cudaMemsetAsync(dCost.p, 0, 8, h->stream));
+        k_km_assign<<<ablocks, KM_WARPS * 32, smem, h->stream>>>(dX.as<double>(), n, d, dC.as<double>(), k, dA.as<int32_t>(), dCost.as<double>());
+        KM(cudaGetLastError());
+        if (it == iters) break;
+        KM(cudaMemsetAsync(dS.p, 0, (size_t)k * d * 8, h->stream));
+        KM(cudaMemsetAsync(dN.p, 0, (size_t)k * 8, h->stream));
+        k_km_accum<<<grid_for(n * d, 256), 256, 0, h->stream>>>(dX.as<double>(), n, d, dA.as<int32_t>(), dS.as<double>(), dN.as<unsigned long long>());
+        KM(cudaGetLastError());
+        k_km_update<<<grid_for((int64_t)k * d, 256), 256, 0, h->stream>>>(dX.as<double>(), d, k, dS.as<double>(), dN.as<unsigned long long>(),
+                                                                         dR.as<int64_t>() + (size_t)it * k, dC.as<double>());
+        KM(cudaGetLastError());
+    }
+    KM(cudaMemcpyAsync(C, dC.p, (size_t)k * d * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (assign) KM(cudaMemcpyAsync(assign, dA.p, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (cost) KM(cudaMemcpyAsync(cost, dCost.p, 8, cudaMemcpyDeviceToHost, h->stream));
+    KM(cudaStreamSynchronize(h->stream));
+#undef KM
+    freeall();
     return B2L_OK;
 }
 

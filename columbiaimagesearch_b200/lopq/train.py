@@ -41,6 +41,21 @@ def _assign_device(X, C):
     return coarse[:, 0].astype(np.int64)
 
 
+_KM = {}
+
+
+def _kmeans_handle():
+    """one bare library handle per process for b2l_kmeans (needs no model)"""
+    import os
+    from .. import _native
+    ent = _KM.get(os.getpid())
+    if ent is None:
+        _KM.clear()
+        ent = _native.Handle()
+        _KM[os.getpid()] = ent
+    return ent
+
+
 def _use_device(device):
     """device=None means the GPU, like every other arithmetic step of this package (no silent host fallback: without a
     CUDA device the library fails loudly).  device=False keeps the assignments on the host (NumPy) -- training has no
@@ -64,6 +79,17 @@ def kmeans(X, k, iters, rng, n_init=1, device=False):
     runs on the GPU (_assign_device); the centroid update is a segmented sum on the host."""
     X = np.asarray(X, dtype=np.float64)
     best, best_cost = None, np.inf
+    if device:
+        # the whole Lloyd loop on the GPU (b2l_kmeans): assignments in NumPy's float64 order, centroid sums by atomics
+        from .. import _native
+        h = _kmeans_handle()
+        for _ in range(max(1, n_init)):
+            C0 = X[rng.choice(X.shape[0], size=k, replace=X.shape[0] < k)].copy()
+            reseed = rng.randint(0, X.shape[0], size=(max(1, iters), k))
+            C, _, cost = h.kmeans(X, C0, iters, reseed)
+            if cost < best_cost:
+                best, best_cost = C, cost
+        return best
     for _ in range(max(1, n_init)):
         C = X[rng.choice(X.shape[0], size=k, replace=X.shape[0] < k)].copy()
         for _it in range(iters):

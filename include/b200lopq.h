@@ -182,6 +182,16 @@ int     b2l_search_sharded(b2l_handle h, const void* Qhome, int q_is_f64, int nq
                            void* block, int block_on_device);
 int     b2l_comm_error(b2l_handle h);
 
+/* ---- training support ------------------------------------------------------------------------------------------------
+ * The k-means fits of training (model.py:290-336: coarse quantizers and sub-quantizers; the reference uses sklearn's
+ * MiniBatchKMeans) as Lloyd iterations on the device.  X [n][d] float64; C [k][d] float64: initial centroids in, trained
+ * centroids out; assignment = utils.predict_cluster over rows (utils.py:33-53: direct-form squared L2 in NumPy order, first
+ * minimum); an empty cluster takes row reseed[it][c] of X (reseed: int64 [iters][k]).  `iters` updates are followed by a
+ * final assignment: assign [n] int32 and the summed squared error *cost (either may be NULL).  Host pointers.  Needs no
+ * model on the handle.  Training has no parity contract (models are inputs of the hot path). */
+int b2l_kmeans(b2l_handle h, const double* X, int64_t n, int d, int k, int iters, double* C, const int64_t* reseed,
+               int32_t* assign, double* cost);
+
 /* ---- introspection (counters of the most recent b2l_search / b2l_search_local) ------------------ */
 typedef struct b2l_stats {
     double  scan_ms;          /* device time of the ADC scan kernel (CUDA events)            */

@@ -310,3 +310,41 @@ def test_training_on_the_gpu_statistical_parity():
         return lopq.eval.get_recall_batch(s, Q, d2.argmin(1), quota=2000, thresholds=(1, 10), batch=64)
     r_ref, r_gpu = recall(ref_model), recall(m_gpu)
     assert r_gpu[1] >= r_ref[1] - 0.1, (r_gpu, r_ref)
+
+
+def test_device_kmeans():
+    """b2l_kmeans: Lloyd iterations on the device.  The final assignment is utils.predict_cluster over rows (bit-exact with
+    the oracle for the returned centroids), the cost is the summed squared error, it does not increase with more
+    iterations, it is on a par with the host NumPy Lloyd from the same start, and empty clusters are re-seeded."""
+    from columbiaimagesearch_b200 import _native
+    from columbiaimagesearch_b200.lopq import train as T
+    rng = np.random.RandomState(0)
+    centres = rng.randn(12, 10) * 4.0
+    X = centres[rng.randint(0, 12, size=6000)] + 0.5 * rng.randn(6000, 10)
+    h = _native.Handle()
+    C0 = X[rng.choice(6000, size=12, replace=False)].copy()
+    reseed = rng.randint(0, 6000, size=(15, 12))
+    costs = []
+    for iters in (0, 1, 5, 15):
+        C, a, cost = h.kmeans(X, C0, iters, reseed[:max(1, iters)])
+        costs.append(cost)
+        want = np.array([int(orc.predict_cluster(x, C)) for x in X[:400]])
+        assert np.array_equal(a[:400], want)
+        np.testing.assert_allclose(cost, ((X - C[a]) ** 2).sum(), rtol=1e-9)
+    assert all(costs[i + 1] <= costs[i] * (1 + 1e-12) for i in range(3))
+    # host Lloyd from the same start
+    Ch = C0.copy()
+    for _ in range(15):
+        ah = T._assign(X, Ch, device=False)
+        cnt = np.bincount(ah, minlength=12)
+        Ch = np.where((cnt == 0)[:, None], Ch, T._segment_sum(X, ah, 12) / np.maximum(cnt, 1)[:, None])
+    cost_h = ((X - Ch[T._assign(X, Ch, device=False)]) ** 2).sum()
+    assert costs[-1] <= cost_h * 1.02
+    # an empty cluster (a start far away from all data) takes the re-seed row
+    C1 = C0.copy()
+    C1[3] = 1e6
+    C, a, _ = h.kmeans(X, C1, 1, reseed[:1])
+    np.testing.assert_array_equal(C[3], X[reseed[0, 3]])
+    # the public trainer uses it
+    m = T.kmeans(X, 12, 10, np.random.RandomState(1), n_init=2, device=True)
+    assert m.shape == (12, 10) and ((X - m[T._assign(X, m, device=False)]) ** 2).sum() < 1.2 * costs[-1] * 1.5
