@@ -31,6 +31,9 @@ CONFIGS = {
     # BASELINE.json configs[3] (headline metric) and configs[1]
     "c4": dict(metric="LOPQ queries/sec @ recall@10, 10Mx128-d, V=8 M=16", n_db=10_000_000, D=128, V=8, M=16,
                model="dlib128_V8_M16.npz", quota=330_000, style="dlib"),
+    # configs[0]: the reference's own CPU-runnable case (>= 100 CPU queries beside the GPU line)
+    "c1": dict(metric="LOPQ queries/sec @ recall@10, 100kx128-d, V=4 M=8", n_db=100_000, D=128, V=4, M=8,
+               model="dlib128_V4_M8.npz", quota=20_000, style="dlib", cpu_queries=100),
     "c2": dict(metric="LOPQ queries/sec @ recall@10, 1Mx128-d, V=8 M=16, batch=1024", n_db=1_000_000, D=128, V=8, M=16,
                model="dlib128_V8_M16.npz", quota=33_000, style="dlib"),
     # configs[2]: DeepSentibank-style 2048-d; the model is trained at start-up (134 MB of rotations: not a fixture)
@@ -51,8 +54,9 @@ def workload_string(a, cfg, name=None):
     if name == "c5":
         return "c5: compute_codes (LOPQModel.predict over rows), %dM x %d-d dlib-style synthetic rows, V=%d M=%d K=256" % (
             cfg["n_db"] // 1_000_000, cfg["D"], cfg["V"], cfg["M"])
-    return ("%s: %dM x %d-d %s-style synthetic (4096-centre GMM, L2-normalised), V=%d M=%d K=256, near-duplicate queries (rho=%.2f), "
-            "quota=%d, top-%d" % (name, cfg["n_db"] // 1_000_000, cfg["D"], cfg["style"], cfg["V"], cfg["M"], a.rho, cfg.get("quota", 0), a.k))
+    size = "%dM" % (cfg["n_db"] // 1_000_000) if cfg["n_db"] >= 1_000_000 else "%dk" % (cfg["n_db"] // 1000)
+    return ("%s: %s x %d-d %s-style synthetic (4096-centre GMM, L2-normalised), V=%d M=%d K=256, near-duplicate queries (rho=%.2f), "
+            "quota=%d, top-%d" % (name, size, cfg["D"], cfg["style"], cfg["V"], cfg["M"], a.rho, cfg.get("quota", 0), a.k))
 
 
 def parse():
@@ -84,6 +88,8 @@ def parse():
         cfg["n_db"] = a.n_db
     if a.quota:
         cfg["quota"] = a.quota
+    if "cpu_queries" in cfg and a.cpu_queries == 6:
+        a.cpu_queries = cfg["cpu_queries"]
     a.cfg = cfg
     return a
 
