@@ -2090,3 +2090,10 @@ int b2l_comm_error(b2l_handle h) {
 }
 
 }  // extern "C"
+
+#ifdef SCAN1_TRACE
+// developer builds only (profiles/dev/scan1_trace_probe.py): the block phase stamps of the last k_scan1 launch
+extern "C" int b2l_debug_scan1_trace(unsigned long long* out, int n) {
+    return (int)cudaMemcpyFromSymbol(out, g_scan1_trace, (size_t)n * 8);
+}
+#endif

@@ -47,6 +47,15 @@ __device__ __forceinline__ float adc_row1(const uint32_t (&w)[MP / 4], const uin
     return a;
 }
 
+// -DSCAN1_TRACE (developer builds only, profiles/dev/): %globaltimer stamps of every block's phases, first item only
+#ifdef SCAN1_TRACE
+__device__ unsigned long long g_scan1_trace[1024 * 8];
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define TR(i) do { if (threadIdx.x == 0 && blockIdx.x < 1024 && !tr_done[i]) { g_scan1_trace[blockIdx.x * 8 + (i)] = gtimer(); tr_done[i] = true; } } while (0)
+#else
+#define TR(i) do {} while (0)
+#endif
+
 struct Item1 {                     // decoded work item
     int cell, q, lut0, lut1, count;
     unsigned int posbase;
@@ -67,6 +76,10 @@ k_scan1(ScanArgs a) {
     const PlanView& pv = a.pv;
     if (smem_u32(smem) != SCAN_LUT_SADDR) __trap();
     const float INF = __int_as_float(0x7f800000);
+#ifdef SCAN1_TRACE
+    bool tr_done[8] = {false, false, false, false, false, false, false, false};
+#endif
+    TR(0);
 
     uint32_t cc[W];                                  // byte b of cc[T] = 4 * (g*MP + (jl ^ (4T+b))): column of this lane's look-up
 #pragma unroll
@@ -120,6 +133,7 @@ k_scan1(ScanArgs a) {
     unsigned int item = s_misc[2];
     int buf = 0, tab_q = -1;                          // tab_q: the query whose lane minima the block's bound table holds
     if (item < n_items) { decode(item, cur); fetch_lut(cur, 0); }
+    TR(1);
     while (item < n_items) {
         if (tid == 0) s_misc[3] = atomicAdd(&pv.cnt->next_item, 1u);
         // bound table: what finished items of the query left in gtab -- unless the block's previous item was the same query
@@ -129,6 +143,7 @@ k_scan1(ScanArgs a) {
         if (tid == 0) { s_misc[0] = *(volatile unsigned int*)&a.gthr[cur.q]; s_misc[1] = 0u; }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();                                                  // tables of `cur` landed; s_misc published
+        TR(2);
         const unsigned int nxt = s_misc[3];
         Item1 nx;
         if (nxt < n_items) { decode(nxt, nx); fetch_lut(nx, buf ^ 1); }   // overlaps the scan below
@@ -235,6 +250,10 @@ k_scan1(ScanArgs a) {
         };
         uint32_t wa[U][W];
         if (warp < nchunk) load_chunk(wa, warp);
+#ifdef SCAN1_TRACE
+        if (tid == 0 && !tr_done[3]) { volatile uint32_t sink = wa[0][0]; (void)sink; }
+#endif
+        TR(3);
 #pragma unroll
         for (int pf = 1; pf < SCAN1_PF; ++pf) {
             const int cp = warp + pf * SCAN_WARPS;
@@ -256,14 +275,17 @@ k_scan1(ScanArgs a) {
             refresh();
             __syncthreads();
         }
+        TR(4);
         for (int c = warp; c < nchunk; c += SCAN_WARPS) eval_chunk(wa, c);
         if (warp < nchunk) {
             const int e = ent + LPS * (gen & (a.GEN - 1));
             tab[e] = fminf(tab[e], mn);
         }
         __syncthreads();
+        TR(5);
         refresh();                                                         // the item's final bound (every warp computes the same)
         __syncthreads();
+        TR(6);
         // staged candidates at or below the final bound -> the query's global list
         {
             const unsigned int thr = s_misc[0];
@@ -294,4 +316,5 @@ k_scan1(ScanArgs a) {
         buf ^= 1;
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
+    TR(7);
 }
