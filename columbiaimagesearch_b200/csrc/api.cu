@@ -288,20 +288,27 @@ int encode_device(b2l_handle h, const void* dX, int x_is_f64, int64_t n, const i
         CU(cudaFuncSetAttribute(k_fine_argmin<DSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));     \
         k_fine_argmin<DSV><<<b2, FINE_THREADS, sm2, h->stream>>>(mv, h->w_px.as<double>(), n, d_fine, kchunk);   \
     } while (0)
-#define FINE32(DSV)                                                                                             \
+#define FINE32(DSV, RV)                                                                                         \
     do {                                                                                                        \
-        const size_t sm3 = (size_t)mv.K * DSV * 4;                                                              \
-        if (sm3 > 48 * 1024) CU(cudaFuncSetAttribute(k_fine_argmin32<DSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3)); \
-        k_fine_argmin32<DSV><<<b2, FINE_THREADS, sm3, h->stream>>>(mv, h->w_px.as<double>(), n, d_fine, h->d_nguard); \
+        const size_t sma = (size_t)mv.M * mv.K * (DSV + 1) * 4;                                                 \
+        if (DSV <= 16 && sma <= 200 * 1024) {                                       \
+            CU(cudaFuncSetAttribute(k_fine_argmin32_all<DSV, RV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sma)); \
+            k_fine_argmin32_all<DSV, RV><<<h->num_sms, FINE_ALL_THREADS, sma, h->stream>>>(mv, h->w_px.as<double>(), n, d_fine, h->d_nguard); \
+            break;                                                                                              \
+        }                                                                                                       \
+        const size_t sm3 = (size_t)256 * (DSV + 1) * 4 * 2;                                                     \
+        const unsigned b3 = (unsigned)((n + (int64_t)FINE_THREADS * RV - 1) / ((int64_t)FINE_THREADS * RV));     \
+        if (sm3 > 48 * 1024) CU(cudaFuncSetAttribute(k_fine_argmin32<DSV, RV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3)); \
+        k_fine_argmin32<DSV, RV><<<b3, FINE_THREADS, sm3, h->stream>>>(mv, h->w_px.as<double>(), n, d_fine, h->d_nguard); \
     } while (0)
         const bool f32stage = h->fine_mode == 0 && n >= 2048;    // float32 first stage + float64 guard (same codes)
         switch (mv.ds) {
-            case 2: if (f32stage) FINE32(2); else FINE(2); break;
-            case 4: if (f32stage) FINE32(4); else FINE(4); break;
-            case 8: if (f32stage) FINE32(8); else FINE(8); break;
-            case 16: if (f32stage) FINE32(16); else FINE(16); break;
-            case 32: if (f32stage) FINE32(32); else FINE(0); break;
-            case 64: if (f32stage) FINE32(64); else FINE(0); break;
+            case 2: if (f32stage) FINE32(2, 4); else FINE(2); break;
+            case 4: if (f32stage) FINE32(4, 4); else FINE(4); break;
+            case 8: if (f32stage) FINE32(8, 4); else FINE(8); break;
+            case 16: if (f32stage) FINE32(16, 2); else FINE(16); break;
+            case 32: if (f32stage) FINE32(32, 1); else FINE(0); break;
+            case 64: if (f32stage) FINE32(64, 1); else FINE(0); break;
             default:
                 if (mv.ds > 128) FAIL(B2L_ERR_UNSUPPORTED, "sub-vector length D/M = %d > 128 not supported", mv.ds);
                 FINE(0);
@@ -1400,13 +1407,18 @@ int b2l_set_model(b2l_handle h, int D, int V, int M, int K, int coarse_is_f32, c
     CU(cudaMemcpyAsync(h->dmus.p, mus, nC * 8, cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(h->dRt.p, rt.data(), nR * 8, cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(h->dsubs.p, subs, nS * 8, cudaMemcpyHostToDevice, h->stream));
-    std::vector<float> s32(nS), c2(M);
+    std::vector<float> s32(nS + (size_t)M * K), c2(M);       // float32 centroids, then their half norms [M][K] (k_fine_argmin32)
     for (int j = 0; j < M; ++j) {
         double mx = 0.0;
         for (int k = 0; k < K; ++k) {
             double n2 = 0.0;
             for (int d = 0; d < mv.ds; ++d) { const double v = subs[((size_t)j * K + k) * mv.ds + d]; n2 += v * v; s32[((size_t)j * K + k) * mv.ds + d] = (float)v; }
             mx = std::max(mx, n2);
+        }
+        for (int k = 0; k < K; ++k) {
+            float hn = 0.0f;
+            for (int d = 0; d < mv.ds; ++d) { const float v = s32[((size_t)j * K + k) * mv.ds + d]; hn = std::fmaf(v, v, hn); }
+            s32[nS + (size_t)j * K + k] = 0.5f * hn;
         }
         c2[j] = (float)(mx * 1.001 + 1e-30);
         h->c2m = std::max(j ? h->c2m : 0.0f, c2[j]);
@@ -1415,9 +1427,9 @@ int b2l_set_model(b2l_handle h, int D, int V, int M, int K, int coarse_is_f32, c
     for (int j = 0; j < M; ++j)
         for (int k = 0; k < K; ++k)
             for (int d = 0; d < mv.ds; ++d) s32t[((size_t)j * mv.ds + d) * K + k] = s32[((size_t)j * K + k) * mv.ds + d];
-    CU(h->dsubs32.reserve(nS * 4)); CU(h->dsubs32T.reserve(nS * 4)); CU(h->dc2max.reserve((size_t)M * 4));
+    CU(h->dsubs32.reserve((nS + (size_t)M * K) * 4)); CU(h->dsubs32T.reserve(nS * 4)); CU(h->dc2max.reserve((size_t)M * 4));
     CU(cudaMemcpyAsync(h->dsubs32T.p, s32t.data(), nS * 4, cudaMemcpyHostToDevice, h->stream));
-    CU(cudaMemcpyAsync(h->dsubs32.p, s32.data(), nS * 4, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->dsubs32.p, s32.data(), (nS + (size_t)M * K) * 4, cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(h->dc2max.p, c2.data(), (size_t)M * 4, cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     mv.subs32 = h->dsubs32.as<float>(); mv.subs32T = h->dsubs32T.as<float>(); mv.c2max = h->dc2max.as<float>();

@@ -183,58 +183,197 @@ k_coarse_assign(ModelView mv, const XT* __restrict__ X, int64_t n, int32_t* __re
     }
 }
 
+// one centroid from shared memory, in the widest loads its (compile-time) length allows; p is 16-byte aligned for DS % 4 == 0
+template <int DS> __device__ __forceinline__ void lds_centroid(const float* p, float (&c)[DS]) {
+    if (DS % 4 == 0) {
+#pragma unroll
+        for (int t = 0; t < DS / 4; ++t) { const float4 v = *((const float4*)p + t); c[4 * t] = v.x; c[4 * t + 1] = v.y; c[4 * t + 2] = v.z; c[4 * t + 3] = v.w; }
+    } else if (DS % 2 == 0) {
+#pragma unroll
+        for (int t = 0; t < DS / 2; ++t) { const float2 v = *((const float2*)p + t); c[2 * t] = v.x; c[2 * t + 1] = v.y; }
+    } else {
+#pragma unroll
+        for (int t = 0; t < DS; ++t) c[t] = p[t];
+    }
+}
+
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+
 // ---- fine argmin, float32 first stage with a float64 guard ------------------------------------------
-// Same result as k_fine_argmin (bit-exact with the reference), 3x less work on the float64 pipe: every distance is first
-// evaluated in float32 (FSUB + FFMA); the float32 winner is accepted only if the runner-up is farther than a rigorous
-// bound on the float32 evaluation error of both,
-//     |d32 - d| <= E(d) = 8 * 2^-24 * ( sqrt(d * (|p|^2 + max_k |c_k|^2)) + ds * d )
-// (input rounding of p and c, the subtraction, the products and the FMA chain; Cauchy-Schwarz on the cross terms).
-// Otherwise -- a near tie or an exact tie, a few rows per 100 000 -- that sub-vector is redone in float64 in NumPy's
-// order with the first-minimum rule (utils.py:33-53).
-template <int DS>
+// Same result as k_fine_argmin (bit-exact with the reference), on the float32 pipe at ONE FFMA per dimension: the argmin
+// of |p - c_k|^2 is the argmin of the score  s_k = |c_k|^2 / 2 - p.c_k  (the |p|^2 term is common), evaluated as an FMA chain
+// that starts from the precomputed half norm; a thread scores R rows against each centroid it reads from shared memory
+// (one broadcast load of c_k serves R x DS FFMAs).  The float32 winner is accepted only if the runner-up is farther than
+// three times a rigorous bound on the float32 evaluation error of a score,
+//     |s32 - s| <= E = (DS + 4) * 2^-24 * (|p| + max_k |c_k|)^2
+// (rounding of p and c to float32, of the half norm, and of the DS-step FMA chain; |p.c| <= |p||c|): then every other
+// centroid is strictly farther in exact arithmetic, by a margin (>= E) far above what float64 rounding could flip.
+// Otherwise -- a near tie or an exact tie, a few sub-vectors per 100 000 -- that sub-vector is redone in float64 in
+// NumPy's order with the first-minimum rule (utils.py:33-53).
+// Two table buffers at compile-time offsets (K <= 256): the table of sub-quantizer j+1 arrives by cp.async while j is
+// scored, so a sub-quantizer costs one barrier and no load phase; the body is instantiated once per buffer so that every
+// table address is a constant.
+template <int DS, int R>
+__device__ __forceinline__ void fine32_score(const ModelView& mv, const double* __restrict__ PX, int64_t n, uint8_t* __restrict__ fine,
+                                             int j, int64_t i0, const float* sm_sub32, const float* c2h, unsigned int& guards) {
+        const float U = 5.9604645e-08f;
+        float pn[R][DS], p2[R], best[R], second[R];
+        int bestk[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int64_t i = (i0 + r < n) ? i0 + r : i0;                 // (a dead second row repeats the first: not stored)
+            const double* p64 = PX + i * (int64_t)mv.D + (int64_t)j * DS;
+            p2[r] = 0.0f;
+#pragma unroll
+            for (int d = 0; d < DS; ++d) { const float v = (float)p64[d]; pn[r][d] = -v; p2[r] = fmaf(v, v, p2[r]); }
+            best[r] = 3.0e38f; second[r] = 3.0e38f; bestk[r] = 0;
+        }
+        // centroids four at a time: the two smallest scores of the four merge into (best, second) with 3 min/max operations
+        // per score instead of 5 (those run on the half-rate ALU pipe), and only the winning GROUP is tracked: its four
+        // scores are recomputed (same FMA chains, same bits) after the loop to name the centroid
+        const int K4 = mv.K & ~3;
+#pragma unroll 1
+        for (int k = 0; k < K4; k += 4) {
+            float sc[R][4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float c[DS];
+#pragma unroll
+                for (int t = 0; t < DS; ++t) c[t] = sm_sub32[(k + q) * DS + t];
+                const float hn = c2h[k + q];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    float v = hn;
+#pragma unroll
+                    for (int t = 0; t < DS; ++t) v = fmaf(pn[r][t], c[t], v);
+                    sc[r][q] = v;
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const float a = fminf(sc[r][0], sc[r][1]), b = fmaxf(sc[r][0], sc[r][1]);
+                const float c = fminf(sc[r][2], sc[r][3]), d = fmaxf(sc[r][2], sc[r][3]);
+                const float lo1 = fminf(a, c);
+                const float lo2 = fminf(fminf(fmaxf(a, c), b), d);               // second smallest of the four
+                second[r] = fminf(fminf(second[r], fmaxf(best[r], lo1)), lo2);   // an exact tie leaves second == best
+                if (lo1 < best[r]) bestk[r] = k;                                  // first group holding the minimum
+                best[r] = fminf(best[r], lo1);
+            }
+        }
+        for (int k = K4; k < mv.K; ++k) {                                         // (K not a multiple of 4)
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                float v = c2h[k];
+#pragma unroll
+                for (int t = 0; t < DS; ++t) v = fmaf(pn[r][t], sm_sub32[k * DS + t], v);
+                second[r] = fminf(second[r], fmaxf(v, best[r]));
+                if (v < best[r]) bestk[r] = k;
+                best[r] = fminf(best[r], v);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {                                             // the winner inside its group
+            const int k0 = bestk[r];
+            if (k0 < K4) {
+                int kk = k0 + 3;
+#pragma unroll
+                for (int q = 3; q >= 0; --q) {
+                    float v = c2h[k0 + q];
+#pragma unroll
+                    for (int t = 0; t < DS; ++t) v = fmaf(pn[r][t], sm_sub32[(k0 + q) * DS + t], v);
+                    if (v == best[r]) kk = k0 + q;                                // first of equal ones (a tie goes to the guard anyway)
+                }
+                bestk[r] = kk;
+            }
+        }
+        const float cm = sqrtf(mv.c2max[j]);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (i0 + r >= n) break;
+            const float sp = sqrtf(p2[r]) + cm;
+            const float E = (float)(DS + 4) * U * sp * sp * 1.01f + 1e-30f;
+            int bk = bestk[r];
+            if (!(second[r] - best[r] > 3.0f * E)) {       // cannot be proven in float32: exact evaluation of this sub-vector
+                const double* p64 = PX + (i0 + r) * (int64_t)mv.D + (int64_t)j * DS;
+                double pj[DS];
+#pragma unroll
+                for (int d = 0; d < DS; ++d) pj[d] = p64[d];
+                double b64 = 1e300;
+                for (int k = 0; k < mv.K; ++k) {
+                    const double d64 = sqdist_np<double>(pj, mv.subs + ((int64_t)j * mv.K + k) * DS, DS);
+                    if (d64 < b64) { b64 = d64; bk = k; }
+                }
+                ++guards;
+            }
+            fine[(i0 + r) * (int64_t)mv.M + j] = (uint8_t)bk;
+        }
+}
+
+template <int DS, int R>
 __global__ void __launch_bounds__(FINE_THREADS)
 k_fine_argmin32(ModelView mv, const double* __restrict__ PX, int64_t n, uint8_t* __restrict__ fine, unsigned long long* __restrict__ nguard) {
-    extern __shared__ float sm_sub32[];   // [K][DS]
-    const int64_t i = (int64_t)blockIdx.x * FINE_THREADS + threadIdx.x;
-    const bool live = i < n;
-    const float U8 = 8.0f * 5.9604645e-08f;
+    extern __shared__ __align__(16) float sm_fine[];     // 2 x ([256][DS] centroids + [256] half norms)
+    const int64_t i0 = ((int64_t)blockIdx.x * FINE_THREADS + threadIdx.x) * R;
+    const float* c2h_all = mv.subs32 + (int64_t)mv.M * mv.K * DS;   // half norms: stored after the centroids
+    const bool wide = (mv.K % 4 == 0);
+    auto fetch = [&](int j, int buf) {
+        float* dst = sm_fine + buf * (256 * (DS + 1));
+        const float* sc = mv.subs32 + (int64_t)j * mv.K * DS;
+        const float* sh = c2h_all + (int64_t)j * mv.K;
+        if (wide) {
+            for (int e = threadIdx.x * 4; e < mv.K * DS; e += FINE_THREADS * 4) cp_async16(dst + e, sc + e);
+            for (int e = threadIdx.x * 4; e < mv.K; e += FINE_THREADS * 4) cp_async16(dst + 256 * DS + e, sh + e);
+        } else {
+            for (int e = threadIdx.x; e < mv.K * DS; e += FINE_THREADS) cp_async4(dst + e, sc + e);
+            for (int e = threadIdx.x; e < mv.K; e += FINE_THREADS) cp_async4(dst + 256 * DS + e, sh + e);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    fetch(0, 0);
     unsigned int guards = 0;
-    for (int j = 0; j < mv.M; ++j) {
+    for (int j = 0; j < mv.M; j += 2) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                     // table j landed for everybody; everybody is through with table j-1
+        if (j + 1 < mv.M) fetch(j + 1, 1);
+        if (i0 < n) fine32_score<DS, R>(mv, PX, n, fine, j, i0, sm_fine, sm_fine + 256 * DS, guards);
+        if (j + 1 >= mv.M) break;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
-        const float* src = mv.subs32 + (int64_t)j * mv.K * DS;
-        for (int e = threadIdx.x; e < mv.K * DS; e += FINE_THREADS) sm_sub32[e] = src[e];
-        __syncthreads();
-        if (!live) continue;
-        const double* p64 = PX + i * (int64_t)mv.D + (int64_t)j * DS;
-        float p[DS];
-        float p2 = 0.0f;
-#pragma unroll
-        for (int d = 0; d < DS; ++d) { p[d] = (float)p64[d]; p2 = fmaf(p[d], p[d], p2); }
-        float best = 3.0e38f, second = 3.0e38f;
-        int bestk = 0;
-#pragma unroll 4
-        for (int k = 0; k < mv.K; ++k) {
-            const float* c = sm_sub32 + k * DS;
-            float d = 0.0f;
-#pragma unroll
-            for (int t = 0; t < DS; ++t) { const float df = p[t] - c[t]; d = fmaf(df, df, d); }
-            if (d < best) { second = best; best = d; bestk = k; }
-            else second = fminf(second, d);
-        }
-        const float s2 = (p2 + mv.c2max[j]) * 1.0001f + 1e-30f;
-        const float err = U8 * (sqrtf(second * s2) + (float)DS * second) + 1e-13f * s2;
-        if (!(second - best > 2.0f * err)) {           // cannot be proven in float32: exact evaluation of this sub-vector
-            double pj[DS];
-#pragma unroll
-            for (int d = 0; d < DS; ++d) pj[d] = p64[d];
-            double b64 = 1e300;
-            for (int k = 0; k < mv.K; ++k) {
-                const double d64 = sqdist_np<double>(pj, mv.subs + ((int64_t)j * mv.K + k) * DS, DS);
-                if (d64 < b64) { b64 = d64; bestk = k; }
-            }
-            ++guards;
-        }
-        fine[i * (int64_t)mv.M + j] = (uint8_t)bestk;
+        if (j + 2 < mv.M) fetch(j + 2, 0);
+        if (i0 < n) fine32_score<DS, R>(mv, PX, n, fine, j + 1, i0, sm_fine + 256 * (DS + 1), sm_fine + 256 * (DS + 1) + 256 * DS, guards);
+    }
+    if (guards && nguard) atomicAdd(nguard, (unsigned long long)guards);
+}
+
+// All M tables resident (M * K * (DS + 1) floats fit one block's shared memory: D <= ~190 at K = 256): one persistent block
+// per SM, the tables are loaded once, and the warps never meet again -- each takes 32 x R rows at a time through all M
+// sub-quantizers (no barrier per sub-quantizer: in k_fine_argmin32 a fifth of the warp time is spent waiting for the
+// slowest warp of the block at every table switch).
+#define FINE_ALL_THREADS 640
+template <int DS, int R>
+__global__ void __launch_bounds__(FINE_ALL_THREADS, 1)
+k_fine_argmin32_all(ModelView mv, const double* __restrict__ PX, int64_t n, uint8_t* __restrict__ fine, unsigned long long* __restrict__ nguard) {
+    extern __shared__ __align__(16) float sm_fine[];     // [M][K][DS] centroids, then [M][K] half norms: the layout of mv.subs32
+    const int nfl = mv.M * mv.K * (DS + 1);
+    if (nfl % 4 == 0) for (int e = threadIdx.x * 4; e < nfl; e += FINE_ALL_THREADS * 4) cp_async16(sm_fine + e, mv.subs32 + e);
+    else for (int e = threadIdx.x; e < nfl; e += FINE_ALL_THREADS) cp_async4(sm_fine + e, mv.subs32 + e);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    const float* c2h_all = sm_fine + mv.M * mv.K * DS;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t ntile = (n + 32 * R - 1) / (32 * R);
+    unsigned int guards = 0;
+    for (int64_t tile = (int64_t)blockIdx.x * (FINE_ALL_THREADS / 32) + warp; tile < ntile; tile += (int64_t)gridDim.x * (FINE_ALL_THREADS / 32)) {
+        const int64_t i0 = (tile * 32 + lane) * R;
+        if (i0 >= n) continue;
+        for (int j = 0; j < mv.M; ++j)
+            fine32_score<DS, R>(mv, PX, n, fine, j, i0, sm_fine + j * mv.K * DS, c2h_all + j * mv.K, guards);
     }
     if (guards && nguard) atomicAdd(nguard, (unsigned long long)guards);
 }
