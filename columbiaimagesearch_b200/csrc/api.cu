@@ -237,7 +237,8 @@ int encode_device(b2l_handle h, const void* dX, int x_is_f64, int64_t n, const i
     const unsigned blocks = (unsigned)((n + ENC_WARPS - 1) / ENC_WARPS);
     const size_t smem = (size_t)ENC_WARPS * mv.h * 8;
     // batch encode of the common shape: coarse assignment, then the rotation as a grouped float64 tensor-core GEMM
-    const bool gemm = d_fine && !d_coarse_in && d_coarse && mv.h % 64 == 0 && n >= 2048 && n < ((int64_t)1 << 31);
+    const bool gemm = d_fine && !d_coarse_in && d_coarse && mv.h % 64 == 0 && n >= 2048 && n < ((int64_t)1 << 31) &&
+                      ((uintptr_t)x % 16 == 0);    // (the h = 64 kernel copies raw rows with 16-byte cp.async)
     // coarse assignment only (utils.predict_cluster over rows; the assignment step of k-means training): no projection
     const bool coarse_only = !d_fine && !d_coarse_in && d_coarse;
     double* px_out = (gemm || coarse_only) ? nullptr : h->w_px.as<double>();
@@ -272,10 +273,17 @@ int encode_device(b2l_handle h, const void* dX, int x_is_f64, int64_t n, const i
             else { CU(cudaFuncSetAttribute(k_rotate_dmma_g<float, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr));
                 k_rotate_dmma_g<float, 0><<<g2, 128, smr, h->stream>>>(mv, (const float*)x, n, cnt, base, tile_base, perm, nullptr, h->w_px.as<double>()); }
         } else
-        if (xf64) { CU(cudaFuncSetAttribute(k_rotate_dmma<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr));
-            k_rotate_dmma<double><<<tiles, 128, smr, h->stream>>>(mv, (const double*)x, n, cnt, base, tile_base, perm, h->w_px.as<double>()); }
-        else { CU(cudaFuncSetAttribute(k_rotate_dmma<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr));
-            k_rotate_dmma<float><<<tiles, 128, smr, h->stream>>>(mv, (const float*)x, n, cnt, base, tile_base, perm, h->w_px.as<double>()); }
+        {
+            // consecutive tiles per block: enough blocks for ~6 per resident slot, at most 8 tiles each
+            const int tpb = (int)std::max<int64_t>(1, std::min<int64_t>(8, (int64_t)tiles / ((int64_t)h->num_sms * 18)));
+            const unsigned g1 = (tiles + (unsigned)tpb - 1) / (unsigned)tpb;
+            if (xf64) { const size_t sm1 = rotate_smem_bytes<double>();
+                CU(cudaFuncSetAttribute(k_rotate_dmma<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
+                k_rotate_dmma<double><<<g1, 128, sm1, h->stream>>>(mv, (const double*)x, n, cnt, base, tile_base, perm, h->w_px.as<double>(), tpb); }
+            else { const size_t sm1 = rotate_smem_bytes<float>();
+                CU(cudaFuncSetAttribute(k_rotate_dmma<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
+                k_rotate_dmma<float><<<g1, 128, sm1, h->stream>>>(mv, (const float*)x, n, cnt, base, tile_base, perm, h->w_px.as<double>(), tpb); }
+        }
         LAUNCHED();
     }
     if (d_fine) {

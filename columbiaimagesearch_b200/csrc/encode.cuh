@@ -449,67 +449,108 @@ __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, do
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-// one block (4 warps) per 64-row tile of one bucket; h == 64.  dynamic smem: Rt[64][68] | resid[64][68] doubles | rows[64] int
+// h == 64.  A block (4 warps) walks `tpb` consecutive 64-row tiles (tiles are numbered bucket by bucket, so they mostly share
+// one R[c]): R[c], C[c], mu[c] are loaded when the bucket changes, the raw rows of tile t+1 arrive by cp.async in the other
+// buffer while tile t is contracted (row indices are fetched two tiles ahead), and the coarse residual is formed on the
+// fly when the A fragments are read -- one barrier per tile, no load phase in front of the tensor-core loop.
+// dynamic smem: Rt[64][68] doubles | C[64], mu[64] doubles | raw[2][64][68] XT | rows[2][64] int
 #define ROT_H 64
 #define ROT_LD 68
+template <typename XT>
+size_t rotate_smem_bytes() { return (size_t)ROT_H * ROT_LD * 8 + 128 * 8 + (size_t)2 * 64 * ROT_LD * sizeof(XT) + 2 * 64 * 4; }
+
 template <typename XT>
 __global__ void __launch_bounds__(128)
 k_rotate_dmma(ModelView mv, const XT* __restrict__ X, int64_t n, const unsigned int* __restrict__ cnt,
               const unsigned int* __restrict__ base, const unsigned int* __restrict__ tile_base, const unsigned int* __restrict__ perm,
-              double* __restrict__ PX) {
-    extern __shared__ double sm_rot[];
-    double* Rs = sm_rot;                       // Rs[d][t] = Rt[d][t]
-    double* Es = sm_rot + ROT_H * ROT_LD;      // Es[row][d]
-    int* rows = (int*)(Es + ROT_H * ROT_LD);
+              double* __restrict__ PX, int tpb) {
+    extern __shared__ __align__(16) double sm_rot[];
+    double* Rs = sm_rot;                           // Rs[d][t] = Rt[d][t]
+    double* Cm = Rs + ROT_H * ROT_LD;              // C[64] | mu[64]
+    XT* Xs = (XT*)(Cm + 128);                      // raw rows, two tiles
+    int* rows = (int*)(Xs + 2 * 64 * ROT_LD);
     const int V = mv.V, nb = 2 * V;
-    const unsigned int tile = blockIdx.x;
-    if (tile >= tile_base[nb]) return;
-    int lo = 0, hi = nb;                       // tile_base[lo] <= tile < tile_base[hi]
-    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (tile_base[mid] <= tile) lo = mid; else hi = mid; }
-    const int b = lo, s = b / V;
-    const unsigned int row0 = (tile - tile_base[b]) * 64u;
-    const int nrow = (int)min(64u, cnt[b] - row0);
+    const unsigned int total = tile_base[nb];
+    const unsigned int t0 = blockIdx.x * (unsigned)tpb;
+    if (t0 >= total) return;
+    const unsigned int t1 = min(total, t0 + (unsigned)tpb);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const double* Rt = mv.Rt + (int64_t)b * ROT_H * ROT_H;
-    const double* C = mv.Cs + (int64_t)b * ROT_H;
-    const double* mu = mv.mus + (int64_t)b * ROT_H;
-    if (tid < 64) rows[tid] = tid < nrow ? (int)perm[(size_t)s * n + base[b] + row0 + tid] : -1;
-    for (int e = tid; e < ROT_H * ROT_H; e += 128) Rs[(e >> 6) * ROT_LD + (e & 63)] = Rt[e];
-    __syncthreads();
-    for (int e = tid; e < ROT_H * ROT_H; e += 128) {
-        const int r = e >> 6, d = e & 63;
-        const int i = rows[r];
-        Es[r * ROT_LD + d] = i >= 0 ? coarse_residual<XT>(X[(int64_t)i * mv.D + s * ROT_H + d], C[d], mu[d], mv.coarse_f32) : 0.0;
-    }
-    __syncthreads();
-    double acc[2][8][2];
-#pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) { acc[mt][nt][0] = 0.0; acc[mt][nt][1] = 0.0; }
     const int ar = lane >> 2, ak = lane & 3;
-#pragma unroll 4
-    for (int k0 = 0; k0 < ROT_H; k0 += 4) {
-        double a[2], bb[8];
+    const int cr = tid >> 1, chalf = tid & 1;      // this thread copies half `chalf` of row `cr` of a tile
+    constexpr int HALF = ROT_H / 2, NCP = HALF * (int)sizeof(XT) / 16;
+
+    auto bucket_from = [&](int b, unsigned int t) { while (tile_base[b + 1] <= t) ++b; return b; };   // (empty buckets have no tiles)
+    auto row_index = [&](unsigned int t, int b) -> int {                 // source row of this thread's copy row in tile t
+        const unsigned int row0 = (t - tile_base[b]) * 64u;
+        return (row0 + (unsigned)cr < cnt[b]) ? (int)perm[(size_t)(b / V) * n + base[b] + row0 + cr] : -1;
+    };
+    auto issue = [&](int idx, int b, int buf) {
+        if (idx >= 0) {
+            const XT* src = X + (int64_t)idx * mv.D + (b / V) * ROT_H + chalf * HALF;
+            XT* dst = Xs + (size_t)(buf * 64 + cr) * ROT_LD + chalf * HALF;
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) a[mt] = Es[(16 * warp + 8 * mt + ar) * ROT_LD + k0 + ak];
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) bb[nt] = Rs[(k0 + ak) * ROT_LD + 8 * nt + ar];
+            for (int c = 0; c < NCP; ++c) cp_async16((char*)dst + 16 * c, (const char*)src + 16 * c);
+        }
+        if (chalf == 0) rows[buf * 64 + cr] = idx;
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    int bcur;
+    {
+        int lo = 0, hi = nb;                       // tile_base[lo] <= t0 < tile_base[hi]
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (tile_base[mid] <= t0) lo = mid; else hi = mid; }
+        bcur = bucket_from(lo, t0);
+    }
+    issue(row_index(t0, bcur), bcur, 0);
+    int bnext = bcur, idx1 = -1;
+    if (t0 + 1 < t1) { bnext = bucket_from(bcur, t0 + 1); idx1 = row_index(t0 + 1, bnext); }
+    int bload = -1;
+    for (unsigned int t = t0; t < t1; ++t) {
+        const int buf = (int)((t - t0) & 1u);
+        if (bcur != bload) {                       // another bucket: its rotation, centroid and mean
+            if (bload >= 0) __syncthreads();       // (the previous tile still reads the old ones)
+            const double* Rt = mv.Rt + (int64_t)bcur * ROT_H * ROT_H;
+            for (int e = tid; e < ROT_H * ROT_H; e += 128) Rs[(e >> 6) * ROT_LD + (e & 63)] = Rt[e];
+            if (tid < 64) Cm[tid] = mv.Cs[(int64_t)bcur * ROT_H + tid];
+            else Cm[tid] = mv.mus[(int64_t)bcur * ROT_H + tid - 64];
+            bload = bcur;
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                           // tile t (and R) in place; everybody is through with tile t-1
+        if (t + 1 < t1) issue(idx1, bnext, buf ^ 1);
+        int b2 = bnext, idx2 = -1;
+        if (t + 2 < t1) { b2 = bucket_from(bnext, t + 2); idx2 = row_index(t + 2, b2); }   // (latency overlaps the contraction)
+        const int s = bcur / V;
+        double acc[2][8][2];
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-            for (int nt = 0; nt < 8; ++nt) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], a[mt], bb[nt]);
-    }
+            for (int nt = 0; nt < 8; ++nt) { acc[mt][nt][0] = 0.0; acc[mt][nt][1] = 0.0; }
+        const XT* xt = Xs + (size_t)(buf * 64 + 16 * warp + ar) * ROT_LD + ak;
+#pragma unroll 4
+        for (int k0 = 0; k0 < ROT_H; k0 += 4) {
+            double a[2], bb[8];
+            const double cc = Cm[k0 + ak], mm = Cm[64 + k0 + ak];
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {
-        const int i = rows[16 * warp + 8 * mt + ar];
-        if (i < 0) continue;
-        double* o = PX + (int64_t)i * mv.D + s * ROT_H + 2 * ak;
+            for (int mt = 0; mt < 2; ++mt) a[mt] = coarse_residual<XT>(xt[(size_t)8 * mt * ROT_LD + k0], cc, mm, mv.coarse_f32);
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) *(double2*)(o + 8 * nt) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+            for (int nt = 0; nt < 8; ++nt) bb[nt] = Rs[(k0 + ak) * ROT_LD + 8 * nt + ar];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], a[mt], bb[nt]);
+        }
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            const int i = rows[buf * 64 + 16 * warp + 8 * mt + ar];
+            if (i < 0) continue;
+            double* o = PX + (int64_t)i * mv.D + s * ROT_H + 2 * ak;
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) *(double2*)(o + 8 * nt) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+        }
+        bcur = bnext; bnext = b2; idx1 = idx2;
     }
 }
-
 
 // ---- the same grouped GEMM for any h that is a multiple of 64 (2048-d models: h = 1024) -------------------------------
 // grid = (64-row tiles, h / 64 column blocks).  A block produces a 64 x 64 tile of P = Resid . R[c]^T, walking the
