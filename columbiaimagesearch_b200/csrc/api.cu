@@ -205,6 +205,30 @@ template <int MP> int launch_scan1(b2l_handle h, const ScanArgs& a) {
     return B2L_OK;
 }
 
+// grouped rotation GEMM for h > 64 (encode.cuh): the pipelined kernel, or the plain one when the input is not 16-byte aligned
+template <int MODE>
+int launch_rotate_g(b2l_handle h, const void* x, int xf64, int64_t n, const unsigned int* cnt, const unsigned int* base,
+                    const unsigned int* tile_base, const unsigned int* perm, const int32_t* desc, double* out, unsigned tiles) {
+    const ModelView& mv = h->mv;
+    const dim3 g2(tiles, (unsigned)(mv.h / 64));
+    const bool aligned = ((uintptr_t)x % 16 == 0) && (((size_t)mv.D * (xf64 ? 8 : 4)) % 16 == 0);
+    if (aligned) {
+        if (xf64) { const size_t sm = rotate_g_smem_bytes<double>();
+            CU(cudaFuncSetAttribute(k_rotate_dmma_g<double, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            k_rotate_dmma_g<double, MODE><<<g2, 128, sm, h->stream>>>(mv, (const double*)x, n, cnt, base, tile_base, perm, desc, out); }
+        else { const size_t sm = rotate_g_smem_bytes<float>();
+            CU(cudaFuncSetAttribute(k_rotate_dmma_g<float, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            k_rotate_dmma_g<float, MODE><<<g2, 128, sm, h->stream>>>(mv, (const float*)x, n, cnt, base, tile_base, perm, desc, out); }
+    } else {
+        const size_t smr = (size_t)2 * 64 * ROT_LD * 8 + 64 * 4;
+        if (xf64) { CU(cudaFuncSetAttribute(k_rotate_dmma_g0<double, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr));
+            k_rotate_dmma_g0<double, MODE><<<g2, 128, smr, h->stream>>>(mv, (const double*)x, n, cnt, base, tile_base, perm, desc, out); }
+        else { CU(cudaFuncSetAttribute(k_rotate_dmma_g0<float, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr));
+            k_rotate_dmma_g0<float, MODE><<<g2, 128, smr, h->stream>>>(mv, (const float*)x, n, cnt, base, tile_base, perm, desc, out); }
+    }
+    return B2L_OK;
+}
+
 // copy helper honouring on_device
 int copy_in(b2l_handle h, void* dst, const void* src, size_t bytes, int on_device) {
     CU(cudaMemcpyAsync(dst, src, bytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
@@ -265,13 +289,9 @@ int encode_device(b2l_handle h, const void* dX, int x_is_f64, int64_t n, const i
         k_enc_scatter<<<grid_for(n, 256), 256, 0, h->stream>>>(d_coarse, n, mv.V, base, cursor, perm);
         LAUNCHED();
         const unsigned tiles = (unsigned)(2 * ((n + 63) / 64) + nb);       // upper bound; surplus blocks leave at once
-        const size_t smr = (size_t)2 * ROT_H * ROT_LD * 8 + 64 * 4;
         if (mv.h != ROT_H) {             // large models (2048-d: h = 1024): 64 x 64 output tiles, contraction in chunks of 64
-            const dim3 g2(tiles, (unsigned)(mv.h / 64));
-            if (xf64) { CU(cudaFuncSetAttribute(k_rotate_dmma_g<double, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr));
-                k_rotate_dmma_g<double, 0><<<g2, 128, smr, h->stream>>>(mv, (const double*)x, n, cnt, base, tile_base, perm, nullptr, h->w_px.as<double>()); }
-            else { CU(cudaFuncSetAttribute(k_rotate_dmma_g<float, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr));
-                k_rotate_dmma_g<float, 0><<<g2, 128, smr, h->stream>>>(mv, (const float*)x, n, cnt, base, tile_base, perm, nullptr, h->w_px.as<double>()); }
+            int rc = launch_rotate_g<0>(h, x, xf64, n, cnt, base, tile_base, perm, nullptr, h->w_px.as<double>(), tiles);
+            if (rc) return rc;
         } else
         {
             // consecutive tiles per block: enough blocks for ~6 per resident slot, at most 8 tiles each
@@ -674,12 +694,7 @@ int search_large_impl(b2l_handle h, const void* x, int xf64, int nq, int64_t quo
                 LAUNCHED();
                 k_slot_scatter<<<sg, 256, 0, h->stream>>>(wv.lut_desc, &wv.cnt->n_lut, mv.V, nl, bbase, bcur, perm);
                 LAUNCHED();
-                const dim3 g2((unsigned)(nl / 64 + nb2), (unsigned)(mv.h / 64));
-                const size_t smr = (size_t)2 * 64 * ROT_LD * 8 + 64 * 4;
-                if (xf64) { CU(cudaFuncSetAttribute(k_rotate_dmma_g<double, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr));
-                    k_rotate_dmma_g<double, 1><<<g2, 128, smr, h->stream>>>(mv, (const double*)xs, (int64_t)nl, bc, bbase, btile, perm, wv.lut_desc, h->w_p64.as<double>()); }
-                else { CU(cudaFuncSetAttribute(k_rotate_dmma_g<float, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr));
-                    k_rotate_dmma_g<float, 1><<<g2, 128, smr, h->stream>>>(mv, (const float*)xs, (int64_t)nl, bc, bbase, btile, perm, wv.lut_desc, h->w_p64.as<double>()); }
+                if ((rc = launch_rotate_g<1>(h, xs, xf64, (int64_t)nl, bc, bbase, btile, perm, wv.lut_desc, h->w_p64.as<double>(), (unsigned)(nl / 64 + nb2)))) return rc;
                 LAUNCHED();
             } else {
                 // shapes without the grouped GEMM: one block per slot computes the projection (k_lut with no table output)
@@ -982,12 +997,7 @@ int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_
             LAUNCHED();
             k_slot_scatter<<<sg, 256, 0, h->stream>>>(pv.lut_desc, &pv.cnt->n_lut, mv.V, cap_lut, bbase, bcur, perm);
             LAUNCHED();
-            const dim3 g2((unsigned)(cap_lut / 64 + nb2), (unsigned)(mv.h / 64));
-            const size_t smr = (size_t)2 * 64 * ROT_LD * 8 + 64 * 4;
-            if (xf64) { CU(cudaFuncSetAttribute(k_rotate_dmma_g<double, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr));
-                k_rotate_dmma_g<double, 1><<<g2, 128, smr, h->stream>>>(mv, (const double*)x, (int64_t)cap_lut, bc, bbase, btile, perm, pv.lut_desc, h->w_p64.as<double>()); }
-            else { CU(cudaFuncSetAttribute(k_rotate_dmma_g<float, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr));
-                k_rotate_dmma_g<float, 1><<<g2, 128, smr, h->stream>>>(mv, (const float*)x, (int64_t)cap_lut, bc, bbase, btile, perm, pv.lut_desc, h->w_p64.as<double>()); }
+            if ((rc = launch_rotate_g<1>(h, x, xf64, (int64_t)cap_lut, bc, bbase, btile, perm, pv.lut_desc, h->w_p64.as<double>(), (unsigned)(cap_lut / 64 + nb2)))) return rc;
             LAUNCHED();
             if (packed) {
                 constexpr int SB = 4;

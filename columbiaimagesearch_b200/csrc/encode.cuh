@@ -562,7 +562,7 @@ k_rotate_dmma(ModelView mv, const XT* __restrict__ X, int64_t n, const unsigned 
 //         `n` is then the slot capacity (row stride of perm).
 template <typename XT, int MODE>
 __global__ void __launch_bounds__(128)
-k_rotate_dmma_g(ModelView mv, const XT* __restrict__ X, int64_t n, const unsigned int* __restrict__ cnt,
+k_rotate_dmma_g0(ModelView mv, const XT* __restrict__ X, int64_t n, const unsigned int* __restrict__ cnt,
                 const unsigned int* __restrict__ base, const unsigned int* __restrict__ tile_base, const unsigned int* __restrict__ perm,
                 const int32_t* __restrict__ desc, double* __restrict__ OUT) {
     extern __shared__ double sm_rot[];
@@ -610,6 +610,99 @@ k_rotate_dmma_g(ModelView mv, const XT* __restrict__ X, int64_t n, const unsigne
             for (int mt = 0; mt < 2; ++mt) a[mt] = Es[(16 * warp + 8 * mt + ar) * ROT_LD + k0 + ak];
 #pragma unroll
             for (int nt = 0; nt < 8; ++nt) bb[nt] = Rs[(k0 + ak) * ROT_LD + 8 * nt + ar];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], a[mt], bb[nt]);
+        }
+    }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+        const int i = rows[16 * warp + 8 * mt + ar];
+        if (i < 0) continue;
+        double* o = (MODE == 0 ? OUT + (int64_t)i * mv.D + s * h : OUT + (int64_t)i * h) + t0 + 2 * ak;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) *(double2*)(o + 8 * nt) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+    }
+}
+
+// The same, pipelined (k_rotate_dmma_g0 stays as the path for inputs that are not 16-byte aligned): the R chunk, the raw
+// row chunk and the C / mu chunk of contraction step c+1 arrive by cp.async in the other buffers while step c runs on the
+// tensor cores; the residual is formed when the A fragments are read.  One barrier per 64-wide contraction step.
+// dynamic smem: R[2][64][68] doubles | Cmu[2][128] doubles | raw[2][64][68] XT | rows[64] int
+template <typename XT>
+size_t rotate_g_smem_bytes() { return (size_t)2 * 64 * ROT_LD * 8 + 2 * 128 * 8 + (size_t)2 * 64 * ROT_LD * sizeof(XT) + 64 * 4; }
+
+template <typename XT, int MODE>
+__global__ void __launch_bounds__(128)
+k_rotate_dmma_g(ModelView mv, const XT* __restrict__ X, int64_t n, const unsigned int* __restrict__ cnt,
+                const unsigned int* __restrict__ base, const unsigned int* __restrict__ tile_base, const unsigned int* __restrict__ perm,
+                const int32_t* __restrict__ desc, double* __restrict__ OUT) {
+    extern __shared__ __align__(16) double sm_rot[];
+    double* Rs = sm_rot;                           // [2][64][68]: Rs[buf][d][t]
+    double* Cm = Rs + 2 * 64 * ROT_LD;             // [2][C 64 | mu 64]
+    XT* Xs = (XT*)(Cm + 2 * 128);                  // [2][64][68] raw rows
+    int* rows = (int*)(Xs + 2 * 64 * ROT_LD);
+    const int V = mv.V, nb = 2 * V, h = mv.h;
+    const unsigned int tile = blockIdx.x;
+    if (tile >= tile_base[nb]) return;
+    int lo = 0, hi = nb;
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (tile_base[mid] <= tile) lo = mid; else hi = mid; }
+    const int b = lo, s = b / V;
+    const unsigned int row0 = (tile - tile_base[b]) * 64u;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int t0 = blockIdx.y * 64;
+    const double* Rt = mv.Rt + (int64_t)b * h * (int64_t)h + t0;
+    const double* C = mv.Cs + (int64_t)b * h;
+    const double* mu = mv.mus + (int64_t)b * h;
+    const int cr = tid >> 1, chalf = tid & 1;      // this thread copies half `chalf` of row `cr` of every chunk
+    constexpr int NCX = 32 * (int)sizeof(XT) / 16;
+    int myrow = -1;
+    if (row0 + (unsigned)cr < cnt[b]) myrow = (int)perm[(size_t)s * n + base[b] + row0 + cr];
+    if (chalf == 0) rows[cr] = myrow;
+    const XT* xrow = nullptr;
+    if (myrow >= 0) xrow = (MODE == 0 ? X + (int64_t)myrow * mv.D : X + (int64_t)desc[3 * myrow] * mv.D) + s * h + chalf * 32;
+    auto issue = [&](int d0, int buf) {
+        // R chunk: rows d0 .. d0+63 of Rt, 64 doubles each (512 B = 32 x 16 B): thread -> (row cr, half chalf): 16 copies
+        {
+            const char* src = (const char*)(Rt + (int64_t)(d0 + cr) * h + chalf * 32);
+            char* dst = (char*)(Rs + (size_t)(buf * 64 + cr) * ROT_LD + chalf * 32);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) cp_async16(dst + 16 * c, src + 16 * c);
+        }
+        if (xrow) {
+            const char* src = (const char*)(xrow + d0);
+            char* dst = (char*)(Xs + (size_t)(buf * 64 + cr) * ROT_LD + chalf * 32);
+#pragma unroll
+            for (int c = 0; c < NCX; ++c) cp_async16(dst + 16 * c, src + 16 * c);
+        }
+        if (tid < 32) cp_async16(Cm + buf * 128 + 2 * tid, C + d0 + 2 * tid);
+        else if (tid < 64) cp_async16(Cm + buf * 128 + 64 + 2 * (tid - 32), mu + d0 + 2 * (tid - 32));
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    double acc[2][8][2];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) { acc[mt][nt][0] = 0.0; acc[mt][nt][1] = 0.0; }
+    const int ar = lane >> 2, ak = lane & 3;
+    issue(0, 0);
+    int buf = 0;
+    for (int d0 = 0; d0 < h; d0 += 64, buf ^= 1) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                           // chunk d0 landed for everybody; everybody is through with chunk d0-64
+        if (d0 + 64 < h) issue(d0 + 64, buf ^ 1);
+        const XT* xt = Xs + (size_t)(buf * 64 + 16 * warp + ar) * ROT_LD + ak;
+        const double* rs = Rs + (size_t)buf * 64 * ROT_LD;
+        const double* cm = Cm + buf * 128;
+#pragma unroll 4
+        for (int k0 = 0; k0 < 64; k0 += 4) {
+            double a[2], bb[8];
+            const double cc = cm[k0 + ak], mm = cm[64 + k0 + ak];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) a[mt] = coarse_residual<XT>(xt[(size_t)8 * mt * ROT_LD + k0], cc, mm, mv.coarse_f32);
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) bb[nt] = rs[(k0 + ak) * ROT_LD + 8 * nt + ar];
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
