@@ -267,8 +267,15 @@ int encode_device(b2l_handle h, const void* dX, int x_is_f64, int64_t n, const i
     const bool coarse_only = !d_fine && !d_coarse_in && d_coarse;
     double* px_out = (gemm || coarse_only) ? nullptr : h->w_px.as<double>();
     if ((gemm || coarse_only) && mv.h % 8 == 0 && mv.h <= 128) {
-        if (xf64) k_coarse_assign<double><<<blocks, ENC_WARPS * 32, 0, h->stream>>>(mv, (const double*)x, n, d_coarse);
-        else k_coarse_assign<float><<<blocks, ENC_WARPS * 32, 0, h->stream>>>(mv, (const float*)x, n, d_coarse);
+        const size_t tsz = (!xf64 && mv.coarse_f32) ? 4 : 8, xsz = xf64 ? 8 : 4;
+        const size_t cb = tsz == 4 ? coarse_c_bytes<float>(mv.V, mv.h) : coarse_c_bytes<double>(mv.V, mv.h);
+        const int c_smem = cb <= 48 * 1024 ? 1 : 0;
+        const size_t smc = (c_smem ? cb : 0) + (size_t)COARSE_WARPS * mv.D * xsz;
+        const unsigned cgrid = (unsigned)std::min<int64_t>((n + COARSE_WARPS - 1) / COARSE_WARPS, (int64_t)h->num_sms * 8);
+        if (xf64) { CU(cudaFuncSetAttribute(k_coarse_assign<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smc));
+            k_coarse_assign<double><<<cgrid, COARSE_WARPS * 32, smc, h->stream>>>(mv, (const double*)x, n, d_coarse, c_smem); }
+        else { CU(cudaFuncSetAttribute(k_coarse_assign<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smc));
+            k_coarse_assign<float><<<cgrid, COARSE_WARPS * 32, smc, h->stream>>>(mv, (const float*)x, n, d_coarse, c_smem); }
     } else if (xf64) { CU(cudaFuncSetAttribute(k_coarse_project<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_coarse_project<double><<<blocks, ENC_WARPS * 32, smem, h->stream>>>(mv, (const double*)x, n, d_coarse_in, d_coarse, px_out); }
     else { CU(cudaFuncSetAttribute(k_coarse_project<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

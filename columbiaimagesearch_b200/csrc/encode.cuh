@@ -138,20 +138,32 @@ k_fine_argmin(ModelView mv, const double* __restrict__ PX, int64_t n, uint8_t* _
 // eight strided accumulators r_j = sum_i term(j + 8 i) combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)).  Lane (v, j)
 // builds r_j of centroid v and an xor-butterfly over the 8 lanes performs exactly those additions (IEEE addition is
 // commutative), so the distance bits equal sqdist_np's -- with 8x the lanes busy of the one-lane-per-centroid form.
-template <typename XT, typename T>
-__device__ __forceinline__ void coarse_argmin_split(const ModelView& mv, const XT* x, int s, int lane, int& bestv_out) {
-    const int h = mv.h, V = mv.V;
+template <typename XT, typename T, typename CT, int HC>
+__device__ __forceinline__ void coarse_argmin_split(int h_rt, int V, const XT* x, const CT* Cs, int ldc, int lane, int& bestv_out) {
+    // x: the row's split (h values), Cs: the split's centroids [V][h] (float64 model values, or already converted to T)
+    // HC: compile-time h (the 8-term strided sums unroll completely), 0: runtime h
+    const int h = HC ? HC : h_rt;
     T best = (T)3.0e38;
     int bestv = 0x7fffffff;
     for (int t0 = 0; t0 < V * 8; t0 += 32) {
         const int task = t0 + lane, v = task >> 3, j = task & 7;
         T r = (T)0;
         if (v < V) {
-            const double* C = mv.Cs + ((int64_t)s * V + v) * h;
-            for (int i = j; i < h; i += 8) {
-                const T t = Ex<T>::sub((T)x[s * h + i], (T)C[i]);
-                const T sq = Ex<T>::mul(t, t);
-                r = (i == j) ? sq : Ex<T>::add(r, sq);
+            const CT* C = Cs + (int64_t)v * ldc + j;          // ldc: row stride of Cs (padded in shared memory: no bank conflicts
+            const XT* xj = x + j;                             //      between the four centroid groups of a warp)
+            if (HC) {
+#pragma unroll
+                for (int i = 0; i < (HC ? HC : 8); i += 8) {
+                    const T t = Ex<T>::sub((T)xj[i], (T)C[i]);
+                    const T sq = Ex<T>::mul(t, t);
+                    r = (i == 0) ? sq : Ex<T>::add(r, sq);
+                }
+            } else {
+                for (int i = 0; i + j < h; i += 8) {
+                    const T t = Ex<T>::sub((T)xj[i], (T)C[i]);
+                    const T sq = Ex<T>::mul(t, t);
+                    r = (i == 0) ? sq : Ex<T>::add(r, sq);
+                }
             }
         }
         r = Ex<T>::add(r, __shfl_xor_sync(0xffffffffu, r, 1));
@@ -167,20 +179,133 @@ __device__ __forceinline__ void coarse_argmin_split(const ModelView& mv, const X
     bestv_out = bestv;
 }
 
-template <typename XT>
-__global__ void __launch_bounds__(ENC_WARPS * 32)
-k_coarse_assign(ModelView mv, const XT* __restrict__ X, int64_t n, int32_t* __restrict__ coarse_out) {
+// Persistent blocks; a warp takes a row at a time.  The row is staged in shared memory by coalesced loads (the next row
+// is already in flight in registers), and when they fit (2 V h values <= 48 KB: every search model) so are the centroids,
+// converted once to the arithmetic type -- the inner loop then reads shared memory only.  c_smem = 0: centroids from
+// global memory (k-means training with thousands of clusters).
+#define COARSE_WARPS 8
+// shared memory of a block: [c_smem: centroids as T [2][V][h] | centroids as float [2][V][h] | half norms [2V] | max norm [2]] | rows [COARSE_WARPS][D] XT
+template <typename T> __host__ __device__ inline size_t coarse_c_bytes(int V, int h) {
+    return (((size_t)2 * V * (h + 8) * (sizeof(T) + 4) + (size_t)(2 * V + 2) * 4 + 15) / 16) * 16;
+}
+
+// With the centroids in shared memory the assignment is first scored in float32, like the fine argmin: score_v =
+// |c_v|^2 / 2 - x.c_v, one FFMA per dimension instead of a float64 subtract, multiply and add; the winner is accepted when
+// the runner-up is more than 3 E away, E = (h + 16) 2^-24 (|x| + max|c|)^2 bounding the float32 evaluation error of a
+// score (inputs rounded to float32, half norm, FMA chain, butterfly sum) plus, for float32 models, the rounding of the
+// reference's own float32 distances.  Near ties (and everything when the centroids stay in global memory) take the
+// exact path below, bit-compatible with NumPy's pairwise sums.
+template <typename XT, typename T, int HC>
+__device__ __forceinline__ void coarse_assign_rows(const ModelView& mv, const XT* __restrict__ X, int64_t n, int32_t* __restrict__ coarse_out,
+                                                   unsigned char* smem_raw, int c_smem) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t i = (int64_t)blockIdx.x * ENC_WARPS + warp;
-    if (i >= n) return;
-    const XT* x = X + i * (int64_t)mv.D;
-    const bool f32 = (sizeof(XT) == 4) && mv.coarse_f32;
-    for (int s = 0; s < 2; ++s) {
-        int c;
-        if (f32) coarse_argmin_split<XT, float>(mv, x, s, lane, c);
-        else coarse_argmin_split<XT, double>(mv, x, s, lane, c);
-        if (lane == 0) coarse_out[i * 2 + s] = c;
+    const int D = mv.D, h = HC ? HC : mv.h, V = mv.V;
+    T* Cs_s = (T*)smem_raw;
+    const int HP = h + 8;                                    // padded row stride of the staged centroids
+    float* Cf_s = (float*)(Cs_s + (size_t)2 * V * HP);
+    float* hn_s = Cf_s + (size_t)2 * V * HP;                 // [2V] half norms, then [2] max |c| per split
+    const size_t cbytes = c_smem ? coarse_c_bytes<T>(V, h) : 0;
+    XT* xs = (XT*)(smem_raw + cbytes) + (size_t)warp * D;
+    if (c_smem) {
+        for (int e = threadIdx.x; e < 2 * V * h; e += COARSE_WARPS * 32) {
+            const int c = e / h, d = e - c * h;
+            Cs_s[(size_t)c * HP + d] = (T)mv.Cs[e]; Cf_s[(size_t)c * HP + d] = (float)mv.Cs[e];
+        }
+        __syncthreads();
+        for (int c = threadIdx.x; c < 2 * V; c += COARSE_WARPS * 32) {
+            float q = 0.0f;
+            for (int i = 0; i < h; ++i) q = fmaf(Cf_s[(size_t)c * HP + i], Cf_s[(size_t)c * HP + i], q);
+            hn_s[c] = 0.5f * q;
+        }
+        __syncthreads();
+        if (threadIdx.x < 2) {
+            float mx = 0.0f;
+            for (int v = 0; v < V; ++v) mx = fmaxf(mx, hn_s[threadIdx.x * V + v]);
+            hn_s[2 * V + threadIdx.x] = sqrtf(2.0f * mx) * 1.0001f;
+        }
+        __syncthreads();
     }
+    constexpr int NX = 8;                                   // D <= 256: a lane holds up to 8 values of the next row
+    XT nx[NX];
+    int64_t i = (int64_t)blockIdx.x * COARSE_WARPS + warp;
+    const int64_t step = (int64_t)gridDim.x * COARSE_WARPS;
+    if (i < n) {
+#pragma unroll
+        for (int e = 0; e < NX; ++e) if (lane + 32 * e < D) nx[e] = X[i * (int64_t)D + lane + 32 * e];
+    }
+    const float U = 5.9604645e-08f;
+    for (; i < n; i += step) {
+        __syncwarp();
+#pragma unroll
+        for (int e = 0; e < NX; ++e) if (lane + 32 * e < D) xs[lane + 32 * e] = nx[e];
+        __syncwarp();
+        if (i + step < n) {
+#pragma unroll
+            for (int e = 0; e < NX; ++e) if (lane + 32 * e < D) nx[e] = X[(i + step) * (int64_t)D + lane + 32 * e];
+        }
+        for (int s = 0; s < 2; ++s) {
+            int c = -1;
+            if (c_smem) {
+                // float32 stage: lane (v, j) sums the terms j, j+8, ... of centroid v; xor-butterfly over the 8 lanes
+                float best = 3.0e38f, second = 3.0e38f, xx = 0.0f;
+                int bv = 0;
+                const XT* xj = xs + s * h + (lane & 7);
+                for (int t0 = 0; t0 < V * 8; t0 += 32) {
+                    const int v = (t0 + lane) >> 3;
+                    float acc = 0.0f;
+                    if (v < V) {
+                        const float* cf = Cf_s + ((size_t)s * V + v) * HP + (lane & 7);
+                        if (HC) {
+#pragma unroll
+                            for (int k = 0; k < (HC ? HC : 8); k += 8) { const float xv = (float)xj[k]; acc = fmaf(xv, cf[k], acc); if (t0 == 0) xx = fmaf(xv, xv, xx); }
+                        } else {
+                            for (int k = 0; k + (lane & 7) < h; k += 8) { const float xv = (float)xj[k]; acc = fmaf(xv, cf[k], acc); if (t0 == 0) xx = fmaf(xv, xv, xx); }
+                        }
+                    }
+                    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+                    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+                    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+                    if (v < V) {
+                        const float sc = hn_s[s * V + v] - acc;
+                        second = fminf(second, fmaxf(sc, best));
+                        if (sc < best) bv = v;
+                        best = fminf(best, sc);
+                    }
+                }
+                // |x|^2 of the split: lanes 0..7 hold the eight strided partial sums (V >= 1: group 0 always has a centroid)
+                xx += __shfl_xor_sync(0xffffffffu, xx, 1);
+                xx += __shfl_xor_sync(0xffffffffu, xx, 2);
+                xx += __shfl_xor_sync(0xffffffffu, xx, 4);
+                xx = __shfl_sync(0xffffffffu, xx, 0);
+#pragma unroll
+                for (int o = 8; o <= 16; o <<= 1) {            // merge the four centroid groups of the warp
+                    const float ob = __shfl_xor_sync(0xffffffffu, best, o), os = __shfl_xor_sync(0xffffffffu, second, o);
+                    const int ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                    second = fminf(fminf(second, os), fmaxf(best, ob));
+                    if (ob < best) bv = ov;
+                    best = fminf(best, ob);
+                }
+                const float sp = sqrtf(xx) + hn_s[2 * V + s];
+                const float E = (float)(h + 16) * U * sp * sp * 1.01f + 1e-30f;
+                if (second - best > 3.0f * E) c = bv;           // (warp-uniform: every lane holds the merged triple)
+            }
+            if (c < 0) {
+                if (c_smem) coarse_argmin_split<XT, T, T, HC>(h, V, xs + s * h, Cs_s + (size_t)s * V * HP, HP, lane, c);
+                else coarse_argmin_split<XT, T, double, HC>(h, V, xs + s * h, mv.Cs + (int64_t)s * V * h, h, lane, c);
+            }
+            if (lane == 0) coarse_out[i * 2 + s] = c;
+        }
+    }
+}
+
+template <typename XT>
+__global__ void __launch_bounds__(COARSE_WARPS * 32)
+k_coarse_assign(ModelView mv, const XT* __restrict__ X, int64_t n, int32_t* __restrict__ coarse_out, int c_smem) {
+    extern __shared__ __align__(16) unsigned char sm_coarse[];
+    const bool f32 = (sizeof(XT) == 4) && mv.coarse_f32;
+    if (mv.h == 64) { if (f32) coarse_assign_rows<XT, float, 64>(mv, X, n, coarse_out, sm_coarse, c_smem); else coarse_assign_rows<XT, double, 64>(mv, X, n, coarse_out, sm_coarse, c_smem); }
+    else if (f32) coarse_assign_rows<XT, float, 0>(mv, X, n, coarse_out, sm_coarse, c_smem);
+    else coarse_assign_rows<XT, double, 0>(mv, X, n, coarse_out, sm_coarse, c_smem);
 }
 
 // one centroid from shared memory, in the widest loads its (compile-time) length allows; p is 16-byte aligned for DS % 4 == 0
