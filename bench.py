@@ -1044,11 +1044,13 @@ def run_encode(a):
                 "e2e": {"value": a.steps * eb * env.world / e2e_s, "unit": "codes/s", "h2d_bytes_per_step": eb * D * 4 * env.world,
                         "d2h_bytes_per_step": eb * (8 + M) * env.world, "api": "Handle.encode (b2l_encode, pinned host rows in, host codes out)"},
                 "gpu_launches": int(h.stats()["kernel_launches"]) * a.steps,
-                "roofline": {"bound": "tensor", "kernel": "b2l_encode pipeline (k_coarse_assign, k_rotate_dmma, k_fine_argmin32)",
+                "roofline": {"bound": "tensor", "kernel": "b2l_encode pipeline (k_coarse_assign, k_rotate_dmma, k_fine_tc + k_fine_redo)",
                              "achieved": value / env.world * flops_row / 1e12, "peak": 75.0, "unit": "TFLOP/s",
                              "frac": value / env.world * flops_row / 1e12 / 75.0, "traffic": None,
-                             "note": "SURVEY 8d flops per row (3VD + D^2 + 3KD = %d) over the fp32 FFMA peak of the part (~75 TFLOP/s: the fine "
-                                     "argmin, 83%% of the flops, runs in float32 with a float64 guard; the rotation on the float64 tensor cores)" % flops_row},
+                             "note": "SURVEY 8d flops per row (3VD + D^2 + 3KD = %d) over the fp32 FFMA peak of the part (~75 TFLOP/s), kept as "
+                                     "the yardstick of earlier rounds: the fine argmin, 83%% of these flops, now runs on the tcgen05 tensor cores "
+                                     "(kind::tf32, three TF32 pieces per float32 product, accumulators in tensor memory) with a float64 list pass "
+                                     "for what its guard cannot decide; the rotation on the float64 tensor cores (DMMA)" % flops_row},
                 "guard_subvectors_total": guards, "cpu_baseline": cpu, "clocks": clocks}
         print(json.dumps(line))
     if env.world > 1:

@@ -44,6 +44,7 @@ SIGNATURES = {
     "b2l_encode": (_i, [_h, _vp, _i, _i64, _i, _vp, _vp]),
     "b2l_set_fine_mode": (_i, [_h, _i]),
     "b2l_encode_guard_count": (_i64, [_h, _i]),
+    "b2l_debug_fine_scores": (_i, [_h, _vp, _i, _i64, _i, _vp, _vp]),
     "b2l_apply_pca": (_i, [_h, _vp, _i, _i64, _i, _vp]),
     "b2l_apply_pca64": (_i, [_h, _vp, _i, _i64, _i, _vp]),
     "b2l_project_lut": (_i, [_h, _vp, _i, _i64, _vp, _vp, _vp]),
@@ -201,6 +202,14 @@ class Handle(object):
 
     def set_fine_mode(self, mode):
         self._check(self.lib.b2l_set_fine_mode(self.h, int(mode)))
+
+    def debug_fine_scores(self, X, j):
+        """Tensor-core scores [128][256] of sub-quantizer j for the first 128 rows, and their float64 projections."""
+        X, f64 = _as_queries(X)
+        scores = np.empty((128, 256), np.float32)
+        px = np.empty((128, self.D), np.float64)
+        self._check(self.lib.b2l_debug_fine_scores(self.h, _ptr(X), f64, X.shape[0], int(j), _ptr(scores), _ptr(px)))
+        return scores, px
 
     def encode_guard_count(self, reset=False):
         return int(self._check(self.lib.b2l_encode_guard_count(self.h, int(bool(reset)))))

@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "comm.cuh"
 #include "encode.cuh"
+#include "fine_tc.cuh"
 #include "exact.cuh"
 #include "index.cuh"
 #include "plan.cuh"
@@ -81,7 +82,7 @@ struct b2l_ctx {
     // model
     bool has_model = false, has_pca = false;
     ModelView mv = {};
-    DevBuf dCs, dmus, dRt, dsubs, dsubs32, dsubs32T, dc2max, dP, dpmu;
+    DevBuf dCs, dmus, dRt, dsubs, dsubs32, dsubs32T, dc2max, dP, dpmu, dftc;
     // index: master copy in insertion order
     int64_t n_items = 0;
     DevBuf m_coarse, m_fine, m_rowid;
@@ -107,7 +108,12 @@ struct b2l_ctx {
     int64_t fb_items = 0;
     float c2m = 0.0f;                  // max_j max_k |subs[j][k]|^2 (upper bound), for the float32 table error model
     int force_redo = 0;                // test knob: bit 0 / 1 = treat every query as uncertified after the first / second stage
-    int fine_mode = 0;                 // 0: float32 first stage + float64 guard in the fine argmin, 1: float64 only
+    int fine_mode = 0;                 // fine argmin: 0 tensor-core stage (fine_tc.cuh) where the model allows, else as 2; 1: float64 only;
+                                       // 2: float32 SIMT stage + float64 guard
+    const float* ftc_tabs = nullptr;   // centroid operand images of the tensor-core stage (NULL: model shape not covered)
+    DevBuf w_redo, w_ftc_dbg;          // undecided sub-vectors of the tensor-core stage; diagnostic score dump
+    unsigned int* d_nredo = nullptr;
+    int ftc_dbg_j = -1;
     unsigned long long* d_nguard = nullptr;   // sub-vectors the guard re-evaluated in float64 (device counter)
     int scan_mode = 0;                 // 0: packed 16-bit tables first (default), 1: float32 tables only
     int kp_min = 0;                    // lower limit of the preselection width KP (0: k + 8 rounded up to a power of two)
@@ -336,7 +342,32 @@ int encode_device(b2l_handle h, const void* dX, int x_is_f64, int64_t n, const i
         if (sm3 > 48 * 1024) CU(cudaFuncSetAttribute(k_fine_argmin32<DSV, RV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3)); \
         k_fine_argmin32<DSV, RV><<<b3, FINE_THREADS, sm3, h->stream>>>(mv, h->w_px.as<double>(), n, d_fine, h->d_nguard); \
     } while (0)
-        const bool f32stage = h->fine_mode == 0 && n >= 2048;    // float32 first stage + float64 guard (same codes)
+        const bool f32stage = h->fine_mode != 1 && n >= 2048;    // float32 first stage + float64 guard (same codes)
+        // tensor-core stage (tcgen05, fine_tc.cuh) + float64 list pass for what it cannot decide (same codes)
+        if (h->fine_mode == 0 && h->ftc_tabs && h->d_nredo && (n >= 2048 || h->ftc_dbg_j >= 0) && n < ((int64_t)1 << 31)) {
+            FtcArgs fa;
+            fa.PX = h->w_px.as<double>(); fa.n = n; fa.fine = d_fine; fa.tabs = h->ftc_tabs;
+            fa.redo_cap = (unsigned int)std::max<int64_t>(4096, n * mv.M / 64);
+            CU(h->w_redo.reserve((size_t)fa.redo_cap * 8));
+            fa.redo = h->w_redo.as<unsigned long long>(); fa.nredo = h->d_nredo; fa.nguard = h->d_nguard;
+            fa.dbg = h->ftc_dbg_j >= 0 ? h->w_ftc_dbg.as<float>() : nullptr; fa.dbg_j = h->ftc_dbg_j;
+            CU(cudaMemsetAsync(h->d_nredo, 0, 4, h->stream));
+            const int64_t ntile = (n + FTC_TILE - 1) / FTC_TILE;
+            const unsigned g = (unsigned)std::min<int64_t>(ntile, 2 * (int64_t)h->num_sms);     // two blocks per SM
+            if (mv.ds == 8) {
+                CU(cudaFuncSetAttribute(k_fine_tc<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, FtcGeo<8>::SMEM));
+                k_fine_tc<8><<<g, FTC_THREADS, FtcGeo<8>::SMEM, h->stream>>>(mv, fa);
+                LAUNCHED();
+                k_fine_redo<8><<<h->num_sms, 256, 0, h->stream>>>(mv, fa);
+            } else {
+                CU(cudaFuncSetAttribute(k_fine_tc<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, FtcGeo<16>::SMEM));
+                k_fine_tc<16><<<g, FTC_THREADS, FtcGeo<16>::SMEM, h->stream>>>(mv, fa);
+                LAUNCHED();
+                k_fine_redo<16><<<h->num_sms, 256, 0, h->stream>>>(mv, fa);
+            }
+            LAUNCHED();
+            return B2L_OK;
+        }
         switch (mv.ds) {
             case 2: if (f32stage) FINE32(2, 4); else FINE(2); break;
             case 4: if (f32stage) FINE32(4, 4); else FINE(4); break;
@@ -1243,6 +1274,7 @@ int b2l_create(int device, b2l_handle* out) {
     }
     h->num_sms = prop.multiProcessorCount;
     if (cudaMalloc((void**)&h->d_nguard, 8) == cudaSuccess) cudaMemset(h->d_nguard, 0, 8);
+    if (cudaMalloc((void**)&h->d_nredo, 4) == cudaSuccess) cudaMemset(h->d_nredo, 0, 4);
     if (prop.major < 10) {
         g_create_error = "b2l_create: device is not sm_100 class (the library is built for sm_100a only)";
         delete h;
@@ -1257,13 +1289,14 @@ int b2l_destroy(b2l_handle h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     if (h->parent) { std::lock_guard<std::mutex> lk(h->parent->mu); --h->parent->n_siblings; }
-    DevBuf* bufs[] = {&h->dCs, &h->dmus, &h->dRt, &h->dsubs, &h->dsubs32, &h->dsubs32T, &h->dc2max, &h->dP, &h->dpmu, &h->m_coarse, &h->m_fine, &h->m_rowid, &h->codes,
+    DevBuf* bufs[] = {&h->dCs, &h->dmus, &h->dRt, &h->dsubs, &h->dsubs32, &h->dsubs32T, &h->dc2max, &h->dP, &h->dpmu, &h->dftc, &h->w_redo, &h->w_ftc_dbg, &h->m_coarse, &h->m_fine, &h->m_rowid, &h->codes,
                       &h->rowids, &h->cell_start, &h->lsize, &h->gsize, &h->sorted_first, &h->w_q, &h->w_xq, &h->w_px,
                       &h->w_coarse, &h->w_fine, &h->w_lut32, &h->w_lut64, &h->w_p64, &h->w_cellq, &h->w_cand, &h->w_gtab, &h->w_lut16, &h->w_quant, &h->w_plan,
                       &h->w_sort_a, &h->w_sort_b, &h->w_sort_tmp, &h->w_rec, &h->w_rec2, &h->w_out, &h->w_out2, &h->w_misc, &h->w_bkt, &h->w_perm, &h->w_need2, &h->w_segc, &h->d_ucell, &h->d_ustart, &h->d_hkeys, &h->d_hvals, &h->w_walk, &h->w_walk2};
     for (DevBuf* b : bufs) b->release();
     if (h->h_out) cudaFreeHost(h->h_out);
     if (h->d_nguard) cudaFree(h->d_nguard);
+    if (h->d_nredo) cudaFree(h->d_nredo);
     for (int r = 0; r < COMM_MAX_WORLD; ++r) if (h->comm.opened[r]) cudaIpcCloseMemHandle(h->comm.peer[r]);
     h->comm.window.release(); h->comm.cnt_out.release();
     if (h->comm.d_err) cudaFree(h->comm.d_err);
@@ -1295,11 +1328,11 @@ int b2l_create_sibling(b2l_handle p, b2l_handle* out) {
     rc = b2l_create(p->device, &s);
     if (rc) { p->err = g_create_error; return rc; }
     s->has_model = true; s->has_pca = p->has_pca; s->mv = p->mv; s->c2m = p->c2m;
-    s->fine_mode = p->fine_mode; s->scan_mode = p->scan_mode; s->kp_min = p->kp_min; s->force_redo = p->force_redo;
-    DevBuf* src[] = {&p->dCs, &p->dmus, &p->dRt, &p->dsubs, &p->dsubs32, &p->dsubs32T, &p->dc2max, &p->dP, &p->dpmu, &p->m_coarse, &p->m_fine,
+    s->fine_mode = p->fine_mode; s->ftc_tabs = p->ftc_tabs; s->scan_mode = p->scan_mode; s->kp_min = p->kp_min; s->force_redo = p->force_redo;
+    DevBuf* src[] = {&p->dCs, &p->dmus, &p->dRt, &p->dsubs, &p->dsubs32, &p->dsubs32T, &p->dc2max, &p->dP, &p->dpmu, &p->dftc, &p->m_coarse, &p->m_fine,
                      &p->m_rowid, &p->codes, &p->rowids, &p->cell_start, &p->lsize, &p->gsize, &p->sorted_first, &p->d_ucell, &p->d_ustart,
                      &p->d_hkeys, &p->d_hvals};
-    DevBuf* dst[] = {&s->dCs, &s->dmus, &s->dRt, &s->dsubs, &s->dsubs32, &s->dsubs32T, &s->dc2max, &s->dP, &s->dpmu, &s->m_coarse, &s->m_fine,
+    DevBuf* dst[] = {&s->dCs, &s->dmus, &s->dRt, &s->dsubs, &s->dsubs32, &s->dsubs32T, &s->dc2max, &s->dP, &s->dpmu, &s->dftc, &s->m_coarse, &s->m_fine,
                      &s->m_rowid, &s->codes, &s->rowids, &s->cell_start, &s->lsize, &s->gsize, &s->sorted_first, &s->d_ucell, &s->d_ustart,
                      &s->d_hkeys, &s->d_hvals};
     for (size_t i = 0; i < sizeof(src) / sizeof(src[0]); ++i) dst[i]->borrow(*src[i]);
@@ -1353,7 +1386,7 @@ int b2l_debug_force_redo(b2l_handle h, int mask) {
 }
 
 int b2l_set_fine_mode(b2l_handle h, int mode) {
-    if (!h || mode < 0 || mode > 1) return B2L_ERR_ARG;
+    if (!h || mode < 0 || mode > 2) return B2L_ERR_ARG;
     std::lock_guard<std::mutex> lk(h->mu);
     h->fine_mode = mode;
     return B2L_OK;
@@ -1456,6 +1489,16 @@ int b2l_set_model(b2l_handle h, int D, int V, int M, int K, int coarse_is_f32, c
     CU(cudaMemcpyAsync(h->dsubs32T.p, s32t.data(), nS * 4, cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(h->dsubs32.p, s32.data(), (nS + (size_t)M * K) * 4, cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(h->dc2max.p, c2.data(), (size_t)M * 4, cudaMemcpyHostToDevice, h->stream));
+    h->ftc_tabs = nullptr;
+    std::vector<float> ftab;
+    if (M > 64) {}                     // (the kernel keeps per-sub-quantizer constants for M <= 64)
+    else if (mv.ds == 8) { ftab.resize((size_t)M * (FtcGeo<8>::B_BYTES / 4)); ftc_build_tables<8>(M, K, subs, ftab.data()); }
+    else if (mv.ds == 16) { ftab.resize((size_t)M * (FtcGeo<16>::B_BYTES / 4)); ftc_build_tables<16>(M, K, subs, ftab.data()); }
+    if (!ftab.empty()) {
+        CU(h->dftc.reserve(ftab.size() * 4));
+        CU(cudaMemcpyAsync(h->dftc.p, ftab.data(), ftab.size() * 4, cudaMemcpyHostToDevice, h->stream));
+        h->ftc_tabs = h->dftc.as<float>();
+    }
     CU(cudaStreamSynchronize(h->stream));
     mv.subs32 = h->dsubs32.as<float>(); mv.subs32T = h->dsubs32T.as<float>(); mv.c2max = h->dc2max.as<float>();
     mv.Cs = h->dCs.as<double>(); mv.mus = h->dmus.as<double>(); mv.Rt = h->dRt.as<double>(); mv.subs = h->dsubs.as<double>();
@@ -1514,6 +1557,29 @@ int b2l_encode(b2l_handle h, const void* X, int x_is_f64, int64_t n, int on_devi
     }
     CU(cudaStreamSynchronize(h->stream));
     h->stats.kernel_launches = h->launches;
+    return B2L_OK;
+}
+
+int b2l_debug_fine_scores(b2l_handle h, const void* X, int x_is_f64, int64_t n, int j, float* scores, double* px) {
+    if (!h) return B2L_ERR_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(cudaSetDevice(h->device));
+    if (!h->has_model) FAIL(B2L_ERR_STATE, "no model set");
+    const ModelView& mv = h->mv;
+    if (!h->ftc_tabs || h->fine_mode != 0) FAIL(B2L_ERR_UNSUPPORTED, "the tensor-core fine argmin does not cover this model (ds = %d) or is switched off", mv.ds);
+    if (!X || !scores || n < 128 || n > ((int64_t)1 << 20) || j < 0 || j >= mv.M) FAIL(B2L_ERR_ARG, "bad arguments (need 128 <= n <= 2^20 host rows, 0 <= j < M)");
+    const int Din = h->has_pca ? mv.D0 : mv.D;
+    const size_t esz = x_is_f64 ? 8 : 4;
+    CU(h->w_q.reserve((size_t)n * Din * esz)); CU(h->w_coarse.reserve((size_t)n * 8)); CU(h->w_fine.reserve((size_t)n * mv.M));
+    CU(h->w_ftc_dbg.reserve((size_t)128 * 256 * 4));
+    CU(cudaMemcpyAsync(h->w_q.p, X, (size_t)n * Din * esz, cudaMemcpyHostToDevice, h->stream));
+    h->ftc_dbg_j = j;
+    const int rc = encode_device(h, h->w_q.p, x_is_f64, n, nullptr, h->w_coarse.as<int32_t>(), h->w_fine.as<uint8_t>());
+    h->ftc_dbg_j = -1;
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(scores, h->w_ftc_dbg.p, (size_t)128 * 256 * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (px) CU(cudaMemcpyAsync(px, h->w_px.p, (size_t)128 * mv.D * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
     return B2L_OK;
 }
 

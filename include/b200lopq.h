@@ -71,11 +71,19 @@ int b2l_set_pca(b2l_handle h, int D0, const double* P, const double* mu, int ren
  * (predict_coarse, model.py:563-573; utils.predict_cluster, utils.py:33-53). */
 int b2l_encode(b2l_handle h, const void* X, int x_is_f64, int64_t n, int on_device,
                int32_t* coarse, uint8_t* fine);
-/* Fine-argmin arithmetic of b2l_encode.  0 (default): every distance first in float32, the winner accepted only when a
- * rigorous bound on the float32 error separates it from the runner-up, otherwise that sub-vector is redone in float64
- * (same codes, ~3x less float64 work).  1: float64 only.  b2l_encode_guard_count: sub-vectors redone in float64 so far. */
+/* Fine-argmin arithmetic of b2l_encode (predict_fine, model.py:575-602; the codes are the same in every mode).
+ * 0 (default): sub-vector lengths 8 and 16 are scored on the tensor cores (tcgen05 kind::tf32, three TF32 pieces per
+ * float32 product, accumulators in tensor memory) and a centroid is accepted only when it is the single score below
+ * min + 3E, E a bound on the evaluation error; other shapes as mode 2.  1: float64 only.  2: float32 on the SIMT pipe with
+ * the same kind of guard.  What a guard cannot decide is redone in float64 in NumPy's summation order.
+ * b2l_encode_guard_count: sub-vectors redone in float64 so far. */
 int     b2l_set_fine_mode(b2l_handle h, int mode);
 int64_t b2l_encode_guard_count(b2l_handle h, int reset);
+/* Diagnostic of the tensor-core stage: encodes the n host rows X (128 <= n <= 2^20) as b2l_encode does and returns the
+ * float32 scores |c_k|^2 / 2 - p.c_k [128][256] the tensor cores produced for rows 0..127 against sub-quantizer j, and
+ * (px != NULL) the float64 projections [128][D] of those rows (project, model.py:604-641).  The tests bound
+ * |score - exact| by the E of the guard. */
+int     b2l_debug_fine_scores(b2l_handle h, const void* X, int x_is_f64, int64_t n, int j, float* scores, double* px);
 /* apply_PCA alone (model.py:961-978): Y [n][D] float32. */
 int b2l_apply_pca(b2l_handle h, const void* X, int x_is_f64, int64_t n, int on_device, float* Y);
 /* the same before the final cast (apply_PCA(x, dtype=numpy.float64), model.py:961): Y [n][D] float64. */

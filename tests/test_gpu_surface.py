@@ -348,3 +348,78 @@ def test_device_kmeans():
     # the public trainer uses it
     m = T.kmeans(X, 12, 10, np.random.RandomState(1), n_init=2, device=True)
     assert m.shape == (12, 10) and ((X - m[T._assign(X, m, device=False)]) ** 2).sum() < 1.2 * costs[-1] * 1.5
+
+
+@pytest.mark.parametrize("shape", [(128, 4, 16, 256), (128, 4, 8, 256), (64, 3, 8, 100)], ids=lambda s: "D%d_M%d_K%d" % (s[0], s[2], s[3]))
+def test_tensor_core_fine_scores_stay_inside_the_guard_bound(shape):
+    """fine_tc.cuh: the scores |c_k|^2/2 - p.c_k the tensor cores produce (three TF32 pieces per float32 product, float32
+    accumulation in tensor memory) against float64 scores of the same float64 projections.  The guard accepts a centroid
+    only when it is the single score below min + 3E, E = 16 * 2^-24 (|p| + max|c|)^2: the measured error has to stay a
+    factor 4 inside E.  Rows of unused centroids (K < 256) must never be able to win."""
+    lopq = _lopq()
+    D, V, M, K = shape
+    params = random_model_params(D, V, M, K, seed=D + M + K)
+    model = lopq.LOPQModel(parameters=params)
+    db = random_data(params, 4096, seed=11)
+    h = model._native()
+    ds, m = D // M, M // 2
+    worst = 0.0
+    for j in (0, M // 2, M - 1):
+        sc, px = h.debug_fine_scores(db, j)
+        sub = np.asarray(params[3][j // m][j % m], np.float64)
+        p = px[:, j * ds:(j + 1) * ds]
+        exact = 0.5 * (sub ** 2).sum(1)[None, :] - p @ sub.T
+        unit = (np.sqrt((p ** 2).sum(1)) + np.sqrt((sub ** 2).sum(1).max())) ** 2 * 2.0 ** -24
+        worst = max(worst, float((np.abs(sc[:, :K] - exact) / unit[:, None]).max()))
+        assert np.array_equal(sc[:, :K].argmin(1), exact.argmin(1))
+        if K < 256:
+            assert sc[:, K:].min() > 1e29
+    assert worst < 4.0, worst
+
+
+def test_tensor_core_fine_argmin_all_exact_ties_and_list_overflow():
+    """Every sub-centroid k has an identical twin k + 128: every sub-vector is an exact tie, nothing can be decided on the
+    tensor cores, the list of undecided sub-vectors overflows (its capacity is n M / 64) and the rest is settled in
+    place -- all in float64 with the first-minimum rule of utils.py:33-53: codes equal the oracle's, all below 128."""
+    lopq = _lopq()
+    D, V, M, K, n = 64, 3, 8, 256, 12000
+    Cs, Rs, mus, subs = random_model_params(D, V, M, K, seed=77)
+    subs = tuple([np.concatenate([c[:128], c[:128]]) for c in half] for half in subs)
+    params = (Cs, Rs, mus, subs)
+    model = lopq.LOPQModel(parameters=params)
+    omodel = orc.OracleModel(*params)
+    db = random_data(params, n, seed=9)
+    h = model._native()
+    h.encode_guard_count(reset=True)
+    coarse, fine = h.encode(db)
+    assert h.encode_guard_count(reset=True) == n * M
+    ocoarse, ofine = orc.encode_batch(omodel, db)
+    assert np.array_equal(coarse, ocoarse) and np.array_equal(fine, ofine)
+    assert fine.max() < 128
+
+
+def test_fine_argmin_modes_agree_on_a_trained_model():
+    """b2l_set_fine_mode: tensor-core stage (0), float64 only (1), float32 SIMT stage (2) -- same codes on the bench model
+    (ds = 8) and on float64 input; the guards of both float32 stages stay rare."""
+    lopq = _lopq()
+    from columbiaimagesearch_b200 import synth
+    z = np.load(os.path.join(ROOT, "bench_models", "dlib128_V8_M16.npz"))
+    model = lopq.LOPQModel.from_npz(z)
+    X = synth.dlib_style(60000, 128, seed=31)
+    h = model._native()
+    out = {}
+    try:
+        for mode in (0, 1, 2):
+            h.set_fine_mode(mode)
+            h.encode_guard_count(reset=True)
+            out[mode] = h.encode(X) + (h.encode_guard_count(reset=True),)
+        h.set_fine_mode(0)
+        c64, f64, _ = h.encode(X.astype(np.float64)) + (0,)
+    finally:
+        h.set_fine_mode(0)
+    for mode in (0, 2):
+        assert np.array_equal(out[mode][0], out[1][0]) and np.array_equal(out[mode][1], out[1][1]), mode
+        assert 0 < out[mode][2] < X.shape[0] * model.M // 200, (mode, out[mode][2])
+    oc, of = orc.encode_batch(orc.OracleModel.from_npz(z), X[:3000])
+    assert np.array_equal(out[0][0][:3000], oc) and np.array_equal(out[0][1][:3000], of)
+    assert np.array_equal(f64[:3000], orc.encode_batch(orc.OracleModel.from_npz(z), X[:3000].astype(np.float64))[1])
