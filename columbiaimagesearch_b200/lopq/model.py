@@ -176,6 +176,57 @@ class LOPQModel(object):
         """model.py:709-710."""
         return (int(cell_id // self.V), int(cell_id % self.V))
 
+    # ---- the reference's own file formats ----------------------------------------------------------
+    def export_mat(self, filename):
+        """model.py:712-728 -- Cs [2,V,h], Rs [2,V,h,h], mus [2,V,h], subs [2,M/2,K,ds], V, M in a .mat file."""
+        from scipy.io import savemat
+        savemat(filename, {"Cs": np.stack([np.asarray(c) for c in self.Cs]), "Rs": np.stack([np.asarray(r) for r in self.Rs]),
+                           "mus": np.stack([np.asarray(m) for m in self.mus]),
+                           "subs": np.stack([np.stack([np.asarray(s) for s in half]) for half in self.subquantizers]),
+                           "V": self.V, "M": self.M})
+
+    @staticmethod
+    def load_mat(filename):
+        """model.py:730-746."""
+        from scipy.io import loadmat
+        d = loadmat(filename)
+        return LOPQModel(parameters=(tuple(d["Cs"]), tuple(d["Rs"]), tuple(d["mus"]),
+                                     tuple([sub for sub in half] for half in d["subs"])))
+
+    def export_proto(self, f):
+        """model.py:748-786 -- LOPQModelParams (lopq_model_pb2.py) with float32 values; `f` is a path or a binary file
+        object (closed afterwards, as in the reference).  Missing parameter groups are left out."""
+        from . import proto
+        D = 2 * self.Cs[0].shape[1] if self.Cs is not None else 0
+        buf = proto.encode_model(D, self.V, self.M, self.subquantizer_clusters, self.Cs, self.Rs, self.mus, self.subquantizers)
+        if isinstance(f, str):
+            f = open(f, "wb")
+        f.write(buf)
+        f.close()
+
+    @staticmethod
+    def load_proto(filename):
+        """model.py:788-820 -- a model from the protobuf format; None (and a message) when the file cannot be opened."""
+        from . import proto
+        try:
+            with open(filename, "rb") as fh:
+                p = proto.decode_model(fh.read())
+        except IOError:
+            print(str(filename) + ": Could not open file.")
+            return None
+        halves = lambda a: [a[:len(a) // 2], a[len(a) // 2:]]
+        Cs = Rs = mus = subs = None
+        if p["Cs"]:
+            Cs = p["Cs"]
+        if p["Rs"]:
+            Rs = [np.stack(h) for h in halves(p["Rs"])]
+        if p["mus"]:
+            mus = [np.stack(h) for h in halves(p["mus"])]
+        if p["subs"]:
+            subs = halves(p["subs"])
+        return LOPQModel(V=p["V"] or 8, M=p["M"] or 4, subquantizer_clusters=p["num_subquantizers"] or 256,
+                         parameters=(Cs, Rs, mus, subs))
+
     # ---- flat persistence (the product pickles models; this is the fixture format) -----------------
     def to_npz_dict(self):
         d = {"C0": np.asarray(self.Cs[0]), "C1": np.asarray(self.Cs[1]),

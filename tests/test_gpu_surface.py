@@ -423,3 +423,18 @@ def test_fine_argmin_modes_agree_on_a_trained_model():
     oc, of = orc.encode_batch(orc.OracleModel.from_npz(z), X[:3000])
     assert np.array_equal(out[0][0][:3000], oc) and np.array_equal(out[0][1][:3000], of)
     assert np.array_equal(f64[:3000], orc.encode_batch(orc.OracleModel.from_npz(z), X[:3000].astype(np.float64))[1])
+
+
+def test_model_loaded_from_protobuf_encodes_like_the_oracle(tmp_path):
+    """A model that went through export_proto / load_proto (float32 values, model.py:748-820) drives the device exactly as
+    the oracle built from the same (rounded) parameters."""
+    lopq = _lopq()
+    params = random_model_params(64, 4, 8, 256, seed=21)
+    path = str(tmp_path / "model.lopq")
+    lopq.LOPQModel(parameters=params).export_proto(path)
+    model = lopq.LOPQModel.load_proto(path)
+    omodel = orc.OracleModel(model.Cs, model.Rs, model.mus, model.subquantizers)
+    db = random_data(params, 5000, seed=2)
+    oc, of = orc.encode_batch(omodel, db)
+    coarse, fine = lopq.utils.compute_codes_arrays(db, model)
+    assert np.array_equal(coarse, oc) and np.array_equal(fine, of)

@@ -133,3 +133,46 @@ def test_lmdb_searcher_persistence_branch_with_a_stand_in_module(monkeypatch):
     assert sorted(s2._items) == sorted(store)
     k5 = array.array("H", [int(coarse[2, 0]), int(coarse[2, 1])]).tobytes() + b"sha1_02"
     assert s2._items[k5].tolist() == fine[2][::-1].tolist()
+
+
+def test_model_protobuf_and_mat_formats(tmp_path):
+    """export_proto / load_proto (model.py:748-820) through the package's own wire codec: byte-identical to what the
+    protobuf runtime writes with the reference's schema (committed fixture; regenerated live when the reference is
+    present), float32 values back as float64 arrays in the reference's container layout; a missing file gives None;
+    export_mat / load_mat (model.py:712-746) round-trip."""
+    import os
+    import columbiaimagesearch_b200.lopq as lopq
+    from tests.golden import make_proto
+    params = make_proto.small_params()
+    model = lopq.LOPQModel(parameters=params)
+    golden = open(os.path.join(os.path.dirname(make_proto.__file__), "ref_model_proto.pb"), "rb").read()
+    path = str(tmp_path / "m.lopq")
+    model.export_proto(path)
+    assert open(path, "rb").read() == golden
+    model.export_proto(open(path, "wb"))                      # a file object works too
+    assert open(path, "rb").read() == golden
+    if os.path.exists(make_proto.REF_PB2):
+        assert make_proto.serialize_like_reference(params, 3, 4, 16) == golden
+    back = lopq.LOPQModel.load_proto(path)
+    assert (back.V, back.M, back.subquantizer_clusters, back.num_fine_splits) == (3, 4, 16, 2)
+    f32 = lambda a: np.asarray(a).astype(np.float32).astype(np.float64)
+    for s in (0, 1):
+        assert back.Cs[s].dtype == np.float64 and np.array_equal(back.Cs[s], f32(params[0][s]))
+        assert back.Rs[s].shape == (3, 4, 4) and np.array_equal(back.Rs[s], f32(params[1][s]))
+        assert back.mus[s].shape == (3, 4) and np.array_equal(back.mus[s], f32(params[2][s]))
+        assert len(back.subquantizers[s]) == 2
+        for j in (0, 1):
+            assert np.array_equal(back.subquantizers[s][j], f32(params[3][s][j]))
+    assert lopq.LOPQModel.load_proto(str(tmp_path / "missing.lopq")) is None
+    # a partial model (coarse centroids only), as the reference allows while training in stages
+    part = lopq.LOPQModel(V=3, M=4, subquantizer_clusters=16, parameters=(params[0], None, None, None))
+    part.export_proto(path)
+    back = lopq.LOPQModel.load_proto(path)
+    assert back.Rs is None and back.subquantizers is None and np.array_equal(back.Cs[1], f32(params[0][1])) and back.M == 4
+    mat = str(tmp_path / "m.mat")
+    model.export_mat(mat)
+    back = lopq.LOPQModel.load_mat(mat)
+    assert back.M == 4 and back.V == 3
+    for s in (0, 1):
+        assert np.array_equal(back.Cs[s], params[0][s]) and np.array_equal(back.Rs[s], params[1][s])
+        assert np.array_equal(back.mus[s], params[2][s]) and np.array_equal(back.subquantizers[s][1], params[3][s][1])
