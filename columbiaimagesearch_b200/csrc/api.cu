@@ -82,7 +82,7 @@ struct b2l_ctx {
     // model
     bool has_model = false, has_pca = false;
     ModelView mv = {};
-    DevBuf dCs, dmus, dRt, dsubs, dsubs32, dsubs32T, dc2max, dP, dpmu, dftc;
+    DevBuf dCs, dmus, dRt, dsubs, dsubs32, dsubs32T, dc2max, dP, dpmu, dftc, dCs32;
     // index: master copy in insertion order
     int64_t n_items = 0;
     DevBuf m_coarse, m_fine, m_rowid;
@@ -272,6 +272,27 @@ int encode_device(b2l_handle h, const void* dX, int x_is_f64, int64_t n, const i
     // coarse assignment only (utils.predict_cluster over rows; the assignment step of k-means training): no projection
     const bool coarse_only = !d_fine && !d_coarse_in && d_coarse;
     double* px_out = (gemm || coarse_only) ? nullptr : h->w_px.as<double>();
+    const size_t cb_coarse = (!xf64 && mv.coarse_f32) ? coarse_c_bytes<float>(mv.V, mv.h) : coarse_c_bytes<double>(mv.V, mv.h);
+    if ((gemm || coarse_only) && cb_coarse > 48 * 1024 && (mv.h == 32 || mv.h == 64 || mv.h == 128) && h->d_nredo && h->fine_mode != 1 &&
+        n < ((int64_t)1 << 30) && (uintptr_t)x % 16 == 0) {
+        // many centroids (they do not fit the shared memory of k_coarse_assign): float32 scores against streamed chunks,
+        // exact arithmetic for the listed near ties
+        CU(h->w_redo.reserve((size_t)2 * n * 8));
+        CU(cudaMemsetAsync(h->d_nredo, 0, 4, h->stream));
+        const unsigned gb = (unsigned)((n + CBIG_THREADS - 1) / CBIG_THREADS);
+        unsigned long long* rl = h->w_redo.as<unsigned long long>();
+#define CBIG(XTV, HV)                                                                                           \
+    do {                                                                                                        \
+        CU(cudaFuncSetAttribute(k_coarse_big<XTV, HV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cbig_smem_bytes<HV>())); \
+        k_coarse_big<XTV, HV><<<gb, CBIG_THREADS, cbig_smem_bytes<HV>(), h->stream>>>(mv, (const XTV*)x, n, d_coarse, rl, h->d_nredo); \
+    } while (0)
+        if (xf64) { if (mv.h == 32) CBIG(double, 32); else if (mv.h == 64) CBIG(double, 64); else CBIG(double, 128); }
+        else { if (mv.h == 32) CBIG(float, 32); else if (mv.h == 64) CBIG(float, 64); else CBIG(float, 128); }
+#undef CBIG
+        LAUNCHED();
+        if (xf64) k_coarse_redo<double><<<h->num_sms * 2, 256, 0, h->stream>>>(mv, (const double*)x, d_coarse, rl, h->d_nredo);
+        else k_coarse_redo<float><<<h->num_sms * 2, 256, 0, h->stream>>>(mv, (const float*)x, d_coarse, rl, h->d_nredo);
+    } else
     if ((gemm || coarse_only) && mv.h % 8 == 0 && mv.h <= 128) {
         const size_t tsz = (!xf64 && mv.coarse_f32) ? 4 : 8, xsz = xf64 ? 8 : 4;
         const size_t cb = tsz == 4 ? coarse_c_bytes<float>(mv.V, mv.h) : coarse_c_bytes<double>(mv.V, mv.h);
@@ -1289,7 +1310,7 @@ int b2l_destroy(b2l_handle h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     if (h->parent) { std::lock_guard<std::mutex> lk(h->parent->mu); --h->parent->n_siblings; }
-    DevBuf* bufs[] = {&h->dCs, &h->dmus, &h->dRt, &h->dsubs, &h->dsubs32, &h->dsubs32T, &h->dc2max, &h->dP, &h->dpmu, &h->dftc, &h->w_redo, &h->w_ftc_dbg, &h->m_coarse, &h->m_fine, &h->m_rowid, &h->codes,
+    DevBuf* bufs[] = {&h->dCs, &h->dmus, &h->dRt, &h->dsubs, &h->dsubs32, &h->dsubs32T, &h->dc2max, &h->dP, &h->dpmu, &h->dftc, &h->dCs32, &h->w_redo, &h->w_ftc_dbg, &h->m_coarse, &h->m_fine, &h->m_rowid, &h->codes,
                       &h->rowids, &h->cell_start, &h->lsize, &h->gsize, &h->sorted_first, &h->w_q, &h->w_xq, &h->w_px,
                       &h->w_coarse, &h->w_fine, &h->w_lut32, &h->w_lut64, &h->w_p64, &h->w_cellq, &h->w_cand, &h->w_gtab, &h->w_lut16, &h->w_quant, &h->w_plan,
                       &h->w_sort_a, &h->w_sort_b, &h->w_sort_tmp, &h->w_rec, &h->w_rec2, &h->w_out, &h->w_out2, &h->w_misc, &h->w_bkt, &h->w_perm, &h->w_need2, &h->w_segc, &h->d_ucell, &h->d_ustart, &h->d_hkeys, &h->d_hvals, &h->w_walk, &h->w_walk2};
@@ -1329,10 +1350,10 @@ int b2l_create_sibling(b2l_handle p, b2l_handle* out) {
     if (rc) { p->err = g_create_error; return rc; }
     s->has_model = true; s->has_pca = p->has_pca; s->mv = p->mv; s->c2m = p->c2m;
     s->fine_mode = p->fine_mode; s->ftc_tabs = p->ftc_tabs; s->scan_mode = p->scan_mode; s->kp_min = p->kp_min; s->force_redo = p->force_redo;
-    DevBuf* src[] = {&p->dCs, &p->dmus, &p->dRt, &p->dsubs, &p->dsubs32, &p->dsubs32T, &p->dc2max, &p->dP, &p->dpmu, &p->dftc, &p->m_coarse, &p->m_fine,
+    DevBuf* src[] = {&p->dCs, &p->dmus, &p->dRt, &p->dsubs, &p->dsubs32, &p->dsubs32T, &p->dc2max, &p->dP, &p->dpmu, &p->dftc, &p->dCs32, &p->m_coarse, &p->m_fine,
                      &p->m_rowid, &p->codes, &p->rowids, &p->cell_start, &p->lsize, &p->gsize, &p->sorted_first, &p->d_ucell, &p->d_ustart,
                      &p->d_hkeys, &p->d_hvals};
-    DevBuf* dst[] = {&s->dCs, &s->dmus, &s->dRt, &s->dsubs, &s->dsubs32, &s->dsubs32T, &s->dc2max, &s->dP, &s->dpmu, &s->dftc, &s->m_coarse, &s->m_fine,
+    DevBuf* dst[] = {&s->dCs, &s->dmus, &s->dRt, &s->dsubs, &s->dsubs32, &s->dsubs32T, &s->dc2max, &s->dP, &s->dpmu, &s->dftc, &s->dCs32, &s->m_coarse, &s->m_fine,
                      &s->m_rowid, &s->codes, &s->rowids, &s->cell_start, &s->lsize, &s->gsize, &s->sorted_first, &s->d_ucell, &s->d_ustart,
                      &s->d_hkeys, &s->d_hvals};
     for (size_t i = 0; i < sizeof(src) / sizeof(src[0]); ++i) dst[i]->borrow(*src[i]);
@@ -1489,6 +1510,23 @@ int b2l_set_model(b2l_handle h, int D, int V, int M, int K, int coarse_is_f32, c
     CU(cudaMemcpyAsync(h->dsubs32T.p, s32t.data(), nS * 4, cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(h->dsubs32.p, s32.data(), (nS + (size_t)M * K) * 4, cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(h->dc2max.p, c2.data(), (size_t)M * 4, cudaMemcpyHostToDevice, h->stream));
+    {   // float32 coarse centroids + half norms + max norm per split (k_coarse_big)
+        std::vector<float> c32(nC + 2 * (size_t)V + 2);
+        for (int sp = 0; sp < 2; ++sp) {
+            float mx = 0.0f;
+            for (int v = 0; v < V; ++v) {
+                float q = 0.0f;
+                for (size_t d = 0; d < hh; ++d) { const float c = (float)Cs[((size_t)sp * V + v) * hh + d]; c32[((size_t)sp * V + v) * hh + d] = c; q = std::fmaf(c, c, q); }
+                c32[nC + (size_t)sp * V + v] = 0.5f * q;
+                mx = std::max(mx, q);
+            }
+            c32[nC + 2 * (size_t)V + sp] = std::sqrt(mx) * 1.0001f;
+        }
+        CU(h->dCs32.reserve(c32.size() * 4));
+        CU(cudaMemcpyAsync(h->dCs32.p, c32.data(), c32.size() * 4, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaStreamSynchronize(h->stream));             // (c32 goes out of scope)
+        mv.Cs32 = h->dCs32.as<float>(); mv.Chn32 = mv.Cs32 + nC; mv.Cmax32 = mv.Chn32 + 2 * (size_t)V;
+    }
     h->ftc_tabs = nullptr;
     std::vector<float> ftab;
     if (M > 64) {}                     // (the kernel keeps per-sub-quantizer constants for M <= 64)

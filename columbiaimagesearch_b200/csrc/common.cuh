@@ -23,6 +23,9 @@ struct ModelView {
     const float* subs32;       // [M][K][ds] the same, rounded to float32 (first stage of the fine argmin)
     const float* subs32T;      // [M][ds][K] float32, centroid index fastest (coalesced one-thread-per-centroid reads)
     const float* c2max;        // [M] upper bound on max_k |subs[j][k]|^2
+    const float* Cs32;         // [2][V][h] coarse centroids rounded to float32, [2][V] their half norms, [2] max |c| per split
+    const float* Chn32;        //   (first stage of the coarse assignment against many centroids, k_coarse_big)
+    const float* Cmax32;
     // PCA (LOPQModelPCA)
     int D0, renorm;
     const double* P;           // [D0][D]

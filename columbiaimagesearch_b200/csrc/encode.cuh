@@ -503,6 +503,134 @@ k_fine_argmin32_all(ModelView mv, const double* __restrict__ PX, int64_t n, uint
     if (guards && nguard) atomicAdd(nguard, (unsigned long long)guards);
 }
 
+// ---- coarse assignment against MANY centroids (V in the thousands: the product's V = 2048 / 4096 models) ------------
+// predict_coarse (model.py:563-573 -> utils.py:33-53) when the centroids do not fit the shared memory of k_coarse_assign.
+// One row per thread (its split in registers), the split's centroids stream through shared memory in chunks of
+// CBIG_CK (float32 copies + half norms, double-buffered by cp.async); scores |c|^2/2 - x.c, four centroids at a time, the
+// same bookkeeping and the same kind of guard as k_fine_argmin32:  E = (h + 16) 2^-24 (|x| + max|c|)^2  (float32 inputs,
+// half norm, FMA chain, and for float32 models the rounding of the reference's own float32 distances).  A row whose
+// runner-up is not more than 3 E away goes to a list that k_coarse_redo settles with the exact NumPy-order arithmetic.
+#define CBIG_THREADS 256
+#define CBIG_CK 128
+template <int HC> __host__ __device__ constexpr size_t cbig_smem_bytes() { return (size_t)2 * CBIG_CK * (HC + 1) * 4; }
+
+template <typename XT, int HC>
+__global__ void __launch_bounds__(CBIG_THREADS, (HC <= 64 ? 2 : 1))
+k_coarse_big(ModelView mv, const XT* __restrict__ X, int64_t n, int32_t* __restrict__ coarse_out,
+             unsigned long long* __restrict__ redo, unsigned int* __restrict__ nredo) {
+    extern __shared__ __align__(16) float sm_cbig[];      // 2 x ([CBIG_CK][HC] centroids + [CBIG_CK] half norms)
+    const float U = 5.9604645e-08f;
+    const int V = mv.V;
+    const int64_t i = (int64_t)blockIdx.x * CBIG_THREADS + threadIdx.x;
+    const bool live = i < n;
+    for (int s = 0; s < 2; ++s) {
+        const float* C32 = mv.Cs32 + (int64_t)s * V * HC;
+        const float* H32 = mv.Chn32 + (int64_t)s * V;
+        auto fetch = [&](int c0, int buf) {
+            float* dst = sm_cbig + buf * (CBIG_CK * (HC + 1));
+            const int cnt = min(CBIG_CK, V - c0);
+            for (int e = threadIdx.x * 4; e < cnt * HC; e += CBIG_THREADS * 4) cp_async16(dst + e, C32 + (int64_t)c0 * HC + e);
+            for (int e = threadIdx.x; e < cnt; e += CBIG_THREADS) cp_async4(dst + CBIG_CK * HC + e, H32 + c0 + e);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        fetch(0, 0);
+        float pn[HC], xx = 0.0f;
+        {
+            const XT* x = X + (live ? i : 0) * (int64_t)mv.D + s * HC;       // 16-byte aligned (checked by the caller)
+            if (sizeof(XT) == 4) {
+#pragma unroll
+                for (int d = 0; d < HC; d += 4) {
+                    const float4 v = *(const float4*)((const float*)x + d);
+                    pn[d] = -v.x; pn[d + 1] = -v.y; pn[d + 2] = -v.z; pn[d + 3] = -v.w;
+                }
+            } else {
+#pragma unroll
+                for (int d = 0; d < HC; d += 2) {
+                    const double2 v = *(const double2*)((const double*)x + d);
+                    pn[d] = -(float)v.x; pn[d + 1] = -(float)v.y;
+                }
+            }
+#pragma unroll
+            for (int d = 0; d < HC; ++d) xx = fmaf(pn[d], pn[d], xx);
+        }
+        float best = 3.0e38f, second = 3.0e38f;
+        int bestg = 0;                                    // first centroid of the group (of up to four) that holds the minimum
+        int buf = 0;
+        for (int c0 = 0; c0 < V; c0 += CBIG_CK, buf ^= 1) {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads();                              // chunk landed for everybody; everybody is through with the other buffer
+            if (c0 + CBIG_CK < V) fetch(c0 + CBIG_CK, buf ^ 1);
+            const float* cs = sm_cbig + buf * (CBIG_CK * (HC + 1));
+            const float* hn = cs + CBIG_CK * HC;
+            const int cnt = min(CBIG_CK, V - c0), cnt4 = cnt & ~3;
+#pragma unroll 1
+            for (int k = 0; k < cnt4; k += 4) {
+                float sc[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float v = hn[k + q];
+#pragma unroll
+                    for (int t = 0; t < HC; t += 4) {
+                        const float4 c = *(const float4*)(cs + (k + q) * HC + t);
+                        v = fmaf(pn[t], c.x, v); v = fmaf(pn[t + 1], c.y, v); v = fmaf(pn[t + 2], c.z, v); v = fmaf(pn[t + 3], c.w, v);
+                    }
+                    sc[q] = v;
+                }
+                const float a = fminf(sc[0], sc[1]), b = fmaxf(sc[0], sc[1]);
+                const float c = fminf(sc[2], sc[3]), d = fmaxf(sc[2], sc[3]);
+                const float lo1 = fminf(a, c);
+                const float lo2 = fminf(fminf(fmaxf(a, c), b), d);
+                second = fminf(fminf(second, fmaxf(best, lo1)), lo2);
+                if (lo1 < best) bestg = c0 + k;
+                best = fminf(best, lo1);
+            }
+            for (int k = cnt4; k < cnt; ++k) {            // (V not a multiple of 4): groups of one
+                float v = hn[k];
+#pragma unroll
+                for (int t = 0; t < HC; ++t) v = fmaf(pn[t], cs[k * HC + t], v);
+                second = fminf(second, fmaxf(v, best));
+                if (v < best) bestg = c0 + k;
+                best = fminf(best, v);
+            }
+        }
+        __syncthreads();                                  // the buffers are refilled for the next split
+        if (!live) continue;
+        // the winner inside its group: the same FMA chains again, from the float32 copies in global memory
+        int bv = bestg;
+        const int gsz = ((bestg & (CBIG_CK - 1)) < (min(CBIG_CK, V - (bestg & ~(CBIG_CK - 1))) & ~3)) ? 4 : 1;
+        for (int q = gsz - 1; q >= 0; --q) {
+            float v = H32[bestg + q];
+#pragma unroll
+            for (int t = 0; t < HC; ++t) v = fmaf(pn[t], C32[(int64_t)(bestg + q) * HC + t], v);
+            if (v == best) bv = bestg + q;                // first of equal ones (a tie goes to the list anyway)
+        }
+        const float sp = sqrtf(xx) + mv.Cmax32[s];
+        const float E = (float)(HC + 16) * U * sp * sp * 1.01f + 1e-30f;
+        if (second - best > 3.0f * E) coarse_out[i * 2 + s] = bv;
+        else redo[atomicAdd(nredo, 1u)] = ((unsigned long long)i << 1) | (unsigned long long)s;     // (capacity 2 n: cannot overflow)
+    }
+}
+
+// the listed (row, split) pairs in exact arithmetic: one warp each
+template <typename XT>
+__global__ void __launch_bounds__(256) k_coarse_redo(ModelView mv, const XT* __restrict__ X, int32_t* __restrict__ coarse_out,
+                                                     const unsigned long long* __restrict__ redo, const unsigned int* __restrict__ nredo) {
+    const unsigned int cnt = *nredo;
+    const int lane = threadIdx.x & 31;
+    const unsigned int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    const bool f32 = (sizeof(XT) == 4) && mv.coarse_f32;
+    for (unsigned int e = wid; e < cnt; e += nw) {
+        const int64_t i = (int64_t)(redo[e] >> 1);
+        const int s = (int)(redo[e] & 1);
+        const XT* x = X + i * (int64_t)mv.D + s * mv.h;
+        const double* C = mv.Cs + (int64_t)s * mv.V * mv.h;
+        int c;
+        if (f32) coarse_argmin_split<XT, float, double, 0>(mv.h, mv.V, x, C, mv.h, lane, c);
+        else coarse_argmin_split<XT, double, double, 0>(mv.h, mv.V, x, C, mv.h, lane, c);
+        if (lane == 0) coarse_out[i * 2 + s] = c;
+    }
+}
+
 // ---- float64 LUT rows for explicit probes (get_subquantizer_distances, model.py:673-704) ------
 // one block per vector, thread per sub-centroid; lut [n][M][K] float64
 __global__ void __launch_bounds__(256)
