@@ -113,6 +113,8 @@ struct b2l_ctx {
     const float* ftc_tabs = nullptr;   // centroid operand images of the tensor-core stage (NULL: model shape not covered)
     DevBuf w_redo, w_ftc_dbg;          // undecided sub-vectors of the tensor-core stage; diagnostic score dump
     unsigned int* d_nredo = nullptr;
+    cudaStream_t copy_stream = nullptr;        // host-resident encode: rows of block i+1 arrive while block i is encoded
+    cudaEvent_t ev_in[2] = {}, ev_free[2] = {};
     int ftc_dbg_j = -1;
     unsigned long long* d_nguard = nullptr;   // sub-vectors the guard re-evaluated in float64 (device counter)
     int scan_mode = 0;                 // 0: packed 16-bit tables first (default), 1: float32 tables only
@@ -273,10 +275,11 @@ int encode_device(b2l_handle h, const void* dX, int x_is_f64, int64_t n, const i
     const bool coarse_only = !d_fine && !d_coarse_in && d_coarse;
     double* px_out = (gemm || coarse_only) ? nullptr : h->w_px.as<double>();
     const size_t cb_coarse = (!xf64 && mv.coarse_f32) ? coarse_c_bytes<float>(mv.V, mv.h) : coarse_c_bytes<double>(mv.V, mv.h);
-    if ((gemm || coarse_only) && cb_coarse > 48 * 1024 && (mv.h == 32 || mv.h == 64 || mv.h == 128) && h->d_nredo && h->fine_mode != 1 &&
+    // (fine mode 2 keeps the warp-per-row kernel for models whose centroids fit its shared memory: the A/B switch of the probes)
+    if ((gemm || coarse_only) && (cb_coarse > 48 * 1024 || h->fine_mode == 0) && (mv.h == 32 || mv.h == 64 || mv.h == 128) && h->d_nredo && h->fine_mode != 1 &&
         n < ((int64_t)1 << 30) && (uintptr_t)x % 16 == 0) {
-        // many centroids (they do not fit the shared memory of k_coarse_assign): float32 scores against streamed chunks,
-        // exact arithmetic for the listed near ties
+        // one row per thread, float32 scores against centroid chunks streamed through shared memory (any V: the only path for
+        // centroids that do not fit the shared memory of k_coarse_assign), exact arithmetic for the listed near ties
         CU(h->w_redo.reserve((size_t)2 * n * 8));
         CU(cudaMemsetAsync(h->d_nredo, 0, 4, h->stream));
         const unsigned gb = (unsigned)((n + CBIG_THREADS - 1) / CBIG_THREADS);
@@ -1326,6 +1329,8 @@ int b2l_destroy(b2l_handle h) {
         for (int i = 0; i < 5; ++i) if (h->ring[r].ev[i]) cudaEventDestroy(h->ring[r].ev[i]);
         if (h->ring[r].h_pc) cudaFreeHost(h->ring[r].h_pc);
     }
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    for (int b = 0; b < 2; ++b) { if (h->ev_in[b]) cudaEventDestroy(h->ev_in[b]); if (h->ev_free[b]) cudaEventDestroy(h->ev_free[b]); }
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return B2L_OK;
@@ -1574,24 +1579,50 @@ int b2l_encode(b2l_handle h, const void* X, int x_is_f64, int64_t n, int on_devi
     // chunk so that the float64 projection workspace stays <= 1 GiB
     int64_t chunk = std::max<int64_t>(1024, ((int64_t)1 << 30) / ((int64_t)mv.D * 8));
     chunk = std::min<int64_t>(chunk, (int64_t)1 << 22);
-    for (int64_t a = 0; a < n; a += chunk) {
-        const int64_t c = std::min(chunk, n - a);
-        const void* dx;
-        int32_t* dco; uint8_t* dfi;
-        if (on_device) {
-            dx = (const char*)X + (size_t)a * Din * esz; dco = coarse + a * 2; dfi = fine ? fine + a * mv.M : nullptr;
-        } else {
-            CU(h->w_q.reserve((size_t)c * Din * esz)); CU(h->w_coarse.reserve((size_t)c * 8)); CU(h->w_fine.reserve((size_t)c * mv.M));
-            CU(cudaMemcpyAsync(h->w_q.p, (const char*)X + (size_t)a * Din * esz, (size_t)c * Din * esz, cudaMemcpyHostToDevice, h->stream));
-            dx = h->w_q.p; dco = h->w_coarse.as<int32_t>(); dfi = fine ? h->w_fine.as<uint8_t>() : nullptr;
+    if (on_device) {
+        for (int64_t a = 0; a < n; a += chunk) {
+            const int64_t c = std::min(chunk, n - a);
+            int rc = encode_device(h, (const char*)X + (size_t)a * Din * esz, x_is_f64, c, nullptr, coarse + a * 2, fine ? fine + a * mv.M : nullptr);
+            if (rc) return rc;
         }
-        int rc = encode_device(h, dx, x_is_f64, c, nullptr, dco, dfi);
-        if (rc) return rc;
-        if (!on_device) {
+    } else if (n) {
+        // host rows: blocks of <= 256K rows through two staging buffers; the rows of block i+1 travel on a second stream
+        // while block i is encoded (pinned host memory makes the copies asynchronous; pageable memory still works)
+        const int64_t blk = std::min<int64_t>(chunk, (int64_t)1 << 18);
+        if (!h->copy_stream) {
+            CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+            for (int b = 0; b < 2; ++b) { CU(cudaEventCreateWithFlags(&h->ev_in[b], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&h->ev_free[b], cudaEventDisableTiming)); }
+        }
+        const size_t qb = (((size_t)blk * Din * esz) + 255) & ~(size_t)255, cb = (size_t)blk * 8, fb = (((size_t)blk * mv.M) + 255) & ~(size_t)255;
+        CU(h->w_q.reserve(2 * qb)); CU(h->w_coarse.reserve(2 * cb)); CU(h->w_fine.reserve(2 * fb));
+        CU(cudaStreamSynchronize(h->stream));              // earlier work on the staging buffers is over
+        // the copy of block i+1 is enqueued BEFORE block i's results are read back: a read-back into pageable host memory
+        // blocks the calling thread until block i is done, and the next rows travel meanwhile
+        auto rows_in = [&](int i) -> int {
+            const int b = i & 1;
+            const int64_t a = (int64_t)i * blk, c = std::min(blk, n - a);
+            if (i >= 2) CU(cudaStreamWaitEvent(h->copy_stream, h->ev_free[b], 0));      // block i-2 is through with this buffer
+            CU(cudaMemcpyAsync((char*)h->w_q.p + b * qb, (const char*)X + (size_t)a * Din * esz, (size_t)c * Din * esz, cudaMemcpyHostToDevice, h->copy_stream));
+            CU(cudaEventRecord(h->ev_in[b], h->copy_stream));
+            return B2L_OK;
+        };
+        const int nblk = (int)((n + blk - 1) / blk);
+        { int rc = rows_in(0); if (rc) return rc; }
+        for (int i = 0; i < nblk; ++i) {
+            const int b = i & 1;
+            const int64_t a = (int64_t)i * blk, c = std::min(blk, n - a);
+            char* dq = (char*)h->w_q.p + b * qb;
+            int32_t* dco = (int32_t*)((char*)h->w_coarse.p + b * cb);
+            uint8_t* dfi = fine ? (uint8_t*)h->w_fine.p + b * fb : nullptr;
+            if (i + 1 < nblk) { int rc = rows_in(i + 1); if (rc) return rc; }
+            CU(cudaStreamWaitEvent(h->stream, h->ev_in[b], 0));
+            int rc = encode_device(h, dq, x_is_f64, c, nullptr, dco, dfi);
+            if (rc) { cudaStreamSynchronize(h->copy_stream); cudaStreamSynchronize(h->stream); return rc; }
+            CU(cudaEventRecord(h->ev_free[b], h->stream));
             CU(cudaMemcpyAsync(coarse + a * 2, dco, (size_t)c * 8, cudaMemcpyDeviceToHost, h->stream));
             if (fine) CU(cudaMemcpyAsync(fine + a * mv.M, dfi, (size_t)c * mv.M, cudaMemcpyDeviceToHost, h->stream));
-            CU(cudaStreamSynchronize(h->stream));   // the staging buffers are reused by the next chunk
         }
+        CU(cudaStreamSynchronize(h->copy_stream));
     }
     CU(cudaStreamSynchronize(h->stream));
     h->stats.kernel_launches = h->launches;

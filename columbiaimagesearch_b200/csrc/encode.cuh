@@ -511,14 +511,18 @@ k_fine_argmin32_all(ModelView mv, const double* __restrict__ PX, int64_t n, uint
 // half norm, FMA chain, and for float32 models the rounding of the reference's own float32 distances).  A row whose
 // runner-up is not more than 3 E away goes to a list that k_coarse_redo settles with the exact NumPy-order arithmetic.
 #define CBIG_THREADS 256
-#define CBIG_CK 128
-template <int HC> __host__ __device__ constexpr size_t cbig_smem_bytes() { return (size_t)2 * CBIG_CK * (HC + 1) * 4; }
+#define CBIG_CK 64
+// shared memory: row tile [CBIG_THREADS][HC + 4] floats (float32 rows arrive by coalesced cp.async and each thread then reads
+// its own row: stride HC + 4 keeps the 16-byte reads of a quarter warp on different banks) | 2 centroid chunk buffers
+template <int HC> __host__ __device__ constexpr size_t cbig_smem_bytes() { return (size_t)CBIG_THREADS * (HC + 4) * 4 + (size_t)2 * CBIG_CK * (HC + 1) * 4; }
 
 template <typename XT, int HC>
 __global__ void __launch_bounds__(CBIG_THREADS, (HC <= 64 ? 2 : 1))
 k_coarse_big(ModelView mv, const XT* __restrict__ X, int64_t n, int32_t* __restrict__ coarse_out,
              unsigned long long* __restrict__ redo, unsigned int* __restrict__ nredo) {
-    extern __shared__ __align__(16) float sm_cbig[];      // 2 x ([CBIG_CK][HC] centroids + [CBIG_CK] half norms)
+    extern __shared__ __align__(16) float sm_cbig_all[];  // row tile | 2 x ([CBIG_CK][HC] centroids + [CBIG_CK] half norms)
+    float* tile = sm_cbig_all;
+    float* sm_cbig = sm_cbig_all + CBIG_THREADS * (HC + 4);
     const float U = 5.9604645e-08f;
     const int V = mv.V;
     const int64_t i = (int64_t)blockIdx.x * CBIG_THREADS + threadIdx.x;
@@ -533,26 +537,35 @@ k_coarse_big(ModelView mv, const XT* __restrict__ X, int64_t n, int32_t* __restr
             for (int e = threadIdx.x; e < cnt; e += CBIG_THREADS) cp_async4(dst + CBIG_CK * HC + e, H32 + c0 + e);
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
-        fetch(0, 0);
         float pn[HC], xx = 0.0f;
-        {
-            const XT* x = X + (live ? i : 0) * (int64_t)mv.D + s * HC;       // 16-byte aligned (checked by the caller)
-            if (sizeof(XT) == 4) {
-#pragma unroll
-                for (int d = 0; d < HC; d += 4) {
-                    const float4 v = *(const float4*)((const float*)x + d);
-                    pn[d] = -v.x; pn[d + 1] = -v.y; pn[d + 2] = -v.z; pn[d + 3] = -v.w;
-                }
-            } else {
-#pragma unroll
-                for (int d = 0; d < HC; d += 2) {
-                    const double2 v = *(const double2*)((const double*)x + d);
-                    pn[d] = -(float)v.x; pn[d + 1] = -(float)v.y;
-                }
+        if (sizeof(XT) == 4) {
+            // the block's rows of this split, coalesced: 16-byte pieces in row order (rows past the end repeat the last one)
+            const int64_t r0 = (int64_t)blockIdx.x * CBIG_THREADS;
+            for (int e = threadIdx.x; e < CBIG_THREADS * (HC / 4); e += CBIG_THREADS) {
+                const int r = e / (HC / 4), f = e - r * (HC / 4);
+                const int64_t row = (r0 + r < n) ? r0 + r : n - 1;
+                cp_async16(tile + r * (HC + 4) + f * 4, (const float*)X + row * (int64_t)mv.D + s * HC + f * 4);
             }
-#pragma unroll
-            for (int d = 0; d < HC; ++d) xx = fmaf(pn[d], pn[d], xx);
         }
+        fetch(0, 0);                                      // (commits the row tile together with the first chunk)
+        if (sizeof(XT) == 4) {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads();
+#pragma unroll
+            for (int d = 0; d < HC; d += 4) {
+                const float4 v = *(const float4*)(tile + threadIdx.x * (HC + 4) + d);
+                pn[d] = -v.x; pn[d + 1] = -v.y; pn[d + 2] = -v.z; pn[d + 3] = -v.w;
+            }
+        } else {
+            const XT* x = X + (live ? i : 0) * (int64_t)mv.D + s * HC;       // 16-byte aligned (checked by the caller)
+#pragma unroll
+            for (int d = 0; d < HC; d += 2) {
+                const double2 v = *(const double2*)((const double*)x + d);
+                pn[d] = -(float)v.x; pn[d + 1] = -(float)v.y;
+            }
+        }
+#pragma unroll
+        for (int d = 0; d < HC; ++d) xx = fmaf(pn[d], pn[d], xx);
         float best = 3.0e38f, second = 3.0e38f;
         int bestg = 0;                                    // first centroid of the group (of up to four) that holds the minimum
         int buf = 0;
