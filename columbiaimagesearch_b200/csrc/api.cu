@@ -282,15 +282,23 @@ int encode_device(b2l_handle h, const void* dX, int x_is_f64, int64_t n, const i
         // centroids that do not fit the shared memory of k_coarse_assign), exact arithmetic for the listed near ties
         CU(h->w_redo.reserve((size_t)2 * n * 8));
         CU(cudaMemsetAsync(h->d_nredo, 0, 4, h->stream));
-        const unsigned gb = (unsigned)((n + CBIG_THREADS - 1) / CBIG_THREADS);
+        // two rows per thread once the centroids dominate the shared-memory traffic (h <= 64: the rows fit the registers)
+        const int rpt = (mv.V >= 256 && mv.h <= 64) ? 2 : 1;
+        const unsigned gb = (unsigned)((n + CBIG_THREADS * rpt - 1) / (CBIG_THREADS * rpt));
         unsigned long long* rl = h->w_redo.as<unsigned long long>();
-#define CBIG(XTV, HV)                                                                                           \
+#define CBIG(XTV, HV, RV)                                                                                       \
     do {                                                                                                        \
-        CU(cudaFuncSetAttribute(k_coarse_big<XTV, HV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cbig_smem_bytes<HV>())); \
-        k_coarse_big<XTV, HV><<<gb, CBIG_THREADS, cbig_smem_bytes<HV>(), h->stream>>>(mv, (const XTV*)x, n, d_coarse, rl, h->d_nredo); \
+        CU(cudaFuncSetAttribute(k_coarse_big<XTV, HV, RV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cbig_smem_bytes<HV>())); \
+        k_coarse_big<XTV, HV, RV><<<gb, CBIG_THREADS, cbig_smem_bytes<HV>(), h->stream>>>(mv, (const XTV*)x, n, d_coarse, rl, h->d_nredo); \
     } while (0)
-        if (xf64) { if (mv.h == 32) CBIG(double, 32); else if (mv.h == 64) CBIG(double, 64); else CBIG(double, 128); }
-        else { if (mv.h == 32) CBIG(float, 32); else if (mv.h == 64) CBIG(float, 64); else CBIG(float, 128); }
+#define CBIG_H(XTV)                                                                                             \
+    do {                                                                                                        \
+        if (mv.h == 32) { if (rpt == 2) CBIG(XTV, 32, 2); else CBIG(XTV, 32, 1); }                              \
+        else if (mv.h == 64) { if (rpt == 2) CBIG(XTV, 64, 2); else CBIG(XTV, 64, 1); }                         \
+        else CBIG(XTV, 128, 1);                                                                                 \
+    } while (0)
+        if (xf64) CBIG_H(double); else CBIG_H(float);
+#undef CBIG_H
 #undef CBIG
         LAUNCHED();
         if (xf64) k_coarse_redo<double><<<h->num_sms * 2, 256, 0, h->stream>>>(mv, (const double*)x, d_coarse, rl, h->d_nredo);

@@ -516,8 +516,11 @@ k_fine_argmin32_all(ModelView mv, const double* __restrict__ PX, int64_t n, uint
 // its own row: stride HC + 4 keeps the 16-byte reads of a quarter warp on different banks) | 2 centroid chunk buffers
 template <int HC> __host__ __device__ constexpr size_t cbig_smem_bytes() { return (size_t)CBIG_THREADS * (HC + 4) * 4 + (size_t)2 * CBIG_CK * (HC + 1) * 4; }
 
-template <typename XT, int HC>
-__global__ void __launch_bounds__(CBIG_THREADS, (HC <= 64 ? 2 : 1))
+// R rows per thread: a centroid read from shared memory then serves R x HC FFMAs -- with one row per thread the kernel is
+// bound by the shared-memory pipe (one 16-byte broadcast read per 4 FFMAs) as soon as V is large; R = 2 halves that
+// traffic (one block of 8 warps per SM, 8 independent FMA chains per thread).  A block takes R x CBIG_THREADS rows.
+template <typename XT, int HC, int R>
+__global__ void __launch_bounds__(CBIG_THREADS, ((HC <= 64 && R == 1) ? 2 : 1))
 k_coarse_big(ModelView mv, const XT* __restrict__ X, int64_t n, int32_t* __restrict__ coarse_out,
              unsigned long long* __restrict__ redo, unsigned int* __restrict__ nredo) {
     extern __shared__ __align__(16) float sm_cbig_all[];  // row tile | 2 x ([CBIG_CK][HC] centroids + [CBIG_CK] half norms)
@@ -525,8 +528,7 @@ k_coarse_big(ModelView mv, const XT* __restrict__ X, int64_t n, int32_t* __restr
     float* sm_cbig = sm_cbig_all + CBIG_THREADS * (HC + 4);
     const float U = 5.9604645e-08f;
     const int V = mv.V;
-    const int64_t i = (int64_t)blockIdx.x * CBIG_THREADS + threadIdx.x;
-    const bool live = i < n;
+    const int64_t r0 = (int64_t)blockIdx.x * (CBIG_THREADS * R);
     for (int s = 0; s < 2; ++s) {
         const float* C32 = mv.Cs32 + (int64_t)s * V * HC;
         const float* H32 = mv.Chn32 + (int64_t)s * V;
@@ -537,37 +539,43 @@ k_coarse_big(ModelView mv, const XT* __restrict__ X, int64_t n, int32_t* __restr
             for (int e = threadIdx.x; e < cnt; e += CBIG_THREADS) cp_async4(dst + CBIG_CK * HC + e, H32 + c0 + e);
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
-        float pn[HC], xx = 0.0f;
-        if (sizeof(XT) == 4) {
-            // the block's rows of this split, coalesced: 16-byte pieces in row order (rows past the end repeat the last one)
-            const int64_t r0 = (int64_t)blockIdx.x * CBIG_THREADS;
-            for (int e = threadIdx.x; e < CBIG_THREADS * (HC / 4); e += CBIG_THREADS) {
-                const int r = e / (HC / 4), f = e - r * (HC / 4);
-                const int64_t row = (r0 + r < n) ? r0 + r : n - 1;
-                cp_async16(tile + r * (HC + 4) + f * 4, (const float*)X + row * (int64_t)mv.D + s * HC + f * 4);
+        float pn[R][HC], xx[R];
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) {
+            const int64_t i = r0 + rr * CBIG_THREADS + threadIdx.x;
+            if (sizeof(XT) == 4) {
+                // CBIG_THREADS rows of this split, coalesced: 16-byte pieces in row order (rows past the end repeat the last one)
+                if (rr) __syncthreads();                  // everybody has taken the previous rows out of the tile
+                for (int e = threadIdx.x; e < CBIG_THREADS * (HC / 4); e += CBIG_THREADS) {
+                    const int r = e / (HC / 4), f = e - r * (HC / 4);
+                    const int64_t row = min(r0 + rr * CBIG_THREADS + r, n - 1);
+                    cp_async16(tile + r * (HC + 4) + f * 4, (const float*)X + row * (int64_t)mv.D + s * HC + f * 4);
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                __syncthreads();
+#pragma unroll
+                for (int d = 0; d < HC; d += 4) {
+                    const float4 v = *(const float4*)(tile + threadIdx.x * (HC + 4) + d);
+                    pn[rr][d] = -v.x; pn[rr][d + 1] = -v.y; pn[rr][d + 2] = -v.z; pn[rr][d + 3] = -v.w;
+                }
+            } else {
+                const XT* x = X + min(i, n - 1) * (int64_t)mv.D + s * HC;         // 16-byte aligned (checked by the caller)
+#pragma unroll
+                for (int d = 0; d < HC; d += 2) {
+                    const double2 v = *(const double2*)((const double*)x + d);
+                    pn[rr][d] = -(float)v.x; pn[rr][d + 1] = -(float)v.y;
+                }
             }
+            xx[rr] = 0.0f;
+#pragma unroll
+            for (int d = 0; d < HC; ++d) xx[rr] = fmaf(pn[rr][d], pn[rr][d], xx[rr]);
         }
-        fetch(0, 0);                                      // (commits the row tile together with the first chunk)
-        if (sizeof(XT) == 4) {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-            __syncthreads();
+        fetch(0, 0);
+        float best[R], second[R];
+        int bestg[R];                                     // first centroid of the group (of up to four) that holds the minimum
 #pragma unroll
-            for (int d = 0; d < HC; d += 4) {
-                const float4 v = *(const float4*)(tile + threadIdx.x * (HC + 4) + d);
-                pn[d] = -v.x; pn[d + 1] = -v.y; pn[d + 2] = -v.z; pn[d + 3] = -v.w;
-            }
-        } else {
-            const XT* x = X + (live ? i : 0) * (int64_t)mv.D + s * HC;       // 16-byte aligned (checked by the caller)
-#pragma unroll
-            for (int d = 0; d < HC; d += 2) {
-                const double2 v = *(const double2*)((const double*)x + d);
-                pn[d] = -(float)v.x; pn[d + 1] = -(float)v.y;
-            }
-        }
-#pragma unroll
-        for (int d = 0; d < HC; ++d) xx = fmaf(pn[d], pn[d], xx);
-        float best = 3.0e38f, second = 3.0e38f;
-        int bestg = 0;                                    // first centroid of the group (of up to four) that holds the minimum
+        for (int rr = 0; rr < R; ++rr) { best[rr] = 3.0e38f; second[rr] = 3.0e38f; bestg[rr] = 0; }
         int buf = 0;
         for (int c0 = 0; c0 < V; c0 += CBIG_CK, buf ^= 1) {
             asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -578,49 +586,66 @@ k_coarse_big(ModelView mv, const XT* __restrict__ X, int64_t n, int32_t* __restr
             const int cnt = min(CBIG_CK, V - c0), cnt4 = cnt & ~3;
 #pragma unroll 1
             for (int k = 0; k < cnt4; k += 4) {
-                float sc[4];
+                float sc[R][4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    float v = hn[k + q];
+                    float v[R];
+#pragma unroll
+                    for (int rr = 0; rr < R; ++rr) v[rr] = hn[k + q];
 #pragma unroll
                     for (int t = 0; t < HC; t += 4) {
                         const float4 c = *(const float4*)(cs + (k + q) * HC + t);
-                        v = fmaf(pn[t], c.x, v); v = fmaf(pn[t + 1], c.y, v); v = fmaf(pn[t + 2], c.z, v); v = fmaf(pn[t + 3], c.w, v);
+#pragma unroll
+                        for (int rr = 0; rr < R; ++rr) {
+                            v[rr] = fmaf(pn[rr][t], c.x, v[rr]); v[rr] = fmaf(pn[rr][t + 1], c.y, v[rr]);
+                            v[rr] = fmaf(pn[rr][t + 2], c.z, v[rr]); v[rr] = fmaf(pn[rr][t + 3], c.w, v[rr]);
+                        }
                     }
-                    sc[q] = v;
+#pragma unroll
+                    for (int rr = 0; rr < R; ++rr) sc[rr][q] = v[rr];
                 }
-                const float a = fminf(sc[0], sc[1]), b = fmaxf(sc[0], sc[1]);
-                const float c = fminf(sc[2], sc[3]), d = fmaxf(sc[2], sc[3]);
-                const float lo1 = fminf(a, c);
-                const float lo2 = fminf(fminf(fmaxf(a, c), b), d);
-                second = fminf(fminf(second, fmaxf(best, lo1)), lo2);
-                if (lo1 < best) bestg = c0 + k;
-                best = fminf(best, lo1);
+#pragma unroll
+                for (int rr = 0; rr < R; ++rr) {
+                    const float a = fminf(sc[rr][0], sc[rr][1]), b = fmaxf(sc[rr][0], sc[rr][1]);
+                    const float c = fminf(sc[rr][2], sc[rr][3]), d = fmaxf(sc[rr][2], sc[rr][3]);
+                    const float lo1 = fminf(a, c);
+                    const float lo2 = fminf(fminf(fmaxf(a, c), b), d);
+                    second[rr] = fminf(fminf(second[rr], fmaxf(best[rr], lo1)), lo2);
+                    if (lo1 < best[rr]) bestg[rr] = c0 + k;
+                    best[rr] = fminf(best[rr], lo1);
+                }
             }
             for (int k = cnt4; k < cnt; ++k) {            // (V not a multiple of 4): groups of one
-                float v = hn[k];
 #pragma unroll
-                for (int t = 0; t < HC; ++t) v = fmaf(pn[t], cs[k * HC + t], v);
-                second = fminf(second, fmaxf(v, best));
-                if (v < best) bestg = c0 + k;
-                best = fminf(best, v);
+                for (int rr = 0; rr < R; ++rr) {
+                    float v = hn[k];
+#pragma unroll
+                    for (int t = 0; t < HC; ++t) v = fmaf(pn[rr][t], cs[k * HC + t], v);
+                    second[rr] = fminf(second[rr], fmaxf(v, best[rr]));
+                    if (v < best[rr]) bestg[rr] = c0 + k;
+                    best[rr] = fminf(best[rr], v);
+                }
             }
         }
         __syncthreads();                                  // the buffers are refilled for the next split
-        if (!live) continue;
-        // the winner inside its group: the same FMA chains again, from the float32 copies in global memory
-        int bv = bestg;
-        const int gsz = ((bestg & (CBIG_CK - 1)) < (min(CBIG_CK, V - (bestg & ~(CBIG_CK - 1))) & ~3)) ? 4 : 1;
-        for (int q = gsz - 1; q >= 0; --q) {
-            float v = H32[bestg + q];
 #pragma unroll
-            for (int t = 0; t < HC; ++t) v = fmaf(pn[t], C32[(int64_t)(bestg + q) * HC + t], v);
-            if (v == best) bv = bestg + q;                // first of equal ones (a tie goes to the list anyway)
+        for (int rr = 0; rr < R; ++rr) {
+            const int64_t i = r0 + rr * CBIG_THREADS + threadIdx.x;
+            if (i >= n) continue;
+            // the winner inside its group: the same FMA chains again, from the float32 copies in global memory
+            int bv = bestg[rr];
+            const int gsz = ((bestg[rr] & (CBIG_CK - 1)) < (min(CBIG_CK, V - (bestg[rr] & ~(CBIG_CK - 1))) & ~3)) ? 4 : 1;
+            for (int q = gsz - 1; q >= 0; --q) {
+                float v = H32[bestg[rr] + q];
+#pragma unroll
+                for (int t = 0; t < HC; ++t) v = fmaf(pn[rr][t], C32[(int64_t)(bestg[rr] + q) * HC + t], v);
+                if (v == best[rr]) bv = bestg[rr] + q;    // first of equal ones (a tie goes to the list anyway)
+            }
+            const float sp = sqrtf(xx[rr]) + mv.Cmax32[s];
+            const float E = (float)(HC + 16) * U * sp * sp * 1.01f + 1e-30f;
+            if (second[rr] - best[rr] > 3.0f * E) coarse_out[i * 2 + s] = bv;
+            else redo[atomicAdd(nredo, 1u)] = ((unsigned long long)i << 1) | (unsigned long long)s;     // (capacity 2 n: cannot overflow)
         }
-        const float sp = sqrtf(xx) + mv.Cmax32[s];
-        const float E = (float)(HC + 16) * U * sp * sp * 1.01f + 1e-30f;
-        if (second - best > 3.0f * E) coarse_out[i * 2 + s] = bv;
-        else redo[atomicAdd(nredo, 1u)] = ((unsigned long long)i << 1) | (unsigned long long)s;     // (capacity 2 n: cannot overflow)
     }
 }
 
