@@ -329,7 +329,7 @@ int encode_device(b2l_handle h, const void* dX, int x_is_f64, int64_t n, const i
         CU(cudaMemsetAsync(cnt, 0, (size_t)nb * 4, h->stream));
         k_enc_hist<<<grid_for(n, 256), 256, 0, h->stream>>>(d_coarse, n, mv.V, cnt);
         LAUNCHED();
-        k_enc_offsets<<<1, 32, 0, h->stream>>>(mv.V, cnt, base, cursor, tile_base);
+        k_enc_offsets<<<1, 1024, 0, h->stream>>>(mv.V, cnt, base, cursor, tile_base);
         LAUNCHED();
         k_enc_scatter<<<grid_for(n, 256), 256, 0, h->stream>>>(d_coarse, n, mv.V, base, cursor, perm);
         LAUNCHED();
@@ -760,7 +760,7 @@ int search_large_impl(b2l_handle h, const void* x, int xf64, int nq, int64_t quo
                 const unsigned sg = (unsigned)std::min<size_t>((nl + 255) / 256, 2048);
                 k_slot_hist<<<sg, 256, 0, h->stream>>>(wv.lut_desc, &wv.cnt->n_lut, mv.V, bc);
                 LAUNCHED();
-                k_enc_offsets<<<1, 32, 0, h->stream>>>(mv.V, bc, bbase, bcur, btile);
+                k_enc_offsets<<<1, 1024, 0, h->stream>>>(mv.V, bc, bbase, bcur, btile);
                 LAUNCHED();
                 k_slot_scatter<<<sg, 256, 0, h->stream>>>(wv.lut_desc, &wv.cnt->n_lut, mv.V, nl, bbase, bcur, perm);
                 LAUNCHED();
@@ -804,17 +804,28 @@ int search_large_impl(b2l_handle h, const void* x, int xf64, int nq, int64_t quo
             CU(cudaMemcpyAsync(dqo, qoff.data(), (size_t)(ng + 1) * 8, cudaMemcpyHostToDevice, h->stream));
             const unsigned long long* kout = k1;
             const unsigned int* vout = v1;
+            unsigned int nmax = 0;
+            for (int g = 0; g < ng; ++g) nmax = std::max(nmax, ncand[ga + g]);
+            const bool by_select = k <= SELK_MAXK && nmax <= SELK_MAXN;        // first k by selection instead of a full sort
             if (tot > 0) {
                 k_cand_dist<<<grid_for(tot, 256, h->num_sms * 16), 256, 0, h->stream>>>(mv, h->codes.as<uint8_t>(), wv, ga, ng, dqo,
                                                                                           h->w_p64.as<double>(), k1, v1);
                 LAUNCHED();
-                size_t tmp = 0;
-                CU(cub::DeviceSegmentedRadixSort::SortPairs(nullptr, tmp, k1, k2, v1, v2, (int)tot, ng, dqo, dqo + 1, 0, 64, h->stream));
-                CU(h->w_sort_tmp.reserve(tmp));
-                CU(cub::DeviceSegmentedRadixSort::SortPairs(h->w_sort_tmp.p, tmp, k1, k2, v1, v2, (int)tot, ng, dqo, dqo + 1, 0, 64, h->stream));
-                ++h->launches;
-                kout = k2; vout = v2;
+                if (!by_select) {
+                    size_t tmp = 0;
+                    CU(cub::DeviceSegmentedRadixSort::SortPairs(nullptr, tmp, k1, k2, v1, v2, (int)tot, ng, dqo, dqo + 1, 0, 64, h->stream));
+                    CU(h->w_sort_tmp.reserve(tmp));
+                    CU(cub::DeviceSegmentedRadixSort::SortPairs(h->w_sort_tmp.p, tmp, k1, k2, v1, v2, (int)tot, ng, dqo, dqo + 1, 0, 64, h->stream));
+                    ++h->launches;
+                    kout = k2; vout = v2;
+                }
             }
+            if (by_select) {
+                const size_t sms = selk_smem_bytes(std::max(nmax, 1u));
+                CU(cudaFuncSetAttribute(k_select_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sms));
+                k_select_emit<<<ng, SELK_THREADS, sms, h->stream>>>(mv, h->codes.as<uint8_t>(), h->rowids.as<int64_t>(), wv, ga, dqo, k1,
+                                                                    std::max(nmax, 1u), k, d_records, nq, qa0);
+            } else
             k_emit_sorted<<<ng, 128, 0, h->stream>>>(mv, h->codes.as<uint8_t>(), h->rowids.as<int64_t>(), wv, ga, dqo, kout, vout, k,
                                                      d_records, nq, qa0);
             LAUNCHED();
@@ -1063,7 +1074,7 @@ int search_local_impl(b2l_handle h, const void* Q, int q_is_f64, int nq, int on_
             const unsigned sg = (unsigned)std::min<size_t>((cap_lut + 255) / 256, 1024);
             k_slot_hist<<<sg, 256, 0, h->stream>>>(pv.lut_desc, &pv.cnt->n_lut, mv.V, bc);
             LAUNCHED();
-            k_enc_offsets<<<1, 32, 0, h->stream>>>(mv.V, bc, bbase, bcur, btile);
+            k_enc_offsets<<<1, 1024, 0, h->stream>>>(mv.V, bc, bbase, bcur, btile);
             LAUNCHED();
             k_slot_scatter<<<sg, 256, 0, h->stream>>>(pv.lut_desc, &pv.cnt->n_lut, mv.V, cap_lut, bbase, bcur, perm);
             LAUNCHED();

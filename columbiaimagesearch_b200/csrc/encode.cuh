@@ -703,20 +703,41 @@ __global__ void k_enc_hist(const int32_t* __restrict__ coarse, int64_t n, int V,
 }
 
 // single block: per split, exclusive prefix of the bucket sizes (row offsets) and of their 64-row tile counts
-__global__ void k_enc_offsets(int V, const unsigned int* __restrict__ cnt, unsigned int* __restrict__ base,
+__global__ void __launch_bounds__(1024) k_enc_offsets(int V, const unsigned int* __restrict__ cnt, unsigned int* __restrict__ base,
                               unsigned int* __restrict__ cursor, unsigned int* __restrict__ tile_base) {
-    if (threadIdx.x != 0) return;
-    unsigned int tiles = 0;
-    for (int s = 0; s < 2; ++s) {
-        unsigned int rows = 0;
-        for (int c = 0; c < V; ++c) {
-            const int b = s * V + c;
-            base[b] = rows; cursor[b] = 0u; tile_base[b] = tiles;
-            rows += cnt[b];
-            tiles += (cnt[b] + 63u) / 64u;
-        }
+    // one block: every thread owns a contiguous run of the 2 V buckets (split-major), a block scan joins the runs;
+    // rows restart at the split boundary, tiles run through
+    __shared__ unsigned int s_rows[1024], s_tiles[1024];
+    const int nb = 2 * V, per = (nb + 1023) / 1024, lo = min(nb, (int)threadIdx.x * per), hi = min(nb, lo + per);
+    unsigned int rows = 0, tiles = 0;
+    for (int b = lo; b < hi; ++b) { rows += cnt[b]; tiles += (cnt[b] + 63u) / 64u; }
+    s_rows[threadIdx.x] = rows; s_tiles[threadIdx.x] = tiles;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        unsigned int r = 0, t = 0;
+        if ((int)threadIdx.x >= o) { r = s_rows[threadIdx.x - o]; t = s_tiles[threadIdx.x - o]; }
+        __syncthreads();
+        s_rows[threadIdx.x] += r; s_tiles[threadIdx.x] += t;
+        __syncthreads();
     }
-    tile_base[2 * V] = tiles;
+    unsigned int rbase = s_rows[threadIdx.x] - rows, tbase = s_tiles[threadIdx.x] - tiles;     // exclusive prefixes (rows over both splits)
+    // rows of split 0 in total = prefix at the first thread whose run starts at or after V
+    __shared__ unsigned int s_split0;
+    if (threadIdx.x == 0) s_split0 = 0;
+    __syncthreads();
+    if (lo < V && hi >= V) {                                  // the run that crosses (or ends at) the split boundary
+        unsigned int r0 = rbase;
+        for (int b = lo; b < V; ++b) r0 += cnt[b];
+        s_split0 = r0;
+    }
+    __syncthreads();
+    const unsigned int split0 = s_split0;
+    for (int b = lo; b < hi; ++b) {
+        base[b] = (b >= V) ? rbase - split0 : rbase;
+        cursor[b] = 0u; tile_base[b] = tbase;
+        rbase += cnt[b]; tbase += (cnt[b] + 63u) / 64u;
+    }
+    if (threadIdx.x == 1023) tile_base[nb] = s_tiles[1023];
 }
 
 __global__ void k_enc_scatter(const int32_t* __restrict__ coarse, int64_t n, int V, const unsigned int* __restrict__ base,

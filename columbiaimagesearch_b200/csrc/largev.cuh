@@ -480,3 +480,129 @@ k_emit_sorted(ModelView mv, const uint8_t* __restrict__ codes, const int64_t* __
     }
 }
 
+
+// The same result without sorting everything: the product asks for the first 100 of ~10 000 retrieved codes per query.
+// One block per query: its keys in shared memory, an 8-pass radix SELECT finds the k-th smallest key T exactly, the block
+// keeps every key < T and, of the keys equal to T, the ones with the smallest retrieval positions (ordered compaction: the
+// stable order of the reference's sorted(), search.py:210), sorts those k pairs (bitonic, by (key, position)) and writes
+// the records.  Replaces 11 segmented radix-sort passes + k_emit_sorted for k <= SELK_MAXK and <= SELK_MAXN candidates.
+#define SELK_THREADS 256
+#define SELK_MAXK 1024
+#define SELK_MAXN 12288
+inline size_t selk_smem_bytes(unsigned int nmax) { return (size_t)nmax * 8 + (size_t)SELK_MAXK * 12 + 64; }
+
+__global__ void __launch_bounds__(SELK_THREADS)
+k_select_emit(ModelView mv, const uint8_t* __restrict__ codes, const int64_t* __restrict__ rowids, WalkView wv, int qa,
+              const unsigned long long* __restrict__ qoff, const unsigned long long* __restrict__ keys, unsigned int nmax,
+              int k, void* recbuf, int nq_rec, int qrec0) {
+    extern __shared__ __align__(16) unsigned long long sm_selk[];      // keys [nmax] | wkey [SELK_MAXK] | widx [SELK_MAXK]
+    __shared__ unsigned int hist[256], wsum[SELK_THREADS / 32];
+    __shared__ unsigned int s_cnt, s_digit, s_rem;
+    unsigned long long* skey = sm_selk;
+    unsigned long long* wkey = sm_selk + nmax;
+    unsigned int* widx = (unsigned int*)(wkey + SELK_MAXK);
+    const int g = blockIdx.x, q = qa + g, tid = threadIdx.x;
+    const int qr = qrec0 + q;
+    RecView rv = rec_view(recbuf, nq_rec, k, mv.M);
+    const unsigned long long o = qoff[g];
+    const unsigned int n = wv.ncand[q];
+    const unsigned int kk = min((unsigned int)k, n);
+    if (tid == 0) {
+        rv.lb[qr] = __longlong_as_double(0x7FF0000000000000ll);      // every retrieved code was ranked exactly
+        rv.count[qr] = (int32_t)kk;
+        rv.visited[qr] = wv.nvis[q];
+        rv.ncand[qr] = (int64_t)n;
+    }
+    if (kk == 0) return;
+    for (unsigned int i = tid; i < n; i += SELK_THREADS) skey[i] = keys[o + i];
+    // ---- radix select: T = the kk-th smallest key, rem = how many keys equal to T belong to the first kk
+    unsigned long long prefix = 0ull, mask = 0ull;
+    unsigned int rem = kk;
+    for (int shift = 56; shift >= 0; shift -= 8) {
+        hist[tid] = 0u;
+        __syncthreads();
+        for (unsigned int i = tid; i < n; i += SELK_THREADS) {
+            const unsigned long long key = skey[i];
+            if ((key & mask) == prefix) atomicAdd(&hist[(unsigned int)(key >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (tid < 32) {                                              // first digit whose cumulative count reaches rem
+            unsigned int c[8], tot = 0;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { c[e] = hist[tid * 8 + e]; tot += c[e]; }
+            unsigned int incl = tot;
+            for (int d = 1; d < 32; d <<= 1) { const unsigned int v = __shfl_up_sync(0xffffffffu, incl, d); if (tid >= d) incl += v; }
+            unsigned int before = incl - tot;
+            const bool mine = before < rem && rem <= incl;          // exactly one lane
+            if (mine) {
+                int e = 0;
+                while (before + c[e] < rem) { before += c[e]; ++e; }
+                s_digit = (unsigned int)(tid * 8 + e); s_rem = rem - before;
+            }
+        }
+        __syncthreads();
+        prefix |= (unsigned long long)s_digit << shift;
+        mask |= 0xFFull << shift;
+        rem = s_rem;
+        __syncthreads();
+    }
+    const unsigned long long T = prefix;
+    // ---- keep: key < T (all of them), key == T (the first `rem` in retrieval order)
+    if (tid == 0) s_cnt = 0u;
+    __syncthreads();
+    unsigned int ties_seen = 0;
+    for (unsigned int b0 = 0; b0 < n; b0 += SELK_THREADS) {
+        const unsigned int i = b0 + tid;
+        const unsigned long long key = (i < n) ? skey[i] : ~0ull;
+        const bool lt = (i < n) && key < T, tie = (i < n) && key == T;
+        const unsigned int bal = __ballot_sync(0xffffffffu, tie);
+        if ((tid & 31) == 0) wsum[tid >> 5] = __popc(bal);
+        __syncthreads();
+        unsigned int ord = ties_seen, tot = 0;
+#pragma unroll
+        for (int w = 0; w < SELK_THREADS / 32; ++w) { if (w < (tid >> 5)) ord += wsum[w]; tot += wsum[w]; }
+        ord += __popc(bal & ((1u << (tid & 31)) - 1u));
+        if (lt || (tie && ord < rem)) {
+            const unsigned int slot = atomicAdd(&s_cnt, 1u);
+            wkey[slot] = key; widx[slot] = i;
+        }
+        ties_seen += tot;
+        __syncthreads();
+    }
+    // ---- sort the kk pairs by (key, position)
+    unsigned int P = 1;
+    while (P < kk) P <<= 1;
+    for (unsigned int i = kk + tid; i < P; i += SELK_THREADS) { wkey[i] = ~0ull; widx[i] = 0xFFFFFFFFu; }
+    __syncthreads();
+    for (unsigned int kb = 2; kb <= P; kb <<= 1) {
+        for (unsigned int j = kb >> 1; j > 0; j >>= 1) {
+            for (unsigned int i = tid; i < P; i += SELK_THREADS) {
+                const unsigned int ixj = i ^ j;
+                if (ixj > i) {
+                    const unsigned long long ka = wkey[i], kc = wkey[ixj];
+                    const unsigned int ia = widx[i], ic = widx[ixj];
+                    const bool gt = ka > kc || (ka == kc && ia > ic);
+                    if (gt == ((i & kb) == 0)) { wkey[i] = kc; wkey[ixj] = ka; widx[i] = ic; widx[ixj] = ia; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // ---- records (as k_emit_sorted)
+    const uint4* segq = wv.seg + (size_t)q * wv.segcap;
+    const int ns = wv.nseg[q];
+    for (unsigned int i = tid; i < kk; i += SELK_THREADS) {
+        const unsigned int pos = widx[i];
+        int a = 0, b = ns;
+        while (b - a > 1) { const int mid = (a + b) >> 1; if (segq[mid].z <= pos) a = mid; else b = mid; }
+        const uint4 sg = segq[a];
+        const unsigned int incell = pos - sg.z;
+        const int64_t row = (int64_t)sg.x + incell;
+        const int64_t e = (int64_t)qr * k + i;
+        rv.d64[e] = __longlong_as_double((long long)wkey[i]);
+        rv.pos[e] = pos;
+        rv.rowid[e] = rowids[row];
+        rv.cell[e] = (int32_t)sg.w;
+        for (int j = 0; j < mv.M; ++j) rv.fine[e * mv.M + j] = code_byte(codes + row * mv.MP, (int64_t)incell, j, mv.SW);
+    }
+}
