@@ -107,6 +107,7 @@ struct b2l_ctx {
     int fb_nq = 0, fb_segc = 0;        // last collected fast search: batch size, segment length, work items it produced
     int64_t fb_items = 0;
     float c2m = 0.0f;                  // max_j max_k |subs[j][k]|^2 (upper bound), for the float32 table error model
+    float c2sum = 0.0f;                // sum_j max_k |subs[j][k]|^2 (upper bound): |c|^2 of any code (float32 preselection at large V)
     int force_redo = 0;                // test knob: bit 0 / 1 = treat every query as uncertified after the first / second stage
     int fine_mode = 0;                 // fine argmin: 0 tensor-core stage (fine_tc.cuh) where the model allows, else as 2; 1: float64 only;
                                        // 2: float32 SIMT stage + float64 guard
@@ -782,6 +783,15 @@ int search_large_impl(b2l_handle h, const void* x, int xf64, int nq, int64_t quo
                 CU(cudaStreamSynchronize(h->stream));     // pcs is a local
             }
         }
+        // ---- float32 copies of the projections + their norms (float32 preselection of the retrieved codes)
+        const bool presel_shape = k <= PRS_SCAP / 2 && nl > 0 && h->scan_mode != 1;     // (scan mode 1: full float64 evaluation, the A/B switch)
+        float* P32 = nullptr; float* n2s = nullptr;
+        if (presel_shape) {
+            CU(h->w_lut32.reserve(align256(nl * mv.h * 4) + nl * 4));                     // (the dense-plan tables are not used at large V)
+            P32 = h->w_lut32.as<float>(); n2s = (float*)(h->w_lut32.as<unsigned char>() + align256(nl * mv.h * 4));
+            k_slot_prep<<<(unsigned)std::min<size_t>((nl + 7) / 8, (size_t)h->num_sms * 8), 256, 0, h->stream>>>(h->w_p64.as<double>(), &wv.cnt->n_lut, mv.h, P32, n2s);
+            LAUNCHED();
+        }
         // ---- groups of queries with at most ~48M candidates: exact distances, stable segmented sort, emit
         const int64_t budget = (int64_t)48 << 20;
         for (int ga = 0; ga < nqc;) {
@@ -807,6 +817,20 @@ int search_large_impl(b2l_handle h, const void* x, int xf64, int nq, int64_t quo
             unsigned int nmax = 0;
             for (int g = 0; g < ng; ++g) nmax = std::max(nmax, ncand[ga + g]);
             const bool by_select = k <= SELK_MAXK && nmax <= SELK_MAXN;        // first k by selection instead of a full sort
+            bool done = false;
+            if (presel_shape && nmax <= PRS_MAXN && tot > 0) {                // float32 preselection, exact distances of the survivors only
+                CU(cudaMemsetAsync(&wv.cnt->presel_fallback, 0, 4, h->stream));
+                const size_t sms = presel_smem_bytes(nmax);
+                CU(cudaFuncSetAttribute(k_presel_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sms));
+                k_presel_emit<<<ng, PRS_THREADS, sms, h->stream>>>(mv, h->codes.as<uint8_t>(), h->rowids.as<int64_t>(), wv, ga, h->w_p64.as<double>(),
+                                                                   P32, n2s, h->c2sum, nmax, k, d_records, nq, qa0);
+                LAUNCHED();
+                unsigned int fb = 0;
+                CU(cudaMemcpyAsync(&fb, &wv.cnt->presel_fallback, 4, cudaMemcpyDeviceToHost, h->stream));
+                CU(cudaStreamSynchronize(h->stream));
+                done = (fb == 0);                                             // else: massive near ties somewhere -- the whole group in full
+            }
+            if (done) { ga = gb; continue; }
             if (tot > 0) {
                 k_cand_dist<<<grid_for(tot, 256, h->num_sms * 16), 256, 0, h->stream>>>(mv, h->codes.as<uint8_t>(), wv, ga, ng, dqo,
                                                                                           h->w_p64.as<double>(), k1, v1);
@@ -1372,7 +1396,7 @@ int b2l_create_sibling(b2l_handle p, b2l_handle* out) {
     b2l_handle s = nullptr;
     rc = b2l_create(p->device, &s);
     if (rc) { p->err = g_create_error; return rc; }
-    s->has_model = true; s->has_pca = p->has_pca; s->mv = p->mv; s->c2m = p->c2m;
+    s->has_model = true; s->has_pca = p->has_pca; s->mv = p->mv; s->c2m = p->c2m; s->c2sum = p->c2sum;
     s->fine_mode = p->fine_mode; s->ftc_tabs = p->ftc_tabs; s->scan_mode = p->scan_mode; s->kp_min = p->kp_min; s->force_redo = p->force_redo;
     DevBuf* src[] = {&p->dCs, &p->dmus, &p->dRt, &p->dsubs, &p->dsubs32, &p->dsubs32T, &p->dc2max, &p->dP, &p->dpmu, &p->dftc, &p->dCs32, &p->m_coarse, &p->m_fine,
                      &p->m_rowid, &p->codes, &p->rowids, &p->cell_start, &p->lsize, &p->gsize, &p->sorted_first, &p->d_ucell, &p->d_ustart,
@@ -1525,6 +1549,7 @@ int b2l_set_model(b2l_handle h, int D, int V, int M, int K, int coarse_is_f32, c
         }
         c2[j] = (float)(mx * 1.001 + 1e-30);
         h->c2m = std::max(j ? h->c2m : 0.0f, c2[j]);
+        h->c2sum = (j ? h->c2sum : 0.0f) + c2[j] * 1.0001f;
     }
     std::vector<float> s32t(nS);
     for (int j = 0; j < M; ++j)

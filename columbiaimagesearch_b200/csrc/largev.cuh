@@ -102,6 +102,8 @@ struct WalkCounters {
     unsigned int n_lut;               // projection slots (query, split, coarse code)
     unsigned int err;                 // 1: a distance slab could not be bounded (mass tie of coarse distances); 2: segment list overflow
     unsigned long long cand_total;    // retrieved codes, all queries
+    unsigned int presel_fallback;     // queries of the current group whose float32 preselection kept too many candidates
+    unsigned int pad_;
 };
 
 struct WalkView {                     // per-batch arrays of the large-V plan
@@ -600,6 +602,182 @@ k_select_emit(ModelView mv, const uint8_t* __restrict__ codes, const int64_t* __
         const int64_t row = (int64_t)sg.x + incell;
         const int64_t e = (int64_t)qr * k + i;
         rv.d64[e] = __longlong_as_double((long long)wkey[i]);
+        rv.pos[e] = pos;
+        rv.rowid[e] = rowids[row];
+        rv.cell[e] = (int32_t)sg.w;
+        for (int j = 0; j < mv.M; ++j) rv.fine[e * mv.M + j] = code_byte(codes + row * mv.MP, (int64_t)incell, j, mv.SW);
+    }
+}
+
+// ---- float32 preselection of the retrieved codes -------------------------------------------------------------------------
+// The exact float64 ADC of EVERY retrieved code (k_cand_dist) is bound by the float64 pipe (3 non-fused operations per
+// dimension and candidate); the reference only reports the first k.  One block per query:
+//   A. every candidate's distance in float32 (FFMA, float32 copies of the projections and of the codebook) with a rigorous
+//      error bound  |d32 - d| <= E = (D + 4) 2^-24 * 1.01 * 2 (|p|^2 + sum_j max_k |c_jk|^2)  (inputs rounded to float32: 2u
+//      on every difference, 4u (|p_i| + |c_i|)^2 on its square; D-term FMA accumulation: D u sum t_i^2; sum_i (|p_i| + |c_i|)^2
+//      <= 2 (|p|^2 + |c|^2)) -> lower / upper bounds in shared memory;
+//   B. U = the k-th smallest UPPER bound (radix select on the float bits): at least k candidates have d <= U;
+//   C. survivors = candidates whose LOWER bound is <= U: every member of the exact first k (ties included) is one of them;
+//   D. the exact float64 ADC of the survivors only (k plus a handful), bitonic sort by (distance, retrieval position) -- the
+//      order of the reference's stable sorted() (search.py:210) -- and the records.
+// Same records as the full evaluation, bit for bit; a query that keeps more than PRS_SCAP survivors (massive near ties)
+// raises presel_fallback and the host sends the group through the full evaluation.
+#define PRS_THREADS 512
+#define PRS_MAXN 12288
+#define PRS_SCAP 2048
+inline size_t presel_smem_bytes(unsigned int nmax) { return (size_t)nmax * 8 + (size_t)PRS_SCAP * 12 + 64; }
+
+// float32 copies of the projection slots and their squared norms (rounded up)
+__global__ void __launch_bounds__(256) k_slot_prep(const double* __restrict__ P64, const unsigned int* __restrict__ nslot_p, int h,
+                                                  float* __restrict__ P32, float* __restrict__ n2) {
+    const unsigned int nslot = *nslot_p;
+    const int lane = threadIdx.x & 31;
+    const unsigned int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (unsigned int sl = wid; sl < nslot; sl += nw) {
+        double acc = 0.0;
+        for (int t = lane; t < h; t += 32) {
+            const double v = P64[(size_t)sl * h + t];
+            P32[(size_t)sl * h + t] = (float)v;
+            acc += v * v;
+        }
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) n2[sl] = __double2float_ru(acc * (1.0 + 1e-12));
+    }
+}
+
+__global__ void __launch_bounds__(PRS_THREADS, 1)
+k_presel_emit(ModelView mv, const uint8_t* __restrict__ codes, const int64_t* __restrict__ rowids, WalkView wv, int qa,
+              const double* __restrict__ P64, const float* __restrict__ P32, const float* __restrict__ n2, float c2tot,
+              unsigned int nmax, int k, void* recbuf, int nq_rec, int qrec0) {
+    extern __shared__ __align__(16) unsigned char sm_prs[];           // lowb [nmax] | upb [nmax] | skey [SCAP] | spos [SCAP]
+    __shared__ unsigned int hist[256];
+    __shared__ unsigned int s_cnt, s_digit, s_rem;
+    float* lowb = (float*)sm_prs;
+    float* upb = lowb + nmax;
+    unsigned long long* skey = (unsigned long long*)(upb + nmax);
+    unsigned int* spos = (unsigned int*)(skey + PRS_SCAP);
+    const int g = blockIdx.x, q = qa + g, tid = threadIdx.x;
+    const int qr = qrec0 + q;
+    RecView rv = rec_view(recbuf, nq_rec, k, mv.M);
+    const unsigned int n = wv.ncand[q];
+    const unsigned int kk = min((unsigned int)k, n);
+    if (tid == 0) {
+        rv.lb[qr] = __longlong_as_double(0x7FF0000000000000ll);      // every possible member of the first k was ranked exactly
+        rv.count[qr] = (int32_t)kk;
+        rv.visited[qr] = wv.nvis[q];
+        rv.ncand[qr] = (int64_t)n;
+    }
+    if (kk == 0) return;
+    const uint4* segq = wv.seg + (size_t)q * wv.segcap;
+    const int ns = wv.nseg[q];
+    const int32_t* sl0 = wv.slot0 + (size_t)q * mv.V;
+    const int32_t* sl1 = wv.slot1 + (size_t)q * mv.V;
+    const float U24 = 5.9604645e-08f;
+    auto segment_of = [&](unsigned int pos) {
+        int a = 0, b = ns;
+        while (b - a > 1) { const int mid = (a + b) >> 1; if (segq[mid].z <= pos) a = mid; else b = mid; }
+        return a;
+    };
+    // ---- A: float32 distances and their bounds
+    for (unsigned int pos = tid; pos < n; pos += PRS_THREADS) {
+        const uint4 sg = segq[segment_of(pos)];
+        const unsigned int incell = pos - sg.z;
+        const unsigned int c0 = sg.w / (unsigned int)mv.V, c1 = sg.w - c0 * (unsigned int)mv.V;
+        const int s0 = sl0[c0], s1 = sl1[c1];
+        const uint8_t* code = codes + (int64_t)(sg.x + incell) * mv.MP;
+        float d32 = 0.0f;
+        for (int j = 0; j < mv.M; ++j) {
+            const int s = j / mv.m;
+            const float* p = P32 + (size_t)(s ? s1 : s0) * mv.h + (j - s * mv.m) * mv.ds;
+            const float* c = mv.subs32 + ((size_t)j * mv.K + code_byte(code, (int64_t)incell, j, mv.SW)) * mv.ds;
+            for (int t = 0; t < mv.ds; ++t) { const float df = p[t] - c[t]; d32 = fmaf(df, df, d32); }
+        }
+        const float S = 2.0f * (n2[s0] + n2[s1] + c2tot);
+        const float E = ((float)(mv.D + 4) * U24 * 1.01f * S + 4.0f * U24 * d32) * 1.001f + 1e-37f;     // (+ the rounding of d32 +- E itself)
+        lowb[pos] = fmaxf(d32 - E, 0.0f);
+        upb[pos] = d32 + E;
+    }
+    __syncthreads();
+    // ---- B: U = the kk-th smallest upper bound (non-negative floats: the bit patterns order like the values)
+    unsigned int prefix = 0u, mask = 0u, rem = kk;
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        if (tid < 256) hist[tid] = 0u;
+        __syncthreads();
+        for (unsigned int i = tid; i < n; i += PRS_THREADS) {
+            const unsigned int key = __float_as_uint(upb[i]);
+            if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (tid < 32) {
+            unsigned int c[8], tot = 0;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { c[e] = hist[tid * 8 + e]; tot += c[e]; }
+            unsigned int incl = tot;
+            for (int d = 1; d < 32; d <<= 1) { const unsigned int v = __shfl_up_sync(0xffffffffu, incl, d); if (tid >= d) incl += v; }
+            unsigned int before = incl - tot;
+            if (before < rem && rem <= incl) {
+                int e = 0;
+                while (before + c[e] < rem) { before += c[e]; ++e; }
+                s_digit = (unsigned int)(tid * 8 + e); s_rem = rem - before;
+            }
+        }
+        __syncthreads();
+        prefix |= s_digit << shift;
+        mask |= 0xFFu << shift;
+        rem = s_rem;
+        __syncthreads();
+    }
+    const float Ustar = __uint_as_float(prefix);
+    // ---- C: survivors
+    if (tid == 0) s_cnt = 0u;
+    __syncthreads();
+    for (unsigned int i = tid; i < n; i += PRS_THREADS) {
+        if (lowb[i] <= Ustar) {
+            const unsigned int slot = atomicAdd(&s_cnt, 1u);
+            if (slot < PRS_SCAP) spos[slot] = i;
+        }
+    }
+    __syncthreads();
+    const unsigned int nsurv = s_cnt;
+    if (nsurv > PRS_SCAP) {                                           // too many near ties: the host reruns the group in full
+        if (tid == 0) atomicAdd(&wv.cnt->presel_fallback, 1u);
+        return;
+    }
+    // ---- D: exact distances of the survivors, sorted by (distance, retrieval position)
+    for (unsigned int i = tid; i < nsurv; i += PRS_THREADS) {
+        const unsigned int pos = spos[i];
+        const uint4 sg = segq[segment_of(pos)];
+        const unsigned int incell = pos - sg.z;
+        const unsigned int c0 = sg.w / (unsigned int)mv.V, c1 = sg.w - c0 * (unsigned int)mv.V;
+        const double d = exact_adc(mv, codes + (int64_t)(sg.x + incell) * mv.MP, (int64_t)incell,
+                                   P64 + (int64_t)sl0[c0] * mv.h, P64 + (int64_t)sl1[c1] * mv.h);
+        skey[i] = (unsigned long long)__double_as_longlong(d);
+    }
+    unsigned int P = 1;
+    while (P < nsurv) P <<= 1;
+    for (unsigned int i = nsurv + tid; i < P; i += PRS_THREADS) { skey[i] = ~0ull; spos[i] = 0xFFFFFFFFu; }
+    __syncthreads();
+    for (unsigned int kb = 2; kb <= P; kb <<= 1) {
+        for (unsigned int j = kb >> 1; j > 0; j >>= 1) {
+            for (unsigned int i = tid; i < P; i += PRS_THREADS) {
+                const unsigned int ixj = i ^ j;
+                if (ixj > i) {
+                    const unsigned long long ka = skey[i], kc = skey[ixj];
+                    const unsigned int ia = spos[i], ic = spos[ixj];
+                    const bool gt = ka > kc || (ka == kc && ia > ic);
+                    if (gt == ((i & kb) == 0)) { skey[i] = kc; skey[ixj] = ka; spos[i] = ic; spos[ixj] = ia; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (unsigned int i = tid; i < kk; i += PRS_THREADS) {
+        const unsigned int pos = spos[i];
+        const uint4 sg = segq[segment_of(pos)];
+        const unsigned int incell = pos - sg.z;
+        const int64_t row = (int64_t)sg.x + incell;
+        const int64_t e = (int64_t)qr * k + i;
+        rv.d64[e] = __longlong_as_double((long long)skey[i]);
         rv.pos[e] = pos;
         rv.rowid[e] = rowids[row];
         rv.cell[e] = (int32_t)sg.w;
