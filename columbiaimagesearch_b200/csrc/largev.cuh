@@ -612,20 +612,20 @@ k_select_emit(ModelView mv, const uint8_t* __restrict__ codes, const int64_t* __
 // ---- float32 preselection of the retrieved codes -------------------------------------------------------------------------
 // The exact float64 ADC of EVERY retrieved code (k_cand_dist) is bound by the float64 pipe (3 non-fused operations per
 // dimension and candidate); the reference only reports the first k.  One block per query:
-//   A. every candidate's distance in float32 (FFMA, float32 copies of the projections and of the codebook) with a rigorous
-//      error bound  |d32 - d| <= E = (D + 4) 2^-24 * 1.01 * 2 (|p|^2 + sum_j max_k |c_jk|^2)  (inputs rounded to float32: 2u
-//      on every difference, 4u (|p_i| + |c_i|)^2 on its square; D-term FMA accumulation: D u sum t_i^2; sum_i (|p_i| + |c_i|)^2
-//      <= 2 (|p|^2 + |c|^2)) -> lower / upper bounds in shared memory;
-//   B. U = the k-th smallest UPPER bound (radix select on the float bits): at least k candidates have d <= U;
-//   C. survivors = candidates whose LOWER bound is <= U: every member of the exact first k (ties included) is one of them;
+//   A. every candidate's distance in float32 (FFMA, float32 copies of the projections and of the codebook), kept in shared
+//      memory, with a rigorous error bound per query  |d32 - d| <= E = (D + 4) 2^-24 * 1.01 * 2 (max |p|^2 + sum_j max_k |c_jk|^2)
+//      (inputs rounded to float32: 2u on every difference, 4u (|p_i| + |c_i|)^2 on its square; D-term FMA accumulation:
+//      D u sum t_i^2; sum_i (|p_i| + |c_i|)^2 <= 2 (|p|^2 + |c|^2));
+//   B. d32_k = the k-th smallest float32 distance (radix select on the float bits): at least k candidates have d <= d32_k + E;
+//   C. survivors = candidates with d32 <= d32_k + 2 E: every member of the exact first k (ties included) is one of them;
 //   D. the exact float64 ADC of the survivors only (k plus a handful), bitonic sort by (distance, retrieval position) -- the
 //      order of the reference's stable sorted() (search.py:210) -- and the records.
 // Same records as the full evaluation, bit for bit; a query that keeps more than PRS_SCAP survivors (massive near ties)
 // raises presel_fallback and the host sends the group through the full evaluation.
-#define PRS_THREADS 512
+#define PRS_THREADS 256
 #define PRS_MAXN 12288
 #define PRS_SCAP 2048
-inline size_t presel_smem_bytes(unsigned int nmax) { return (size_t)nmax * 8 + (size_t)PRS_SCAP * 12 + 64; }
+inline size_t presel_smem_bytes(unsigned int nmax) { return (size_t)nmax * 4 + (size_t)PRS_SCAP * 12 + 64; }
 
 // float32 copies of the projection slots and their squared norms (rounded up)
 __global__ void __launch_bounds__(256) k_slot_prep(const double* __restrict__ P64, const unsigned int* __restrict__ nslot_p, int h,
@@ -645,16 +645,16 @@ __global__ void __launch_bounds__(256) k_slot_prep(const double* __restrict__ P6
     }
 }
 
-__global__ void __launch_bounds__(PRS_THREADS, 1)
+__global__ void __launch_bounds__(PRS_THREADS, 3)
 k_presel_emit(ModelView mv, const uint8_t* __restrict__ codes, const int64_t* __restrict__ rowids, WalkView wv, int qa,
               const double* __restrict__ P64, const float* __restrict__ P32, const float* __restrict__ n2, float c2tot,
               unsigned int nmax, int k, void* recbuf, int nq_rec, int qrec0) {
-    extern __shared__ __align__(16) unsigned char sm_prs[];           // lowb [nmax] | upb [nmax] | skey [SCAP] | spos [SCAP]
+    extern __shared__ __align__(16) unsigned char sm_prs[];           // d32 [nmax] | skey [SCAP] | spos [SCAP]
     __shared__ unsigned int hist[256];
     __shared__ unsigned int s_cnt, s_digit, s_rem;
-    float* lowb = (float*)sm_prs;
-    float* upb = lowb + nmax;
-    unsigned long long* skey = (unsigned long long*)(upb + nmax);
+    __shared__ float s_smax[PRS_THREADS / 32];
+    float* d32s = (float*)sm_prs;
+    unsigned long long* skey = (unsigned long long*)(sm_prs + (((size_t)nmax * 4 + 15) & ~(size_t)15));
     unsigned int* spos = (unsigned int*)(skey + PRS_SCAP);
     const int g = blockIdx.x, q = qa + g, tid = threadIdx.x;
     const int qr = qrec0 + q;
@@ -678,7 +678,8 @@ k_presel_emit(ModelView mv, const uint8_t* __restrict__ codes, const int64_t* __
         while (b - a > 1) { const int mid = (a + b) >> 1; if (segq[mid].z <= pos) a = mid; else b = mid; }
         return a;
     };
-    // ---- A: float32 distances and their bounds
+    // ---- A: float32 distances; S = the largest |p|^2 of a candidate of this query (one error bound per query)
+    float smax = 0.0f;
     for (unsigned int pos = tid; pos < n; pos += PRS_THREADS) {
         const uint4 sg = segq[segment_of(pos)];
         const unsigned int incell = pos - sg.z;
@@ -692,19 +693,23 @@ k_presel_emit(ModelView mv, const uint8_t* __restrict__ codes, const int64_t* __
             const float* c = mv.subs32 + ((size_t)j * mv.K + code_byte(code, (int64_t)incell, j, mv.SW)) * mv.ds;
             for (int t = 0; t < mv.ds; ++t) { const float df = p[t] - c[t]; d32 = fmaf(df, df, d32); }
         }
-        const float S = 2.0f * (n2[s0] + n2[s1] + c2tot);
-        const float E = ((float)(mv.D + 4) * U24 * 1.01f * S + 4.0f * U24 * d32) * 1.001f + 1e-37f;     // (+ the rounding of d32 +- E itself)
-        lowb[pos] = fmaxf(d32 - E, 0.0f);
-        upb[pos] = d32 + E;
+        d32s[pos] = d32;
+        smax = fmaxf(smax, n2[s0] + n2[s1]);
     }
+    for (int o = 16; o > 0; o >>= 1) smax = fmaxf(smax, __shfl_xor_sync(0xffffffffu, smax, o));
+    if ((tid & 31) == 0) s_smax[tid >> 5] = smax;
     __syncthreads();
-    // ---- B: U = the kk-th smallest upper bound (non-negative floats: the bit patterns order like the values)
+    smax = s_smax[0];
+#pragma unroll
+    for (int w = 1; w < PRS_THREADS / 32; ++w) smax = fmaxf(smax, s_smax[w]);
+    const float E = (float)(mv.D + 4) * U24 * 1.01f * 2.0f * (smax * 1.0001f + c2tot) * 1.001f + 1e-37f;
+    // ---- B: the kk-th smallest float32 distance (non-negative floats: the bit patterns order like the values)
     unsigned int prefix = 0u, mask = 0u, rem = kk;
     for (int shift = 24; shift >= 0; shift -= 8) {
-        if (tid < 256) hist[tid] = 0u;
+        hist[tid] = 0u;
         __syncthreads();
         for (unsigned int i = tid; i < n; i += PRS_THREADS) {
-            const unsigned int key = __float_as_uint(upb[i]);
+            const unsigned int key = __float_as_uint(d32s[i]);
             if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
         }
         __syncthreads();
@@ -727,12 +732,13 @@ k_presel_emit(ModelView mv, const uint8_t* __restrict__ codes, const int64_t* __
         rem = s_rem;
         __syncthreads();
     }
-    const float Ustar = __uint_as_float(prefix);
+    // at least kk candidates have d <= d32_k + E; a candidate of the exact first kk has d32 - E <= d <= d32_k + E
+    const float Ustar = (__uint_as_float(prefix) + 2.0f * E) * (1.0f + 8.0f * U24);
     // ---- C: survivors
     if (tid == 0) s_cnt = 0u;
     __syncthreads();
     for (unsigned int i = tid; i < n; i += PRS_THREADS) {
-        if (lowb[i] <= Ustar) {
+        if (d32s[i] <= Ustar) {
             const unsigned int slot = atomicAdd(&s_cnt, 1u);
             if (slot < PRS_SCAP) spos[slot] = i;
         }
