@@ -691,7 +691,17 @@ k_presel_emit(ModelView mv, const uint8_t* __restrict__ codes, const int64_t* __
             const int s = j / mv.m;
             const float* p = P32 + (size_t)(s ? s1 : s0) * mv.h + (j - s * mv.m) * mv.ds;
             const float* c = mv.subs32 + ((size_t)j * mv.K + code_byte(code, (int64_t)incell, j, mv.SW)) * mv.ds;
-            for (int t = 0; t < mv.ds; ++t) { const float df = p[t] - c[t]; d32 = fmaf(df, df, d32); }
+            if ((mv.ds & 3) == 0) {                                   // 16-byte reads (rows, sub-vectors and centroids are 16-byte aligned)
+                for (int t = 0; t < mv.ds; t += 4) {
+                    const float4 pv = *(const float4*)(p + t), cv = *(const float4*)(c + t);
+                    float df = pv.x - cv.x; d32 = fmaf(df, df, d32);
+                    df = pv.y - cv.y; d32 = fmaf(df, df, d32);
+                    df = pv.z - cv.z; d32 = fmaf(df, df, d32);
+                    df = pv.w - cv.w; d32 = fmaf(df, df, d32);
+                }
+            } else {
+                for (int t = 0; t < mv.ds; ++t) { const float df = p[t] - c[t]; d32 = fmaf(df, df, d32); }
+            }
         }
         d32s[pos] = d32;
         smax = fmaxf(smax, n2[s0] + n2[s1]);
