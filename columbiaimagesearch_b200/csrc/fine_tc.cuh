@@ -8,16 +8,18 @@
 // with p = p_hi + p_lo, c = c_hi + c_lo split into TF32 pieces (round to nearest) and h = |c_k|^2 / 2 in three pieces: the
 // "3 x TF32" scheme, so the product carries ~22 significant bits although the tensor cores multiply 11-bit mantissas.
 // It runs as tcgen05.mma.kind::tf32 (UTCHMMA in SASS) with both operands in shared memory (K-major, no swizzle: 8-row x
-// 16-byte core matrices) and the 128 x 256 float32 accumulator in TENSOR MEMORY; the 256-column accumulator is
-// double-buffered (all 512 columns), so the product of unit u+1 runs while the threads reduce unit u.  The centroid
-// operand of a sub-quantizer (prebuilt on the host in its shared-memory image) arrives by one bulk copy
-// (cp.async.bulk + mbarrier complete_tx, UBLKCP) and serves FTC_T row tiles.
+// 16-byte core matrices) and the 128 x 256 float32 accumulator in TENSOR MEMORY (256 columns per block).  Two blocks share
+// an SM (all 512 columns): one reduces its scores while the product of the other runs.  The centroid operand of a
+// sub-quantizer (prebuilt on the host in its shared-memory image) arrives by one bulk copy (cp.async.bulk + mbarrier
+// complete_tx, UBLKCP; double-buffered where two blocks still fit the SM) and serves FTC_T row tiles; the product signals
+// its completion through tcgen05.commit on an mbarrier.
 //
-// Reduction (tcgen05.ld, one accumulator row per thread, four warps per lane quarter each keeping 64 columns in registers):
-//   pass 1: m = min_k s_k                               (FMNMX3: half an instruction per score)
-//   pass 2: acc = sum_k [s_k < m + 3E] * (1024 + k)       (FFMA.SAT + FFMA per score, both on the FMA pipe)
+// Reduction (tcgen05.ld 32x32b.x32, one accumulator row per thread, two warps per lane quarter each taking 128 columns in
+// 32-column pieces, the next piece in flight while the current one is reduced):
+//   pass 1: m = min_k s_k                               (FMNMX3: half an instruction per score, four independent chains)
+//   pass 2: acc = sum_k [s_k < m + 3E] * (1024 + k)       (FFMA.SAT + FFMA per score, both on the FMA pipe, four sums)
 // [.] is evaluated as sat((thr - s) * 2^64), exactly 0 or 1 whenever 2^-39 <= |thr| < 2^62 (two distinct floats that close
-// to thr differ by >= 2^-63).  acc in [1024, 1024 + 63] in exactly one column quarter <=> exactly one score lies below
+// to thr differ by >= 2^-63).  acc in [1024, 1024 + 127] in exactly one column half <=> exactly one score lies below
 // m + 3E: that centroid is the float64 argmin, because every score is within
 //     E = 16 * 2^-24 * (|p| + max_k |c_k|)^2
 // of its exact value (input rounding to float32 2^-24, the TF32 split 2^-22 per operand, the dropped lo.lo term 2^-22, the
