@@ -52,3 +52,67 @@ def test_quantised_sum_is_a_lower_bound():
         lb = b.astype(np.float64).sum() + delta * (S - 0.1)
         assert (d >= lb * (1 - 1e-12) - 1e-300).all()
         assert S.max() <= 65535
+
+
+def test_large_v_preselection_bound():
+    """largev.cuh k_presel_emit: the float32 ADC distance of a retrieved code (float32 copies of projection and codebook,
+    FSUB + one FFMA chain over all D dimensions) against the float64 distance:
+        |d32 - d| <= E = (D + 4) * 2^-24 * 1.01 * 2 * (|p|^2 + |c|^2)
+    (the kernel uses upper bounds of |p|^2 and |c|^2, which only widens E).  Emulated over magnitudes, near-equal vectors
+    (cancellation) and mixed scales per dimension; also the selection argument: with d32_k the k-th smallest d32, every
+    member of the exact first k has d32 <= d32_k + 2E."""
+    rng = np.random.RandomState(7)
+    u = 5.9604645e-08
+    worst = 0.0
+    for D in (32, 128, 256):
+        for scale in (1e-4, 0.05, 1.0, 300.0):
+            for gap in (0.0, 1e-6, 1e-3, 0.3, 3.0):
+                n = 4000
+                c = rng.randn(n, D) * scale * np.exp(rng.randn(1, D))              # uneven dimensions
+                p = c * (1.0 + gap * rng.randn(n, D)) + gap * scale * rng.randn(n, D)
+                p32 = p.astype(np.float32).astype(np.float64)                        # the kernel reads float32 copies of both
+                d = ((p - c) ** 2).sum(1)
+                d32, _ = _d32(p, c)
+                E = (D + 4) * u * 1.01 * 2.0 * ((p ** 2).sum(1) + (c ** 2).sum(1))
+                err = np.abs(d32.astype(np.float64) - d)
+                assert (err <= E + 1e-300).all(), (D, scale, gap, float((err / np.maximum(E, 1e-300)).max()))
+                worst = max(worst, float((err / np.maximum(E, 1e-300)).max()))
+                # selection: one query against n candidates
+                k = 50
+                q = rng.randn(D) * scale
+                dq = ((q[None, :] - c) ** 2).sum(1)
+                dq32, _ = _d32(np.repeat(q[None, :], n, 0), c)
+                Eq = float(((D + 4) * u * 1.01 * 2.0 * ((q ** 2).sum() + (c ** 2).sum(1))).max())
+                kth32 = np.sort(dq32.astype(np.float64))[k - 1]
+                first_k = np.argsort(dq, kind="stable")[:k]
+                assert (dq32[first_k].astype(np.float64) <= kth32 + 2.0 * Eq).all(), (D, scale, gap)
+    assert worst < 0.5          # the bound is an upper bound with head-room, not an estimate
+
+
+def test_score_form_guard_bound():
+    """encode.cuh k_fine_argmin32 / k_coarse_big: the score  s = |c|^2 / 2 - x.c  evaluated in float32 (x and c rounded to
+    float32, half norm by an FFMA chain over the float32 centroid, then one FFMA per dimension starting from it) against
+    its float64 value:  |s32 - s| <= E = (n + 4) * 2^-24 * (|x| + |c|)^2  (the coarse kernel uses n + 16).  A centroid is
+    accepted only when the runner-up is more than 3 E away, so E has to be an upper bound over magnitudes and sizes."""
+    rng = np.random.RandomState(11)
+    u = 5.9604645e-08
+    worst = 0.0
+    for nd in (2, 8, 16, 64, 128):
+        for scale in (1e-3, 0.2, 1.0, 50.0):
+            for near in (0.0, 1e-5, 1e-2, 1.0):
+                n = 5000
+                c = rng.randn(n, nd) * scale
+                x = c * (1.0 + near * rng.randn(n, nd)) + near * scale * rng.randn(n, nd)
+                s = 0.5 * (c ** 2).sum(1) - (x * c).sum(1)
+                x32, c32 = x.astype(np.float32), c.astype(np.float32)
+                hn = np.zeros(n, np.float32)
+                for t in range(nd):
+                    hn = (c32[:, t].astype(np.float64) * c32[:, t].astype(np.float64) + hn.astype(np.float64)).astype(np.float32)
+                v = (np.float32(0.5) * hn).astype(np.float32)
+                for t in range(nd):
+                    v = ((-x32[:, t]).astype(np.float64) * c32[:, t].astype(np.float64) + v.astype(np.float64)).astype(np.float32)
+                E = (nd + 4) * u * (np.sqrt((x ** 2).sum(1)) + np.sqrt((c ** 2).sum(1))) ** 2
+                err = np.abs(v.astype(np.float64) - s)
+                assert (err <= E + 1e-300).all(), (nd, scale, near, float((err / np.maximum(E, 1e-300)).max()))
+                worst = max(worst, float((err / np.maximum(E, 1e-300)).max()))
+    assert worst < 0.6
