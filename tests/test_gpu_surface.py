@@ -438,3 +438,25 @@ def test_model_loaded_from_protobuf_encodes_like_the_oracle(tmp_path):
     oc, of = orc.encode_batch(omodel, db)
     coarse, fine = lopq.utils.compute_codes_arrays(db, model)
     assert np.array_equal(coarse, oc) and np.array_equal(fine, of)
+
+
+def test_eval_helpers_follow_the_reference_definitions():
+    """eval.py:41-63 (nearest neighbours sharing the multi-index cell) and eval.py:145-161 (per-sub-quantizer distortion on
+    the locally projected residuals) through the device encode / project calls, against NumPy restatements on the oracle."""
+    lopq = _lopq()
+    import columbiaimagesearch_b200.lopq.eval as ev
+    z, omodel = load_case("A")
+    _, db, _, _ = case_inputs("A")
+    model = lopq.LOPQModel.from_npz(z)
+    X = db[:700]
+    nns = ev.compute_all_neighbors(X)
+    assert (nns == np.arange(700)).mean() > 0.9               # (a point is its own nearest neighbour, duplicates aside)
+    nn2 = ev.compute_all_neighbors(X, just_nn=False)[:, 1]    # the nearest OTHER point
+    oc, of = orc.encode_batch(omodel, X)
+    want = float(np.count_nonzero(np.all(oc == oc[nn2], axis=1))) / 700
+    assert ev.get_proportion_nns_with_same_coarse_codes(X, model, nns=nn2) == want
+    px = np.stack([orc.project(omodel, x, c) for x, c in zip(X, oc)])
+    suball = list(omodel.subquantizers[0]) + list(omodel.subquantizers[1])
+    ds = px.shape[1] // len(suball)
+    want_d = np.array([((px[:, j * ds:(j + 1) * ds] - C[of[:, j]]) ** 2).sum() for j, C in enumerate(suball)]) / 700
+    np.testing.assert_allclose(ev.get_subquantizer_distortion(X, model), want_d, rtol=1e-9)

@@ -96,3 +96,17 @@ def test_train_pca_matches_reference():
     sign = np.sign((P * rp["P"]).sum(0))
     np.testing.assert_allclose(P * sign, rp["P"], rtol=0, atol=1e-8)
     assert eigenvalue_allocation(2, rp["E"]).tolist() == ref.model.eigenvalue_allocation(2, rp["E"]).tolist()
+
+
+def test_mirror_compute_all_neighbors_matches_reference():
+    """eval.py:7-38 (the ground-truth helper of the recall harness): the mirror's chunked evaluation returns the
+    reference's indices, nearest-only and fully ranked."""
+    import columbiaimagesearch_b200.lopq.eval as ev
+    ref = ref_loader.load()
+    rng = np.random.RandomState(0)
+    a, b = rng.randn(300, 16), rng.randn(500, 16)
+    b[17] = b[3]                                              # a tie: argmin / argsort order of the reference
+    assert np.array_equal(ev.compute_all_neighbors(a, b, chunk=64), ref.eval.compute_all_neighbors(a, b))
+    assert np.array_equal(ev.compute_all_neighbors(a, chunk=77), ref.eval.compute_all_neighbors(a))
+    assert np.array_equal(ev.compute_all_neighbors(a[:40], b[:60], just_nn=False, chunk=7),
+                          ref.eval.compute_all_neighbors(a[:40], b[:60], just_nn=False))
