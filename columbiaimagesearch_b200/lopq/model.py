@@ -41,6 +41,64 @@ def _cluster_handle(centroids):
     return h
 
 
+# ---- module-level training helpers of lopq/lopq/model.py (imported by eval.py:146 and by user scripts) ------------------
+def eigenvalue_allocation(num_buckets, eigenvalues):
+    """model.py:19-71."""
+    from .train import eigenvalue_allocation as f
+    return f(num_buckets, eigenvalues)
+
+
+def compute_residuals(data, C, device=None):
+    """model.py:236-239 -- (data - C[assignments], assignments); the nearest-centroid assignments (utils.predict_cluster over
+    rows) run on the GPU unless device=False."""
+    from .train import _assign, _use_device
+    data = np.asarray(data, dtype=np.float64)
+    C = np.asarray(C, dtype=np.float64)
+    assignments = _assign(data, C, device=_use_device(device))
+    return data - C[assignments], assignments
+
+
+def project_residuals_to_local(residuals, assignments, Rs, mu):
+    """model.py:209-234."""
+    from .train import project_residuals_to_local as f
+    return f(np.asarray(residuals), np.asarray(assignments), np.asarray(Rs), np.asarray(mu))
+
+
+def compute_local_rotations(data, C, num_buckets, device=None):
+    """model.py:74-206 -> (Rs, mus, assignments, residuals)."""
+    from .train import compute_local_rotations as f, _use_device
+    return f(np.asarray(data, dtype=np.float64), np.asarray(C, dtype=np.float64), num_buckets, _use_device(device))
+
+
+def train_coarse(data, V=8, kmeans_coarse_iters=10, n_init=10, random_state=None, device=None):
+    """model.py:290-317 -- centroids [V, D] of one coarse quantizer (Lloyd k-means on the device; the reference uses
+    sklearn's MiniBatchKMeans: statistical parity only)."""
+    from .train import kmeans, _use_device
+    return kmeans(np.asarray(data, dtype=np.float64), V, kmeans_coarse_iters, np.random.RandomState(random_state), n_init, _use_device(device))
+
+
+def train_subquantizers(data, num_buckets, subquantizer_clusters=256, kmeans_local_iters=20, n_init=10, random_state=None, device=None):
+    """model.py:320-336 -- one k-means codebook per sub-vector of the (projected) data."""
+    from .train import kmeans, _use_device
+    rng = np.random.RandomState(random_state)
+    return [kmeans(np.asarray(d, dtype=np.float64), subquantizer_clusters, kmeans_local_iters, rng, n_init, _use_device(device))
+            for d in np.split(np.asarray(data), num_buckets, axis=1)]
+
+
+def train(data, V=8, M=4, subquantizer_clusters=256, parameters=None, kmeans_coarse_iters=10, kmeans_local_iters=20, n_init=10,
+          subquantizer_sample_ratio=1.0, random_state=None, verbose=False, device=None):
+    """model.py:339-437 -> (Cs, Rs, mus, subquantizers)."""
+    from .train import train as f
+    return f(data, V, M, subquantizer_clusters, parameters, kmeans_coarse_iters, kmeans_local_iters, n_init,
+             subquantizer_sample_ratio, random_state, verbose, device)
+
+
+def train_pca(data, dims=256, subsample=None):
+    """model.py:242-287 -> (P, mu)."""
+    from .train import train_pca as f
+    return f(data, dims, subsample)
+
+
 class LOPQModel(object):
     def __init__(self, V=8, M=4, subquantizer_clusters=256, parameters=None):
         """model.py:448-493.  parameters = ((C1, C2), (Rs1, Rs2), (mu1, mu2), (subquantizers1, subquantizers2))."""

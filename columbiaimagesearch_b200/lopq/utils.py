@@ -13,6 +13,42 @@ def iterate_splits(x, splits):
         yield x[start:start + split_size], split
 
 
+def concat_new_first(arrs):
+    """utils.py:24-29 -- arrays stacked along a new first dimension."""
+    return np.concatenate([np.asarray(a)[np.newaxis, ...] for a in arrs], axis=0)
+
+
+_XVECS = {"f": ("<f4", float), "i": ("<u4", int), "b": ("u1", float)}
+
+
+def load_xvecs(filename, base_type="f", max_num=None):
+    """utils.py:64-99 -- the .fvecs / .ivecs / .bvecs files of corpus-texmex.irisa.fr (every vector: uint32 dimension, then
+    D components): an N x D array (float64 for 'f' and 'b', int for 'i', squeezed), read in one pass instead of one
+    struct.unpack per component."""
+    import os
+    code, py_type = _XVECS[base_type]
+    isz = np.dtype(code).itemsize
+    with open(filename, "rb") as f:
+        D = int(np.frombuffer(f.read(4), dtype="<u4")[0])
+    rec = 4 + D * isz
+    N = os.path.getsize(filename) // rec
+    if max_num is None:
+        max_num = N
+    raw = np.fromfile(filename, dtype=np.uint8, count=max_num * rec).reshape(max_num, rec)
+    A = np.ascontiguousarray(raw[:, 4:]).view(code).reshape(max_num, D).astype(py_type)
+    return np.squeeze(A)
+
+
+def save_xvecs(data, filename, base_type="f"):
+    """utils.py:102-131 -- the inverse of load_xvecs (rows of any length; a scalar row is a vector of length 1)."""
+    code, _ = _XVECS[base_type]
+    with open(filename, "wb") as f:
+        for d in data:
+            d = np.atleast_1d(np.asarray(d))
+            f.write(np.array([d.shape[0]], dtype="<u4").tobytes())
+            f.write(d.astype(code).tobytes())
+
+
 def predict_cluster(x, centroids):
     """utils.py:33-53 -- index of the nearest centroid (direct-form squared L2, first minimum),
     returned as the smallest unsigned NumPy integer type that fits.  Evaluated on the device by

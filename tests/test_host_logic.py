@@ -176,3 +176,27 @@ def test_model_protobuf_and_mat_formats(tmp_path):
     for s in (0, 1):
         assert np.array_equal(back.Cs[s], params[0][s]) and np.array_equal(back.Rs[s], params[1][s])
         assert np.array_equal(back.mus[s], params[2][s]) and np.array_equal(back.subquantizers[s][1], params[3][s][1])
+
+
+def test_model_module_training_helpers_host_path():
+    """The module-level helpers of lopq/lopq/model.py that user code imports (eval.py:146: compute_residuals,
+    project_residuals_to_local; train_coarse / train_subquantizers / train / train_pca) exist with the reference's
+    signatures; device=False keeps the assignments on the host so this runs without a GPU."""
+    import inspect
+    import columbiaimagesearch_b200.lopq.model as mm
+    rng = np.random.RandomState(4)
+    X = np.concatenate([rng.randn(300, 6) + 4.0, rng.randn(300, 6) - 4.0])
+    C = mm.train_coarse(X, V=2, kmeans_coarse_iters=8, n_init=2, random_state=0, device=False)
+    assert C.shape == (2, 6) and abs(abs(C[:, 0]).mean() - 4.0) < 0.5
+    res, a = mm.compute_residuals(X, C, device=False)
+    assert res.shape == X.shape and set(a.tolist()) == {0, 1} and np.allclose(res, X - C[a])
+    assert abs(np.bincount(a)[0] - 300) <= 2
+    R, mu, a2, res2 = mm.compute_local_rotations(X, C, 1, device=False)
+    assert R.shape == (2, 6, 6) and np.array_equal(a, a2)
+    proj = mm.project_residuals_to_local(res, a, R, mu)
+    assert np.allclose(np.linalg.norm(proj, axis=1), np.linalg.norm(res - mu[a], axis=1))      # rotations are orthogonal
+    subs = mm.train_subquantizers(proj, 2, subquantizer_clusters=8, kmeans_local_iters=5, n_init=1, random_state=1, device=False)
+    assert len(subs) == 2 and subs[0].shape == (8, 3)
+    assert list(inspect.signature(mm.train_coarse).parameters)[:5] == ["data", "V", "kmeans_coarse_iters", "n_init", "random_state"]
+    assert list(inspect.signature(mm.train_subquantizers).parameters)[:6] == ["data", "num_buckets", "subquantizer_clusters", "kmeans_local_iters", "n_init", "random_state"]
+    assert mm.eigenvalue_allocation(2, np.array([4.0, 3.0, 2.0, 1.0])).shape == (4,)

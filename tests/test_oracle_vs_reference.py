@@ -110,3 +110,28 @@ def test_mirror_compute_all_neighbors_matches_reference():
     assert np.array_equal(ev.compute_all_neighbors(a, chunk=77), ref.eval.compute_all_neighbors(a))
     assert np.array_equal(ev.compute_all_neighbors(a[:40], b[:60], just_nn=False, chunk=7),
                           ref.eval.compute_all_neighbors(a[:40], b[:60], just_nn=False))
+
+
+def test_mirror_xvecs_io_matches_reference(tmp_path):
+    """utils.py:64-131 (.fvecs / .ivecs / .bvecs of corpus-texmex.irisa.fr): files written by either side read back
+    identically by both, max_num and the squeeze of single-column data included."""
+    import columbiaimagesearch_b200.lopq.utils as mu
+    ref = ref_loader.load()
+    rng = np.random.RandomState(2)
+    cases = {"f": rng.randn(7, 5).astype(np.float32), "i": rng.randint(0, 2 ** 31 - 1, size=(6, 3)), "b": rng.randint(0, 256, size=(9, 4))}
+    for bt, data in cases.items():
+        a, b = str(tmp_path / ("ref." + bt)), str(tmp_path / ("mir." + bt))
+        ref.utils.save_xvecs(data, a, base_type=bt)
+        mu.save_xvecs(data, b, base_type=bt)
+        assert open(a, "rb").read() == open(b, "rb").read()
+        for mx in (None, 3):
+            rb = mu.load_xvecs(b, base_type=bt, max_num=mx)
+            if bt == "b":             # (the reference's own 'b' reader unpacks the 4-byte dimension with format 'B' and raises)
+                assert rb.dtype == np.float64 and np.array_equal(rb, data[:mx].astype(np.float64))
+                continue
+            ra = ref.utils.load_xvecs(a, base_type=bt, max_num=mx)
+            assert ra.dtype == rb.dtype and ra.shape == rb.shape and np.array_equal(ra, rb), (bt, mx)
+    one = str(tmp_path / "one.f")
+    mu.save_xvecs(np.arange(5, dtype=np.float32), one)          # scalar rows: vectors of length 1
+    assert np.array_equal(mu.load_xvecs(one), ref.utils.load_xvecs(one)) and mu.load_xvecs(one).shape == (5,)
+    assert np.array_equal(mu.concat_new_first([np.ones((2, 3)), np.zeros((2, 3))]), ref.utils.concat_new_first([np.ones((2, 3)), np.zeros((2, 3))]))
