@@ -23,8 +23,10 @@
 // m + 3E: that centroid is the float64 argmin, because every score is within
 //     E = 16 * 2^-24 * (|p| + max_k |c_k|)^2
 // of its exact value (input rounding to float32 2^-24, the TF32 split 2^-22 per operand, the dropped lo.lo term 2^-22, the
-// float32 accumulation of the tensor core: together below 8 * 2^-24 (|p| + |c|)^2; the largest error measured over
-// 1.5 million scores of six models is 1.41 * 2^-24 (|p| + max|c|)^2, and tests/test_gpu_surface.py keeps it below E / 4).  Everything
+// float32 accumulation of the tensor core, one truncation per instruction: together below 8 * 2^-24 (|p| + |c|)^2 -- emulated
+// in tests/test_error_bounds.py; the largest error measured on the hardware is 1.41 * 2^-24 (|p| + max|c|)^2 over 1.5 million
+// scores of six models and 1.84 * 2^-24 on adversarial rows whose products all have one sign (profiles/dev/
+// ftc_adversarial_probe.py: the bias of a truncating accumulator shows), and tests/test_gpu_surface.py keeps it below E / 4).  Everything
 // else -- near ties, exact ties, NaNs, out-of-range thresholds -- goes to a list that k_fine_redo evaluates in float64 in
 // NumPy's order with the first-minimum rule: the codes are the reference's, bit for bit.
 #pragma once

@@ -116,3 +116,59 @@ def test_score_form_guard_bound():
                 assert (err <= E + 1e-300).all(), (nd, scale, near, float((err / np.maximum(E, 1e-300)).max()))
                 worst = max(worst, float((err / np.maximum(E, 1e-300)).max()))
     assert worst < 0.6
+
+
+def _tf32_rna(x32):
+    """float32 -> nearest TF32 (10 explicit mantissa bits), ties away from zero: cvt.rna.tf32.f32 / ftc_tf32_host."""
+    u = np.asarray(x32, np.float32).view(np.uint32)
+    return ((u + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
+def _to_f32(x64, toward_zero):
+    y = x64.astype(np.float32)
+    if toward_zero:
+        over = np.abs(y.astype(np.float64)) > np.abs(x64)
+        y = np.where(over, np.nextafter(y, np.float32(0.0)), y).astype(np.float32)
+    return y
+
+
+def test_three_tf32_pieces_score_budget():
+    """fine_tc.cuh: the score |c|^2/2 - p.c as the product of ( p_hi | p_hi | p_lo | 1 1 1 ) with ( -c_hi | -c_lo | -c_hi |
+    h_hi h_lo h_lo2 ): TF32 pieces rounded to nearest, products exact, float32 accumulation -- emulated (a) with one
+    round-to-nearest per product and (b) with ONE TRUNCATION PER MMA INSTRUCTION (8 exact products added to the accumulator,
+    then rounded toward zero: the hardware measurement on adversarial rows, profiles/dev/ftc_adversarial_probe.py, shows the
+    positive bias of a truncating accumulator at 1.8 * 2^-24 worst case).  Either way the error stays below
+    8 * 2^-24 (|p| + |c|)^2, half of the E = 16 * 2^-24 (|p| + max|c|)^2 the guard uses.  p == c rows (all products of
+    the winning score have one sign) are the worst case for (b)."""
+    rng = np.random.RandomState(3)
+    u = 5.9604645e-08
+    for ds in (8, 16):
+        for scale in (1e-3, 0.3, 1.0, 40.0):
+            for near in (0.0, 1e-4, 0.1, 1.0):
+                n = 4000
+                c = rng.randn(n, ds) * scale
+                p = c * (1.0 + near * rng.randn(n, ds)) + near * scale * rng.randn(n, ds)
+                s = 0.5 * (c ** 2).sum(1) - (p * c).sum(1)
+                p32, c32 = p.astype(np.float32), c.astype(np.float32)
+                p_hi = _tf32_rna(p32); p_lo = _tf32_rna((p32 - p_hi).astype(np.float32))
+                c_hi = _tf32_rna(c32); c_lo = _tf32_rna((c32 - c_hi).astype(np.float32))
+                h = 0.5 * (c ** 2).sum(1)
+                pieces, res = [], h.copy()
+                for _ in range(3):
+                    piece = _tf32_rna(res.astype(np.float32))
+                    pieces.append(piece)
+                    res = res - piece.astype(np.float64)
+                bound = 8.0 * u * (np.sqrt((p ** 2).sum(1)) + np.sqrt((c ** 2).sum(1))) ** 2
+                terms = [(p_hi[:, t], -c_hi[:, t]) for t in range(ds)] + [(p_hi[:, t], -c_lo[:, t]) for t in range(ds)] + \
+                        [(p_lo[:, t], -c_hi[:, t]) for t in range(ds)] + [(np.ones(n, np.float32), pc) for pc in pieces]
+                for per_instruction_truncation in (False, True):
+                    acc = np.zeros(n, np.float32)
+                    group = 8 if per_instruction_truncation else 1
+                    for g0 in range(0, len(terms), group):
+                        tot = acc.astype(np.float64)
+                        for a, b in terms[g0:g0 + group]:
+                            tot = tot + a.astype(np.float64) * b.astype(np.float64)
+                        acc = _to_f32(tot, per_instruction_truncation)
+                    err = np.abs(acc.astype(np.float64) - s)
+                    assert (err <= bound + 1e-300).all(), (ds, scale, near, per_instruction_truncation,
+                                                           float((err / np.maximum(bound, 1e-300)).max()))
