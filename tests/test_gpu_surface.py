@@ -374,6 +374,20 @@ def test_tensor_core_fine_scores_stay_inside_the_guard_bound(shape):
         assert np.array_equal(sc[:, :K].argmin(1), exact.argmin(1))
         if K < 256:
             assert sc[:, K:].min() > 1e29
+    # adversarial rows: reconstructions of random codes -- every sub-vector projection IS a sub-centroid, so all products of
+    # the winning score have one sign (the worst case for an accumulator that truncates)
+    rng = np.random.RandomState(1)
+    codes = [(tuple(rng.randint(0, V, size=2)), tuple(rng.randint(0, K, size=M))) for _ in range(2048)]
+    X = np.stack([model.reconstruct(c) for c in codes])
+    for j in (0, M - 1):
+        sc, px = h.debug_fine_scores(X, j)
+        sub = np.asarray(params[3][j // m][j % m], np.float64)
+        p = px[:, j * ds:(j + 1) * ds]
+        exact = 0.5 * (sub ** 2).sum(1)[None, :] - p @ sub.T
+        unit = (np.sqrt((p ** 2).sum(1)) + np.sqrt((sub ** 2).sum(1).max())) ** 2 * 2.0 ** -24
+        worst = max(worst, float((np.abs(sc[:, :K] - exact) / unit[:, None]).max()))
+        own = np.array([codes[i][1][j] for i in range(128)])
+        assert np.array_equal(sc[:, :K].argmin(1), own)
     assert worst < 4.0, worst
 
 
